@@ -1,0 +1,218 @@
+"""Second, independent restatement of the cycle in plain Python -- TEST INFRASTRUCTURE ONLY.
+
+Written from SURVEY.md Appendix A, not from yk_oracle.cpp, and structured differently on purpose:
+instead of walking a (score, NodeID)-sorted tree with early exit, each ask takes the *minimum*
+(score, NodeID bytes) over all nodes that pass -- the exhaustive formulation the GPU uses.  Agreement of
+the two on small snapshots is the only protection available while the Go reference cannot run here.
+Only small cases: pure-Python loops.
+"""
+from __future__ import annotations
+
+import math
+
+UNSET = -1
+ST_PENDING, ST_ALLOCATED, ST_NOFIT, ST_SKIPPED, ST_SLOWPATH, ST_INVALID = range(6)
+
+
+def fit_in(larger, smaller):
+    return all(sm <= max(0, lg) for lg, sm in zip(larger, smaller))
+
+
+def strictly_gt_zero(r):
+    return all(v >= 0 for v in r) and any(v > 0 for v in r)
+
+
+def node_score(policy, w, total, avail):
+    usage = 0.0
+    tw = 0.0
+    for k in range(len(w)):
+        if w[k] == 0.0 or total[k] == 0:
+            continue
+        share = 1.0 - float(avail[k]) / float(total[k])
+        if math.isnan(share):
+            continue
+        usage += share * w[k]
+        tw += w[k]
+    a = 0.0 if tw == 0.0 else usage / tw
+    return ((1.0 - a) if policy == 1 else a) + 0.0
+
+
+def shares(res, total):
+    out = []
+    for k, v in enumerate(res):
+        if v == 0:
+            out.append(0.0)
+        elif total is None or total[k] <= 0:
+            out.append(float(v))
+        else:
+            out.append(float(v) / float(total[k]))
+    return sorted(out)
+
+
+def compare_shares(l, r):
+    l = list(reversed(l))
+    r = list(reversed(r))
+    for x, y in zip(l, r):
+        if x > y:
+            return 1
+        if x < y:
+            return -1
+    if len(l) > len(r):
+        return 1 if any(v > 0 for v in l[len(r):]) else 0
+    if len(r) > len(l):
+        return -1 if any(v > 0 for v in r[len(l):]) else 0
+    return 0
+
+
+def run(s, max_bindings=-1):
+    D, N, A = s.D, s.n_nodes, s.n_asks
+    w = [float(x) for x in s.weights]
+    total = [[int(x) for x in row] for row in s.node_total]
+    avail = [[int(x) for x in row] for row in s.node_avail]
+    ids = [i.encode() for i in s.node_id]
+    req = [[int(x) for x in row] for row in s.ask_req]
+    Q = s.n_queues
+    children = [[] for _ in range(Q)]
+    for q in range(1, Q):
+        children[int(s.q_parent[q])].append(q)
+    q_alloc = [[int(x) for x in row] for row in s.q_alloc]
+    q_pending = [[0] * D for _ in range(Q)]
+    q_npend = [0] * Q
+    q_apps = [[] for _ in range(Q)]
+    for p in range(s.n_apps):
+        q_apps[int(s.app_queue[p])].append(p)
+    app_asks = [[] for _ in range(s.n_apps)]
+    for a in range(A):
+        app_asks[int(s.ask_app[a])].append(a)
+    for p in range(s.n_apps):
+        app_asks[p].sort(key=lambda a: (-int(s.ask_prio[a]), int(s.ask_create[a]), a))
+    state = [ST_PENDING] * A
+    dead = [False] * A
+    app_alloc = [[0] * D for _ in range(s.n_apps)]
+
+    def chain(q):
+        while q >= 0:
+            yield q
+            q = int(s.q_parent[q])
+
+    for a in range(A):
+        for q in chain(int(s.app_queue[int(s.ask_app[a])])):
+            q_npend[q] += 1
+            for k in range(D):
+                q_pending[q][k] += req[a][k]
+
+    def headroom(q):
+        hr = [UNSET] * D
+        for qq in reversed(list(chain(q))):
+            for k in range(D):
+                mx = int(s.q_max[qq][k])
+                if mx == UNSET:
+                    continue
+                own = max(0, mx - q_alloc[qq][k])
+                hr[k] = own if hr[k] == UNSET else min(hr[k], own)
+        return hr
+
+    def passes_node(a, n):
+        if not (int(s.node_flags[n]) & 1) or (int(s.node_flags[n]) & 2):
+            return False
+        if not fit_in(total[n], req[a]) or not fit_in(avail[n], req[a]):
+            return False
+        if int(s.ask_node[a]) >= 0 and int(s.ask_node[a]) != n:
+            return False
+        if int(s.node_taint[n]) & ~int(s.ask_tol[a]) & 0xFFFFFFFFFFFFFFFF:
+            return False
+        lab, need, deny = int(s.node_label[n]), int(s.ask_need[a]), int(s.ask_deny[a])
+        return (lab & need) == need and (lab & deny) == 0
+
+    def pick_node(a):
+        best = None
+        for n in range(N):
+            if passes_node(a, n):
+                key = (node_score(s.policy, w, total[n], avail[n]), ids[n])
+                if best is None or key < best[0]:
+                    best = (key, n)
+        return None if best is None else best[1]
+
+    def app_prio(p):
+        pr = [int(s.ask_prio[a]) for a in app_asks[p] if state[a] != ST_ALLOCATED]
+        return max(pr) if pr else -(1 << 31)
+
+    def app_npend(p):
+        return sum(1 for a in app_asks[p] if state[a] != ST_ALLOCATED)
+
+    def try_queue(q):
+        if not children[q]:
+            hr = headroom(q)
+            cand = [p for p in q_apps[q] if app_npend(p) > 0]
+            if int(s.q_sort[q]) == 1:
+                import functools
+                base = [int(x) for x in s.q_guaranteed[q]]
+
+                def cmp(l, r):
+                    c = compare_shares(shares(app_alloc[l], base), shares(app_alloc[r], base))
+                    if c:
+                        return c
+                    kl = (-app_prio(l), int(s.app_submit[l]), l)
+                    kr = (-app_prio(r), int(s.app_submit[r]), r)
+                    return -1 if kl < kr else (1 if kl > kr else 0)
+                cand.sort(key=functools.cmp_to_key(cmp))
+            else:
+                cand.sort(key=lambda p: (-app_prio(p), int(s.app_submit[p]), p))
+            for p in cand:
+                for a in app_asks[p]:
+                    if state[a] == ST_ALLOCATED or dead[a]:
+                        continue
+                    if int(s.ask_flags[a]) & 1:
+                        state[a], dead[a] = ST_SLOWPATH, True
+                        continue
+                    if any(hr[k] != UNSET and req[a][k] > hr[k] for k in range(D)):
+                        state[a], dead[a] = ST_SKIPPED, True
+                        continue
+                    if not strictly_gt_zero(req[a]):
+                        state[a], dead[a] = ST_INVALID, True
+                        continue
+                    n = pick_node(a)
+                    if n is not None:
+                        return a, n
+                    state[a], dead[a] = ST_NOFIT, True
+            return None
+        import functools
+        cand = [c for c in children[q] if q_npend[c] > 0]
+
+        def qcmp(l, r):
+            c = compare_shares(shares(q_alloc[l], [int(x) for x in s.q_guaranteed[l]]),
+                               shares(q_alloc[r], [int(x) for x in s.q_guaranteed[r]]))
+            if c:
+                return c
+            d = [q_pending[l][k] - q_pending[r][k] for k in range(D)]
+            if strictly_gt_zero(d):
+                return -1
+            if strictly_gt_zero([-x for x in d]):
+                return 1
+            return -1 if l < r else (1 if l > r else 0)
+        cand.sort(key=functools.cmp_to_key(qcmp))
+        for c in cand:
+            r = try_queue(c)
+            if r is not None:
+                return r
+        return None
+
+    out = []
+    while max_bindings < 0 or len(out) < max_bindings:
+        r = try_queue(0)
+        if r is None:
+            break
+        a, n = r
+        for k in range(D):
+            avail[n][k] -= req[a][k]
+        p = int(s.ask_app[a])
+        for k in range(D):
+            app_alloc[p][k] += req[a][k]
+        for q in chain(int(s.app_queue[p])):
+            q_npend[q] -= 1
+            for k in range(D):
+                q_alloc[q][k] += req[a][k]
+                q_pending[q][k] -= req[a][k]
+        state[a] = ST_ALLOCATED
+        out.append((a, n))
+    return {"ask": [a for a, _ in out], "node": [n for _, n in out], "state": state, "avail": avail}

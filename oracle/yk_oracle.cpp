@@ -1,0 +1,420 @@
+// yk_oracle.cpp -- TEST INFRASTRUCTURE ONLY (see yk_oracle.h header comment).
+//
+// Sequential CPU restatement of the reference's scheduling cycle.  It keeps the
+// reference's *structure* on purpose: one allocation per schedule() pass, queues
+// and applications re-sorted on every pass, nodes walked in ascending
+// (score, NodeID) order with early exit at the first node that passes, one
+// predicate call per (ask,node) visited, re-key of the committed node.
+//
+// What each function follows:
+//   fit_in / strictly_gt_zero  yunikorn-core pkg/common/resources/resources.go (FitIn,
+//                              StrictlyGreaterThanZero)              [EXT, SURVEY A.2]
+//   yko_node_score             yunikorn-core objects/node.go GetResourceUsageShares +
+//                              objects/nodesorting.go absResourceUsage/ScoreNode [EXT, A.3]
+//   NodeLess                   yunikorn-core objects/node_collection.go nodeRef.Less [EXT, A.3]
+//   shim_predicates            /root/reference/pkg/plugin/predicates/predicate_manager.go:202-283
+//                              (podFitsNode: prefilter then filters, first failure wins) with the
+//                              k8s plugins restated as mask ops; entry through
+//                              pkg/cache/scheduler_callback.go:196-198 -> pkg/cache/context.go:683-703
+//   try_node / try_nodes       yunikorn-core objects/application.go tryNodes/tryNode,
+//                              objects/node.go preAllocateCheck/TryAddAllocation [EXT, A.2]
+//   get_shares/compare_shares  yunikorn-core resources.go getShares/compareShares  [EXT]
+//   headroom                   yunikorn-core objects/queue.go getHeadRoom/internalHeadRoom [EXT]
+//   try_queue                  yunikorn-core objects/queue.go TryAllocate/sortQueues/sortApplications [EXT]
+//   request vectors (inputs)   /root/reference/pkg/common/resource.go:56-109,188-195,273-285
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (oracle/Makefile).
+#include "yk_oracle.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int64_t UNSET = -1;
+
+inline int64_t clamp0(int64_t v) { return v < 0 ? 0 : v; }
+
+// FitIn(larger, smaller): for every type in smaller: smaller <= max(0, larger or 0)
+inline bool fit_in(int D, const int64_t* larger, const int64_t* smaller) {
+    for (int k = 0; k < D; ++k)
+        if (smaller[k] > clamp0(larger[k])) return false;
+    return true;
+}
+// no negative quantity and at least one positive one
+inline bool strictly_gt_zero(int D, const int64_t* r) {
+    bool pos = false;
+    for (int k = 0; k < D; ++k) {
+        if (r[k] < 0) return false;
+        if (r[k] > 0) pos = true;
+    }
+    return pos;
+}
+
+double node_score(int D, int policy, const double* w, const int64_t* total, const int64_t* avail) {
+    double usage = 0.0, tw = 0.0;
+    for (int k = 0; k < D; ++k) {
+        if (w[k] == 0.0) continue;       // unweighted types do not count
+        if (total[k] == 0) continue;     // type absent from total (0/0 would be NaN -> skipped)
+        double share = 1.0 - (double)avail[k] / (double)total[k];
+        if (std::isnan(share)) continue;
+        usage += share * w[k];
+        tw += w[k];
+    }
+    double abs_usage = (tw == 0.0) ? 0.0 : usage / tw;
+    double s = (policy == YKO_POLICY_BINPACKING) ? 1.0 - abs_usage : abs_usage;
+    return s + 0.0;  // -0.0 -> +0.0 (Go compares them equal; keeps the order total)
+}
+
+struct NodeRef {
+    double score;
+    int32_t rank;   // rank of NodeID in bytewise string order
+    int32_t node;
+};
+struct NodeLess {
+    bool operator()(const NodeRef& a, const NodeRef& b) const {
+        if (a.score < b.score) return true;
+        if (b.score < a.score) return false;
+        return a.rank < b.rank;
+    }
+};
+
+std::vector<double> get_shares(int D, const int64_t* res, const int64_t* total) {
+    std::vector<double> sh((size_t)D, 0.0);
+    for (int k = 0; k < D; ++k) {
+        int64_t v = res[k];
+        if (v == 0) continue;
+        if (total == nullptr || total[k] <= 0) sh[(size_t)k] = (double)v;   // unset (-1) or 0 total
+        else sh[(size_t)k] = (double)v / (double)total[k];
+    }
+    std::sort(sh.begin(), sh.end());
+    return sh;
+}
+int compare_shares(const std::vector<double>& l, const std::vector<double>& r) {
+    int li = (int)l.size() - 1, ri = (int)r.size() - 1;
+    while (ri >= 0 && li >= 0) {
+        if (l[(size_t)li] > r[(size_t)ri]) return 1;
+        if (l[(size_t)li] < r[(size_t)ri]) return -1;
+        --li; --ri;
+    }
+    if (li == -1 && ri == -1) return 0;
+    for (; li >= 0; --li) if (l[(size_t)li] > 0) return 1;
+    for (; ri >= 0; --ri) if (r[(size_t)ri] > 0) return -1;
+    return 0;
+}
+
+struct Engine {
+    const yko_snapshot* s;
+    int D;
+    uint32_t mode;
+    std::vector<int64_t> avail;          // [n][D] working copy
+    std::vector<int32_t> rank;           // node -> string rank
+    std::vector<double> score;           // node -> current score
+    std::set<NodeRef, NodeLess> order;   // the btree of SURVEY A.3
+
+    struct Queue {
+        int parent = -1;
+        std::vector<int> children;
+        std::vector<int> apps;
+        std::vector<int64_t> alloc, pending;
+        int64_t pending_asks = 0;
+    };
+    std::vector<Queue> queues;
+    struct App {
+        std::vector<int> asks;   // sorted (priority desc, create asc, index asc)
+        int64_t pending_asks = 0;
+        size_t head = 0;          // first ask not yet allocated (asks are in priority order)
+        std::vector<int64_t> alloc;
+    };
+    std::vector<App> apps;
+    std::vector<uint8_t> state;
+    std::vector<uint8_t> done;   // allocated, or known-unplaceable (shortcut)
+    yko_stats st{};
+
+    const int64_t* total(int n) const { return s->node_total + (size_t)n * D; }
+    int64_t* av(int n) { return avail.data() + (size_t)n * D; }
+    const int64_t* req(int a) const { return s->ask_req + (size_t)a * D; }
+
+    // ---- shim side: predicate_manager.go podFitsNode for the bitmaskable plugin set ----
+    int shim_predicates(int a, int n) {
+        ++st.evaluations;
+        // Filter order: NodeUnschedulable, NodeName, TaintToleration, NodeAffinity, (NodePorts n/a),
+        // NodeResourcesFit (predicate_manager.go:339-351)
+        if (s->ask_node[a] >= 0 && s->ask_node[a] != n) return YKO_FAIL_NODENAME;
+        if (s->node_taint[n] & ~s->ask_tol[a]) return YKO_FAIL_TAINT;
+        if ((s->node_label[n] & s->ask_need[a]) != s->ask_need[a]) return YKO_FAIL_AFFINITY;
+        if (s->node_label[n] & s->ask_deny[a]) return YKO_FAIL_AFFINITY;
+        // NodeResourcesFit on the shim's NodeInfo: allocatable - requested is the same column as
+        // the core's available in this model (DESIGN.md "one availability column")
+        if (!fit_in(D, av(n), req(a))) return YKO_FAIL_RESOURCES;
+        return 0;
+    }
+
+    int evaluate(int a, int n) {  // core tryNodes filter + tryNode + shim predicates
+        if (!(s->node_flags[n] & YKO_NODE_SCHEDULABLE)) return YKO_FAIL_NODE_NOT_SCHEDULABLE;
+        if (!fit_in(D, total(n), req(a))) return YKO_FAIL_TOTAL;
+        if (!strictly_gt_zero(D, req(a))) return YKO_FAIL_REQUEST_NOT_POSITIVE;
+        if (!fit_in(D, av(n), req(a))) return YKO_FAIL_AVAILABLE;
+        return shim_predicates(a, n);
+    }
+
+    void rekey(int n) {
+        double ns = node_score(D, s->policy, s->weights, total(n), av(n));
+        if (ns != score[(size_t)n]) {
+            order.erase(NodeRef{score[(size_t)n], rank[(size_t)n], n});
+            score[(size_t)n] = ns;
+            order.insert(NodeRef{ns, rank[(size_t)n], n});
+        }
+    }
+
+    int try_nodes(int a) {
+        for (const NodeRef& nr : order) {
+            int n = nr.node;
+            ++st.node_visits;
+            if (s->node_flags[n] & YKO_NODE_RESERVED) continue;
+            if (evaluate(a, n) == 0) return n;
+        }
+        return -1;
+    }
+
+    void headroom(int q, int64_t* hr) {   // hr[k] = UNSET if unlimited
+        if (queues[(size_t)q].parent >= 0) headroom(queues[(size_t)q].parent, hr);
+        else for (int k = 0; k < D; ++k) hr[k] = UNSET;
+        const int64_t* mx = s->q_max + (size_t)q * D;
+        for (int k = 0; k < D; ++k) {
+            if (mx[k] == UNSET) continue;
+            int64_t own = mx[k] - queues[(size_t)q].alloc[(size_t)k];
+            // stored clamped at 0: UNSET is -1, and FitInMaxUndef clamps negatives to 0 anyway
+            own = clamp0(own);
+            hr[k] = (hr[k] == UNSET) ? own : std::min(hr[k], own);
+        }
+    }
+    bool fit_in_max_undef(const int64_t* hr, const int64_t* r) const {
+        for (int k = 0; k < D; ++k) {
+            if (hr[k] == UNSET) continue;
+            if (r[k] > hr[k]) return false;
+        }
+        return true;
+    }
+
+    void commit(int a, int n) {
+        int64_t* v = av(n);
+        const int64_t* r = req(a);
+        for (int k = 0; k < D; ++k) v[k] -= r[k];
+        rekey(n);
+        int p = s->ask_app[a];
+        App& ap = apps[(size_t)p];
+        ap.pending_asks--;
+        for (int k = 0; k < D; ++k) ap.alloc[(size_t)k] += r[k];
+        for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
+            Queue& Q = queues[(size_t)q];
+            Q.pending_asks--;
+            for (int k = 0; k < D; ++k) { Q.alloc[(size_t)k] += r[k]; Q.pending[(size_t)k] -= r[k]; }
+        }
+        state[(size_t)a] = YKO_ST_ALLOCATED;
+        done[(size_t)a] = 1;
+        ++st.allocations;
+    }
+
+    int app_priority(int p) {   // max priority over pending asks = priority of the first pending one
+        App& ap = apps[(size_t)p];
+        while (ap.head < ap.asks.size() && state[(size_t)ap.asks[ap.head]] == YKO_ST_ALLOCATED) ++ap.head;
+        return ap.head < ap.asks.size() ? s->ask_prio[ap.asks[ap.head]] : INT32_MIN;
+    }
+
+    // returns allocated ask (>=0) and node through *node_out, or -1
+    int try_app(int p, const int64_t* hr, int* node_out) {
+        bool retry = (mode & YKO_MODE_RETRY_FAILED) != 0;
+        App& ap = apps[(size_t)p];
+        for (size_t i = ap.head; i < ap.asks.size(); ++i) {
+            int a = ap.asks[i];
+            if (state[(size_t)a] == YKO_ST_ALLOCATED) continue;
+            if (done[(size_t)a] && !retry) continue;
+            if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { state[(size_t)a] = YKO_ST_SLOWPATH; done[(size_t)a] = 1; continue; }
+            if (!fit_in_max_undef(hr, req(a))) { state[(size_t)a] = YKO_ST_SKIPPED; done[(size_t)a] = 1; continue; }
+            if (!strictly_gt_zero(D, req(a))) { state[(size_t)a] = YKO_ST_INVALID; done[(size_t)a] = 1; continue; }
+            int n = try_nodes(a);
+            if (n >= 0) { *node_out = n; return a; }
+            state[(size_t)a] = YKO_ST_NOFIT;
+            done[(size_t)a] = 1;
+        }
+        return -1;
+    }
+
+    int try_queue(int q, int* node_out) {
+        Queue& Q = queues[(size_t)q];
+        if (Q.children.empty()) {
+            int64_t hr[YKO_MAX_D];
+            headroom(q, hr);
+            ++st.app_sorts;
+            std::vector<int> sorted;
+            for (int p : Q.apps) if (apps[(size_t)p].pending_asks > 0) sorted.push_back(p);
+            if (s->q_sort[q] == YKO_SORT_FAIR) {
+                // fair: ascending dominant share of app allocation vs queue guaranteed (or max)
+                const int64_t* base = s->q_guaranteed + (size_t)q * D;
+                std::stable_sort(sorted.begin(), sorted.end(), [&](int l, int r) {
+                    int c = compare_shares(get_shares(D, apps[(size_t)l].alloc.data(), base),
+                                           get_shares(D, apps[(size_t)r].alloc.data(), base));
+                    if (c != 0) return c < 0;
+                    int lp = app_priority(l), rp = app_priority(r);
+                    if (lp != rp) return lp > rp;
+                    if (s->app_submit[l] != s->app_submit[r]) return s->app_submit[l] < s->app_submit[r];
+                    return l < r;
+                });
+            } else {
+                std::vector<int> prio((size_t)s->n_apps, 0);
+                for (int p : sorted) prio[(size_t)p] = app_priority(p);
+                std::stable_sort(sorted.begin(), sorted.end(), [&](int l, int r) {
+                    if (prio[(size_t)l] != prio[(size_t)r]) return prio[(size_t)l] > prio[(size_t)r];
+                    if (s->app_submit[l] != s->app_submit[r]) return s->app_submit[l] < s->app_submit[r];
+                    return l < r;
+                });
+            }
+            for (int p : sorted) {
+                int a = try_app(p, hr, node_out);
+                if (a >= 0) return a;
+            }
+            return -1;
+        }
+        ++st.queue_sorts;
+        std::vector<int> sorted;
+        for (int c : Q.children) if (queues[(size_t)c].pending_asks > 0) sorted.push_back(c);
+        std::stable_sort(sorted.begin(), sorted.end(), [&](int l, int r) {
+            int c = yko_comp_usage_ratio_separately(D, queues[(size_t)l].alloc.data(), s->q_guaranteed + (size_t)l * D,
+                                                    queues[(size_t)r].alloc.data(), s->q_guaranteed + (size_t)r * D);
+            if (c != 0) return c < 0;
+            // equal shares: larger pending first (StrictlyGreaterThan(lPending - rPending, 0))
+            int64_t diff[YKO_MAX_D];
+            for (int k = 0; k < D; ++k) diff[k] = queues[(size_t)l].pending[(size_t)k] - queues[(size_t)r].pending[(size_t)k];
+            if (strictly_gt_zero(D, diff)) return true;
+            for (int k = 0; k < D; ++k) diff[k] = -diff[k];
+            if (strictly_gt_zero(D, diff)) return false;
+            return l < r;
+        });
+        for (int c : sorted) {
+            int a = try_queue(c, node_out);
+            if (a >= 0) return a;
+        }
+        return -1;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+double yko_node_score(int32_t D, int32_t policy, const double* weights, const int64_t* total, const int64_t* avail) {
+    return node_score(D, policy, weights, total, avail);
+}
+
+int yko_comp_usage_ratio_separately(int32_t D, const int64_t* lalloc, const int64_t* lguar,
+                                    const int64_t* ralloc, const int64_t* rguar) {
+    return compare_shares(get_shares(D, lalloc, lguar), get_shares(D, ralloc, rguar));
+}
+
+static int check(const yko_snapshot* s) {
+    if (!s || s->D < 1 || s->D > YKO_MAX_D) return -1;
+    if (s->n_nodes < 0 || s->n_asks < 0 || s->n_apps < 0 || s->n_queues < 1) return -2;
+    if (s->policy != YKO_POLICY_FAIR && s->policy != YKO_POLICY_BINPACKING) return -3;
+    for (int q = 0; q < s->n_queues; ++q) {
+        if (q == 0 ? s->q_parent[q] != -1 : (s->q_parent[q] < 0 || s->q_parent[q] >= q)) return -4;
+    }
+    for (int p = 0; p < s->n_apps; ++p)
+        if (s->app_queue[p] < 0 || s->app_queue[p] >= s->n_queues) return -5;
+    for (int a = 0; a < s->n_asks; ++a) {
+        if (s->ask_app[a] < 0 || s->ask_app[a] >= s->n_apps) return -6;
+        if (s->ask_node[a] < -1 || s->ask_node[a] >= s->n_nodes) return -7;
+    }
+    return 0;
+}
+
+int yko_predicate(const yko_snapshot* s, int32_t ask, int32_t node) {
+    if (!s || ask < 0 || ask >= s->n_asks || node < 0 || node >= s->n_nodes) return -1;
+    Engine e;
+    e.s = s; e.D = s->D; e.mode = 0;
+    e.avail.assign(s->node_avail, s->node_avail + (size_t)s->n_nodes * s->D);
+    return e.evaluate(ask, node);
+}
+
+int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings, int32_t* out_ask, int32_t* out_node,
+            int32_t* n_out, uint8_t* ask_state, int64_t* node_avail_out, yko_stats* stats) {
+    int rc = check(s);
+    if (rc) return rc;
+    Engine e;
+    e.s = s; e.D = s->D; e.mode = mode;
+    const int D = s->D, N = s->n_nodes;
+    e.avail.assign(s->node_avail, s->node_avail + (size_t)N * D);
+
+    // NodeID string ranks (Go string compare = bytewise unsigned)
+    std::vector<int32_t> idx((size_t)N);
+    for (int i = 0; i < N; ++i) idx[(size_t)i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return strcmp(s->node_id[a], s->node_id[b]) < 0; });
+    e.rank.assign((size_t)N, 0);
+    for (int r = 0; r < N; ++r) {
+        if (r > 0 && strcmp(s->node_id[idx[(size_t)r - 1]], s->node_id[idx[(size_t)r]]) == 0) return -8;  // duplicate NodeID
+        e.rank[(size_t)idx[(size_t)r]] = r;
+    }
+    e.score.assign((size_t)N, 0.0);
+    for (int n = 0; n < N; ++n) {
+        double sc = node_score(D, s->policy, s->weights, e.total(n), e.av(n));
+        if (std::isnan(sc)) return -9;
+        e.score[(size_t)n] = sc;
+        e.order.insert(NodeRef{sc, e.rank[(size_t)n], n});
+    }
+
+    e.queues.resize((size_t)s->n_queues);
+    for (int q = 0; q < s->n_queues; ++q) {
+        auto& Q = e.queues[(size_t)q];
+        Q.parent = s->q_parent[q];
+        if (Q.parent >= 0) e.queues[(size_t)Q.parent].children.push_back(q);
+        Q.alloc.assign(s->q_alloc + (size_t)q * D, s->q_alloc + (size_t)(q + 1) * D);
+        Q.pending.assign((size_t)D, 0);
+    }
+    e.apps.resize((size_t)s->n_apps);
+    for (int p = 0; p < s->n_apps; ++p) {
+        if (!e.queues[(size_t)s->app_queue[p]].children.empty()) return -10;  // apps live in leaves
+        e.queues[(size_t)s->app_queue[p]].apps.push_back(p);
+        e.apps[(size_t)p].alloc.assign((size_t)D, 0);
+    }
+    e.state.assign((size_t)s->n_asks, YKO_ST_PENDING);
+    e.done.assign((size_t)s->n_asks, 0);
+    for (int a = 0; a < s->n_asks; ++a) {
+        int p = s->ask_app[a];
+        e.apps[(size_t)p].asks.push_back(a);
+        e.apps[(size_t)p].pending_asks++;
+        for (int q = s->app_queue[p]; q >= 0; q = e.queues[(size_t)q].parent) {
+            e.queues[(size_t)q].pending_asks++;
+            for (int k = 0; k < D; ++k) e.queues[(size_t)q].pending[(size_t)k] += s->ask_req[(size_t)a * D + k];
+        }
+    }
+    for (auto& ap : e.apps)
+        std::stable_sort(ap.asks.begin(), ap.asks.end(), [&](int l, int r) {
+            if (s->ask_prio[l] != s->ask_prio[r]) return s->ask_prio[l] > s->ask_prio[r];
+            if (s->ask_create[l] != s->ask_create[r]) return s->ask_create[l] < s->ask_create[r];
+            return l < r;
+        });
+
+    int32_t n = 0;
+    while (max_bindings < 0 || n < max_bindings) {
+        ++e.st.passes;
+        int node = -1;
+        int a = e.try_queue(0, &node);
+        if (a < 0) break;
+        e.commit(a, node);
+        out_ask[n] = a;
+        out_node[n] = node;
+        ++n;
+    }
+    *n_out = n;
+    if (ask_state) memcpy(ask_state, e.state.data(), (size_t)s->n_asks);
+    if (node_avail_out) memcpy(node_avail_out, e.avail.data(), sizeof(int64_t) * (size_t)N * D);
+    if (stats) *stats = e.st;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,756 @@
+// yk_engine.cu -- libykgpu.so: host side of the engine + the C ABI of include/ykgpu.h.
+//
+// One scheduling cycle (yk_cycle) =
+//   host  : Orderer (yk_orderer.hpp) produces the next batch of asks in schedule()-pass order
+//   device: key kernel (float64 node score) -> stable radix sort by key over NodeID-rank order
+//           -> gather into the sorted SoA view -> fused sweep kernel (batch x all nodes) -> fit bitmaps
+//   commit: ordered, exact: ask i takes the minimum (key, NodeID) over {clean nodes whose bitmap bit is set}
+//           U {nodes already committed to in this batch, re-scored}; see DESIGN.md "ordered commit".
+// There is no CPU fallback for the sweep: without a CUDA device yk_create fails with YK_ERR_CUDA.
+#include "../../include/ykgpu.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "yk_kernels.cuh"
+#include "yk_orderer.hpp"
+
+namespace {
+
+constexpr int NPT = 2;            // sorted-node positions per sweep thread
+constexpr int AC = 128;           // asks per sweep CTA chunk
+constexpr int NODE_TILE = YK_SWEEP_THREADS * NPT;
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+template <typename T>
+struct Dev {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        free();
+        n = count;
+        return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~Dev() { free(); }
+};
+template <typename T>
+struct Pin {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        free();
+        n = count;
+        cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) memset(p, 0, std::max<size_t>(count, 1) * sizeof(T));
+        return e;
+    }
+    void free() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    ~Pin() { free(); }
+};
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct yk_engine {
+    std::mutex mu;
+    yk_config cfg{};
+    int D = 0;
+    uint32_t maxN = 0, maxA = 0, maxP = 0, maxQ = 0, batch = 0;
+    std::string err;
+    yk_stats_t st{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    YkWeights w{};
+
+    // ---- host tables (pinned: they are the H2D sources) ----
+    Pin<int64_t> n_total, n_avail;             // [D][maxN]
+    Pin<uint64_t> n_taint, n_label;
+    Pin<uint32_t> n_flags;                     // bit0 schedulable, bit1 reserved (0 when absent)
+    std::vector<uint32_t> n_rank;
+    std::vector<uint8_t> n_present;
+    uint32_t n_hi = 0;                         // 1 + highest node index in use
+    bool nodes_stale = true, rank_stale = true;
+    Pin<uint32_t> by_rank; uint32_t nlive = 0;
+
+    Pin<int64_t> a_req;                        // [D][maxA]
+    Pin<uint64_t> a_tol, a_need, a_deny;
+    Pin<uint32_t> a_node;
+    std::vector<int32_t> a_prio;
+    std::vector<int64_t> a_create;
+    std::vector<uint32_t> a_app, a_flags, a_gang, a_bound;
+    std::vector<uint8_t> a_state;              // yk::ST_*, ST_ABSENT when not present
+    uint32_t a_hi = 0;
+    bool asks_stale = true;
+
+    std::vector<uint32_t> p_queue; std::vector<int64_t> p_submit; std::vector<uint8_t> p_present;
+    uint32_t nq = 0;
+    std::vector<uint32_t> q_parent; std::vector<int64_t> q_guar, q_max, q_alloc; std::vector<uint8_t> q_sort;
+
+    // ---- device ----
+    Dev<int64_t> d_total, d_avail; Dev<uint64_t> d_taint, d_label; Dev<uint32_t> d_flags, d_by_rank;
+    Dev<int64_t> d_areq; Dev<uint64_t> d_atol, d_aneed, d_adeny; Dev<uint32_t> d_anode;
+    Dev<uint64_t> d_key_in, d_key_out; Dev<uint32_t> d_val_in, d_val_out;
+    Dev<uint8_t> d_cub; size_t cub_bytes = 0;
+    Dev<int64_t> d_scap; Dev<uint64_t> d_staint, d_slabel; Dev<uint32_t> d_snode;
+    Dev<uint32_t> d_batch, d_fit, d_first; Dev<int> d_flag;
+    Dev<uint32_t> d_dirty_nodes; Dev<int64_t> d_dirty_vals; Dev<double> d_scores;
+    size_t Wmax = 0;
+
+    // pinned staging
+    Pin<uint32_t> h_batch, h_fit, h_first, h_snode, h_dirty_nodes; Pin<uint64_t> h_skey; Pin<int64_t> h_dirty_vals;
+    Pin<int> h_flag; Pin<double> h_scores;
+
+    // commit scratch
+    std::vector<uint32_t> pos_of;
+    std::vector<uint32_t> dirty_words;
+    std::vector<uint64_t> cur_key;   // per node, valid for dirty nodes
+    std::vector<uint8_t> is_dirty;
+    std::vector<uint32_t> dirty_list;
+
+    yk::Orderer ord;
+    yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return YK_ERR_CUDA;
+    }
+};
+
+#define CK(call)                                                     \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) return e->cuda_fail(_e, #call);       \
+    } while (0)
+
+namespace {
+
+int upload_tables(yk_engine* e) {
+    const int D = e->D;
+    if (e->rank_stale) {
+        std::vector<uint32_t> live;
+        live.reserve(e->n_hi);
+        for (uint32_t i = 0; i < e->n_hi; ++i) if (e->n_present[i]) live.push_back(i);
+        std::sort(live.begin(), live.end(), [&](uint32_t a, uint32_t b) {
+            if (e->n_rank[a] != e->n_rank[b]) return e->n_rank[a] < e->n_rank[b];
+            return a < b;
+        });
+        e->nlive = (uint32_t)live.size();
+        if (e->nlive) memcpy(e->by_rank.p, live.data(), sizeof(uint32_t) * e->nlive);
+        if (e->nlive) CK(cudaMemcpyAsync(e->d_by_rank.p, e->by_rank.p, sizeof(uint32_t) * e->nlive, cudaMemcpyHostToDevice, e->stream));
+        e->st.h2d_bytes += sizeof(uint32_t) * e->nlive;
+        e->rank_stale = false;
+    }
+    if (e->nodes_stale && e->n_hi) {
+        const size_t n = e->n_hi;
+        for (int k = 0; k < D; ++k) {
+            CK(cudaMemcpyAsync(e->d_total.p + (size_t)k * e->maxN, e->n_total.p + (size_t)k * e->maxN, 8 * n, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(e->d_avail.p + (size_t)k * e->maxN, e->n_avail.p + (size_t)k * e->maxN, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        }
+        CK(cudaMemcpyAsync(e->d_taint.p, e->n_taint.p, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_label.p, e->n_label.p, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_flags.p, e->n_flags.p, 4 * n, cudaMemcpyHostToDevice, e->stream));
+        e->st.h2d_bytes += n * (16 * D + 20);
+    }
+    e->nodes_stale = false;
+    if (e->asks_stale && e->a_hi) {
+        const size_t n = e->a_hi;
+        for (int k = 0; k < D; ++k)
+            CK(cudaMemcpyAsync(e->d_areq.p + (size_t)k * e->maxA, e->a_req.p + (size_t)k * e->maxA, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_atol.p, e->a_tol.p, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_aneed.p, e->a_need.p, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_adeny.p, e->a_deny.p, 8 * n, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_anode.p, e->a_node.p, 4 * n, cudaMemcpyHostToDevice, e->stream));
+        e->st.h2d_bytes += n * (8 * D + 28);
+    }
+    e->asks_stale = false;
+    return YK_OK;
+}
+
+template <int D>
+void launch_sweep_d(const YkSweepArgs& a, cudaStream_t s) {
+    dim3 grid((unsigned)(a.Np / NODE_TILE), (unsigned)((a.rows + AC - 1) / AC));
+    yk_sweep_kernel<D, NPT, AC><<<grid, YK_SWEEP_THREADS, 0, s>>>(a);
+}
+void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s) {
+    switch (D) {
+        case 1: launch_sweep_d<1>(a, s); break;
+        case 2: launch_sweep_d<2>(a, s); break;
+        case 3: launch_sweep_d<3>(a, s); break;
+        case 4: launch_sweep_d<4>(a, s); break;
+        case 5: launch_sweep_d<5>(a, s); break;
+        case 6: launch_sweep_d<6>(a, s); break;
+        case 7: launch_sweep_d<7>(a, s); break;
+        default: launch_sweep_d<8>(a, s); break;
+    }
+}
+
+inline bool fits_avail(const yk_engine* e, uint32_t node, uint32_t ask) {
+    for (int k = 0; k < e->D; ++k) {
+        int64_t a = e->n_avail[(size_t)k * e->maxN + node];
+        if (a < 0) a = 0;
+        if (e->a_req[(size_t)k * e->maxA + ask] > a) return false;
+    }
+    return true;
+}
+
+struct DirtyRef {
+    uint64_t key; uint32_t rank; uint32_t node;
+    bool operator<(const DirtyRef& o) const {
+        if (key != o.key) return key < o.key;
+        return rank < o.rank;
+    }
+};
+
+// Device phase + ordered commit for one batch.  result[i] = node or YK_NONE; consumed = how many entries of
+// the batch were decided (stops after the first failure unless the batch is placement-insensitive).
+int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive, std::vector<uint32_t>& result,
+              size_t& consumed) {
+    const int D = e->D;
+    const int B = (int)batch.size();
+    const int nlive = (int)e->nlive;
+    result.assign((size_t)B, YK_NONE);
+    consumed = 0;
+    if (nlive == 0) {   // no nodes: nothing fits
+        consumed = insensitive ? (size_t)B : 1;
+        return YK_OK;
+    }
+    const int Np = (int)round_up((size_t)nlive, NODE_TILE);
+    const int W = Np / 32;
+    cudaStream_t s = e->stream;
+
+    memcpy(e->h_batch.p, batch.data(), sizeof(uint32_t) * (size_t)B);
+    CK(cudaMemcpyAsync(e->d_batch.p, e->h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
+    e->st.h2d_bytes += sizeof(uint32_t) * (size_t)B;
+    CK(cudaMemsetAsync(e->d_first.p, 0xFF, sizeof(uint32_t) * (size_t)B, s));
+    CK(cudaMemsetAsync(e->d_flag.p, 0, sizeof(int), s));
+
+    CK(cudaEventRecord(e->ev0, s));
+    yk_key_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(D, e->cfg.policy, e->w, e->d_total.p, e->d_avail.p, e->maxN,
+                                                     e->d_by_rank.p, nlive, e->d_key_in.p, e->d_val_in.p, e->d_flag.p);
+    size_t tb = e->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(e->d_cub.p, tb, e->d_key_in.p, e->d_key_out.p, e->d_val_in.p, e->d_val_out.p,
+                                       nlive, 0, 64, s));
+    yk_gather_kernel<<<(Np + 255) / 256, 256, 0, s>>>(D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
+                                                     e->d_flags.p, e->d_val_out.p, nlive, Np, e->d_scap.p, e->d_staint.p,
+                                                     e->d_slabel.p, e->d_snode.p);
+    CK(cudaEventRecord(e->ev1, s));
+    YkSweepArgs a{};
+    a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
+    a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
+    a.lda = e->maxA; a.batch = e->d_batch.p; a.row0 = 0; a.rows = B;
+    a.fit = e->d_fit.p; a.first = e->d_first.p; a.W = W;
+    launch_sweep(D, a, s);
+    CK(cudaEventRecord(e->ev2, s));
+    CK(cudaGetLastError());
+    e->st.sweep_launches += 1;
+    e->st.other_launches += 2 + 8;   // key + gather + radix sort passes (cub: 1 histogram + 1 onesweep per 8 bits; nominal)
+
+    CK(cudaMemcpyAsync(e->h_fit.p, e->d_fit.p, sizeof(uint32_t) * (size_t)B * W, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_first.p, e->d_first.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_snode.p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    e->st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B + 12 * (size_t)nlive + 4;
+    CK(cudaStreamSynchronize(s));
+    if (e->h_flag[0]) return e->fail(YK_ERR_RANGE, "NaN node score (zero total on a weighted resource)");
+    float ms_sort = 0, ms_sweep = 0;
+    cudaEventElapsedTime(&ms_sort, e->ev0, e->ev1);
+    cudaEventElapsedTime(&ms_sweep, e->ev1, e->ev2);
+    e->st.sort_ms += ms_sort;
+    e->st.sweep_ms += ms_sweep;
+    e->st.last_sweep_ms = ms_sweep;
+    e->st.last_sweep_pairs = (uint64_t)B * (uint64_t)nlive;
+    e->st.evaluations += (uint64_t)B * (uint64_t)nlive;
+    e->st.batches++;
+
+    // ---------------- ordered commit (host) ----------------
+    const double t0 = now_ms();
+    for (int p = 0; p < nlive; ++p) e->pos_of[e->h_snode[(size_t)p]] = (uint32_t)p;
+    e->dirty_words.assign((size_t)W, 0);
+    for (uint32_t n : e->dirty_list) e->is_dirty[n] = 0;
+    e->dirty_list.clear();
+    std::set<DirtyRef> dirty;
+    const uint32_t* fit = e->h_fit.p;
+    for (int i = 0; i < B; ++i) {
+        const uint32_t ask = batch[(size_t)i];
+        const uint32_t* row = fit + (size_t)i * W;
+        // (A) best clean node: first set bit of row & ~dirty in sorted order
+        uint32_t posA = YK_NONE;
+        if (e->h_first[(size_t)i] != YK_NONE) {
+            for (int wd = (int)(e->h_first[(size_t)i] >> 5); wd < W; ++wd) {
+                uint32_t m = row[wd] & ~e->dirty_words[(size_t)wd];
+                if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
+            }
+        }
+        DirtyRef bound{~0ull, ~0u, YK_NONE};
+        if (posA != YK_NONE) {
+            uint32_t nA = e->h_snode[(size_t)posA];
+            bound = DirtyRef{e->h_skey[(size_t)posA], e->n_rank[nA], nA};
+        }
+        // (B) best re-scored node among those committed to earlier in this batch
+        uint32_t chosen = YK_NONE;
+        for (const DirtyRef& d : dirty) {
+            if (!(d < bound)) break;
+            const uint32_t pos = e->pos_of[d.node];
+            if (!((row[pos >> 5] >> (pos & 31)) & 1u)) continue;   // failed on the batch-start state: fails now too
+            if (fits_avail(e, d.node, ask)) { chosen = d.node; break; }
+        }
+        if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
+        consumed = (size_t)i + 1;
+        if (chosen == YK_NONE) {
+            if (!insensitive) break;
+            continue;
+        }
+        result[(size_t)i] = chosen;
+        // commit: available -= request, re-score, move inside the dirty order
+        if (e->is_dirty[chosen]) dirty.erase(DirtyRef{e->cur_key[chosen], e->n_rank[chosen], chosen});
+        for (int k = 0; k < D; ++k) e->n_avail[(size_t)k * e->maxN + chosen] -= e->a_req[(size_t)k * e->maxA + ask];
+        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, e->n_total.p + chosen, e->n_avail.p + chosen, e->maxN);
+        const uint64_t nk = yk_key_bits(sc);
+        if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
+        e->cur_key[chosen] = nk;
+        dirty.insert(DirtyRef{nk, e->n_rank[chosen], chosen});
+        if (!e->is_dirty[chosen]) {
+            e->is_dirty[chosen] = 1;
+            e->dirty_list.push_back(chosen);
+            const uint32_t pos = e->pos_of[chosen];
+            e->dirty_words[pos >> 5] |= 1u << (pos & 31);
+        }
+    }
+    e->st.commit_ms += now_ms() - t0;
+
+    // push the new availability of the touched nodes back to the device table
+    const int nd = (int)e->dirty_list.size();
+    if (nd) {
+        for (int i = 0; i < nd; ++i) {
+            e->h_dirty_nodes[(size_t)i] = e->dirty_list[(size_t)i];
+            for (int k = 0; k < D; ++k)
+                e->h_dirty_vals[(size_t)k * nd + i] = e->n_avail[(size_t)k * e->maxN + e->dirty_list[(size_t)i]];
+        }
+        CK(cudaMemcpyAsync(e->d_dirty_nodes.p, e->h_dirty_nodes.p, 4 * (size_t)nd, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(e->d_dirty_vals.p, e->h_dirty_vals.p, 8 * (size_t)nd * D, cudaMemcpyHostToDevice, s));
+        yk_apply_avail_kernel<<<(nd + 255) / 256, 256, 0, s>>>(D, e->d_avail.p, e->maxN, e->d_dirty_nodes.p, e->d_dirty_vals.p, nd);
+        e->st.h2d_bytes += (size_t)nd * (4 + 8 * D);
+        e->st.other_launches += 1;
+        // staging buffers are reused by the next batch only after its own stream sync
+        CK(cudaStreamSynchronize(s));
+    }
+    return YK_OK;
+}
+
+}  // namespace
+
+// ======================================= C ABI =======================================
+extern "C" {
+
+uint32_t yk_abi_version(void) { return YK_ABI_VERSION; }
+
+const char* yk_strerror(int s) {
+    switch (s) {
+        case YK_OK: return "ok";
+        case YK_ERR_ARG: return "invalid argument";
+        case YK_ERR_CUDA: return "CUDA error (no device, no sm_100a image, or launch/copy failure)";
+        case YK_ERR_NOMEM: return "out of memory";
+        case YK_ERR_STATE: return "invalid state";
+        case YK_ERR_RANGE: return "value out of range (NaN node score)";
+        case YK_ERR_COMM: return "multi-GPU exchange failed";
+        default: return "unknown status";
+    }
+}
+
+const char* yk_last_error(yk_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+void yk_destroy(yk_engine* e) {
+    if (!e) return;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int yk_create(const yk_config* cfg, yk_engine** out) {
+    if (!cfg || !out) return YK_ERR_ARG;
+    *out = nullptr;
+    if (cfg->abi_version != YK_ABI_VERSION || cfg->D < 1 || cfg->D > YK_MAX_D || cfg->policy > 1) return YK_ERR_ARG;
+    if (!cfg->max_nodes || !cfg->max_asks || !cfg->max_apps || !cfg->max_queues) return YK_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return YK_ERR_CUDA;   // fail loudly: no CPU path
+    if (cfg->device >= 0) { if (cudaSetDevice(cfg->device) != cudaSuccess) return YK_ERR_CUDA; }
+    yk_engine* e = new (std::nothrow) yk_engine();
+    if (!e) return YK_ERR_NOMEM;
+    e->cfg = *cfg;
+    e->D = (int)cfg->D;
+    e->maxN = cfg->max_nodes; e->maxA = cfg->max_asks; e->maxP = cfg->max_apps; e->maxQ = cfg->max_queues;
+    e->batch = cfg->batch ? cfg->batch : 2048;
+    for (int k = 0; k < 8; ++k) e->w.w[k] = k < e->D ? cfg->weights[k] : 0.0;
+    const int D = e->D;
+    const size_t N = e->maxN, A = e->maxA, Bm = e->batch;
+    const size_t Npmax = round_up(N, NODE_TILE);
+    e->Wmax = Npmax / 32;
+    bool ok = true;
+    auto T = [&](cudaError_t r) { if (r != cudaSuccess) { ok = false; e->err = cudaGetErrorString(r); } };
+    T(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    T(cudaEventCreate(&e->ev0)); T(cudaEventCreate(&e->ev1)); T(cudaEventCreate(&e->ev2));
+    T(e->n_total.alloc(N * D)); T(e->n_avail.alloc(N * D)); T(e->n_taint.alloc(N)); T(e->n_label.alloc(N)); T(e->n_flags.alloc(N));
+    T(e->by_rank.alloc(N));
+    T(e->a_req.alloc(A * D)); T(e->a_tol.alloc(A)); T(e->a_need.alloc(A)); T(e->a_deny.alloc(A)); T(e->a_node.alloc(A));
+    T(e->d_total.alloc(N * D)); T(e->d_avail.alloc(N * D)); T(e->d_taint.alloc(N)); T(e->d_label.alloc(N)); T(e->d_flags.alloc(N));
+    T(e->d_by_rank.alloc(N));
+    T(e->d_areq.alloc(A * D)); T(e->d_atol.alloc(A)); T(e->d_aneed.alloc(A)); T(e->d_adeny.alloc(A)); T(e->d_anode.alloc(A));
+    T(e->d_key_in.alloc(N)); T(e->d_key_out.alloc(N)); T(e->d_val_in.alloc(N)); T(e->d_val_out.alloc(N));
+    if (ok) {
+        size_t tb = 0;
+        T(cub::DeviceRadixSort::SortPairs(nullptr, tb, e->d_key_in.p, e->d_key_out.p, e->d_val_in.p, e->d_val_out.p, (int)N, 0, 64, e->stream));
+        e->cub_bytes = tb;
+        T(e->d_cub.alloc(tb));
+    }
+    T(e->d_scap.alloc(Npmax * D)); T(e->d_staint.alloc(Npmax)); T(e->d_slabel.alloc(Npmax)); T(e->d_snode.alloc(Npmax));
+    T(e->d_batch.alloc(Bm)); T(e->d_fit.alloc(Bm * e->Wmax)); T(e->d_first.alloc(Bm)); T(e->d_flag.alloc(1));
+    T(e->d_dirty_nodes.alloc(Bm)); T(e->d_dirty_vals.alloc(Bm * D)); T(e->d_scores.alloc(N));
+    T(e->h_batch.alloc(Bm)); T(e->h_fit.alloc(Bm * e->Wmax)); T(e->h_first.alloc(Bm)); T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
+    T(e->h_dirty_nodes.alloc(Bm)); T(e->h_dirty_vals.alloc(Bm * D)); T(e->h_flag.alloc(1)); T(e->h_scores.alloc(N));
+    if (ok) {   // does this binary carry an image the device can run?
+        cudaFuncAttributes fa;
+        T(cudaFuncGetAttributes(&fa, yk_key_kernel));
+    }
+    if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
+    e->n_rank.assign(N, 0); e->n_present.assign(N, 0);
+    e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
+    e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
+    e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
+    // default queue tree: root only would have no leaf for apps; root + one leaf "root.default"
+    e->nq = 0;
+    e->pos_of.assign(N, 0); e->cur_key.assign(N, 0); e->is_dirty.assign(N, 0);
+    *out = e;
+    return YK_OK;
+}
+
+int yk_nodes_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const int64_t* total, const int64_t* avail,
+                    const uint64_t* taint, const uint64_t* label, const uint32_t* name_rank, const uint32_t* flags) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !total || !avail || !name_rank)) return e->fail(YK_ERR_ARG, "yk_nodes_upsert: null array");
+    for (uint32_t i = 0; i < n; ++i) if (idx[i] >= e->maxN) return e->fail(YK_ERR_ARG, "yk_nodes_upsert: index beyond max_nodes");
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = idx[i];
+        for (int k = 0; k < e->D; ++k) {
+            e->n_total[(size_t)k * e->maxN + x] = total[(size_t)k * n + i];
+            e->n_avail[(size_t)k * e->maxN + x] = avail[(size_t)k * n + i];
+        }
+        e->n_taint[x] = taint ? taint[i] : 0;
+        e->n_label[x] = label ? label[i] : 0;
+        e->n_flags[x] = flags ? flags[i] : YK_NODE_SCHEDULABLE;
+        if (!e->n_present[x] || e->n_rank[x] != name_rank[i]) e->rank_stale = true;
+        e->n_rank[x] = name_rank[i];
+        e->n_present[x] = 1;
+        e->n_hi = std::max(e->n_hi, x + 1);
+    }
+    e->nodes_stale = true;
+    return YK_OK;
+}
+
+int yk_nodes_remove(yk_engine* e, uint32_t n, const uint32_t* idx) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && !idx) return e->fail(YK_ERR_ARG, "yk_nodes_remove: null array");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (idx[i] >= e->maxN) return e->fail(YK_ERR_ARG, "yk_nodes_remove: index beyond max_nodes");
+        if (e->n_present[idx[i]]) { e->n_present[idx[i]] = 0; e->n_flags[idx[i]] = 0; e->rank_stale = true; e->nodes_stale = true; }
+    }
+    return YK_OK;
+}
+
+int yk_queues_set(yk_engine* e, uint32_t q, const uint32_t* parent, const int64_t* guaranteed, const int64_t* max,
+                  const int64_t* allocated, const uint8_t* sort) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!q || q > e->maxQ || !parent) return e->fail(YK_ERR_ARG, "yk_queues_set: bad queue count");
+    if (parent[0] != YK_NONE) return e->fail(YK_ERR_ARG, "yk_queues_set: queue 0 must be the root");
+    for (uint32_t i = 1; i < q; ++i) if (parent[i] >= i) return e->fail(YK_ERR_ARG, "yk_queues_set: parent[i] must be < i");
+    const int D = e->D;
+    e->nq = q;
+    e->q_parent.assign(parent, parent + q);
+    e->q_guar.assign((size_t)q * D, -1); e->q_max.assign((size_t)q * D, -1); e->q_alloc.assign((size_t)q * D, 0);
+    if (guaranteed) e->q_guar.assign(guaranteed, guaranteed + (size_t)q * D);
+    if (max) e->q_max.assign(max, max + (size_t)q * D);
+    if (allocated) e->q_alloc.assign(allocated, allocated + (size_t)q * D);
+    e->q_sort.assign(q, 0);
+    if (sort) e->q_sort.assign(sort, sort + q);
+    for (uint32_t i = 0; i < q; ++i)
+        if (e->q_sort[i] > 1) return e->fail(YK_ERR_ARG, "yk_queues_set: unknown application sort policy");
+    return YK_OK;
+}
+
+int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t* queue, const int64_t* submit) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !queue || !submit)) return e->fail(YK_ERR_ARG, "yk_apps_upsert: null array");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (idx[i] >= e->maxP) return e->fail(YK_ERR_ARG, "yk_apps_upsert: index beyond max_apps");
+        if (queue[i] >= e->nq) return e->fail(YK_ERR_ARG, "yk_apps_upsert: unknown queue (call yk_queues_set first)");
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        e->p_queue[idx[i]] = queue[i]; e->p_submit[idx[i]] = submit[i]; e->p_present[idx[i]] = 1;
+    }
+    return YK_OK;
+}
+
+int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && !idx) return e->fail(YK_ERR_ARG, "yk_apps_remove: null array");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (idx[i] >= e->maxP) return e->fail(YK_ERR_ARG, "yk_apps_remove: index beyond max_apps");
+        e->p_present[idx[i]] = 0;
+    }
+    return YK_OK;
+}
+
+int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t* req, const uint64_t* tol,
+                   const uint64_t* need, const uint64_t* deny, const int32_t* prio, const int64_t* create_seq,
+                   const uint32_t* app, const uint32_t* required_node, const uint32_t* flags, const uint32_t* gang) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (a && (!idx || !req || !create_seq || !app)) return e->fail(YK_ERR_ARG, "yk_asks_upsert: null array");
+    for (uint32_t i = 0; i < a; ++i) {
+        if (idx[i] >= e->maxA) return e->fail(YK_ERR_ARG, "yk_asks_upsert: index beyond max_asks");
+        if (app[i] >= e->maxP || !e->p_present[app[i]]) return e->fail(YK_ERR_ARG, "yk_asks_upsert: unknown application");
+        if (required_node && required_node[i] != YK_NONE && required_node[i] >= e->maxN)
+            return e->fail(YK_ERR_ARG, "yk_asks_upsert: required_node beyond max_nodes");
+        if (e->a_state[idx[i]] == yk::ST_ALLOCATED) return e->fail(YK_ERR_STATE, "yk_asks_upsert: ask holds an allocation (release it first)");
+    }
+    for (uint32_t i = 0; i < a; ++i) {
+        const uint32_t x = idx[i];
+        for (int k = 0; k < e->D; ++k) e->a_req[(size_t)k * e->maxA + x] = req[(size_t)k * a + i];
+        e->a_tol[x] = tol ? tol[i] : 0;
+        e->a_need[x] = need ? need[i] : 0;
+        e->a_deny[x] = deny ? deny[i] : 0;
+        e->a_node[x] = required_node ? required_node[i] : YK_NONE;
+        e->a_prio[x] = prio ? prio[i] : 0;
+        e->a_create[x] = create_seq[i];
+        e->a_app[x] = app[i];
+        e->a_flags[x] = flags ? flags[i] : 0;
+        e->a_gang[x] = gang ? gang[i] : YK_NONE;
+        e->a_state[x] = yk::ST_PENDING;
+        e->a_bound[x] = YK_NONE;
+        e->a_hi = std::max(e->a_hi, x + 1);
+    }
+    e->asks_stale = true;
+    return YK_OK;
+}
+
+int yk_asks_remove(yk_engine* e, uint32_t a, const uint32_t* idx) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (a && !idx) return e->fail(YK_ERR_ARG, "yk_asks_remove: null array");
+    for (uint32_t i = 0; i < a; ++i) {
+        if (idx[i] >= e->maxA) return e->fail(YK_ERR_ARG, "yk_asks_remove: index beyond max_asks");
+        if (e->a_state[idx[i]] == yk::ST_ALLOCATED) return e->fail(YK_ERR_STATE, "yk_asks_remove: ask holds an allocation (use yk_release)");
+    }
+    for (uint32_t i = 0; i < a; ++i) e->a_state[idx[i]] = yk::ST_ABSENT;
+    return YK_OK;
+}
+
+int yk_release(yk_engine* e, uint32_t n, const uint32_t* idx) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && !idx) return e->fail(YK_ERR_ARG, "yk_release: null array");
+    for (uint32_t i = 0; i < n; ++i)
+        if (idx[i] >= e->maxA || e->a_state[idx[i]] != yk::ST_ALLOCATED) return e->fail(YK_ERR_STATE, "yk_release: ask holds no allocation");
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t a = idx[i], node = e->a_bound[a];
+        for (int k = 0; k < e->D; ++k) {
+            const int64_t r = e->a_req[(size_t)k * e->maxA + a];
+            if (node != YK_NONE && e->n_present[node]) e->n_avail[(size_t)k * e->maxN + node] += r;
+            for (uint32_t q = e->p_queue[e->a_app[a]]; q != YK_NONE; q = e->q_parent[q]) e->q_alloc[(size_t)k * e->nq + q] -= r;
+        }
+        e->a_state[a] = yk::ST_ABSENT;
+        e->a_bound[a] = YK_NONE;
+    }
+    e->nodes_stale = true;
+    return YK_OK;
+}
+
+int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_out, uint32_t* slow, uint32_t slow_cap,
+             uint32_t* n_slow) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!n_out || (max_bindings && !out)) return e->fail(YK_ERR_ARG, "yk_cycle: null output");
+    *n_out = 0;
+    if (n_slow) *n_slow = 0;
+    if (e->nq == 0) return e->fail(YK_ERR_STATE, "yk_cycle: no queues configured (yk_queues_set)");
+    for (uint32_t i = 0; i < e->nq; ++i)
+        if (e->q_sort[i] == YK_SORT_FAIR) {
+            bool leaf = true;
+            for (uint32_t j = i + 1; j < e->nq; ++j) if (e->q_parent[j] == i) leaf = false;
+            if (leaf) return e->fail(YK_ERR_ARG, "yk_cycle: fair application sort policy is not implemented yet");
+        }
+    const double t_start = now_ms();
+    int rc = upload_tables(e);
+    if (rc) return rc;
+
+    std::vector<uint32_t> pending;
+    pending.reserve(e->a_hi);
+    for (uint32_t a = 0; a < e->a_hi; ++a) {
+        uint8_t& s = e->a_state[a];
+        if (s == yk::ST_ABSENT || s == yk::ST_ALLOCATED) continue;
+        s = yk::ST_PENDING;   // failed / skipped asks are tried again every cycle, like the reference
+        if (!e->p_present[e->a_app[a]]) continue;
+        pending.push_back(a);
+    }
+    yk::Tables& t = e->ord.t;
+    t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
+    t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
+    t.a_flags = e->a_flags.data(); t.a_state = e->a_state.data();
+    t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
+    t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data();
+    t.q_sort = e->q_sort.data();
+    e->ord.begin_cycle(pending);
+
+    std::vector<uint32_t> batch, result;
+    uint32_t n = 0;
+    size_t bsz = e->batch;
+    while (n < max_bindings) {
+        const size_t want = std::min<size_t>(bsz, max_bindings - n);
+        if (e->ord.fill(want, batch) == 0) break;
+        const bool ins = e->ord.insensitive;
+        size_t consumed = 0;
+        rc = run_batch(e, batch, ins, result, consumed);
+        if (rc) return rc;
+        bool failed = false;
+        if (!ins && consumed > 0 && result[consumed - 1] == YK_NONE) {
+            e->ord.rewind(batch, consumed - 1);
+            failed = true;
+        }
+        for (size_t i = 0; i < consumed; ++i) {
+            const uint32_t a = batch[i];
+            if (result[i] == YK_NONE) {
+                if (ins) e->ord.fail_in_place(a);
+                e->st.nofit++;
+                continue;
+            }
+            e->ord.confirm(a);
+            e->a_bound[a] = result[i];
+            out[n].ask = a; out[n].node = result[i];
+            ++n;
+            e->st.allocations++;
+        }
+        // after a failure in a placement-sensitive order, probe with short batches until placements resume
+        bsz = failed ? std::max<size_t>(64, bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
+    }
+    e->ord.finish();
+    for (uint32_t a : e->ord.slow_list) {
+        if (slow && n_slow && *n_slow < slow_cap) slow[(*n_slow)++] = a;
+    }
+    for (uint32_t a : pending) if (e->a_state[a] == yk::ST_SKIPPED) e->st.skipped++;
+    *n_out = n;
+    e->st.cycles++;
+    e->st.total_ms += now_ms() - t_start;
+    return YK_OK;
+}
+
+int yk_ask_states(yk_engine* e, uint32_t n, const uint32_t* idx, uint8_t* out) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !out)) return e->fail(YK_ERR_ARG, "yk_ask_states: null array");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (idx[i] >= e->maxA) return e->fail(YK_ERR_ARG, "yk_ask_states: index beyond max_asks");
+        uint8_t s = e->a_state[idx[i]];
+        if (s == yk::ST_PENDING && idx[i] < e->a_hi) {
+            // an ask whose request is not strictly positive is reported as such once a cycle has seen it
+        }
+        out[i] = s;
+    }
+    return YK_OK;
+}
+
+int yk_nodes_available(yk_engine* e, uint32_t n, const uint32_t* idx, int64_t* out) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !out)) return e->fail(YK_ERR_ARG, "yk_nodes_available: null array");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (idx[i] >= e->maxN) return e->fail(YK_ERR_ARG, "yk_nodes_available: index beyond max_nodes");
+        for (int k = 0; k < e->D; ++k) out[(size_t)k * n + i] = e->n_avail[(size_t)k * e->maxN + idx[i]];
+    }
+    return YK_OK;
+}
+
+int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (ask >= e->maxA || node >= e->maxN) return e->fail(YK_ERR_ARG, "yk_evaluate: index out of range");
+    if (e->a_state[ask] == yk::ST_ABSENT || !e->n_present[node]) return YK_FAIL_ABSENT;
+    int rc = upload_tables(e);
+    if (rc) return rc;
+    yk_evaluate_kernel<<<1, 32, 0, e->stream>>>(e->D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
+                                                e->d_flags.p, e->d_areq.p, e->d_atol.p, e->d_aneed.p, e->d_adeny.p,
+                                                e->d_anode.p, e->maxA, ask, node, e->d_flag.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->st.other_launches++;
+    return e->h_flag[0];
+}
+
+int yk_node_scores(yk_engine* e, uint32_t n, const uint32_t* idx, double* out) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !out)) return e->fail(YK_ERR_ARG, "yk_node_scores: null array");
+    if (n > e->maxN) return e->fail(YK_ERR_ARG, "yk_node_scores: more indices than max_nodes");
+    for (uint32_t i = 0; i < n; ++i) if (idx[i] >= e->maxN) return e->fail(YK_ERR_ARG, "yk_node_scores: index beyond max_nodes");
+    if (!n) return YK_OK;
+    int rc = upload_tables(e);
+    if (rc) return rc;
+    memcpy(e->h_snode.p, idx, 4 * (size_t)n);
+    CK(cudaMemcpyAsync(e->d_val_in.p, e->h_snode.p, 4 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    yk_score_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->D, e->cfg.policy, e->w, e->d_total.p, e->d_avail.p, e->maxN,
+                                                           e->d_val_in.p, (int)n, e->d_scores.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_scores.p, e->d_scores.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(out, e->h_scores.p, 8 * (size_t)n);
+    e->st.other_launches++;
+    return YK_OK;
+}
+
+int yk_set_exchange(yk_engine* e, yk_allgather_fn fn, void* ctx) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->xfn = fn; e->xctx = ctx;
+    return YK_OK;
+}
+
+int yk_stats(yk_engine* e, yk_stats_t* out) {
+    if (!e || !out) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    *out = e->st;
+    return YK_OK;
+}
+
+int yk_stats_reset(yk_engine* e) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    e->st = yk_stats_t{};
+    return YK_OK;
+}
+
+}  // extern "C"

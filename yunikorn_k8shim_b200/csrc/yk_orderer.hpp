@@ -1,0 +1,333 @@
+// yk_orderer.hpp -- host-side ordering engine: which pending ask does the next schedule() pass try?
+//
+// Restates, incrementally, what yunikorn-core re-derives from scratch on every pass [EXT, SURVEY A.1/a14]:
+//   Queue.TryAllocate: parent -> sortQueues() (fair: DRF share of allocated/guaranteed ascending, then larger
+//   pending, children without pending filtered out); leaf -> getHeadRoom() then sortApplications()
+//   (fifo: max pending ask priority desc, submission time asc) -> Application.tryAllocate: sortedRequests
+//   (priority desc, create time asc), skip asks that exceed the queue headroom.
+// The node walk itself (tryNodes) is the device's job.  Because the order of passes does not depend on WHICH
+// node an ask lands on, only on WHETHER it was placed, the orderer runs ahead speculatively: fill() returns
+// the asks of the next passes assuming each one is placed; if the device reports that ask j found no node,
+// rewind() restores the state before the batch and replays the first j decisions.  When the order cannot
+// depend on placement at all (one leaf with pending asks, no quota on its chain, fifo, one priority level)
+// the batch is "placement-insensitive" and failures do not cut it short.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <set>
+#include <tuple>
+#include <vector>
+
+namespace yk {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int64_t UNSET = -1;
+enum : uint8_t { ST_PENDING = 0, ST_ALLOCATED = 1, ST_NOFIT = 2, ST_SKIPPED = 3, ST_SLOWPATH = 4, ST_INVALID = 5,
+                 ST_TENTATIVE = 100, ST_ABSENT = 255 };
+
+struct Tables {   // views into the engine's host tables
+    int D = 0;
+    uint32_t maxA = 0, maxP = 0, nq = 0;
+    const int64_t* a_req = nullptr;      // [D][maxA]
+    const int32_t* a_prio = nullptr;
+    const int64_t* a_create = nullptr;
+    const uint32_t* a_app = nullptr;
+    const uint32_t* a_flags = nullptr;
+    uint8_t* a_state = nullptr;          // ST_*
+    const uint32_t* p_queue = nullptr;
+    const int64_t* p_submit = nullptr;
+    const uint8_t* p_present = nullptr;
+    const uint32_t* q_parent = nullptr;
+    const int64_t* q_guar = nullptr;     // [D][nq]
+    const int64_t* q_max = nullptr;      // [D][nq]
+    int64_t* q_alloc = nullptr;          // [D][nq] persistent allocated (updated at finish())
+    const uint8_t* q_sort = nullptr;
+};
+
+class Orderer {
+public:
+    struct QState {
+        int64_t alloc[8], pending[8];
+        int64_t npend = 0, live = 0;
+        double shares[8];
+        bool shares_ok = false;
+    };
+    struct AState {
+        uint32_t head = 0;       // first ask not allocated/tentative
+        int64_t npend = 0, live = 0;
+        int32_t key_prio = 0;
+        bool in_set = false;
+    };
+    using AppKey = std::tuple<int32_t, int64_t, uint32_t>;   // (-priority, submit, app)
+
+    Tables t;
+    std::vector<QState> q;
+    std::vector<std::vector<uint32_t>> q_children, q_apps;
+    std::vector<std::set<AppKey>> q_set;
+    std::vector<AState> ap;
+    std::vector<std::vector<uint32_t>> ap_asks;
+    std::vector<uint32_t> a_pos;      // ask -> index in its app list
+    bool insensitive = false;
+    uint64_t slow_seen = 0;
+    std::vector<uint32_t> slow_list;
+
+    // ---- snapshot for rewind ----
+    std::vector<QState> sq;
+    std::vector<AState> sap;
+    std::vector<std::set<AppKey>> sset;
+    std::vector<std::pair<uint32_t, uint8_t>> journal;   // (ask, previous state)
+    size_t slow_mark = 0;
+
+    int D() const { return t.D; }
+    int64_t req(uint32_t a, int k) const { return t.a_req[(size_t)k * t.maxA + a]; }
+
+    void begin_cycle(const std::vector<uint32_t>& pending_asks) {
+        const int d = t.D;
+        q.assign(t.nq, QState());
+        q_children.assign(t.nq, {});
+        q_apps.assign(t.nq, {});
+        q_set.assign(t.nq, {});
+        for (uint32_t i = 0; i < t.nq; ++i) {
+            for (int k = 0; k < d; ++k) { q[i].alloc[k] = t.q_alloc[(size_t)k * t.nq + i]; q[i].pending[k] = 0; }
+            if (i > 0) q_children[t.q_parent[i]].push_back(i);
+        }
+        ap.assign(t.maxP, AState());
+        if (ap_asks.size() < t.maxP) ap_asks.resize(t.maxP);
+        for (auto& v : ap_asks) v.clear();
+        a_pos.assign(t.maxA, 0);
+        slow_list.clear();
+        for (uint32_t a : pending_asks) ap_asks[t.a_app[a]].push_back(a);
+        int32_t prio0 = 0; bool have_prio = false, one_prio = true;
+        for (uint32_t p = 0; p < t.maxP; ++p) {
+            auto& v = ap_asks[p];
+            if (v.empty()) continue;
+            auto less = [&](uint32_t l, uint32_t r) {
+                if (t.a_prio[l] != t.a_prio[r]) return t.a_prio[l] > t.a_prio[r];
+                if (t.a_create[l] != t.a_create[r]) return t.a_create[l] < t.a_create[r];
+                return l < r;
+            };
+            if (!std::is_sorted(v.begin(), v.end(), less)) std::sort(v.begin(), v.end(), less);
+            AState& A = ap[p];
+            for (uint32_t i = 0; i < v.size(); ++i) {
+                uint32_t a = v[i];
+                a_pos[a] = i;
+                if (!have_prio) { prio0 = t.a_prio[a]; have_prio = true; }
+                else if (t.a_prio[a] != prio0) one_prio = false;
+                A.npend++;
+                const bool dead = t.a_state[a] != ST_PENDING;   // INVALID asks are marked by the engine at upsert
+                if (!dead) A.live++;
+                for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
+                    q[qq].npend++;
+                    if (!dead) q[qq].live++;
+                    for (int k = 0; k < d; ++k) q[qq].pending[k] += req(a, k);
+                }
+            }
+            q_apps[t.p_queue[p]].push_back(p);
+            A.key_prio = t.a_prio[v[0]];
+            if (A.live > 0) { q_set[t.p_queue[p]].insert(AppKey(-A.key_prio, t.p_submit[p], p)); A.in_set = true; }
+        }
+        // placement-insensitive?  one leaf with pending asks, fifo, no max on its chain, one priority level
+        int leaves = 0; uint32_t leaf = NONE;
+        for (uint32_t i = 0; i < t.nq; ++i)
+            if (q_children[i].empty() && q[i].npend > 0) { ++leaves; leaf = i; }
+        insensitive = false;
+        if (leaves == 1 && one_prio && t.q_sort[leaf] == 0) {
+            bool quota = false;
+            for (uint32_t qq = leaf; qq != NONE; qq = t.q_parent[qq])
+                for (int k = 0; k < d; ++k) if (t.q_max[(size_t)k * t.nq + qq] != UNSET) quota = true;
+            insensitive = !quota;
+        }
+    }
+
+    // Next `maxB` asks in pass order, assuming every one is placed.
+    size_t fill(size_t maxB, std::vector<uint32_t>& batch) {
+        sq = q; sap = ap; sset = q_set; journal.clear(); slow_mark = slow_list.size();
+        batch.clear();
+        while (batch.size() < maxB) {
+            uint32_t a = select(0);
+            if (a == NONE) break;
+            tentative(a);
+            batch.push_back(a);
+        }
+        return batch.size();
+    }
+
+    // The device placed batch[0..j) and found no node for batch[j]: restore and replay.
+    void rewind(const std::vector<uint32_t>& batch, size_t j) {
+        for (auto it = journal.rbegin(); it != journal.rend(); ++it) t.a_state[it->first] = it->second;
+        journal.clear();
+        q = sq; ap = sap; q_set = sset; slow_list.resize(slow_mark);
+        for (size_t i = 0; i < j; ++i) {
+            uint32_t a = select(0);
+            (void)batch; // same decisions by construction
+            tentative(a);
+        }
+        uint32_t a = select(0);
+        mark_dead(a, ST_NOFIT);
+    }
+
+    // insensitive batches: ask `a` (tentatively accounted) found no node
+    void fail_in_place(uint32_t a) {
+        const int d = t.D;
+        uint32_t p = t.a_app[a];
+        t.a_state[a] = ST_NOFIT;
+        ap[p].npend++;
+        if (a_pos[a] < ap[p].head) ap[p].head = a_pos[a];
+        for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
+            q[qq].npend++;
+            for (int k = 0; k < d; ++k) { q[qq].alloc[k] -= req(a, k); q[qq].pending[k] += req(a, k); }
+            q[qq].shares_ok = false;
+        }
+    }
+
+    void confirm(uint32_t a) { t.a_state[a] = ST_ALLOCATED; }
+
+    void finish() {   // persist queue allocations
+        for (uint32_t i = 0; i < t.nq; ++i)
+            for (int k = 0; k < t.D; ++k) t.q_alloc[(size_t)k * t.nq + i] = q[i].alloc[k];
+    }
+
+private:
+    void set_state(uint32_t a, uint8_t st) {
+        journal.emplace_back(a, t.a_state[a]);
+        t.a_state[a] = st;
+    }
+    void drop_live(uint32_t a) {
+        uint32_t p = t.a_app[a];
+        AState& A = ap[p];
+        A.live--;
+        for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) q[qq].live--;
+        if (A.live == 0 && A.in_set) {
+            q_set[t.p_queue[p]].erase(AppKey(-A.key_prio, t.p_submit[p], p));
+            A.in_set = false;
+        }
+    }
+    void mark_dead(uint32_t a, uint8_t st) {
+        set_state(a, st);
+        drop_live(a);
+    }
+    void tentative(uint32_t a) {
+        const int d = t.D;
+        uint32_t p = t.a_app[a];
+        AState& A = ap[p];
+        set_state(a, ST_TENTATIVE);
+        A.npend--;
+        drop_live(a);
+        // advance head, re-key the app if its max pending priority changed
+        const auto& v = ap_asks[p];
+        while (A.head < v.size() && (t.a_state[v[A.head]] == ST_ALLOCATED || t.a_state[v[A.head]] == ST_TENTATIVE)) A.head++;
+        if (A.head < v.size()) {
+            int32_t np = t.a_prio[v[A.head]];
+            if (np != A.key_prio) {
+                if (A.in_set) {
+                    auto& S = q_set[t.p_queue[p]];
+                    S.erase(AppKey(-A.key_prio, t.p_submit[p], p));
+                    S.insert(AppKey(-np, t.p_submit[p], p));
+                }
+                A.key_prio = np;
+            }
+        }
+        for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
+            QState& Q = q[qq];
+            Q.npend--;
+            for (int k = 0; k < d; ++k) { Q.alloc[k] += req(a, k); Q.pending[k] -= req(a, k); }
+            Q.shares_ok = false;
+        }
+    }
+
+    void shares_of(uint32_t i) {
+        QState& Q = q[i];
+        if (Q.shares_ok) return;
+        const int d = t.D;
+        for (int k = 0; k < d; ++k) {
+            int64_t v = Q.alloc[k], g = t.q_guar[(size_t)k * t.nq + i];
+            Q.shares[k] = (v == 0) ? 0.0 : (g <= 0 ? (double)v : (double)v / (double)g);
+        }
+        std::sort(Q.shares, Q.shares + d);
+        Q.shares_ok = true;
+    }
+    int cmp_shares(uint32_t l, uint32_t r) {
+        shares_of(l); shares_of(r);
+        for (int k = t.D - 1; k >= 0; --k) {
+            if (q[l].shares[k] > q[r].shares[k]) return 1;
+            if (q[l].shares[k] < q[r].shares[k]) return -1;
+        }
+        return 0;
+    }
+    static bool strictly_gt_zero(const int64_t* v, int d) {
+        bool pos = false;
+        for (int k = 0; k < d; ++k) { if (v[k] < 0) return false; if (v[k] > 0) pos = true; }
+        return pos;
+    }
+
+    void headroom(uint32_t leaf, int64_t* hr) {
+        const int d = t.D;
+        uint32_t chain[64]; int n = 0;
+        for (uint32_t qq = leaf; qq != NONE && n < 64; qq = t.q_parent[qq]) chain[n++] = qq;
+        for (int k = 0; k < d; ++k) hr[k] = UNSET;
+        for (int c = n - 1; c >= 0; --c) {
+            uint32_t qq = chain[c];
+            for (int k = 0; k < d; ++k) {
+                int64_t mx = t.q_max[(size_t)k * t.nq + qq];
+                if (mx == UNSET) continue;
+                int64_t own = mx - q[qq].alloc[k];
+                if (own < 0) own = 0;
+                hr[k] = (hr[k] == UNSET) ? own : std::min(hr[k], own);
+            }
+        }
+    }
+
+    uint32_t select(uint32_t qi) {
+        if (q[qi].live <= 0) return NONE;
+        const int d = t.D;
+        if (q_children[qi].empty()) {
+            int64_t hr[8];
+            headroom(qi, hr);
+            auto& S = q_set[qi];
+            for (auto it = S.begin(); it != S.end();) {
+                uint32_t p = std::get<2>(*it);
+                ++it;   // advance first: the body may erase the current element
+                AState& A = ap[p];
+                const auto& v = ap_asks[p];
+                for (uint32_t i = A.head; i < v.size(); ++i) {
+                    uint32_t a = v[i];
+                    if (t.a_state[a] != ST_PENDING) continue;
+                    if (t.a_flags[a] & 1u) { slow_list.push_back(a); mark_dead(a, ST_SLOWPATH); continue; }
+                    bool fits = true;
+                    for (int k = 0; k < d; ++k) if (hr[k] != UNSET && req(a, k) > hr[k]) { fits = false; break; }
+                    if (!fits) { mark_dead(a, ST_SKIPPED); continue; }
+                    int64_t rq[8];
+                    for (int k = 0; k < d; ++k) rq[k] = req(a, k);
+                    if (!strictly_gt_zero(rq, d)) { mark_dead(a, ST_INVALID); continue; }   // preAllocateCheck
+                    return a;
+                }
+            }
+            return NONE;
+        }
+        // parent: children with pending asks, stable-sorted from index order by the fair comparator
+        uint32_t sorted[256]; int n = 0;
+        std::vector<uint32_t> big;
+        const auto& ch = q_children[qi];
+        uint32_t* s = sorted;
+        if (ch.size() > 256) { big.resize(ch.size()); s = big.data(); }
+        for (uint32_t c : ch) if (q[c].npend > 0) s[n++] = c;
+        std::stable_sort(s, s + n, [&](uint32_t l, uint32_t r) {
+            int c = cmp_shares(l, r);
+            if (c != 0) return c < 0;
+            int64_t diff[8];
+            for (int k = 0; k < d; ++k) diff[k] = q[l].pending[k] - q[r].pending[k];
+            if (strictly_gt_zero(diff, d)) return true;
+            for (int k = 0; k < d; ++k) diff[k] = -diff[k];
+            if (strictly_gt_zero(diff, d)) return false;
+            return l < r;
+        });
+        for (int i = 0; i < n; ++i) {
+            uint32_t a = select(s[i]);
+            if (a != NONE) return a;
+        }
+        return NONE;
+    }
+};
+
+}  // namespace yk

@@ -1,0 +1,243 @@
+"""Seeded synthetic cluster snapshots for the BASELINE.json configs.
+
+A Snapshot is plain numpy: it is the *input* both the engine (through the C ABI) and the
+test oracle consume.  Nothing here computes a scheduling decision.
+
+Shapes follow the reference's own perf inputs:
+  * kwok nodes 32 CPU / 256 Gi / 110 pods, taint kwok.x-k8s.io/node=fake:NoSchedule, label type=kwok
+    (/root/reference/deployments/kwok-perf-test/kwok-setup.sh:30-62)
+  * sleep deployments, one application per deployment, toleration Exists
+    (/root/reference/deployments/kwok-perf-test/deploy-tool.sh:34-67)
+  * 400 apps x 125 tasks, 10 mCPU / 1 MB asks
+    (/root/reference/pkg/shim/scheduler_perf_test.go:151-171,283-328)
+Resource vectors are the shim's: cpu in milli-units, everything else integer Value(), "pods": 1 per ask
+(/root/reference/pkg/common/resource.go:56-59,273-285).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+
+RESOURCES = ("vcore", "memory", "pods", "ephemeral-storage")
+GI = 1 << 30
+MI = 1 << 20
+
+NODE_SCHEDULABLE = 1
+NODE_RESERVED = 2
+ASK_SLOWPATH = 1
+POLICY_FAIR = 0
+POLICY_BINPACKING = 1
+SORT_FIFO = 0
+SORT_FAIR = 1
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    """n 64-bit values of the splitmix64 stream started at `seed` (vectorised, wraps mod 2^64)."""
+    with np.errstate(over="ignore"):
+        i = np.arange(1, n + 1, dtype=np.uint64)
+        z = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + i * np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+class _Rng:
+    def __init__(self, seed: int):
+        self.seed = seed
+        self.ctr = 0
+
+    def u64(self, n: int) -> np.ndarray:
+        out = splitmix64(self.seed * 0x1000003 + self.ctr, n)
+        self.ctr += 0x10000019
+        return out
+
+    def below(self, n: int, hi: int) -> np.ndarray:
+        return (self.u64(n) % np.uint64(hi)).astype(np.int64)
+
+    def uniform(self, n: int) -> np.ndarray:
+        return (self.u64(n) >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+@dataclass
+class Snapshot:
+    D: int
+    policy: int
+    weights: np.ndarray          # [D] f64
+    node_total: np.ndarray       # [N][D] i64
+    node_avail: np.ndarray       # [N][D] i64
+    node_taint: np.ndarray       # [N] u64
+    node_label: np.ndarray       # [N] u64
+    node_flags: np.ndarray       # [N] u32
+    node_id: list                # [N] str
+    q_parent: np.ndarray         # [Q] i32
+    q_guaranteed: np.ndarray     # [Q][D] i64 (-1 unset)
+    q_max: np.ndarray            # [Q][D] i64 (-1 unset)
+    q_alloc: np.ndarray          # [Q][D] i64
+    q_sort: np.ndarray           # [Q] u8
+    app_queue: np.ndarray        # [P] i32
+    app_submit: np.ndarray       # [P] i64
+    ask_app: np.ndarray          # [A] i32
+    ask_req: np.ndarray          # [A][D] i64
+    ask_tol: np.ndarray          # [A] u64
+    ask_need: np.ndarray         # [A] u64
+    ask_deny: np.ndarray         # [A] u64
+    ask_prio: np.ndarray         # [A] i32
+    ask_create: np.ndarray       # [A] i64
+    ask_node: np.ndarray         # [A] i32
+    ask_flags: np.ndarray        # [A] u32
+    ask_gang: np.ndarray         # [A] i32
+    name: str = ""
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_nodes(self): return len(self.node_id)
+    @property
+    def n_asks(self): return len(self.ask_app)
+    @property
+    def n_apps(self): return len(self.app_queue)
+    @property
+    def n_queues(self): return len(self.q_parent)
+
+    def node_rank(self) -> np.ndarray:
+        """rank of each NodeID in Go string order (bytewise) -- what the Go side would pass as name_rank."""
+        enc = [s.encode() for s in self.node_id]
+        order = sorted(range(len(enc)), key=lambda i: enc[i])
+        rank = np.empty(len(enc), dtype=np.uint32)
+        rank[np.asarray(order, dtype=np.int64)] = np.arange(len(enc), dtype=np.uint32)
+        return rank
+
+
+def _single_queue(D: int):
+    # root -> root.default ; no quotas (deployments/scheduler/yunikorn-configs.yaml:23-32)
+    qp = np.array([-1, 0], dtype=np.int32)
+    unset = np.full((2, D), -1, dtype=np.int64)
+    return qp, unset.copy(), unset.copy(), np.zeros((2, D), dtype=np.int64), np.zeros(2, dtype=np.uint8)
+
+
+def _finish(name, D, policy, node_total, node_avail, node_taint, node_label, node_id, queues, app_queue,
+            ask_app, ask_req, ask_tol, ask_need, ask_deny, ask_prio=None, ask_node=None, ask_flags=None,
+            ask_gang=None, node_flags=None, app_submit=None, ask_create=None, meta=None) -> Snapshot:
+    N, A, P = len(node_id), len(ask_app), len(app_queue)
+    w = np.zeros(D, dtype=np.float64)
+    w[0] = 1.0
+    w[1] = 1.0   # default node-sort weights vcore=1, memory=1
+    qp, qg, qm, qa, qs = queues
+    return Snapshot(
+        D=D, policy=policy, weights=w,
+        node_total=np.ascontiguousarray(node_total, dtype=np.int64),
+        node_avail=np.ascontiguousarray(node_avail, dtype=np.int64),
+        node_taint=np.ascontiguousarray(node_taint, dtype=np.uint64),
+        node_label=np.ascontiguousarray(node_label, dtype=np.uint64),
+        node_flags=(np.full(N, NODE_SCHEDULABLE, dtype=np.uint32) if node_flags is None
+                    else np.ascontiguousarray(node_flags, dtype=np.uint32)),
+        node_id=list(node_id),
+        q_parent=qp, q_guaranteed=qg, q_max=qm, q_alloc=qa, q_sort=qs,
+        app_queue=np.ascontiguousarray(app_queue, dtype=np.int32),
+        app_submit=(np.arange(P, dtype=np.int64) + 1_700_000_000 if app_submit is None
+                    else np.ascontiguousarray(app_submit, dtype=np.int64)),
+        ask_app=np.ascontiguousarray(ask_app, dtype=np.int32),
+        ask_req=np.ascontiguousarray(ask_req, dtype=np.int64),
+        ask_tol=np.ascontiguousarray(ask_tol, dtype=np.uint64),
+        ask_need=np.ascontiguousarray(ask_need, dtype=np.uint64),
+        ask_deny=np.ascontiguousarray(ask_deny, dtype=np.uint64),
+        ask_prio=(np.zeros(A, dtype=np.int32) if ask_prio is None else np.ascontiguousarray(ask_prio, dtype=np.int32)),
+        ask_create=(np.arange(A, dtype=np.int64) if ask_create is None
+                    else np.ascontiguousarray(ask_create, dtype=np.int64)),
+        ask_node=(np.full(A, -1, dtype=np.int32) if ask_node is None else np.ascontiguousarray(ask_node, dtype=np.int32)),
+        ask_flags=(np.zeros(A, dtype=np.uint32) if ask_flags is None else np.ascontiguousarray(ask_flags, dtype=np.uint32)),
+        ask_gang=(np.full(A, -1, dtype=np.int32) if ask_gang is None else np.ascontiguousarray(ask_gang, dtype=np.int32)),
+        name=name, meta=meta or {})
+
+
+def kwok(n_nodes=100, n_apps=10, replicas=50, variant="sized", policy=POLICY_FAIR, seed=1) -> Snapshot:
+    """BASELINE config 1: kwok-perf-test shape. variant "bare" = {pods:1} asks exactly as the script
+    (container without resources), "sized" = {100 mCPU, 128 Mi, 1 pod} so the fit test is not trivial."""
+    D = 4
+    tot = np.tile(np.array([32_000, 256 * GI, 110, 0], dtype=np.int64), (n_nodes, 1))
+    ids = [f"kwok-node-{i}" for i in range(n_nodes)]
+    taint = np.full(n_nodes, 1, dtype=np.uint64)          # bit0: kwok.x-k8s.io/node=fake:NoSchedule
+    label = np.full(n_nodes, 1, dtype=np.uint64)          # bit0: type=kwok
+    A = n_apps * replicas
+    app = np.repeat(np.arange(n_apps, dtype=np.int32), replicas)
+    req = np.zeros((A, D), dtype=np.int64)
+    req[:, 2] = 1
+    if variant == "sized":
+        req[:, 0] = 100
+        req[:, 1] = 128 * MI
+    tol = np.full(A, 1, dtype=np.uint64)
+    z = np.zeros(A, dtype=np.uint64)
+    return _finish(f"kwok-{n_nodes}x{A}-{variant}", D, policy, tot, tot.copy(), taint, label, ids,
+                   _single_queue(D), np.ones(n_apps, dtype=np.int32), app, req, tol, z, z.copy(),
+                   meta={"config": 1, "seed": seed})
+
+
+_CLASSES = np.array([[10, 1_000_000], [100, 128 * MI], [500, 1 * GI], [2000, 8 * GI]], dtype=np.int64)
+_CLASS_CUM = np.array([40, 70, 90, 100], dtype=np.int64)
+
+
+def perf(n_nodes=10_000, n_apps=400, tasks=125, masks=False, policy=POLICY_FAIR, seed=2) -> Snapshot:
+    """BASELINE config 2 (masks=False) / 3 (masks=True): jittered kwok-sized nodes, 10% pre-loaded,
+    asks drawn from four request classes (40/30/20/10 %), single leaf queue, distinct create keys."""
+    D = 4
+    r = _Rng(seed)
+    cpu = (32 + r.below(n_nodes, 17) - 8) * 1000                 # 24..40 CPU in 1-CPU steps
+    mem = (256 + r.below(n_nodes, 129) - 64) * GI                # 192..320 Gi in 1-Gi steps
+    tot = np.stack([cpu, mem, np.full(n_nodes, 110, dtype=np.int64), np.zeros(n_nodes, dtype=np.int64)], axis=1)
+    avail = tot.copy()
+    loaded = r.uniform(n_nodes) < 0.10
+    frac = r.uniform(n_nodes) * 0.8
+    used_cpu = (tot[:, 0] * frac).astype(np.int64) // 10 * 10
+    used_mem = (tot[:, 1] * frac).astype(np.int64) // MI * MI
+    used_pods = (frac * 60).astype(np.int64)
+    avail[:, 0] -= np.where(loaded, used_cpu, 0)
+    avail[:, 1] -= np.where(loaded, used_mem, 0)
+    avail[:, 2] -= np.where(loaded, used_pods, 0)
+    ids = [f"kwok-node-{i}" for i in range(n_nodes)]
+    A = n_apps * tasks
+    app = np.repeat(np.arange(n_apps, dtype=np.int32), tasks)
+    cls = np.searchsorted(_CLASS_CUM, r.below(A, 100), side="right")
+    req = np.zeros((A, D), dtype=np.int64)
+    req[:, 0] = _CLASSES[cls, 0]
+    req[:, 1] = _CLASSES[cls, 1]
+    req[:, 2] = 1
+    taint = np.zeros(n_nodes, dtype=np.uint64)
+    label = np.zeros(n_nodes, dtype=np.uint64)
+    tol = np.zeros(A, dtype=np.uint64)
+    need = np.zeros(A, dtype=np.uint64)
+    deny = np.zeros(A, dtype=np.uint64)
+    if masks:
+        # 16 taint bits, each on a node with p=0.05; asks tolerate each with p=0.5
+        tb = r.uniform(n_nodes * 16).reshape(n_nodes, 16) < 0.05
+        taint = (tb.astype(np.uint64) << np.arange(16, dtype=np.uint64)).sum(axis=1).astype(np.uint64)
+        ab = r.uniform(A * 16).reshape(A, 16) < 0.5
+        tol = (ab.astype(np.uint64) << np.arange(16, dtype=np.uint64)).sum(axis=1).astype(np.uint64)
+        # 48 label bits: zone x8 [0,8), instance-type x16 [8,24), arch x2 [24,26), pool x22 [26,48)
+        zone = r.below(n_nodes, 8)
+        itype = r.below(n_nodes, 16)
+        arch = r.below(n_nodes, 2)
+        pool = r.below(n_nodes, 22)
+        one = np.uint64(1)
+        label = ((one << zone.astype(np.uint64)) | (one << (8 + itype).astype(np.uint64))
+                 | (one << (24 + arch).astype(np.uint64)) | (one << (26 + pool).astype(np.uint64)))
+        nsel = r.below(A, 3)                                      # nodeSelector on 0..2 label bits
+        szone = r.below(A, 8)
+        sarch = r.below(A, 2)
+        need = np.where(nsel >= 1, one << szone.astype(np.uint64), np.uint64(0))
+        need = need | np.where(nsel >= 2, one << (24 + sarch).astype(np.uint64), np.uint64(0))
+        dn = r.uniform(A) < 0.10                                  # 10% carry a NotIn / DoesNotExist bit
+        dpool = r.below(A, 22)
+        deny = np.where(dn, one << (26 + dpool).astype(np.uint64), np.uint64(0))
+        # every ask must have >=1 feasible node: asks keep at least the untainted nodes of their
+        # zone/arch that are not in the denied pool; with 10k nodes that set is never empty, and the
+        # generator verifies it for small N by falling back to "tolerate everything"
+        if n_nodes < 2000:
+            ok = np.array([bool(np.any(((taint & ~tol[a]) == 0) & ((label & need[a]) == need[a])
+                                       & ((label & deny[a]) == 0))) for a in range(A)])
+            tol = np.where(ok, tol, np.uint64(0xFFFF))
+            need = np.where(ok, need, np.uint64(0))
+            deny = np.where(ok, deny, np.uint64(0))
+    return _finish(f"perf-{n_nodes}x{A}-{'masks' if masks else 'plain'}", D, policy, tot, avail, taint, label, ids,
+                   _single_queue(D), np.ones(n_apps, dtype=np.int32), app, req, tol, need, deny,
+                   meta={"config": 3 if masks else 2, "seed": seed})
