@@ -1,0 +1,43 @@
+// Host-only harness around yunikorn_k8shim_b200/csrc/yk_orderer.hpp so the ordering engine can be tested
+// on a CPU box: it plays the role of the device and answers "placed" (or "no node" for asks listed in
+// fail[]) for every ask the orderer proposes, with rewind on failure exactly as yk_cycle does.
+#include "../../yunikorn_k8shim_b200/csrc/yk_orderer.hpp"
+#include <cstdint>
+#include <vector>
+
+extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req /*[D][nA]*/,
+                           const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app, const uint32_t* a_flags,
+                           const uint32_t* p_queue, const int64_t* p_submit, const uint32_t* q_parent,
+                           const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+                           const uint8_t* fail /*[nA] 1 = device finds no node*/, uint32_t batch,
+                           uint32_t* out_order, uint32_t* n_out, uint8_t* state_out, int* insensitive_out) {
+    yk::Orderer o;
+    std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1);
+    o.t.D = D; o.t.maxA = nA; o.t.maxP = nP; o.t.nq = nQ;
+    o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags;
+    o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
+    o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.q_sort = q_sort;
+    std::vector<uint32_t> pending(nA);
+    for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
+    o.begin_cycle(pending);
+    *insensitive_out = o.insensitive ? 1 : 0;
+    std::vector<uint32_t> b;
+    uint32_t n = 0;
+    while (o.fill(batch, b) > 0) {
+        size_t consumed = b.size();
+        bool failed = false;
+        for (size_t i = 0; i < b.size(); ++i)
+            if (fail[b[i]] && !o.insensitive) { consumed = i + 1; failed = true; break; }
+        if (failed) o.rewind(b, consumed - 1);
+        for (size_t i = 0; i < consumed; ++i) {
+            uint32_t a = b[i];
+            if (fail[a]) { if (o.insensitive) o.fail_in_place(a); continue; }
+            o.confirm(a);
+            out_order[n++] = a;
+        }
+    }
+    o.finish();
+    *n_out = n;
+    for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
+    return 0;
+}

@@ -1,0 +1,90 @@
+"""Host logic without a GPU: the ordering engine (csrc/yk_orderer.hpp, compiled into a host-only harness)
+must propose asks in exactly the order the oracle's schedule() passes allocate them, including DRF queue
+sorting, headroom skips, priorities, and rewind after a placement failure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from yunikorn_k8shim_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("orderer") / "orderer_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out,
+                           os.path.join(HERE, "host", "orderer_shim.cpp")])
+    return C.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def run_orderer(shim, s, fail=None, batch=256):
+    A, P, Q, D = s.n_asks, s.n_apps, s.n_queues, s.D
+    req = np.ascontiguousarray(s.ask_req.T)
+    par = s.q_parent.astype(np.int64).copy()
+    par[par < 0] = 0xFFFFFFFF
+    par = par.astype(np.uint32)
+    guar, mx = np.ascontiguousarray(s.q_guaranteed.T), np.ascontiguousarray(s.q_max.T)
+    alloc = np.ascontiguousarray(s.q_alloc.T).copy()
+    fail = np.zeros(A, dtype=np.uint8) if fail is None else np.ascontiguousarray(fail, dtype=np.uint8)
+    out = np.zeros(A, dtype=np.uint32)
+    n = C.c_uint32(0)
+    state = np.zeros(A, dtype=np.uint8)
+    ins = C.c_int(0)
+    app, flags, queue = s.ask_app.astype(np.uint32), s.ask_flags.astype(np.uint32), s.app_queue.astype(np.uint32)
+    shim.orderer_run(C.c_int(D), C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(req), _p(s.ask_prio), _p(s.ask_create),
+                     _p(app), _p(flags), _p(queue), _p(s.app_submit), _p(par), _p(guar), _p(mx), _p(alloc), _p(s.q_sort),
+                     _p(fail), C.c_uint32(batch), _p(out), C.byref(n), _p(state), C.byref(ins))
+    return out[:n.value].copy(), state, bool(ins.value), alloc.T.copy()
+
+
+@pytest.mark.parametrize("batch", [1, 7, 256, 100000])
+@pytest.mark.parametrize("prio", [False, True])
+def test_order_matches_oracle_hierarchical(shim, oracle, batch, prio):
+    s = synth.hier(40, 4, 4, 3, 30, priorities=prio, big_nodes=True, seed=11)
+    want = oracle.run(s)
+    got, state, ins, _ = run_orderer(shim, s, batch=batch)
+    assert not ins
+    assert np.array_equal(got, want["ask"])
+    assert np.array_equal(state, want["state"])          # ALLOCATED vs SKIPPED (headroom)
+    assert (want["state"] == 3).sum() > 0, "fixture should exercise headroom skips"
+
+
+def test_order_single_queue_is_placement_insensitive(shim, oracle):
+    s = synth.perf(50, 8, 40)
+    s.node_total[:, :3] = 1 << 40
+    s.node_avail[:] = s.node_total
+    want = oracle.run(s)
+    got, state, ins, _ = run_orderer(shim, s, batch=64)
+    assert ins
+    assert np.array_equal(got, want["ask"])
+
+
+def test_rewind_after_placement_failure(shim, oracle):
+    """Asks that find no node: emulate with asks that no node can hold (request > every node total); the oracle
+    leaves them NOFIT and the DRF order afterwards differs from the all-placed order, which is what rewind handles."""
+    batch = 16
+    s = synth.hier(40, 3, 3, 2, 25, priorities=True, big_nodes=True, seed=5)
+    rng = np.random.default_rng(3)
+    bad = rng.random(s.n_asks) < 0.15
+    s.ask_req[bad, 2] = (1 << 31)          # more pods than any node has
+    want = oracle.run(s)
+    for b in (1, batch, 4096):
+        got, state, ins, qalloc = run_orderer(shim, s, fail=bad.astype(np.uint8), batch=b)
+        assert np.array_equal(got, want["ask"]), f"batch={b}"
+        assert np.array_equal(state, want["state"]), f"batch={b}"
+    # queue accounting after the cycle = sum of what was really allocated
+    leaf_alloc = np.zeros_like(s.q_alloc)
+    for a in want["ask"]:
+        q = s.app_queue[s.ask_app[a]]
+        while q >= 0:
+            leaf_alloc[q] += s.ask_req[a]
+            q = s.q_parent[q]
+    assert np.array_equal(qalloc, leaf_alloc)

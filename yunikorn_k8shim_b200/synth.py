@@ -241,3 +241,53 @@ def perf(n_nodes=10_000, n_apps=400, tasks=125, masks=False, policy=POLICY_FAIR,
     return _finish(f"perf-{n_nodes}x{A}-{'masks' if masks else 'plain'}", D, policy, tot, avail, taint, label, ids,
                    _single_queue(D), np.ones(n_apps, dtype=np.int32), app, req, tol, need, deny,
                    meta={"config": 3 if masks else 2, "seed": seed})
+
+
+def hier(n_nodes=50_000, n_parents=8, leaves_per_parent=8, apps_per_leaf=5, tasks=625, masks=False,
+         policy=POLICY_FAIR, seed=4, quota_frac=1.2, priorities=False, big_nodes=False) -> Snapshot:
+    """BASELINE config 4: 3-level queue tree (root -> parents -> leaves), guaranteed + max per leaf, fifo apps
+    in the leaves, fair (DRF) parents; demand is `quota_frac` x some leaf maxima so the headroom checks bite.
+    Default sizes: 50k nodes, 64 leaves x 5 apps x 625 tasks = 200k asks."""
+    base = perf(n_nodes, n_parents * leaves_per_parent * apps_per_leaf, tasks, masks=masks, policy=policy, seed=seed)
+    D = base.D
+    r = _Rng(seed * 7919 + 13)
+    L = n_parents * leaves_per_parent
+    Q = 1 + n_parents + L
+    qp = np.empty(Q, dtype=np.int32)
+    qp[0] = -1
+    qp[1:1 + n_parents] = 0
+    qp[1 + n_parents:] = 1 + np.repeat(np.arange(n_parents, dtype=np.int32), leaves_per_parent)
+    guar = np.full((Q, D), -1, dtype=np.int64)
+    mx = np.full((Q, D), -1, dtype=np.int64)
+    app_leaf = np.repeat(np.arange(L, dtype=np.int32), apps_per_leaf)
+    app_queue = 1 + n_parents + app_leaf
+    ask_leaf = app_leaf[base.ask_app]
+    demand = np.zeros((L, D), dtype=np.int64)
+    np.add.at(demand, ask_leaf, base.ask_req)
+    # guaranteed: a random 20..60 % of the leaf's demand on cpu/memory; max on every third leaf at demand/quota_frac
+    gfrac = 0.2 + 0.4 * r.uniform(L)
+    for li in range(L):
+        q = 1 + n_parents + li
+        guar[q, 0] = max(1000, int(demand[li, 0] * gfrac[li]) // 1000 * 1000)
+        guar[q, 1] = max(GI, int(demand[li, 1] * gfrac[li]) // GI * GI)
+        if li % 3 == 0:
+            mx[q, 0] = max(1000, int(demand[li, 0] / quota_frac) // 1000 * 1000)
+            mx[q, 1] = max(GI, int(demand[li, 1] / quota_frac) // GI * GI)
+    for pi in range(n_parents):
+        q = 1 + pi
+        kids = np.nonzero(qp == q)[0]
+        guar[q, 0] = guar[kids, 0].sum()
+        guar[q, 1] = guar[kids, 1].sum()
+    prio = None
+    if priorities:
+        prio = (r.below(base.n_asks, 3) - 1).astype(np.int32) * 100
+    if big_nodes:   # every node can hold everything: isolates the ordering logic
+        base.node_total[:, 0] = 1 << 40
+        base.node_total[:, 1] = 1 << 50
+        base.node_total[:, 2] = 1 << 30
+        base.node_avail[:] = base.node_total
+    queues = (qp, guar, mx, np.zeros((Q, D), dtype=np.int64), np.zeros(Q, dtype=np.uint8))
+    s = _finish(f"hier-{n_nodes}x{base.n_asks}-q{Q}", D, policy, base.node_total, base.node_avail, base.node_taint,
+                base.node_label, base.node_id, queues, app_queue, base.ask_app, base.ask_req, base.ask_tol,
+                base.ask_need, base.ask_deny, ask_prio=prio, meta={"config": 4, "seed": seed})
+    return s
