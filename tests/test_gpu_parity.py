@@ -50,6 +50,6 @@ def test_config3_full(oracle):
 
 def test_overcommitted_cluster(oracle):
     # far more demand than capacity: many asks must end NOFIT, in the oracle's order
-    snap = synth.perf(40, 10, 200, masks=True)
+    snap = synth.perf(8, 10, 200, masks=True)
     st = _check(snap, oracle, batch=256)
     assert st["nofit"] > 0
