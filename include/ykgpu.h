@@ -124,6 +124,9 @@ typedef struct {
     double sweep_ms, sort_ms, commit_ms, total_ms;   /* CUDA-event / wall accumulations */
     double last_sweep_ms;
     uint64_t last_sweep_pairs;
+    /* host wall-clock split of yk_cycle: 0 table upload + initial device sort, 1 orderer begin_cycle,
+       2 orderer fill/rewind, 3 waiting for device results, 4 ordered commit, 5 order merge, 6 other */
+    double host_ms[8];
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

@@ -140,7 +140,24 @@ def run(s, max_bindings=-1):
     def app_npend(p):
         return sum(1 for a in app_asks[p] if state[a] != ST_ALLOCATED)
 
+    def apply(a, n, sign):
+        for k in range(D):
+            avail[n][k] -= sign * req[a][k]
+        p = int(s.ask_app[a])
+        for k in range(D):
+            app_alloc[p][k] += sign * req[a][k]
+        for qq in chain(int(s.app_queue[p])):
+            q_npend[qq] -= sign
+            for k in range(D):
+                q_alloc[qq][k] += sign * req[a][k]
+                q_pending[qq][k] -= sign * req[a][k]
+        state[a] = ST_ALLOCATED if sign > 0 else ST_PENDING
+
+    stop = [False]
+    room = None
+
     def try_queue(q):
+        nonlocal room
         if not children[q]:
             hr = headroom(q)
             cand = [p for p in q_apps[q] if app_npend(p) > 0]
@@ -159,7 +176,11 @@ def run(s, max_bindings=-1):
             else:
                 cand.sort(key=lambda p: (-app_prio(p), int(s.app_submit[p]), p))
             for p in cand:
+                if stop[0]:
+                    return None
                 for a in app_asks[p]:
+                    if stop[0]:
+                        return None
                     if state[a] == ST_ALLOCATED or dead[a]:
                         continue
                     if int(s.ask_flags[a]) & 1:
@@ -171,9 +192,44 @@ def run(s, max_bindings=-1):
                     if not strictly_gt_zero(req[a]):
                         state[a], dead[a] = ST_INVALID, True
                         continue
+                    g = int(s.ask_gang[a])
+                    if g >= 0:
+                        members = [m for m in app_asks[p] if int(s.ask_gang[m]) == g and state[m] != ST_ALLOCATED and not dead[m]]
+                        if room is not None and len(members) > room:
+                            stop[0] = True
+                            return None
+                        placed, cause = [], 0
+                        hrm = headroom(q)           # queue-side checks of all members first, headroom shrinking
+                        for m in members:
+                            if int(s.ask_flags[m]) & 1:
+                                cause = ST_SLOWPATH
+                            elif any(hrm[k] != UNSET and req[m][k] > hrm[k] for k in range(D)):
+                                cause = ST_SKIPPED
+                            elif not strictly_gt_zero(req[m]):
+                                cause = ST_INVALID
+                            if cause:
+                                break
+                            hrm = [hrm[k] if hrm[k] == UNSET else hrm[k] - req[m][k] for k in range(D)]
+                        for m in members:           # then the node walks
+                            if cause:
+                                break
+                            nm = pick_node(m)
+                            if nm is None:
+                                cause = ST_NOFIT
+                                break
+                            apply(m, nm, +1)
+                            placed.append((m, nm))
+                        if cause:
+                            for m, nm in reversed(placed):
+                                apply(m, nm, -1)
+                            for m in members:
+                                state[m], dead[m] = cause, True
+                            continue
+                        return placed
                     n = pick_node(a)
                     if n is not None:
-                        return a, n
+                        apply(a, n, +1)
+                        return [(a, n)]
                     state[a], dead[a] = ST_NOFIT, True
             return None
         import functools
@@ -193,26 +249,15 @@ def run(s, max_bindings=-1):
         cand.sort(key=functools.cmp_to_key(qcmp))
         for c in cand:
             r = try_queue(c)
-            if r is not None:
+            if r is not None or stop[0]:
                 return r
         return None
 
     out = []
     while max_bindings < 0 or len(out) < max_bindings:
+        room = None if max_bindings < 0 else max_bindings - len(out)
         r = try_queue(0)
         if r is None:
             break
-        a, n = r
-        for k in range(D):
-            avail[n][k] -= req[a][k]
-        p = int(s.ask_app[a])
-        for k in range(D):
-            app_alloc[p][k] += req[a][k]
-        for q in chain(int(s.app_queue[p])):
-            q_npend[q] -= 1
-            for k in range(D):
-                q_alloc[q][k] += req[a][k]
-                q_pending[q][k] -= req[a][k]
-        state[a] = ST_ALLOCATED
-        out.append((a, n))
+        out.extend(r)
     return {"ask": [a for a, _ in out], "node": [n for _, n in out], "state": state, "avail": avail}

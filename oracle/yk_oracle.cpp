@@ -221,14 +221,77 @@ struct Engine {
         ++st.allocations;
     }
 
+    void uncommit(int a, int n) {   // exact inverse of commit (all-or-nothing gangs)
+        int64_t* v = av(n);
+        const int64_t* r = req(a);
+        for (int k = 0; k < D; ++k) v[k] += r[k];
+        rekey(n);
+        int p = s->ask_app[a];
+        App& ap = apps[(size_t)p];
+        ap.pending_asks++;
+        for (int k = 0; k < D; ++k) ap.alloc[(size_t)k] -= r[k];
+        for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
+            Queue& Q = queues[(size_t)q];
+            Q.pending_asks++;
+            for (int k = 0; k < D; ++k) { Q.alloc[(size_t)k] -= r[k]; Q.pending[(size_t)k] += r[k]; }
+        }
+        state[(size_t)a] = YKO_ST_PENDING;
+        done[(size_t)a] = 0;
+        --st.allocations;
+    }
+
+    int gang_of(int a) const { return s->ask_gang ? s->ask_gang[a] : -1; }
+
+    // All-or-nothing placement of the gang that ask `first` belongs to (DESIGN.md "gangs"):
+    // members are placed one after the other in the application's ask order, each exactly like an ordinary
+    // ask (headroom re-read after every member, ordered node walk, commit + re-score); if any member cannot
+    // be placed every earlier member is rolled back and the whole gang is marked with that member's cause.
+    bool try_gang(int p, int first, std::vector<std::pair<int, int>>& out) {
+        const int g = gang_of(first);
+        App& ap = apps[(size_t)p];
+        std::vector<int> members;
+        for (size_t i = ap.head; i < ap.asks.size(); ++i) {
+            int a = ap.asks[i];
+            if (gang_of(a) == g && state[(size_t)a] != YKO_ST_ALLOCATED && !done[(size_t)a]) members.push_back(a);
+        }
+        std::vector<std::pair<int, int>> placed;
+        uint8_t cause = 0;
+        // queue-side checks of every member first (headroom shrinking as if the earlier members were placed) ...
+        {
+            int64_t hr[YKO_MAX_D];
+            headroom(s->app_queue[p], hr);
+            for (int a : members) {
+                if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { cause = YKO_ST_SLOWPATH; break; }
+                if (!fit_in_max_undef(hr, req(a))) { cause = YKO_ST_SKIPPED; break; }
+                if (!strictly_gt_zero(D, req(a))) { cause = YKO_ST_INVALID; break; }
+                for (int k = 0; k < D; ++k) if (hr[k] != UNSET) hr[k] -= req(a)[k];
+            }
+        }
+        // ... then the node walks, member by member
+        for (int a : members) {
+            if (cause) break;
+            int n = try_nodes(a);
+            if (n < 0) { cause = YKO_ST_NOFIT; break; }
+            commit(a, n);
+            placed.emplace_back(a, n);
+        }
+        if (cause) {
+            for (auto it = placed.rbegin(); it != placed.rend(); ++it) uncommit(it->first, it->second);
+            for (int a : members) { state[(size_t)a] = cause; done[(size_t)a] = 1; }
+            return false;
+        }
+        out.insert(out.end(), placed.begin(), placed.end());
+        return true;
+    }
+
     int app_priority(int p) {   // max priority over pending asks = priority of the first pending one
         App& ap = apps[(size_t)p];
         while (ap.head < ap.asks.size() && state[(size_t)ap.asks[ap.head]] == YKO_ST_ALLOCATED) ++ap.head;
         return ap.head < ap.asks.size() ? s->ask_prio[ap.asks[ap.head]] : INT32_MIN;
     }
 
-    // returns allocated ask (>=0) and node through *node_out, or -1
-    int try_app(int p, const int64_t* hr, int* node_out) {
+    // appends the pass's allocation(s) to out (one ask, or a whole gang); returns true if anything was allocated
+    bool try_app(int p, const int64_t* hr, std::vector<std::pair<int, int>>& out, int room) {
         bool retry = (mode & YKO_MODE_RETRY_FAILED) != 0;
         App& ap = apps[(size_t)p];
         for (size_t i = ap.head; i < ap.asks.size(); ++i) {
@@ -238,15 +301,24 @@ struct Engine {
             if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { state[(size_t)a] = YKO_ST_SLOWPATH; done[(size_t)a] = 1; continue; }
             if (!fit_in_max_undef(hr, req(a))) { state[(size_t)a] = YKO_ST_SKIPPED; done[(size_t)a] = 1; continue; }
             if (!strictly_gt_zero(D, req(a))) { state[(size_t)a] = YKO_ST_INVALID; done[(size_t)a] = 1; continue; }
+            if (gang_of(a) >= 0) {
+                int members = 0;
+                for (size_t j = ap.head; j < ap.asks.size(); ++j)
+                    if (gang_of(ap.asks[j]) == gang_of(a) && state[(size_t)ap.asks[j]] != YKO_ST_ALLOCATED && !done[(size_t)ap.asks[j]]) ++members;
+                if (room >= 0 && members > room) { stop = true; return false; }   // gang does not fit in max_bindings: end the cycle
+                if (try_gang(p, a, out)) return true;
+                continue;
+            }
             int n = try_nodes(a);
-            if (n >= 0) { *node_out = n; return a; }
+            if (n >= 0) { commit(a, n); out.emplace_back(a, n); return true; }
             state[(size_t)a] = YKO_ST_NOFIT;
             done[(size_t)a] = 1;
         }
-        return -1;
+        return false;
     }
+    bool stop = false;
 
-    int try_queue(int q, int* node_out) {
+    bool try_queue(int q, std::vector<std::pair<int, int>>& out, int room) {
         Queue& Q = queues[(size_t)q];
         if (Q.children.empty()) {
             int64_t hr[YKO_MAX_D];
@@ -276,10 +348,10 @@ struct Engine {
                 });
             }
             for (int p : sorted) {
-                int a = try_app(p, hr, node_out);
-                if (a >= 0) return a;
+                if (try_app(p, hr, out, room)) return true;
+                if (stop) return false;
             }
-            return -1;
+            return false;
         }
         ++st.queue_sorts;
         std::vector<int> sorted;
@@ -297,10 +369,10 @@ struct Engine {
             return l < r;
         });
         for (int c : sorted) {
-            int a = try_queue(c, node_out);
-            if (a >= 0) return a;
+            if (try_queue(c, out, room)) return true;
+            if (stop) return false;
         }
-        return -1;
+        return false;
     }
 };
 
@@ -400,15 +472,12 @@ int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings, int32_t*
         });
 
     int32_t n = 0;
+    std::vector<std::pair<int, int>> got;
     while (max_bindings < 0 || n < max_bindings) {
         ++e.st.passes;
-        int node = -1;
-        int a = e.try_queue(0, &node);
-        if (a < 0) break;
-        e.commit(a, node);
-        out_ask[n] = a;
-        out_node[n] = node;
-        ++n;
+        got.clear();
+        if (!e.try_queue(0, got, max_bindings < 0 ? -1 : max_bindings - n)) break;
+        for (auto& b : got) { out_ask[n] = b.first; out_node[n] = b.second; ++n; }
     }
     *n_out = n;
     if (ask_state) memcpy(ask_state, e.state.data(), (size_t)s->n_asks);

@@ -6,7 +6,7 @@
 #include <vector>
 
 extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req /*[D][nA]*/,
-                           const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app, const uint32_t* a_flags,
+                           const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app, const uint32_t* a_flags, const uint32_t* a_gang,
                            const uint32_t* p_queue, const int64_t* p_submit, const uint32_t* q_parent,
                            const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
                            const uint8_t* fail /*[nA] 1 = device finds no node*/, uint32_t batch,
@@ -14,7 +14,7 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
     yk::Orderer o;
     std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1);
     o.t.D = D; o.t.maxA = nA; o.t.maxP = nP; o.t.nq = nQ;
-    o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags;
+    o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags; o.t.a_gang = a_gang;
     o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
     o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.q_sort = q_sort;
     std::vector<uint32_t> pending(nA);
@@ -23,19 +23,31 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
     *insensitive_out = o.insensitive ? 1 : 0;
     std::vector<uint32_t> b;
     uint32_t n = 0;
-    while (o.fill(batch, b) > 0) {
-        size_t consumed = b.size();
-        bool failed = false;
-        for (size_t i = 0; i < b.size(); ++i)
-            if (fail[b[i]] && !o.insensitive) { consumed = i + 1; failed = true; break; }
-        if (failed) o.rewind(b, consumed - 1);
+    auto same_gang = [&](uint32_t x, uint32_t y) { return a_gang[x] != yk::NONE && a_gang[x] == a_gang[y] && a_app[x] == a_app[y]; };
+    while (o.fill(batch, (size_t)-1, b) > 0) {
+        // the "device": an ask fails if fail[] says so; a gang fails whole if any member does
+        std::vector<uint8_t> bad(b.size(), 0);
+        for (size_t i = 0; i < b.size();) {
+            size_t j = i + 1;
+            while (j < b.size() && same_gang(b[i], b[j])) ++j;
+            bool f = false;
+            for (size_t x = i; x < j; ++x) f = f || fail[b[x]];
+            for (size_t x = i; x < j; ++x) bad[x] = f;
+            i = j;
+        }
+        size_t consumed = b.size(), first_bad = b.size();
+        if (!o.insensitive)
+            for (size_t i = 0; i < b.size(); ++i)
+                if (bad[i]) { first_bad = i; consumed = i + 1; while (consumed < b.size() && same_gang(b[i], b[consumed])) ++consumed; break; }
+        if (first_bad < b.size()) o.rewind(b, first_bad);
         for (size_t i = 0; i < consumed; ++i) {
             uint32_t a = b[i];
-            if (fail[a]) { if (o.insensitive) o.fail_in_place(a); continue; }
+            if (bad[i]) { if (o.insensitive) o.fail_in_place(a); continue; }
             o.confirm(a);
             out_order[n++] = a;
         }
     }
+    if (o.oversize_gang) return -1;
     o.finish();
     *n_out = n;
     for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];

@@ -53,3 +53,101 @@ def test_overcommitted_cluster(oracle):
     snap = synth.perf(8, 10, 200, masks=True)
     st = _check(snap, oracle, batch=256)
     assert st["nofit"] > 0
+
+
+# ---- config 4: hierarchical queues, DRF parents, quotas, priorities (placement-sensitive order) ----
+@pytest.mark.parametrize("prio", [False, True])
+def test_config4_small(oracle, prio):
+    st = _check(synth.hier(300, 3, 4, 2, 40, masks=True, priorities=prio, seed=21), oracle, batch=128)
+    assert st["skipped"] > 0
+
+
+def test_config4_overcommitted_rewinds(oracle):
+    # too few nodes: placement failures inside a DRF order force rewinds
+    st = _check(synth.hier(6, 3, 3, 2, 60, priorities=True, seed=22), oracle, batch=64)
+    assert st["nofit"] > 0
+
+
+def test_config4_full(oracle):
+    _check(synth.hier(), oracle, batch=4096)
+
+
+# ---- config 5: gangs, all-or-nothing ----
+@pytest.mark.parametrize("policy", [synth.POLICY_FAIR, synth.POLICY_BINPACKING])
+def test_config5_small(oracle, policy):
+    st = _check(synth.gangs(60, 40, 5, fill=1.4, policy=policy), oracle, batch=64)
+    assert st["nofit"] > 0
+
+
+def test_config5_gangs_in_drf_tree(oracle):
+    s = synth.hier(30, 2, 3, 2, 24, seed=9)
+    s.ask_gang[:] = np.arange(s.n_asks) // 4
+    _check(s, oracle, batch=32)
+
+
+def test_config5_full(oracle):
+    st = _check(synth.gangs(), oracle, batch=4096)
+    assert st["nofit"] > 0
+
+
+def test_gang_larger_than_batch_is_an_error(oracle):
+    from yunikorn_k8shim_b200 import YkError
+    s = synth.gangs(30, 4, 20)
+    with Engine.for_snapshot(s, batch=8) as e:
+        with pytest.raises(YkError):
+            e.cycle(s.n_asks)
+
+
+# ---- edge cases the reference tests at this boundary ----
+def test_edges(oracle):
+    s = synth.perf(5, 2, 10)
+    s.node_flags[:] = 0
+    _check(s, oracle, batch=16)                                   # no schedulable node
+    s = synth.perf(5, 2, 10)
+    s.ask_req[::3] = 0
+    _check(s, oracle, batch=16)                                   # invalid requests
+    s = synth.perf(5, 2, 10)
+    s.ask_flags[::2] = 1
+    _check(s, oracle, batch=16)                                   # slow-path asks are left alone
+    s = synth.perf(9, 2, 10)
+    s.ask_node[:] = 3
+    _check(s, oracle, batch=16)                                   # pod.Spec.NodeName
+    s = synth.perf(9, 2, 10)
+    s.node_flags[4] = synth.NODE_SCHEDULABLE | synth.NODE_RESERVED
+    s.node_avail[2, 0] = -5000                                    # over-committed node: FitIn clamps at 0
+    _check(s, oracle, batch=16)
+
+
+def test_max_bindings_and_second_cycle(oracle):
+    s = synth.perf(50, 4, 50, masks=True)
+    want = oracle.run(s, max_bindings=77)
+    full = oracle.run(s)
+    with Engine.for_snapshot(s, batch=32) as e:
+        ask, node, _ = e.cycle(77)
+        assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
+        ask2, node2, _ = e.cycle(s.n_asks)                        # the rest, on the state the first cycle left
+        assert np.array_equal(np.concatenate([ask, ask2]), full["ask"])
+        assert np.array_equal(np.concatenate([node, node2]), full["node"])
+
+
+def test_release_gives_resources_back(oracle):
+    s = synth.perf(6, 2, 300)                                     # overcommitted
+    want = oracle.run(s)
+    with Engine.for_snapshot(s, batch=64) as e:
+        ask, node, _ = e.cycle(s.n_asks)
+        assert np.array_equal(ask, want["ask"])
+        e.release(ask)
+        assert np.array_equal(e.nodes_available(np.arange(s.n_nodes)), s.node_avail)
+
+
+def test_device_score_and_evaluate_match_oracle(oracle):
+    s = synth.perf(200, 4, 20, masks=True)
+    s.node_avail[:, 0] -= np.arange(200) * 37
+    with Engine.for_snapshot(s) as e:
+        sc = e.node_scores(np.arange(s.n_nodes))
+        want = [oracle.node_score(s.policy, s.weights, s.node_total[n], s.node_avail[n]) for n in range(s.n_nodes)]
+        assert sc.tolist() == want                                # float64 bit-exact
+        for a in range(0, s.n_asks, 7):
+            for n in range(0, s.n_nodes, 11):
+                got, exp = e.evaluate(a, n), oracle.predicate(s, a, n)
+                assert (got == 0) == (exp == 0) and (got == exp or {got, exp} <= {4, 8}), (a, n, got, exp)

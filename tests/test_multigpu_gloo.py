@@ -1,0 +1,75 @@
+"""N>1 host-side path on CPU: world_size-2 gloo run of the exchange callback the engine calls once per batch
+(in-place all-gather of row shards) and of the per-cycle agreement check."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from yunikorn_k8shim_b200 import multigpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rows, row_bytes, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        first, rows_per, total = multigpu.shard_rows(n_rows, world, rank)
+        buf = np.zeros(total * row_bytes, dtype=np.uint8)
+        view = buf.reshape(total, row_bytes)
+        view[rank * rows_per:(rank + 1) * rows_per] = (np.arange(rows_per)[:, None] * 7 + rank * 101 + np.arange(row_bytes)[None, :]) % 251
+        fn = multigpu.make_allgather(dist, cuda=False)
+        rc = fn(None, buf.ctypes.data, row_bytes, rank * rows_per, rows_per, total, None)
+        want = np.zeros_like(view)
+        for r in range(world):
+            want[r * rows_per:(r + 1) * rows_per] = (np.arange(rows_per)[:, None] * 7 + r * 101 + np.arange(row_bytes)[None, :]) % 251
+        ok_gather = rc == 0 and np.array_equal(view, want)
+        same = multigpu.check_agreement(dist, np.arange(10), np.arange(10) * 3)
+        diff = multigpu.check_agreement(dist, np.arange(10), np.arange(10) * 3 + (rank == 1))
+        q.put((rank, bool(ok_gather), bool(same), bool(diff), first, rows_per, total))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows", [64, 1001])
+def test_exchange_and_agreement_world2(n_rows):
+    world, row_bytes = 2, 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rows, row_bytes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_gather, same, diff, first, rows_per, total in res:
+        assert ok_gather, f"rank {rank}: gathered rows differ"
+        assert same, "identical bindings must agree"
+        assert not diff, "diverging replicas must be detected"
+        assert rows_per == (n_rows + world - 1) // world and total == rows_per * world
+        assert first == min(n_rows, rank * rows_per)
+
+
+def test_shard_rows_covers_every_row_once():
+    for n in (0, 1, 7, 64, 1000, 4096):
+        for world in (1, 2, 4, 8):
+            seen = np.zeros(n, dtype=int)
+            for r in range(world):
+                first, rows_per, total = multigpu.shard_rows(n, world, r)
+                seen[first:min(n, first + rows_per)] += 1
+                assert total >= n and total % world == 0
+            assert (seen == 1).all()

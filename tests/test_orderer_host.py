@@ -39,9 +39,13 @@ def run_orderer(shim, s, fail=None, batch=256):
     state = np.zeros(A, dtype=np.uint8)
     ins = C.c_int(0)
     app, flags, queue = s.ask_app.astype(np.uint32), s.ask_flags.astype(np.uint32), s.app_queue.astype(np.uint32)
-    shim.orderer_run(C.c_int(D), C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(req), _p(s.ask_prio), _p(s.ask_create),
-                     _p(app), _p(flags), _p(queue), _p(s.app_submit), _p(par), _p(guar), _p(mx), _p(alloc), _p(s.q_sort),
+    gang = s.ask_gang.astype(np.int64).copy()
+    gang[gang < 0] = 0xFFFFFFFF
+    gang = gang.astype(np.uint32)
+    rc = shim.orderer_run(C.c_int(D), C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(req), _p(s.ask_prio), _p(s.ask_create),
+                     _p(app), _p(flags), _p(gang), _p(queue), _p(s.app_submit), _p(par), _p(guar), _p(mx), _p(alloc), _p(s.q_sort),
                      _p(fail), C.c_uint32(batch), _p(out), C.byref(n), _p(state), C.byref(ins))
+    assert rc == 0
     return out[:n.value].copy(), state, bool(ins.value), alloc.T.copy()
 
 
@@ -88,3 +92,23 @@ def test_rewind_after_placement_failure(shim, oracle):
             leaf_alloc[q] += s.ask_req[a]
             q = s.q_parent[q]
     assert np.array_equal(qalloc, leaf_alloc)
+
+
+@pytest.mark.parametrize("batch", [8, 64, 100000])
+def test_gangs_order_and_failure(shim, oracle, batch):
+    """Gangs go through whole or not at all, in a multi-queue (placement-sensitive) tree: members that no node
+    can hold sink their whole gang, and the order afterwards follows the oracle."""
+    s = synth.hier(40, 2, 3, 2, 24, big_nodes=True, seed=9)
+    gid = (np.arange(s.n_asks) // 4).astype(np.int32)      # gangs of 4 consecutive asks of one app (24 % 4 == 0)
+    s.ask_gang[:] = gid
+    rng = np.random.default_rng(1)
+    bad = rng.random(s.n_asks) < 0.03
+    s.ask_req[bad, 2] = (1 << 31)
+    want = oracle.run(s)
+    got, state, ins, _ = run_orderer(shim, s, fail=bad.astype(np.uint8), batch=batch)
+    assert not ins
+    assert np.array_equal(got, want["ask"])
+    assert np.array_equal(state, want["state"])
+    st = want["state"].reshape(-1, 4)
+    assert ((st == st[:, :1]).all(axis=1)).all(), "a gang's members share one fate"
+    assert (st[:, 0] == 2).sum() > 0 and (st[:, 0] == 1).sum() > 0

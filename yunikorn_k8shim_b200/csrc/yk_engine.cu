@@ -18,7 +18,6 @@
 #include <cstring>
 #include <mutex>
 #include <new>
-#include <set>
 #include <string>
 #include <vector>
 
@@ -64,6 +63,68 @@ double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+struct DirtyRef {
+    uint64_t key; uint32_t rank; uint32_t node;
+    bool operator<(const DirtyRef& o) const {
+        if (key != o.key) return key < o.key;
+        return rank < o.rank;
+    }
+};
+
+// Sorted list of the nodes re-scored in the current batch: buckets of <= CAP entries (sqrt decomposition);
+// insert / erase are a binary search over bucket heads plus a short memmove, iteration is sequential.
+struct DirtyList {
+    static constexpr uint32_t CAP = 48;
+    struct Bucket { uint32_t n; DirtyRef v[CAP]; };
+    std::vector<Bucket> pool;
+    std::vector<uint32_t> seq;    // bucket ids in key order
+    uint32_t used = 0, count = 0;
+    void clear() { seq.clear(); used = 0; count = 0; }
+    uint32_t fresh() {
+        if (used == pool.size()) pool.emplace_back();
+        pool[used].n = 0;
+        return used++;
+    }
+    // index in seq of the bucket that should hold x
+    uint32_t locate(const DirtyRef& x) const {
+        uint32_t lo = 0, hi = (uint32_t)seq.size();   // last bucket whose head <= x, else 0
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) / 2;
+            if (x < pool[seq[mid]].v[0]) hi = mid; else lo = mid;
+        }
+        return lo;
+    }
+    void insert(const DirtyRef& x) {
+        if (seq.empty()) seq.push_back(fresh());
+        uint32_t si = locate(x);
+        Bucket* b = &pool[seq[si]];
+        if (b->n == CAP) {   // split
+            uint32_t nb = fresh();
+            b = &pool[seq[si]];
+            Bucket* c = &pool[nb];
+            c->n = CAP / 2;
+            memcpy(c->v, b->v + CAP / 2, sizeof(DirtyRef) * (CAP / 2));
+            b->n = CAP / 2;
+            seq.insert(seq.begin() + si + 1, nb);
+            if (!(x < c->v[0])) { ++si; b = c; }
+        }
+        uint32_t pos = (uint32_t)(std::lower_bound(b->v, b->v + b->n, x) - b->v);
+        memmove(b->v + pos + 1, b->v + pos, sizeof(DirtyRef) * (b->n - pos));
+        b->v[pos] = x;
+        b->n++;
+        count++;
+    }
+    void erase(const DirtyRef& x) {
+        uint32_t si = locate(x);
+        Bucket* b = &pool[seq[si]];
+        uint32_t pos = (uint32_t)(std::lower_bound(b->v, b->v + b->n, x) - b->v);
+        memmove(b->v + pos, b->v + pos + 1, sizeof(DirtyRef) * (b->n - pos - 1));
+        b->n--;
+        count--;
+        if (b->n == 0) seq.erase(seq.begin() + si);
+    }
+};
 
 }  // namespace
 
@@ -119,9 +180,14 @@ struct yk_engine {
     // commit scratch
     std::vector<uint32_t> pos_of;
     std::vector<uint32_t> dirty_words;
-    std::vector<uint64_t> cur_key;   // per node, valid for dirty nodes
+    std::vector<uint64_t> hkey;      // per node: current sort key (monotone bits of the float64 score)
     std::vector<uint8_t> is_dirty;
     std::vector<uint32_t> dirty_list;
+    Pin<uint32_t> h_order[2]; int cur = 0;   // node order (ascending (score, NodeID)), double-buffered
+    Dev<uint32_t> d_order;
+    std::vector<cudaEvent_t> ev_chunk;
+    DirtyList dirty;
+    std::vector<int64_t> hot; int hs = 0;    // per node [avail[D], total[D], taint, label] contiguous: the commit's working copy
 
     yk::Orderer ord;
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
@@ -201,22 +267,63 @@ void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s) {
     }
 }
 
-inline bool fits_avail(const yk_engine* e, uint32_t node, uint32_t ask) {
-    for (int k = 0; k < e->D; ++k) {
-        int64_t a = e->n_avail[(size_t)k * e->maxN + node];
+// Full (ask,node) predicate on the commit's working copy, for nodes already committed to in this batch
+// (such nodes are schedulable and unreserved: they were chosen before).  Same steps as the sweep kernel.
+inline bool fits_now(const yk_engine* e, uint32_t node, uint32_t ask) {
+    const int64_t* h = e->hot.data() + (size_t)node * e->hs;
+    const int D = e->D;
+    const uint64_t taint = (uint64_t)h[2 * D], label = (uint64_t)h[2 * D + 1];
+    if ((taint & ~e->a_tol[ask]) | (~label & e->a_need[ask]) | (label & e->a_deny[ask])) return false;
+    if (e->a_node[ask] != YK_NONE && e->a_node[ask] != node) return false;
+    for (int k = 0; k < D; ++k) {
+        int64_t a = h[k], t = h[D + k];
         if (a < 0) a = 0;
-        if (e->a_req[(size_t)k * e->maxA + ask] > a) return false;
+        if (t < 0) t = 0;
+        const int64_t r = e->a_req[(size_t)k * e->maxA + ask];
+        if (r > a || r > t) return false;
     }
     return true;
 }
 
-struct DirtyRef {
-    uint64_t key; uint32_t rank; uint32_t node;
-    bool operator<(const DirtyRef& o) const {
-        if (key != o.key) return key < o.key;
-        return rank < o.rank;
+// Initial node order of a cycle, computed on the device: float64 score per node (yk_key_kernel), stable radix
+// sort by key over NodeID-rank order = ascending (score, NodeID).  Later batches keep it current by merging.
+int initial_order(yk_engine* e) {
+    const int nlive = (int)e->nlive;
+    if (nlive == 0) return YK_OK;
+    cudaStream_t s = e->stream;
+    CK(cudaMemsetAsync(e->d_flag.p, 0, sizeof(int), s));
+    CK(cudaEventRecord(e->ev0, s));
+    yk_key_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(e->D, e->cfg.policy, e->w, e->d_total.p, e->d_avail.p, e->maxN,
+                                                     e->d_by_rank.p, nlive, e->d_key_in.p, e->d_val_in.p, e->d_flag.p);
+    size_t tb = e->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(e->d_cub.p, tb, e->d_key_in.p, e->d_key_out.p, e->d_val_in.p, e->d_val_out.p,
+                                       nlive, 0, 64, s));
+    CK(cudaEventRecord(e->ev1, s));
+    CK(cudaMemcpyAsync(e->h_order[0].p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    e->st.d2h_bytes += 12 * (size_t)nlive + 4;
+    e->st.other_launches += 11;   // key + cub radix sort (histogram, exclusive sum, 8 onesweep passes for 64-bit keys)
+    if (e->h_flag[0]) return e->fail(YK_ERR_RANGE, "NaN node score (zero total on a weighted resource)");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->st.sort_ms += ms;
+    e->cur = 0;
+    const uint32_t* ord = e->h_order[0].p;
+    e->hs = 2 * e->D + 2;
+    e->hot.resize((size_t)e->n_hi * e->hs);
+    for (int p = 0; p < nlive; ++p) {
+        const uint32_t n = ord[p];
+        e->hkey[n] = e->h_skey[(size_t)p];
+        e->pos_of[n] = (uint32_t)p;
+        int64_t* h = e->hot.data() + (size_t)n * e->hs;
+        for (int k = 0; k < e->D; ++k) { h[k] = e->n_avail[(size_t)k * e->maxN + n]; h[e->D + k] = e->n_total[(size_t)k * e->maxN + n]; }
+        h[2 * e->D] = (int64_t)e->n_taint[n];
+        h[2 * e->D + 1] = (int64_t)e->n_label[n];
     }
-};
+    return YK_OK;
+}
 
 // Device phase + ordered commit for one batch.  result[i] = node or YK_NONE; consumed = how many entries of
 // the batch were decided (stops after the first failure unless the batch is placement-insensitive).
@@ -234,98 +341,168 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
     const int Np = (int)round_up((size_t)nlive, NODE_TILE);
     const int W = Np / 32;
     cudaStream_t s = e->stream;
+    double t0 = now_ms();
+    uint32_t* order = e->h_order[e->cur].p;
 
     memcpy(e->h_batch.p, batch.data(), sizeof(uint32_t) * (size_t)B);
     CK(cudaMemcpyAsync(e->d_batch.p, e->h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
-    e->st.h2d_bytes += sizeof(uint32_t) * (size_t)B;
-    CK(cudaMemsetAsync(e->d_first.p, 0xFF, sizeof(uint32_t) * (size_t)B, s));
-    CK(cudaMemsetAsync(e->d_flag.p, 0, sizeof(int), s));
+    CK(cudaMemcpyAsync(e->d_order.p, order, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyHostToDevice, s));
+    e->st.h2d_bytes += sizeof(uint32_t) * ((size_t)B + (size_t)nlive);
 
-    CK(cudaEventRecord(e->ev0, s));
-    yk_key_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(D, e->cfg.policy, e->w, e->d_total.p, e->d_avail.p, e->maxN,
-                                                     e->d_by_rank.p, nlive, e->d_key_in.p, e->d_val_in.p, e->d_flag.p);
-    size_t tb = e->cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(e->d_cub.p, tb, e->d_key_in.p, e->d_key_out.p, e->d_val_in.p, e->d_val_out.p,
-                                       nlive, 0, 64, s));
+    // this rank's shard of the batch rows (world == 1: all of them)
+    const int world = std::max<int>(1, (int)e->cfg.world);
+    const int rows_per = (B + world - 1) / world;
+    const int row0 = std::min(B, (int)e->cfg.rank * rows_per);
+    const int rows = std::min(B, row0 + rows_per) - row0;
+    const int Bpad = rows_per * world;
+    CK(cudaMemsetAsync(e->d_first.p, 0xFF, sizeof(uint32_t) * (size_t)Bpad, s));
+
     yk_gather_kernel<<<(Np + 255) / 256, 256, 0, s>>>(D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
-                                                     e->d_flags.p, e->d_val_out.p, nlive, Np, e->d_scap.p, e->d_staint.p,
+                                                     e->d_flags.p, e->d_order.p, nlive, Np, e->d_scap.p, e->d_staint.p,
                                                      e->d_slabel.p, e->d_snode.p);
     CK(cudaEventRecord(e->ev1, s));
-    YkSweepArgs a{};
-    a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
-    a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
-    a.lda = e->maxA; a.batch = e->d_batch.p; a.row0 = 0; a.rows = B;
-    a.fit = e->d_fit.p; a.first = e->d_first.p; a.W = W;
-    launch_sweep(D, a, s);
+    if (rows > 0) {
+        YkSweepArgs a{};
+        a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
+        a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
+        a.lda = e->maxA; a.batch = e->d_batch.p; a.row0 = row0; a.rows = rows;
+        a.fit = e->d_fit.p; a.first = e->d_first.p; a.W = W;
+        launch_sweep(D, a, s);
+        e->st.sweep_launches += 1;
+        e->st.evaluations += (uint64_t)rows * (uint64_t)nlive;
+    }
     CK(cudaEventRecord(e->ev2, s));
     CK(cudaGetLastError());
-    e->st.sweep_launches += 1;
-    e->st.other_launches += 2 + 8;   // key + gather + radix sort passes (cub: 1 histogram + 1 onesweep per 8 bits; nominal)
+    e->st.other_launches += 1;
+    if (world > 1) {
+        if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but no exchange function set (yk_set_exchange)");
+        if (e->xfn(e->xctx, e->d_fit.p, (uint64_t)W * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0 ||
+            e->xfn(e->xctx, e->d_first.p, 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
+            return e->fail(YK_ERR_COMM, "exchange callback failed");
+    }
 
-    CK(cudaMemcpyAsync(e->h_fit.p, e->d_fit.p, sizeof(uint32_t) * (size_t)B * W, cudaMemcpyDeviceToHost, s));
+    // read-back in row chunks so the ordered commit overlaps the transfer
+    const int chunk = std::max(128, (B + (int)e->ev_chunk.size() - 1) / (int)e->ev_chunk.size());
+    const int nchunks = (B + chunk - 1) / chunk;
     CK(cudaMemcpyAsync(e->h_first.p, e->d_first.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->h_snode.p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    e->st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B + 12 * (size_t)nlive + 4;
-    CK(cudaStreamSynchronize(s));
-    if (e->h_flag[0]) return e->fail(YK_ERR_RANGE, "NaN node score (zero total on a weighted resource)");
-    float ms_sort = 0, ms_sweep = 0;
-    cudaEventElapsedTime(&ms_sort, e->ev0, e->ev1);
-    cudaEventElapsedTime(&ms_sweep, e->ev1, e->ev2);
-    e->st.sort_ms += ms_sort;
-    e->st.sweep_ms += ms_sweep;
-    e->st.last_sweep_ms = ms_sweep;
-    e->st.last_sweep_pairs = (uint64_t)B * (uint64_t)nlive;
-    e->st.evaluations += (uint64_t)B * (uint64_t)nlive;
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t r0 = (size_t)c * chunk, r1 = std::min<size_t>((size_t)B, r0 + chunk);
+        CK(cudaMemcpyAsync(e->h_fit.p + r0 * W, e->d_fit.p + r0 * W, sizeof(uint32_t) * (r1 - r0) * W, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(e->ev_chunk[(size_t)c], s));
+    }
+    e->st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B;
     e->st.batches++;
 
-    // ---------------- ordered commit (host) ----------------
-    const double t0 = now_ms();
-    for (int p = 0; p < nlive; ++p) e->pos_of[e->h_snode[(size_t)p]] = (uint32_t)p;
+    // ---------------- ordered commit (host), overlapped with the read-back ----------------
     e->dirty_words.assign((size_t)W, 0);
     for (uint32_t n : e->dirty_list) e->is_dirty[n] = 0;
     e->dirty_list.clear();
-    std::set<DirtyRef> dirty;
+    DirtyList& dirty = e->dirty;
+    dirty.clear();
+    int front = 0;   // every position below word `front` is dirty
     const uint32_t* fit = e->h_fit.p;
-    for (int i = 0; i < B; ++i) {
+    double t_wait = 0, t1 = now_ms();
+    e->st.host_ms[6] += t1 - t0;
+    int next_chunk = 0;
+    bool stop = false;
+    // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
+    struct Undo { uint32_t node; uint64_t old_key; bool was_dirty; int64_t old_avail[YK_MAX_D]; };
+    std::vector<Undo> undo;
+    int gang_begin = -1;
+    auto same_gang = [&](int x, int y) {
+        return e->a_gang[batch[(size_t)x]] != YK_NONE && e->a_gang[batch[(size_t)x]] == e->a_gang[batch[(size_t)y]] &&
+               e->a_app[batch[(size_t)x]] == e->a_app[batch[(size_t)y]];
+    };
+    for (int i = 0; i < B && !stop; ++i) {
+        while (i >= next_chunk * chunk) {
+            const double tw = now_ms();
+            CK(cudaEventSynchronize(e->ev_chunk[(size_t)next_chunk]));
+            t_wait += now_ms() - tw;
+            ++next_chunk;
+        }
         const uint32_t ask = batch[(size_t)i];
+        const bool in_gang = e->a_gang[ask] != YK_NONE;
+        if (in_gang && (i == 0 || !same_gang(i - 1, i))) { gang_begin = i; undo.clear(); }
         const uint32_t* row = fit + (size_t)i * W;
+        if (i + 12 < B) {   // rows arrive by DMA and are cache-cold: pull the line the scan will start at
+            const uint32_t* nrow = fit + (size_t)(i + 12) * W;
+            const uint32_t nf = e->h_first[(size_t)(i + 12)];
+            __builtin_prefetch(nrow + std::max<int>(front, nf == YK_NONE ? 0 : (int)(nf >> 5)));
+        }
         // (A) best clean node: first set bit of row & ~dirty in sorted order
         uint32_t posA = YK_NONE;
-        if (e->h_first[(size_t)i] != YK_NONE) {
-            for (int wd = (int)(e->h_first[(size_t)i] >> 5); wd < W; ++wd) {
-                uint32_t m = row[wd] & ~e->dirty_words[(size_t)wd];
+        const uint32_t f = e->h_first[(size_t)i];
+        if (f != YK_NONE) {
+            while (front < W && e->dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
+            for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
+                const uint32_t m = row[wd] & ~e->dirty_words[(size_t)wd];
                 if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
             }
         }
         DirtyRef bound{~0ull, ~0u, YK_NONE};
         if (posA != YK_NONE) {
-            uint32_t nA = e->h_snode[(size_t)posA];
-            bound = DirtyRef{e->h_skey[(size_t)posA], e->n_rank[nA], nA};
+            const uint32_t nA = order[posA];
+            bound = DirtyRef{e->hkey[nA], e->n_rank[nA], nA};
         }
         // (B) best re-scored node among those committed to earlier in this batch
         uint32_t chosen = YK_NONE;
-        for (const DirtyRef& d : dirty) {
-            if (!(d < bound)) break;
-            const uint32_t pos = e->pos_of[d.node];
-            if (!((row[pos >> 5] >> (pos & 31)) & 1u)) continue;   // failed on the batch-start state: fails now too
-            if (fits_avail(e, d.node, ask)) { chosen = d.node; break; }
+        if (f != YK_NONE) {
+            for (uint32_t si = 0; si < dirty.seq.size() && chosen == YK_NONE; ++si) {
+                const DirtyList::Bucket& bk = dirty.pool[dirty.seq[si]];
+                if (!(bk.v[0] < bound)) break;
+                for (uint32_t j = 0; j < bk.n; ++j) {
+                    const DirtyRef& d = bk.v[j];
+                    if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); break; }
+                    // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
+                    // lines were just DMA-written and are cold
+                    if (fits_now(e, d.node, ask)) { chosen = d.node; break; }
+                }
+            }
         }
         if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
         consumed = (size_t)i + 1;
         if (chosen == YK_NONE) {
-            if (!insensitive) break;
+            if (in_gang) {
+                // roll the gang back: undo its commits newest-first, void its results, skip its remaining members
+                for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
+                    const uint32_t n = it->node;
+                    dirty.erase(DirtyRef{e->hkey[n], e->n_rank[n], n});
+                    int64_t* hh = e->hot.data() + (size_t)n * e->hs;
+                    for (int k = 0; k < D; ++k) hh[k] = it->old_avail[k];
+                    e->hkey[n] = it->old_key;
+                    if (it->was_dirty) dirty.insert(DirtyRef{it->old_key, e->n_rank[n], n});
+                    else {
+                        e->is_dirty[n] = 0;
+                        e->dirty_list.pop_back();
+                        const uint32_t pos = e->pos_of[n];
+                        e->dirty_words[pos >> 5] &= ~(1u << (pos & 31));
+                        front = std::min(front, (int)(pos >> 5));
+                    }
+                }
+                undo.clear();
+                int g1 = i + 1;
+                while (g1 < B && same_gang(i, g1)) ++g1;
+                for (int x = gang_begin; x < g1; ++x) result[(size_t)x] = YK_NONE;
+                consumed = (size_t)g1;
+                i = g1 - 1;
+            }
+            if (!insensitive) stop = true;
             continue;
         }
         result[(size_t)i] = chosen;
         // commit: available -= request, re-score, move inside the dirty order
-        if (e->is_dirty[chosen]) dirty.erase(DirtyRef{e->cur_key[chosen], e->n_rank[chosen], chosen});
-        for (int k = 0; k < D; ++k) e->n_avail[(size_t)k * e->maxN + chosen] -= e->a_req[(size_t)k * e->maxA + ask];
-        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, e->n_total.p + chosen, e->n_avail.p + chosen, e->maxN);
+        int64_t* h = e->hot.data() + (size_t)chosen * e->hs;
+        if (in_gang) {
+            Undo u; u.node = chosen; u.old_key = e->hkey[chosen]; u.was_dirty = e->is_dirty[chosen] != 0;
+            for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
+            undo.push_back(u);
+        }
+        if (e->is_dirty[chosen]) dirty.erase(DirtyRef{e->hkey[chosen], e->n_rank[chosen], chosen});
+        for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
+        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, h + D, h, 1);
         const uint64_t nk = yk_key_bits(sc);
         if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
-        e->cur_key[chosen] = nk;
+        e->hkey[chosen] = nk;
         dirty.insert(DirtyRef{nk, e->n_rank[chosen], chosen});
         if (!e->is_dirty[chosen]) {
             e->is_dirty[chosen] = 1;
@@ -334,24 +511,63 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
             e->dirty_words[pos >> 5] |= 1u << (pos & 31);
         }
     }
-    e->st.commit_ms += now_ms() - t0;
+    // all read-back must have landed before the staging buffers are reused
+    {
+        const double tw = now_ms();
+        CK(cudaEventSynchronize(e->ev_chunk[(size_t)nchunks - 1]));
+        t_wait += now_ms() - tw;
+    }
+    const double t2 = now_ms();
+    e->st.host_ms[3] += t_wait;
+    e->st.host_ms[4] += (t2 - t1) - t_wait;
+    e->st.commit_ms += (t2 - t1) - t_wait;
+    float ms_gather = 0, ms_sweep = 0;
+    cudaEventElapsedTime(&ms_sweep, e->ev1, e->ev2);
+    (void)ms_gather;
+    e->st.sweep_ms += ms_sweep;
+    e->st.last_sweep_ms = ms_sweep;
+    e->st.last_sweep_pairs = (uint64_t)rows * (uint64_t)nlive;
 
-    // push the new availability of the touched nodes back to the device table
+    // new node order = merge(previous order minus the touched nodes, touched nodes by new key)
     const int nd = (int)e->dirty_list.size();
     if (nd) {
+        uint32_t* out = e->h_order[e->cur ^ 1].p;
+        int o = 0, p = 0;
+        uint32_t si = 0, j = 0;
+        auto dirty_end = [&]() { return si >= dirty.seq.size(); };
+        auto dirty_cur = [&]() -> const DirtyRef& { return dirty.pool[dirty.seq[si]].v[j]; };
+        auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
+        while (true) {
+            while (p < nlive && e->is_dirty[order[p]]) ++p;
+            if (p >= nlive) break;
+            const uint32_t n = order[p];
+            const DirtyRef c{e->hkey[n], e->n_rank[n], n};
+            while (!dirty_end() && dirty_cur() < c) { out[o++] = dirty_cur().node; dirty_next(); }
+            out[o++] = n;
+            ++p;
+        }
+        while (!dirty_end()) { out[o++] = dirty_cur().node; dirty_next(); }
+        e->cur ^= 1;
+        for (int q = 0; q < nlive; ++q) e->pos_of[out[q]] = (uint32_t)q;
+
+        // push the new availability of the touched nodes back to the device table
         for (int i = 0; i < nd; ++i) {
-            e->h_dirty_nodes[(size_t)i] = e->dirty_list[(size_t)i];
-            for (int k = 0; k < D; ++k)
-                e->h_dirty_vals[(size_t)k * nd + i] = e->n_avail[(size_t)k * e->maxN + e->dirty_list[(size_t)i]];
+            const uint32_t n = e->dirty_list[(size_t)i];
+            e->h_dirty_nodes[(size_t)i] = n;
+            for (int k = 0; k < D; ++k) {
+                const int64_t v = e->hot[(size_t)n * e->hs + k];
+                e->h_dirty_vals[(size_t)k * nd + i] = v;
+                e->n_avail[(size_t)k * e->maxN + n] = v;   // column-major host table stays authoritative between cycles
+            }
         }
         CK(cudaMemcpyAsync(e->d_dirty_nodes.p, e->h_dirty_nodes.p, 4 * (size_t)nd, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(e->d_dirty_vals.p, e->h_dirty_vals.p, 8 * (size_t)nd * D, cudaMemcpyHostToDevice, s));
         yk_apply_avail_kernel<<<(nd + 255) / 256, 256, 0, s>>>(D, e->d_avail.p, e->maxN, e->d_dirty_nodes.p, e->d_dirty_vals.p, nd);
         e->st.h2d_bytes += (size_t)nd * (4 + 8 * D);
         e->st.other_launches += 1;
-        // staging buffers are reused by the next batch only after its own stream sync
-        CK(cudaStreamSynchronize(s));
+        // the staging buffers are rewritten only after the next batch's read-back events, which are later in the stream
     }
+    e->st.host_ms[5] += now_ms() - t2;
     return YK_OK;
 }
 
@@ -383,6 +599,7 @@ void yk_destroy(yk_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
+    for (auto ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -424,7 +641,11 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
         T(e->d_cub.alloc(tb));
     }
     T(e->d_scap.alloc(Npmax * D)); T(e->d_staint.alloc(Npmax)); T(e->d_slabel.alloc(Npmax)); T(e->d_snode.alloc(Npmax));
-    T(e->d_batch.alloc(Bm)); T(e->d_fit.alloc(Bm * e->Wmax)); T(e->d_first.alloc(Bm)); T(e->d_flag.alloc(1));
+    const size_t Bpad = Bm + std::max<uint32_t>(cfg->world, 1);   // rows rounded up to a multiple of world
+    T(e->d_batch.alloc(Bm)); T(e->d_fit.alloc(Bpad * e->Wmax)); T(e->d_first.alloc(Bpad)); T(e->d_flag.alloc(1));
+    T(e->h_order[0].alloc(N)); T(e->h_order[1].alloc(N)); T(e->d_order.alloc(N));
+    e->ev_chunk.assign(16, nullptr);
+    for (auto& ev : e->ev_chunk) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     T(e->d_dirty_nodes.alloc(Bm)); T(e->d_dirty_vals.alloc(Bm * D)); T(e->d_scores.alloc(N));
     T(e->h_batch.alloc(Bm)); T(e->h_fit.alloc(Bm * e->Wmax)); T(e->h_first.alloc(Bm)); T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
     T(e->h_dirty_nodes.alloc(Bm)); T(e->h_dirty_vals.alloc(Bm * D)); T(e->h_flag.alloc(1)); T(e->h_scores.alloc(N));
@@ -439,7 +660,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
     // default queue tree: root only would have no leaf for apps; root + one leaf "root.default"
     e->nq = 0;
-    e->pos_of.assign(N, 0); e->cur_key.assign(N, 0); e->is_dirty.assign(N, 0);
+    e->pos_of.assign(N, 0); e->hkey.assign(N, 0); e->is_dirty.assign(N, 0);
     *out = e;
     return YK_OK;
 }
@@ -607,6 +828,10 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     const double t_start = now_ms();
     int rc = upload_tables(e);
     if (rc) return rc;
+    rc = initial_order(e);
+    if (rc) return rc;
+    double t_a = now_ms();
+    e->st.host_ms[0] += t_a - t_start;
 
     std::vector<uint32_t> pending;
     pending.reserve(e->a_hi);
@@ -620,25 +845,37 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     yk::Tables& t = e->ord.t;
     t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
     t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
-    t.a_flags = e->a_flags.data(); t.a_state = e->a_state.data();
+    t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
     t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
     t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data();
     t.q_sort = e->q_sort.data();
     e->ord.begin_cycle(pending);
+    e->st.host_ms[1] += now_ms() - t_a;
 
     std::vector<uint32_t> batch, result;
     uint32_t n = 0;
     size_t bsz = e->batch;
     while (n < max_bindings) {
-        const size_t want = std::min<size_t>(bsz, max_bindings - n);
-        if (e->ord.fill(want, batch) == 0) break;
+        const double t_f = now_ms();
+        const size_t got = e->ord.fill(bsz, max_bindings - n, batch);
+        e->st.host_ms[2] += now_ms() - t_f;
+        if (e->ord.oversize_gang) {
+            if (bsz < e->batch) { bsz = e->batch; continue; }
+            return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
+        }
+        if (got == 0) break;
         const bool ins = e->ord.insensitive;
         size_t consumed = 0;
         rc = run_batch(e, batch, ins, result, consumed);
         if (rc) return rc;
         bool failed = false;
         if (!ins && consumed > 0 && result[consumed - 1] == YK_NONE) {
-            e->ord.rewind(batch, consumed - 1);
+            const double t_r = now_ms();
+            size_t j = consumed - 1;   // first entry of the failed ask / gang
+            while (j > 0 && e->a_gang[batch[j]] != YK_NONE && e->a_gang[batch[j - 1]] == e->a_gang[batch[j]] &&
+                   e->a_app[batch[j - 1]] == e->a_app[batch[j]] && result[j - 1] == YK_NONE) --j;
+            e->ord.rewind(batch, j);
+            e->st.host_ms[2] += now_ms() - t_r;
             failed = true;
         }
         for (size_t i = 0; i < consumed; ++i) {

@@ -34,6 +34,7 @@ struct Tables {   // views into the engine's host tables
     const int64_t* a_create = nullptr;
     const uint32_t* a_app = nullptr;
     const uint32_t* a_flags = nullptr;
+    const uint32_t* a_gang = nullptr;    // NONE or gang id (all-or-nothing group inside one application)
     uint8_t* a_state = nullptr;          // ST_*
     const uint32_t* p_queue = nullptr;
     const int64_t* p_submit = nullptr;
@@ -69,6 +70,8 @@ public:
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
     bool insensitive = false;
+    std::vector<uint32_t> static_order; size_t static_next = 0;
+    bool oversize_gang = false;   // a gang larger than the batch capacity was met: the caller must raise its batch size
     uint64_t slow_seen = 0;
     std::vector<uint32_t> slow_list;
 
@@ -80,6 +83,11 @@ public:
     size_t slow_mark = 0;
 
     int D() const { return t.D; }
+    static bool strictly_gt_zero(const int64_t* v, int d) {
+        bool pos = false;
+        for (int k = 0; k < d; ++k) { if (v[k] < 0) return false; if (v[k] > 0) pos = true; }
+        return pos;
+    }
     int64_t req(uint32_t a, int k) const { return t.a_req[(size_t)k * t.maxA + a]; }
 
     void begin_cycle(const std::vector<uint32_t>& pending_asks) {
@@ -138,37 +146,81 @@ public:
                 for (int k = 0; k < d; ++k) if (t.q_max[(size_t)k * t.nq + qq] != UNSET) quota = true;
             insensitive = !quota;
         }
+        static_order.clear();
+        static_next = 0;
+        if (insensitive) {   // the whole cycle's pass order is known up front: apps in set order, asks in app order
+            auto cause_of = [&](uint32_t a) -> uint8_t {
+                if (t.a_flags[a] & 1u) return ST_SLOWPATH;
+                int64_t rq[8];
+                for (int k2 = 0; k2 < d; ++k2) rq[k2] = req(a, k2);
+                return strictly_gt_zero(rq, d) ? 0 : ST_INVALID;
+            };
+            std::vector<uint32_t> mem;
+            for (const AppKey& k : q_set[leaf]) {
+                const auto& v = ap_asks[std::get<2>(k)];
+                for (uint32_t a : v) {
+                    if (t.a_state[a] != ST_PENDING) continue;
+                    const uint8_t c = cause_of(a);
+                    if (c) { if (c == ST_SLOWPATH) slow_list.push_back(a); t.a_state[a] = c; continue; }
+                    if (t.a_gang[a] == NONE) { static_order.push_back(a); continue; }
+                    // a gang: all its pending members follow its first member; one bad member sinks the gang
+                    mem.clear();
+                    uint8_t gc = 0;
+                    for (uint32_t m : v)
+                        if (t.a_gang[m] == t.a_gang[a] && t.a_state[m] == ST_PENDING) { mem.push_back(m); if (!gc) gc = cause_of(m); }
+                    for (uint32_t m : mem) {
+                        if (gc) t.a_state[m] = gc; else { t.a_state[m] = ST_TENTATIVE; static_order.push_back(m); }
+                    }
+                }
+            }
+            for (uint32_t a : static_order) t.a_state[a] = ST_PENDING;
+        }
     }
 
-    // Next `maxB` asks in pass order, assuming every one is placed.
-    size_t fill(size_t maxB, std::vector<uint32_t>& batch) {
-        sq = q; sap = ap; sset = q_set; journal.clear(); slow_mark = slow_list.size();
+    // Next asks in pass order, assuming every one is placed: at most cap_batch of them, and never past
+    // cap_user bindings (max_bindings).  A gang is never split: it goes whole into this batch or the next.
+    size_t fill(size_t cap_batch, size_t cap_user, std::vector<uint32_t>& batch) {
+        oversize_gang = false;
         batch.clear();
-        while (batch.size() < maxB) {
-            uint32_t a = select(0);
-            if (a == NONE) break;
-            tentative(a);
-            batch.push_back(a);
+        if (insensitive) {
+            while (static_next < static_order.size()) {
+                const uint32_t a = static_order[static_next];
+                size_t len = 1;
+                if (t.a_gang[a] != NONE)
+                    while (static_next + len < static_order.size() && t.a_gang[static_order[static_next + len]] == t.a_gang[a] &&
+                           t.a_app[static_order[static_next + len]] == t.a_app[a]) ++len;
+                if (batch.size() + len > cap_user) break;                       // max_bindings reached
+                if (batch.size() + len > cap_batch) { if (batch.empty()) oversize_gang = true; break; }
+                batch.insert(batch.end(), static_order.begin() + static_next, static_order.begin() + static_next + len);
+                static_next += len;
+            }
+            return batch.size();
         }
+        journal.clear(); slow_mark = slow_list.size();
+        sq = q; sap = ap; sset = q_set;   // rewind is only ever needed for placement-sensitive orders
+        while (step(cap_batch, cap_user, batch)) {}
         return batch.size();
     }
 
-    // The device placed batch[0..j) and found no node for batch[j]: restore and replay.
+    // The device placed batch[0..j) and found no node for the ask (or gang) starting at batch[j]: restore the
+    // state before the batch, replay the first j decisions, mark the failed ask / gang.
     void rewind(const std::vector<uint32_t>& batch, size_t j) {
         for (auto it = journal.rbegin(); it != journal.rend(); ++it) t.a_state[it->first] = it->second;
         journal.clear();
         q = sq; ap = sap; q_set = sset; slow_list.resize(slow_mark);
-        for (size_t i = 0; i < j; ++i) {
-            uint32_t a = select(0);
-            (void)batch; // same decisions by construction
-            tentative(a);
-        }
-        uint32_t a = select(0);
-        mark_dead(a, ST_NOFIT);
+        std::vector<uint32_t> replay;
+        while (replay.size() < j && step(j, j, replay)) {}
+        const uint32_t a = select(0);   // == batch[j] by construction
+        (void)batch;
+        if (t.a_gang[a] == NONE) { mark_dead(a, ST_NOFIT); return; }
+        std::vector<uint32_t> mem;
+        gang_members(a, mem);
+        for (uint32_t m : mem) mark_dead(m, ST_NOFIT);
     }
 
     // insensitive batches: ask `a` (tentatively accounted) found no node
     void fail_in_place(uint32_t a) {
+        if (insensitive) { t.a_state[a] = ST_NOFIT; return; }
         const int d = t.D;
         uint32_t p = t.a_app[a];
         t.a_state[a] = ST_NOFIT;
@@ -181,7 +233,12 @@ public:
         }
     }
 
-    void confirm(uint32_t a) { t.a_state[a] = ST_ALLOCATED; }
+    void confirm(uint32_t a) {
+        t.a_state[a] = ST_ALLOCATED;
+        if (insensitive)   // static order: queue accounting is not needed to order, only to persist
+            for (uint32_t qq = t.p_queue[t.a_app[a]]; qq != NONE; qq = t.q_parent[qq])
+                for (int k = 0; k < t.D; ++k) q[qq].alloc[k] += req(a, k);
+    }
 
     void finish() {   // persist queue allocations
         for (uint32_t i = 0; i < t.nq; ++i)
@@ -189,6 +246,45 @@ public:
     }
 
 private:
+    void gang_members(uint32_t a, std::vector<uint32_t>& mem) {
+        mem.clear();
+        for (uint32_t m : ap_asks[t.a_app[a]])
+            if (t.a_gang[m] == t.a_gang[a] && t.a_state[m] == ST_PENDING) mem.push_back(m);
+    }
+
+    // one schedule() pass of the speculation: appends one ask, or one whole gang; false = batch is closed
+    bool step(size_t cap_batch, size_t cap_user, std::vector<uint32_t>& batch) {
+        if (batch.size() >= cap_batch || batch.size() >= cap_user) return false;
+        const uint32_t a = select(0);
+        if (a == NONE) return false;
+        if (t.a_gang[a] == NONE) { tentative(a); batch.push_back(a); return true; }
+        const int d = t.D;
+        std::vector<uint32_t> mem;
+        gang_members(a, mem);
+        if (batch.size() + mem.size() > cap_user) return false;                 // max_bindings: the cycle ends here
+        if (batch.size() + mem.size() > cap_batch) { if (batch.empty()) oversize_gang = true; return false; }
+        // host-side checks of every member, with the headroom shrinking as earlier members are counted
+        int64_t hr[8];
+        headroom(t.p_queue[t.a_app[a]], hr);
+        uint8_t cause = 0;
+        for (uint32_t m : mem) {
+            if (t.a_flags[m] & 1u) { cause = ST_SLOWPATH; break; }
+            bool fits = true;
+            for (int k = 0; k < d; ++k) if (hr[k] != UNSET && req(m, k) > hr[k]) { fits = false; break; }
+            if (!fits) { cause = ST_SKIPPED; break; }
+            int64_t rq[8];
+            for (int k = 0; k < d; ++k) rq[k] = req(m, k);
+            if (!strictly_gt_zero(rq, d)) { cause = ST_INVALID; break; }
+            for (int k = 0; k < d; ++k) if (hr[k] != UNSET) hr[k] -= req(m, k);
+        }
+        if (cause) {
+            for (uint32_t m : mem) { if (cause == ST_SLOWPATH && (t.a_flags[m] & 1u)) slow_list.push_back(m); mark_dead(m, cause); }
+            return true;   // nothing added, but the pass moved on
+        }
+        for (uint32_t m : mem) { tentative(m); batch.push_back(m); }
+        return true;
+    }
+
     void set_state(uint32_t a, uint8_t st) {
         journal.emplace_back(a, t.a_state[a]);
         t.a_state[a] = st;
@@ -254,11 +350,6 @@ private:
             if (q[l].shares[k] < q[r].shares[k]) return -1;
         }
         return 0;
-    }
-    static bool strictly_gt_zero(const int64_t* v, int d) {
-        bool pos = false;
-        for (int k = 0; k < d; ++k) { if (v[k] < 0) return false; if (v[k] > 0) pos = true; }
-        return pos;
     }
 
     void headroom(uint32_t leaf, int64_t* hr) {

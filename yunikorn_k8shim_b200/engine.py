@@ -37,10 +37,13 @@ class Stats(C.Structure):
                 ("skipped", C.c_uint64), ("evaluations", C.c_uint64), ("sweep_launches", C.c_uint64),
                 ("other_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("sweep_ms", C.c_double), ("sort_ms", C.c_double), ("commit_ms", C.c_double), ("total_ms", C.c_double),
-                ("last_sweep_ms", C.c_double), ("last_sweep_pairs", C.c_uint64)]
+                ("last_sweep_ms", C.c_double), ("last_sweep_pairs", C.c_uint64),
+                ("host_ms", C.c_double * 8)]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_}
+        d = {f: getattr(self, f) for f, _ in self._fields_}
+        d["host_ms"] = list(d["host_ms"])
+        return d
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p)

@@ -291,3 +291,29 @@ def hier(n_nodes=50_000, n_parents=8, leaves_per_parent=8, apps_per_leaf=5, task
                 base.node_label, base.node_id, queues, app_queue, base.ask_app, base.ask_req, base.ask_tol,
                 base.ask_need, base.ask_deny, ask_prio=prio, meta={"config": 4, "seed": seed})
     return s
+
+
+def gangs(n_nodes=10_000, n_gangs=2000, members=10, seed=5, policy=POLICY_FAIR, fill=1.11) -> Snapshot:
+    """BASELINE config 5: n_gangs gangs of `members` identical members (task-group semantics,
+    /root/reference/pkg/cache/amprotocol.go:47-57), one application per gang, one leaf queue; total demand is
+    `fill` x the cluster's CPU so that roughly the last tenth of the gangs cannot be placed whole."""
+    D = 4
+    base = perf(n_nodes, 1, 1, seed=seed, policy=policy)
+    r = _Rng(seed * 31 + 7)
+    cls = r.below(n_gangs, 4)
+    cpu_cls = np.array([2000, 4000, 8000, 12000], dtype=np.int64)
+    mem_cls = np.array([8, 16, 32, 64], dtype=np.int64) * GI
+    cap = int(base.node_avail[:, 0].sum())
+    demand = int((cpu_cls[cls] * members).sum())
+    scale = fill * cap / demand
+    cpu = np.maximum(100, (cpu_cls[cls] * scale).astype(np.int64) // 100 * 100)
+    A = n_gangs * members
+    app = np.repeat(np.arange(n_gangs, dtype=np.int32), members)
+    req = np.zeros((A, D), dtype=np.int64)
+    req[:, 0] = np.repeat(cpu, members)
+    req[:, 1] = np.repeat(mem_cls[cls], members)
+    req[:, 2] = 1
+    z = np.zeros(A, dtype=np.uint64)
+    return _finish(f"gangs-{n_nodes}x{n_gangs}x{members}", D, policy, base.node_total, base.node_avail, base.node_taint,
+                   base.node_label, base.node_id, _single_queue(D), np.ones(n_gangs, dtype=np.int32), app, req, z,
+                   z.copy(), z.copy(), ask_gang=app.copy(), meta={"config": 5, "seed": seed})
