@@ -14,8 +14,8 @@ def lib():
     return ctypes.CDLL(build.build())
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "ykgpu.h")).read()
+def declared_functions(header="ykgpu.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = set(re.findall(r"\b(yk_[a-z_]+)\s*\(", src))
     names.discard("yk_allgather_fn")
@@ -35,7 +35,14 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_python_stub_lists_the_same_symbols():
     from yunikorn_k8shim_b200 import EXPORTS
+    from yunikorn_k8shim_b200.dictionary import DICT_EXPORTS
     assert sorted(EXPORTS) == declared_functions()
+    assert sorted(DICT_EXPORTS) == declared_functions("ykgpu_dict.h")
+
+
+def test_dictionary_symbols_are_exported(lib):
+    for name in declared_functions("ykgpu_dict.h"):
+        assert hasattr(lib, name), f"{name} declared in ykgpu_dict.h but not exported by libykgpu.so"
 
 
 def test_abi_version_and_strerror(lib):
