@@ -127,6 +127,9 @@ typedef struct {
     /* host wall-clock split of yk_cycle: 0 table upload + initial device sort, 1 orderer begin_cycle,
        2 orderer fill/rewind, 3 waiting for device results, 4 ordered commit, 5 order merge, 6 other */
     double host_ms[8];
+    /* commit counters: 0 bitmap words scanned, 1 re-scored candidates examined, 2 asks won by a re-scored node,
+       3 re-keys of an already re-scored node */
+    uint64_t dbg[4];
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

@@ -6,7 +6,7 @@ from oracle import oracle_ctypes as oc
 
 for snap in (synth.perf(), synth.perf(masks=True)):
     t = time.time(); want = oc.run(snap); t_or = time.time() - t
-    for batch in (1024, 2048, 4096):
+    for batch in (2048, 4096, 8192):
         for rep in range(2):
             with Engine.for_snapshot(snap, batch=batch) as e:
                 t = time.time(); ask, node, _ = e.cycle(snap.n_asks); dt = time.time() - t
@@ -15,4 +15,4 @@ for snap in (synth.perf(), synth.perf(masks=True)):
         print(f"{snap.name} batch={batch} ok={ok} cycle={dt*1e3:.1f}ms oracle={t_or*1e3:.1f}ms "
               f"sweep={st['sweep_ms']:.2f}ms sort={st['sort_ms']:.2f}ms commit={st['commit_ms']:.2f}ms "
               f"batches={st['batches']} evals/s(sweep)={st['evaluations']/max(st['sweep_ms'],1e-9)*1e3:.3e} "
-              f"alloc/s={len(ask)/dt:.3e} host_ms={[round(x,2) for x in st['host_ms'][:7]]}")
+              f"alloc/s={len(ask)/dt:.3e} host_ms={[round(x,2) for x in st['host_ms'][:7]]} dbg={st['dbg']}")

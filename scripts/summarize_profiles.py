@@ -37,11 +37,13 @@ if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units, rows = r[0], r[1], r[2:]
-    keep = re.compile(r"Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write).sum$|dram__cycles_active|gpu__dram_throughput|"
-                      r"sm__throughput.avg.pct|sm__warps_active|launch__(registers_per_thread|grid_size|block_size|waves|occupancy_limit|shared_mem_per_block_static)|"
-                      r"smsp__issue_active.avg.pct|sm__pipe_alu_cycles_active.avg.pct|sm__pipe_fma|sm__inst_executed_pipe_(alu|lsu|fma|uniform)|smsp__inst_executed.sum$|"
-                      r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum$|lts__t_sectors_srcunit_tex_op_(read|write).sum$|lts__t_bytes.sum$|sm__cycles_elapsed.max|"
-                      r"smsp__average_warps_issue_stalled.*_per_issue_active|sm__maximum_warps_per_active_cycle_pct|l1tex__t_bytes_pipe_lsu_mem_global_op_(ld|st).sum$")
+    keep = re.compile(r"^(Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write).sum|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|"
+                      r"sm__throughput.avg.pct_of_peak_sustained_elapsed|sm__warps_active.avg.pct_of_peak_sustained_active|"
+                      r"launch__(registers_per_thread|grid_size|block_size|waves_per_multiprocessor|occupancy_limit_registers|shared_mem_per_block_static)|"
+                      r"smsp__issue_active.avg.pct_of_peak_sustained_active|sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active|"
+                      r"sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active|sm__inst_executed_pipe_(alu|lsu|fma|uniform).avg.pct_of_peak_sustained_active|"
+                      r"smsp__inst_executed.sum|l1tex__data_pipe_lsu_wavefronts_mem_shared.sum|lts__t_bytes.sum|sm__cycles_elapsed.max|sm__cycles_active.avg|"
+                      r"smsp__average_warps_issue_stalled_[a-z_]+_per_issue_active.ratio|sm__maximum_warps_per_active_cycle_pct)$")
     with open(os.path.join(pr, f"{tag}_sweep_ncu_full.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none --import-source on -k regex:yk_sweep ({os.path.basename(rep)}), {len(rows)} launches\n")
         for i, h in enumerate(hdr):

@@ -187,6 +187,7 @@ struct yk_engine {
     Dev<uint32_t> d_order;
     std::vector<cudaEvent_t> ev_chunk;
     DirtyList dirty;
+    int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
     std::vector<int64_t> hot; int hs = 0;    // per node [avail[D], total[D], taint, label] contiguous: the commit's working copy
 
     yk::Orderer ord;
@@ -249,21 +250,39 @@ int upload_tables(yk_engine* e) {
     return YK_OK;
 }
 
+// grid.y (ask splits) is sized so that tiles x splits fills the resident CTA slots of the device exactly once
 template <int D>
-void launch_sweep_d(const YkSweepArgs& a, cudaStream_t s) {
-    dim3 grid((unsigned)(a.Np / NODE_TILE), (unsigned)((a.rows + AC - 1) / AC));
+void launch_sweep_d(YkSweepArgs a, cudaStream_t s, int slots) {
+    const int tiles = a.Np / NODE_TILE;
+    int splits = std::max(1, slots / tiles);
+    a.per = (a.rows + splits - 1) / splits;
+    splits = (a.rows + a.per - 1) / a.per;
+    dim3 grid((unsigned)tiles, (unsigned)splits);
     yk_sweep_kernel<D, NPT, AC><<<grid, YK_SWEEP_THREADS, 0, s>>>(a);
 }
-void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s) {
+template <int D>
+int sweep_slots_d(int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yk_sweep_kernel<D, NPT, AC>, YK_SWEEP_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return per_sm * sms;
+}
+int sweep_slots(int D, int sms) {
     switch (D) {
-        case 1: launch_sweep_d<1>(a, s); break;
-        case 2: launch_sweep_d<2>(a, s); break;
-        case 3: launch_sweep_d<3>(a, s); break;
-        case 4: launch_sweep_d<4>(a, s); break;
-        case 5: launch_sweep_d<5>(a, s); break;
-        case 6: launch_sweep_d<6>(a, s); break;
-        case 7: launch_sweep_d<7>(a, s); break;
-        default: launch_sweep_d<8>(a, s); break;
+        case 1: return sweep_slots_d<1>(sms); case 2: return sweep_slots_d<2>(sms); case 3: return sweep_slots_d<3>(sms);
+        case 4: return sweep_slots_d<4>(sms); case 5: return sweep_slots_d<5>(sms); case 6: return sweep_slots_d<6>(sms);
+        case 7: return sweep_slots_d<7>(sms); default: return sweep_slots_d<8>(sms);
+    }
+}
+void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s, int slots) {
+    switch (D) {
+        case 1: launch_sweep_d<1>(a, s, slots); break;
+        case 2: launch_sweep_d<2>(a, s, slots); break;
+        case 3: launch_sweep_d<3>(a, s, slots); break;
+        case 4: launch_sweep_d<4>(a, s, slots); break;
+        case 5: launch_sweep_d<5>(a, s, slots); break;
+        case 6: launch_sweep_d<6>(a, s, slots); break;
+        case 7: launch_sweep_d<7>(a, s, slots); break;
+        default: launch_sweep_d<8>(a, s, slots); break;
     }
 }
 
@@ -367,7 +386,7 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
         a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
         a.lda = e->maxA; a.batch = e->d_batch.p; a.row0 = row0; a.rows = rows;
         a.fit = e->d_fit.p; a.first = e->d_first.p; a.W = W;
-        launch_sweep(D, a, s);
+        launch_sweep(D, a, s, e->slots);
         e->st.sweep_launches += 1;
         e->st.evaluations += (uint64_t)rows * (uint64_t)nlive;
     }
@@ -435,6 +454,7 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
         if (f != YK_NONE) {
             while (front < W && e->dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
             for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
+                ++e->st.dbg[0];
                 const uint32_t m = row[wd] & ~e->dirty_words[(size_t)wd];
                 if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
             }
@@ -453,12 +473,14 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
                 for (uint32_t j = 0; j < bk.n; ++j) {
                     const DirtyRef& d = bk.v[j];
                     if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); break; }
+                    ++e->st.dbg[1];
                     // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
                     // lines were just DMA-written and are cold
                     if (fits_now(e, d.node, ask)) { chosen = d.node; break; }
                 }
             }
         }
+        if (chosen != YK_NONE) ++e->st.dbg[2];   // a re-scored node won
         if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
         consumed = (size_t)i + 1;
         if (chosen == YK_NONE) {
@@ -497,7 +519,7 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
             for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
             undo.push_back(u);
         }
-        if (e->is_dirty[chosen]) dirty.erase(DirtyRef{e->hkey[chosen], e->n_rank[chosen], chosen});
+        if (e->is_dirty[chosen]) { dirty.erase(DirtyRef{e->hkey[chosen], e->n_rank[chosen], chosen}); ++e->st.dbg[3]; }
         for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
         const double sc = yk_node_score(D, e->cfg.policy, e->w.w, h + D, h, 1);
         const uint64_t nk = yk_key_bits(sc);
@@ -521,9 +543,8 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
     e->st.host_ms[3] += t_wait;
     e->st.host_ms[4] += (t2 - t1) - t_wait;
     e->st.commit_ms += (t2 - t1) - t_wait;
-    float ms_gather = 0, ms_sweep = 0;
+    float ms_sweep = 0;
     cudaEventElapsedTime(&ms_sweep, e->ev1, e->ev2);
-    (void)ms_gather;
     e->st.sweep_ms += ms_sweep;
     e->st.last_sweep_ms = ms_sweep;
     e->st.last_sweep_pairs = (uint64_t)rows * (uint64_t)nlive;
@@ -537,18 +558,26 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
         auto dirty_end = [&]() { return si >= dirty.seq.size(); };
         auto dirty_cur = [&]() -> const DirtyRef& { return dirty.pool[dirty.seq[si]].v[j]; };
         auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
+        int removed = 0;   // touched nodes passed over in the old order so far
         while (true) {
-            while (p < nlive && e->is_dirty[order[p]]) ++p;
+            while (p < nlive && e->is_dirty[order[p]]) { ++p; ++removed; }
             if (p >= nlive) break;
+            if (dirty_end() && removed == nd) {
+                // every touched node has been taken out and put back: the rest of the order is unchanged
+                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
+                o += nlive - p;
+                p = nlive;
+                break;
+            }
             const uint32_t n = order[p];
             const DirtyRef c{e->hkey[n], e->n_rank[n], n};
-            while (!dirty_end() && dirty_cur() < c) { out[o++] = dirty_cur().node; dirty_next(); }
+            while (!dirty_end() && dirty_cur() < c) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
+            e->pos_of[n] = (uint32_t)o;
             out[o++] = n;
             ++p;
         }
-        while (!dirty_end()) { out[o++] = dirty_cur().node; dirty_next(); }
+        while (!dirty_end()) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
         e->cur ^= 1;
-        for (int q = 0; q < nlive; ++q) e->pos_of[out[q]] = (uint32_t)q;
 
         // push the new availability of the touched nodes back to the device table
         for (int i = 0; i < nd; ++i) {
@@ -652,6 +681,10 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     if (ok) {   // does this binary carry an image the device can run?
         cudaFuncAttributes fa;
         T(cudaFuncGetAttributes(&fa, yk_key_kernel));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e->slots = sweep_slots(D, sms);
     }
     if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
     e->n_rank.assign(N, 0); e->n_present.assign(N, 0);

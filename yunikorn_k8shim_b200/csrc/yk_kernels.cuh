@@ -97,45 +97,56 @@ struct YkSweepArgs {
     size_t lda;
     const uint32_t* batch;    // [B] ask indices in commit order
     int row0, rows;           // this launch handles batch rows [row0, row0+rows)
+    int per;                  // rows per CTA along grid.y (multiple of 32)
     // outputs
     uint32_t* fit;            // [B][W]
     uint32_t* first;          // [B], pre-set to YK_NONE_U32
     int W;                    // words per row = Np/32
 };
 
+// One (ask, 32 x NPT nodes) step.  MASKS / WANT are warp-uniform properties of the ask (staged in shared
+// memory as `kind`): an ask without tolerations, selectors or a node name needs no mask work at all -- a node
+// passes its mask test iff it carries no taint, which is a per-node constant hoisted out of the loop.
+template <int D, int NPT, bool MASKS, bool WANT>
+__device__ __forceinline__ void yk_pair_step(const int64_t (&cap)[NPT][D], const uint64_t (&ntaint)[NPT],
+                                             const uint64_t (&nlabel)[NPT], const uint32_t (&nidx)[NPT],
+                                             const bool (&taintfree)[NPT], const int64_t (&rq)[D], uint64_t tol,
+                                             uint64_t need, uint64_t deny, uint32_t want, uint32_t (&word)[NPT]) {
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < D; ++k) ok = ok && (rq[k] <= cap[j][k]);
+        if (MASKS) {
+            const uint64_t bad = (ntaint[j] & ~tol) | (~nlabel[j] & need) | (nlabel[j] & deny);
+            ok = ok && (bad == 0ull);
+        } else {
+            ok = ok && taintfree[j];
+        }
+        if (WANT) ok = ok && (want == nidx[j]);
+        word[j] = __ballot_sync(0xFFFFFFFFu, ok);
+    }
+}
+
+// grid.x = node tiles of YK_SWEEP_THREADS*NPT sorted positions; grid.y = ask splits.  A CTA keeps its node tile
+// in registers and walks its share of the batch rows in sub-chunks of AC asks staged in shared memory, so the
+// host can size grid.y to fill the machine exactly once (no tail wave) whatever the batch size.
 template <int D, int NPT, int AC>
-__global__ void __launch_bounds__(YK_SWEEP_THREADS) yk_sweep_kernel(const YkSweepArgs p) {
-    __shared__ int64_t sh_req[D][AC];
-    __shared__ uint64_t sh_tol[AC], sh_need[AC], sh_deny[AC];
+__global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkSweepArgs p) {
+    __shared__ int64_t sh_req[AC][D];
+    __shared__ uint64_t sh_mask[AC][3];
     __shared__ uint32_t sh_node[AC];
+    __shared__ uint32_t sh_kind[AC];
     __shared__ uint32_t sh_first[AC];
+    __shared__ uint32_t sh_word[YK_SWEEP_THREADS / 32][NPT][32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a0 = p.row0 + blockIdx.y * AC;
-    const int na = min(AC, p.row0 + p.rows - a0);
-
-    // stage the ask chunk (gather by batch order; rows past the end can never fit)
-    for (int i = tid; i < AC; i += YK_SWEEP_THREADS) {
-        if (i < na) {
-            const uint32_t a = p.batch[a0 + i];
-#pragma unroll
-            for (int k = 0; k < D; ++k) sh_req[k][i] = p.a_req[(size_t)k * p.lda + a];
-            sh_tol[i] = p.a_tol[a];
-            sh_need[i] = p.a_need[a];
-            sh_deny[i] = p.a_deny[a];
-            sh_node[i] = p.a_node[a];
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) sh_req[k][i] = INT64_MAX;
-            sh_tol[i] = 0; sh_need[i] = ~0ull; sh_deny[i] = ~0ull; sh_node[i] = YK_NONE_U32;
-        }
-        sh_first[i] = YK_NONE_U32;
-    }
 
     // node tile -> registers (coalesced column reads: consecutive lanes = consecutive positions)
     int64_t cap[NPT][D];
     uint64_t ntaint[NPT], nlabel[NPT];
     uint32_t nidx[NPT];
+    bool taintfree[NPT];
     const int pos0 = blockIdx.x * (YK_SWEEP_THREADS * NPT) + tid;
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
@@ -145,50 +156,84 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS) yk_sweep_kernel(const YkSwee
         ntaint[j] = __ldg(p.s_taint + pos);
         nlabel[j] = __ldg(p.s_label + pos);
         nidx[j] = __ldg(p.s_node + pos);
+        taintfree[j] = ntaint[j] == 0ull;
     }
-    __syncthreads();
-
     const int word0 = blockIdx.x * (YK_SWEEP_THREADS * NPT / 32) + warp;
-    for (int ab = 0; ab < na; ab += 32) {
-        uint32_t keep[NPT];
+
+    // this CTA's rows: [r_begin, r_end), multiples of 32 except at the very end
+    const int r_begin = p.row0 + (int)blockIdx.y * p.per;
+    const int r_end = min(p.row0 + p.rows, r_begin + p.per);
+
+    for (int a0 = r_begin; a0 < r_end; a0 += AC) {
+        const int na = min(AC, r_end - a0);
+        __syncthreads();   // previous sub-chunk fully consumed
+        for (int i = tid; i < AC; i += YK_SWEEP_THREADS) {
+            uint32_t kind = 0;
+            if (i < na) {
+                const uint32_t a = p.batch[a0 + i];
 #pragma unroll
-        for (int j = 0; j < NPT; ++j) keep[j] = 0;
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-            const int i = ab + l;
-            int64_t rq[D];
+                for (int k = 0; k < D; ++k) sh_req[i][k] = p.a_req[(size_t)k * p.lda + a];
+                const uint64_t tol = p.a_tol[a], need = p.a_need[a], deny = p.a_deny[a];
+                const uint32_t want = p.a_node[a];
+                sh_mask[i][0] = tol; sh_mask[i][1] = need; sh_mask[i][2] = deny;
+                sh_node[i] = want;
+                kind = ((tol | need | deny) != 0ull ? 1u : 0u) | (want != YK_NONE_U32 ? 2u : 0u);
+            } else {   // rows past the end can never fit
 #pragma unroll
-            for (int k = 0; k < D; ++k) rq[k] = sh_req[k][i];
-            const uint64_t tol = sh_tol[i], need = sh_need[i], deny = sh_deny[i];
-            const uint32_t want = sh_node[i];
-#pragma unroll
-            for (int j = 0; j < NPT; ++j) {
-                bool ok = true;
-#pragma unroll
-                for (int k = 0; k < D; ++k) ok = ok && (rq[k] <= cap[j][k]);
-                const uint64_t bad = (ntaint[j] & ~tol) | (~nlabel[j] & need) | (nlabel[j] & deny);
-                ok = ok && (bad == 0ull) && (want == YK_NONE_U32 || want == nidx[j]);
-                const uint32_t w = __ballot_sync(0xFFFFFFFFu, ok);
-                if (lane == l) keep[j] = w;
+                for (int k = 0; k < D; ++k) sh_req[i][k] = INT64_MAX;
+                sh_mask[i][0] = 0; sh_mask[i][1] = ~0ull; sh_mask[i][2] = ~0ull; sh_node[i] = YK_NONE_U32;
+                kind = 1u;
             }
+            sh_kind[i] = kind;
+            sh_first[i] = YK_NONE_U32;
         }
-        // lane l now holds the NPT bitmap words of ask (ab + l) for this warp's positions
-        const int i = ab + lane;
-        if (i < na) {
-            uint32_t* row = p.fit + (size_t)(a0 + i) * p.W;
-            uint32_t best = YK_NONE_U32;
+        __syncthreads();
+
+        for (int ab = 0; ab < na; ab += 32) {
+            const int nl = min(32, na - ab);
+#pragma unroll 4
+            for (int l = 0; l < nl; ++l) {
+                const int i = ab + l;
+                int64_t rq[D];
 #pragma unroll
-            for (int j = NPT - 1; j >= 0; --j) {
-                const int widx = word0 + j * (YK_SWEEP_THREADS / 32);
-                row[widx] = keep[j];
-                if (keep[j]) best = (uint32_t)widx * 32u + (uint32_t)(__ffs((int)keep[j]) - 1);
+                for (int k = 0; k < D; ++k) rq[k] = sh_req[i][k];
+                const uint32_t kind = sh_kind[i];
+                uint32_t word[NPT];
+                if (kind == 0u) {
+                    yk_pair_step<D, NPT, false, false>(cap, ntaint, nlabel, nidx, taintfree, rq, 0, 0, 0, 0, word);
+                } else {
+                    const uint64_t tol = sh_mask[i][0], need = sh_mask[i][1], deny = sh_mask[i][2];
+                    const uint32_t want = sh_node[i];
+                    if (kind & 2u) yk_pair_step<D, NPT, true, true>(cap, ntaint, nlabel, nidx, taintfree, rq, tol, need, deny, want, word);
+                    else yk_pair_step<D, NPT, true, false>(cap, ntaint, nlabel, nidx, taintfree, rq, tol, need, deny, want, word);
+                }
+                // park the ballot words in shared memory (LSU pipe) instead of select-chains on the ALU pipe
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < NPT; ++j) sh_word[warp][j][l] = word[j];
+                }
             }
-            if (best != YK_NONE_U32) atomicMin(&sh_first[i], best);
+            __syncwarp();
+            // lane l picks up the NPT bitmap words of ask (ab + l) for this warp's positions
+            const int i = ab + lane;
+            if (i < na) {
+                uint32_t* row = p.fit + (size_t)(a0 + i) * p.W;
+                uint32_t best = YK_NONE_U32;
+#pragma unroll
+                for (int j = NPT - 1; j >= 0; --j) {
+                    const uint32_t w = sh_word[warp][j][lane];
+                    const int widx = word0 + j * (YK_SWEEP_THREADS / 32);
+                    row[widx] = w;
+                    if (w) best = (uint32_t)widx * 32u + (uint32_t)(__ffs((int)w) - 1);
+                }
+                if (best != YK_NONE_U32) atomicMin(&sh_first[i], best);
+            }
+            __syncwarp();
         }
+        __syncthreads();
+        for (int i = tid; i < na; i += YK_SWEEP_THREADS)
+            if (sh_first[i] != YK_NONE_U32) atomicMin(&p.first[a0 + i], sh_first[i]);
     }
-    __syncthreads();
-    for (int i = tid; i < na; i += YK_SWEEP_THREADS)
-        if (sh_first[i] != YK_NONE_U32) atomicMin(&p.first[a0 + i], sh_first[i]);
 }
 
 // ---- one (ask,node) answer in the reference's step order, on the device --------------------------------
