@@ -180,6 +180,14 @@ int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node);
 /* node sort keys as the device computes them (float64 score bits), for known-answer tests */
 int yk_node_scores(yk_engine* e, uint32_t n, const uint32_t* idx, double* score_out);
 
+/* Preemption victim search, batched (ResourceManagerCallback.PreemptionPredicates,
+ * pkg/cache/scheduler_callback.go:200-209 -> context.go:705-729 -> predicate_manager.go:137-175).  Query q: the
+ * smallest index i >= start[q] such that ask[q] passes every predicate on node[q] once the victims
+ * victim_off[q] .. victim_off[q]+i (in the given order) are removed, or -1.  victim_req is [D][victim_off[n]]: what
+ * each victim gives back to the node.  Known answers: TestPreemptionPredicates(+Empty), predicate_manager_test.go:67-134. */
+int yk_preemption_search(yk_engine* e, uint32_t n_queries, const uint32_t* ask, const uint32_t* node,
+                         const uint32_t* victim_off, const int64_t* victim_req, const uint32_t* start, int32_t* index_out);
+
 /* multi-GPU exchange hook: called once per batch on every rank, after the local shard's rows of `buf`
  * (device pointer, row-major, `row_bytes` per ask, rows [first_row, first_row+n_rows) are this rank's)
  * have been written on `stream`; must make all `total_rows` rows valid on every rank (an all-gather). */

@@ -109,6 +109,13 @@ def predicate(s, ask: int, node: int) -> int:
     return lib().yko_predicate(C.byref(st), C.c_int32(ask), C.c_int32(node))
 
 
+def preemption_index(s, ask: int, node: int, victim_req, start: int) -> int:
+    st, keep = _pack(s)
+    v = np.ascontiguousarray(victim_req, dtype=np.int64).reshape(-1, s.D)
+    lib().yko_preemption_index.restype = C.c_int
+    return lib().yko_preemption_index(C.byref(st), C.c_int32(ask), C.c_int32(node), C.c_int32(len(v)), _p(v), C.c_int32(start))
+
+
 def node_score(policy, weights, total, avail) -> float:
     w = np.ascontiguousarray(weights, dtype=np.float64)
     t = np.ascontiguousarray(total, dtype=np.int64)

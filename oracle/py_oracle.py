@@ -166,11 +166,14 @@ def run(s, max_bindings=-1):
                 base = [int(x) for x in s.q_guaranteed[q]]
 
                 def cmp(l, r):
+                    pl, pr = app_prio(l), app_prio(r)
+                    if pl != pr:
+                        return -1 if pl > pr else 1
                     c = compare_shares(shares(app_alloc[l], base), shares(app_alloc[r], base))
                     if c:
                         return c
-                    kl = (-app_prio(l), int(s.app_submit[l]), l)
-                    kr = (-app_prio(r), int(s.app_submit[r]), r)
+                    kl = (int(s.app_submit[l]), l)
+                    kr = (int(s.app_submit[r]), r)
                     return -1 if kl < kr else (1 if kl > kr else 0)
                 cand.sort(key=functools.cmp_to_key(cmp))
             else:

@@ -327,14 +327,16 @@ struct Engine {
             std::vector<int> sorted;
             for (int p : Q.apps) if (apps[(size_t)p].pending_asks > 0) sorted.push_back(p);
             if (s->q_sort[q] == YKO_SORT_FAIR) {
-                // fair: ascending dominant share of app allocation vs queue guaranteed (or max)
+                // fair: max pending priority first (application.sort.priority is enabled by default), then ascending
+                // dominant share of the application's allocation against the queue's guaranteed resource
                 const int64_t* base = s->q_guaranteed + (size_t)q * D;
+                std::vector<int> prio((size_t)s->n_apps, 0);
+                for (int p : sorted) prio[(size_t)p] = app_priority(p);
                 std::stable_sort(sorted.begin(), sorted.end(), [&](int l, int r) {
+                    if (prio[(size_t)l] != prio[(size_t)r]) return prio[(size_t)l] > prio[(size_t)r];
                     int c = compare_shares(get_shares(D, apps[(size_t)l].alloc.data(), base),
                                            get_shares(D, apps[(size_t)r].alloc.data(), base));
                     if (c != 0) return c < 0;
-                    int lp = app_priority(l), rp = app_priority(r);
-                    if (lp != rp) return lp > rp;
                     if (s->app_submit[l] != s->app_submit[r]) return s->app_submit[l] < s->app_submit[r];
                     return l < r;
                 });
@@ -411,6 +413,25 @@ int yko_predicate(const yko_snapshot* s, int32_t ask, int32_t node) {
     e.s = s; e.D = s->D; e.mode = 0;
     e.avail.assign(s->node_avail, s->node_avail + (size_t)s->n_nodes * s->D);
     return e.evaluate(ask, node);
+}
+
+int yko_preemption_index(const yko_snapshot* s, int32_t ask, int32_t node, int32_t n_victims,
+                         const int64_t* victim_req, int32_t start) {
+    if (!s || ask < 0 || ask >= s->n_asks || node < 0 || node >= s->n_nodes) return -2;
+    const int D = s->D;
+    // clone the node, then remove victims one at a time (predicate_manager.go:153-168): the loop body only runs
+    // for i >= start, so with no victims (or start past the end) the answer is -1 even if the pod would fit
+    std::vector<int64_t> avail(s->node_avail + (size_t)node * D, s->node_avail + (size_t)(node + 1) * D);
+    for (int i = 0; i < n_victims; ++i) {
+        for (int k = 0; k < D; ++k) avail[(size_t)k] += victim_req[(size_t)i * D + k];
+        if (i < start) continue;
+        yko_snapshot t = *s;
+        std::vector<int64_t> all(s->node_avail, s->node_avail + (size_t)s->n_nodes * D);
+        std::copy(avail.begin(), avail.end(), all.begin() + (size_t)node * D);
+        t.node_avail = all.data();
+        if (yko_predicate(&t, ask, node) == 0) return i;
+    }
+    return -1;
 }
 
 int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings, int32_t* out_ask, int32_t* out_node,

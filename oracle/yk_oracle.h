@@ -117,6 +117,11 @@ int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings,
 #define YKO_FAIL_RESOURCES            8  /* k8s NodeResourcesFit */
 int yko_predicate(const yko_snapshot* s, int32_t ask, int32_t node);
 
+/* Preemption victim search for one (ask,node): /root/reference/pkg/plugin/predicates/predicate_manager.go:137-175.
+ * victim_req is [n][D] (what removing each victim gives back).  Returns the first index >= start that fits, or -1. */
+int yko_preemption_index(const yko_snapshot* s, int32_t ask, int32_t node, int32_t n_victims,
+                         const int64_t* victim_req, int32_t start);
+
 /* float64 node score exactly as SURVEY A.3 (exposed for known-answer tests) */
 double yko_node_score(int32_t D, int32_t policy, const double* weights,
                       const int64_t* total, const int64_t* avail);

@@ -72,6 +72,10 @@ def test_config4_full(oracle):
     _check(synth.hier(), oracle, batch=4096)
 
 
+def test_fair_leaf_policy(oracle):
+    _check(synth.hier(200, 2, 3, 3, 30, masks=True, priorities=True, seed=23, leaf_sort=synth.SORT_FAIR), oracle, batch=64)
+
+
 # ---- config 5: gangs, all-or-nothing ----
 @pytest.mark.parametrize("policy", [synth.POLICY_FAIR, synth.POLICY_BINPACKING])
 def test_config5_small(oracle, policy):

@@ -86,6 +86,7 @@ def test_node_id_tie_break_is_bytewise_string_order(oracle):
     lambda: synth.perf(80, 8, 25), lambda: synth.perf(80, 8, 25, masks=True),
     lambda: synth.perf(80, 8, 25, masks=True, policy=1), lambda: synth.perf(6, 4, 200),
     lambda: synth.hier(60, 3, 3, 2, 12, priorities=True), lambda: synth.hier(60, 2, 4, 2, 12, masks=True, quota_frac=2.0),
+    lambda: synth.hier(40, 2, 2, 3, 12, priorities=True, leaf_sort=1), lambda: synth.gangs(30, 12, 5), lambda: synth.gangs(40, 20, 4, fill=1.6, policy=1),
 ])
 def test_two_independent_restatements_agree(oracle, make):
     s = make()

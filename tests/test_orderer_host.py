@@ -112,3 +112,20 @@ def test_gangs_order_and_failure(shim, oracle, batch):
     st = want["state"].reshape(-1, 4)
     assert ((st == st[:, :1]).all(axis=1)).all(), "a gang's members share one fate"
     assert (st[:, 0] == 2).sum() > 0 and (st[:, 0] == 1).sum() > 0
+
+
+@pytest.mark.parametrize("batch", [5, 200, 100000])
+def test_fair_leaf_application_sort(shim, oracle, batch):
+    """leaf application.sort.policy = fair: applications are re-ordered by their allocation share after every
+    allocation; with a placement failure now and then (rewind) the order must still follow the oracle."""
+    s = synth.hier(40, 2, 2, 4, 30, priorities=True, big_nodes=True, seed=13, leaf_sort=synth.SORT_FAIR)
+    rng = np.random.default_rng(7)
+    bad = rng.random(s.n_asks) < 0.05
+    s.ask_req[bad, 2] = (1 << 31)
+    want = oracle.run(s)
+    got, state, ins, _ = run_orderer(shim, s, fail=bad.astype(np.uint8), batch=batch)
+    assert not ins
+    assert np.array_equal(got, want["ask"])
+    assert np.array_equal(state, want["state"])
+    fifo = oracle.run(synth.hier(40, 2, 2, 4, 30, priorities=True, big_nodes=True, seed=13))
+    assert not np.array_equal(fifo["ask"][:len(want["ask"])], want["ask"]), "fair must differ from fifo on this fixture"

@@ -159,7 +159,7 @@ struct yk_engine {
     uint32_t a_hi = 0;
     bool asks_stale = true;
 
-    std::vector<uint32_t> p_queue; std::vector<int64_t> p_submit; std::vector<uint8_t> p_present;
+    std::vector<uint32_t> p_queue; std::vector<int64_t> p_submit, p_alloc; std::vector<uint8_t> p_present;
     uint32_t nq = 0;
     std::vector<uint32_t> q_parent; std::vector<int64_t> q_guar, q_max, q_alloc; std::vector<uint8_t> q_sort;
 
@@ -691,6 +691,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
     e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
+    e->p_alloc.assign((size_t)e->maxP * D, 0);
     // default queue tree: root only would have no leaf for apps; root + one leaf "root.default"
     e->nq = 0;
     e->pos_of.assign(N, 0); e->hkey.assign(N, 0); e->is_dirty.assign(N, 0);
@@ -763,6 +764,7 @@ int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t
         if (queue[i] >= e->nq) return e->fail(YK_ERR_ARG, "yk_apps_upsert: unknown queue (call yk_queues_set first)");
     }
     for (uint32_t i = 0; i < n; ++i) {
+        if (!e->p_present[idx[i]]) for (int k = 0; k < e->D; ++k) e->p_alloc[(size_t)k * e->maxP + idx[i]] = 0;
         e->p_queue[idx[i]] = queue[i]; e->p_submit[idx[i]] = submit[i]; e->p_present[idx[i]] = 1;
     }
     return YK_OK;
@@ -836,6 +838,7 @@ int yk_release(yk_engine* e, uint32_t n, const uint32_t* idx) {
             const int64_t r = e->a_req[(size_t)k * e->maxA + a];
             if (node != YK_NONE && e->n_present[node]) e->n_avail[(size_t)k * e->maxN + node] += r;
             for (uint32_t q = e->p_queue[e->a_app[a]]; q != YK_NONE; q = e->q_parent[q]) e->q_alloc[(size_t)k * e->nq + q] -= r;
+            e->p_alloc[(size_t)k * e->maxP + e->a_app[a]] -= r;
         }
         e->a_state[a] = yk::ST_ABSENT;
         e->a_bound[a] = YK_NONE;
@@ -852,12 +855,6 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     *n_out = 0;
     if (n_slow) *n_slow = 0;
     if (e->nq == 0) return e->fail(YK_ERR_STATE, "yk_cycle: no queues configured (yk_queues_set)");
-    for (uint32_t i = 0; i < e->nq; ++i)
-        if (e->q_sort[i] == YK_SORT_FAIR) {
-            bool leaf = true;
-            for (uint32_t j = i + 1; j < e->nq; ++j) if (e->q_parent[j] == i) leaf = false;
-            if (leaf) return e->fail(YK_ERR_ARG, "yk_cycle: fair application sort policy is not implemented yet");
-        }
     const double t_start = now_ms();
     int rc = upload_tables(e);
     if (rc) return rc;
@@ -880,7 +877,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
     t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
     t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
-    t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data();
+    t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
     t.q_sort = e->q_sort.data();
     e->ord.begin_cycle(pending);
     e->st.host_ms[1] += now_ms() - t_a;
@@ -998,6 +995,42 @@ int yk_node_scores(yk_engine* e, uint32_t n, const uint32_t* idx, double* out) {
     CK(cudaMemcpyAsync(e->h_scores.p, e->d_scores.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     memcpy(out, e->h_scores.p, 8 * (size_t)n);
+    e->st.other_launches++;
+    return YK_OK;
+}
+
+int yk_preemption_search(yk_engine* e, uint32_t nq, const uint32_t* ask, const uint32_t* node, const uint32_t* voff,
+                         const int64_t* vreq, const uint32_t* start, int32_t* out) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (nq && (!ask || !node || !voff || !start || !out)) return e->fail(YK_ERR_ARG, "yk_preemption_search: null array");
+    if (!nq) return YK_OK;
+    const uint32_t nv = voff[nq];
+    if (nv && !vreq) return e->fail(YK_ERR_ARG, "yk_preemption_search: null victim_req");
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (ask[i] >= e->maxA || node[i] >= e->maxN || e->a_state[ask[i]] == yk::ST_ABSENT || !e->n_present[node[i]])
+            return e->fail(YK_ERR_ARG, "yk_preemption_search: unknown ask or node");
+        if (voff[i] > voff[i + 1]) return e->fail(YK_ERR_ARG, "yk_preemption_search: victim_off must be non-decreasing");
+    }
+    int rc = upload_tables(e);
+    if (rc) return rc;
+    const int D = e->D;
+    Dev<uint32_t> d_q; Dev<int64_t> d_v; Dev<int32_t> d_o;
+    CK(d_q.alloc((size_t)nq * 4 + 1)); CK(d_v.alloc((size_t)std::max<uint32_t>(nv, 1) * D)); CK(d_o.alloc(nq));
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(d_q.p, ask, 4 * (size_t)nq, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_q.p + nq, node, 4 * (size_t)nq, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_q.p + 2 * (size_t)nq, voff, 4 * ((size_t)nq + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_q.p + 3 * (size_t)nq + 1, start, 4 * (size_t)nq, cudaMemcpyHostToDevice, s));
+    if (nv) CK(cudaMemcpyAsync(d_v.p, vreq, 8 * (size_t)nv * D, cudaMemcpyHostToDevice, s));
+    const int threads = 128, warps_per_block = threads / 32;
+    yk_preempt_kernel<<<(nq + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(
+        D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p, e->d_flags.p, e->d_areq.p, e->d_atol.p,
+        e->d_aneed.p, e->d_adeny.p, e->d_anode.p, e->maxA, (int)nq, d_q.p, d_q.p + nq, d_q.p + 2 * (size_t)nq, d_v.p,
+        std::max<uint32_t>(nv, 1), d_q.p + 3 * (size_t)nq + 1, d_o.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o.p, 4 * (size_t)nq, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     e->st.other_launches++;
     return YK_OK;
 }

@@ -267,6 +267,60 @@ __global__ void yk_evaluate_kernel(int D, const int64_t* __restrict__ total, con
     *out = r;
 }
 
+// ---- preemption victim search (predicate_manager.go:137-175), one warp per query ---------------------
+// Query q: does ask[q] fit node[q] once victims voff[q]..voff[q+1] are removed in order up to index i, for the
+// smallest i >= start[q]?  The victims before start are always removed.  Static predicates (the reference's
+// PreFilter + non-resource Filters) do not depend on the victims: if they fail the answer is -1.  The resource
+// part is a prefix sum of what the victims give back: warp-wide inclusive scan per dimension, 32 victims a step.
+__global__ void yk_preempt_kernel(int D, const int64_t* __restrict__ total, const int64_t* __restrict__ avail, size_t ldn,
+                                  const uint64_t* __restrict__ taint, const uint64_t* __restrict__ label,
+                                  const uint32_t* __restrict__ flags, const int64_t* __restrict__ a_req,
+                                  const uint64_t* __restrict__ a_tol, const uint64_t* __restrict__ a_need,
+                                  const uint64_t* __restrict__ a_deny, const uint32_t* __restrict__ a_node, size_t lda,
+                                  int nq, const uint32_t* __restrict__ q_ask, const uint32_t* __restrict__ q_node,
+                                  const uint32_t* __restrict__ voff, const int64_t* __restrict__ vreq, size_t ldv,
+                                  const uint32_t* __restrict__ start, int32_t* __restrict__ out) {
+    const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint32_t ask = q_ask[q], node = q_node[q];
+    bool stat = (flags[node] & 1u) != 0;
+    stat = stat && !(a_node[ask] != YK_NONE_U32 && a_node[ask] != node);
+    stat = stat && !(taint[node] & ~a_tol[ask]);
+    stat = stat && (label[node] & a_need[ask]) == a_need[ask] && !(label[node] & a_deny[ask]);
+    int64_t rq[8], carry[8];
+    bool pos = false;
+    for (int k = 0; k < D; ++k) {
+        rq[k] = a_req[(size_t)k * lda + ask];
+        const int64_t t = total[(size_t)k * ldn + node];
+        carry[k] = avail[(size_t)k * ldn + node];
+        if (rq[k] < 0 || rq[k] > (t < 0 ? 0 : t)) stat = false;
+        if (rq[k] > 0) pos = true;
+    }
+    stat = stat && pos;
+    const uint32_t v0 = voff[q], v1 = voff[q + 1], st = start[q];
+    int32_t answer = -1;
+    for (uint32_t base = v0; stat && base < v1 && answer < 0; base += 32) {
+        const uint32_t v = base + (uint32_t)lane;
+        bool fit = v < v1;
+        for (int k = 0; k < D; ++k) {
+            int64_t x = (v < v1) ? vreq[(size_t)k * ldv + v] : 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {   // inclusive scan
+                const int64_t y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+                if (lane >= off) x += y;
+            }
+            const int64_t have = carry[k] + x;
+            fit = fit && rq[k] <= (have < 0 ? 0 : have);
+            carry[k] += __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
+        fit = fit && (v - v0) >= st;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, fit);
+        if (m) answer = (int32_t)(base - v0) + (__ffs((int)m) - 1);
+    }
+    if (lane == 0) out[q] = answer;
+}
+
 // scatter new availability for a list of nodes (after the ordered commit)
 __global__ void yk_apply_avail_kernel(int D, int64_t* __restrict__ avail, size_t ldn, const uint32_t* __restrict__ nodes,
                                       const int64_t* __restrict__ vals /*[D][n]*/, int n) {

@@ -43,6 +43,7 @@ struct Tables {   // views into the engine's host tables
     const int64_t* q_guar = nullptr;     // [D][nq]
     const int64_t* q_max = nullptr;      // [D][nq]
     int64_t* q_alloc = nullptr;          // [D][nq] persistent allocated (updated at finish())
+    int64_t* p_alloc = nullptr;          // [D][maxP] persistent per-application allocated (may be null)
     const uint8_t* q_sort = nullptr;
 };
 
@@ -59,8 +60,35 @@ public:
         int64_t npend = 0, live = 0;
         int32_t key_prio = 0;
         bool in_set = false;
+        int64_t alloc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // allocated to the application (fair leaf ordering)
     };
-    using AppKey = std::tuple<int32_t, int64_t, uint32_t>;   // (-priority, submit, app)
+    // application order inside a leaf: (-max pending priority, [fair leaves: allocation shares against the
+    // queue's guaranteed resource, largest first], submission time, app index).  fifo leaves keep sh all zero.
+    struct AppKey {
+        int32_t negprio; double sh[8]; int64_t submit; uint32_t app;
+        bool operator<(const AppKey& o) const {
+            if (negprio != o.negprio) return negprio < o.negprio;
+            for (int k = 0; k < 8; ++k) if (sh[k] != o.sh[k]) return sh[k] < o.sh[k];
+            if (submit != o.submit) return submit < o.submit;
+            return app < o.app;
+        }
+    };
+    AppKey make_key(uint32_t p) const {
+        AppKey k;
+        k.negprio = -ap[p].key_prio; k.submit = t.p_submit[p]; k.app = p;
+        for (int i = 0; i < 8; ++i) k.sh[i] = 0.0;
+        const uint32_t leaf = t.p_queue[p];
+        if (t.q_sort[leaf] == 1) {   // fair
+            double tmp[8];
+            for (int i = 0; i < t.D; ++i) {
+                const int64_t v = ap[p].alloc[i], g = t.q_guar[(size_t)i * t.nq + leaf];
+                tmp[i] = (v == 0) ? 0.0 : (g <= 0 ? (double)v : (double)v / (double)g);
+            }
+            std::sort(tmp, tmp + t.D);
+            for (int i = 0; i < t.D; ++i) k.sh[i] = tmp[t.D - 1 - i];   // largest first
+        }
+        return k;
+    }
 
     Tables t;
     std::vector<QState> q;
@@ -133,7 +161,8 @@ public:
             }
             q_apps[t.p_queue[p]].push_back(p);
             A.key_prio = t.a_prio[v[0]];
-            if (A.live > 0) { q_set[t.p_queue[p]].insert(AppKey(-A.key_prio, t.p_submit[p], p)); A.in_set = true; }
+            if (t.p_alloc) for (int k = 0; k < d; ++k) A.alloc[k] = t.p_alloc[(size_t)k * t.maxP + p];
+            if (A.live > 0) { q_set[t.p_queue[p]].insert(make_key(p)); A.in_set = true; }
         }
         // placement-insensitive?  one leaf with pending asks, fifo, no max on its chain, one priority level
         int leaves = 0; uint32_t leaf = NONE;
@@ -157,7 +186,7 @@ public:
             };
             std::vector<uint32_t> mem;
             for (const AppKey& k : q_set[leaf]) {
-                const auto& v = ap_asks[std::get<2>(k)];
+                const auto& v = ap_asks[k.app];
                 for (uint32_t a : v) {
                     if (t.a_state[a] != ST_PENDING) continue;
                     const uint8_t c = cause_of(a);
@@ -225,6 +254,7 @@ public:
         uint32_t p = t.a_app[a];
         t.a_state[a] = ST_NOFIT;
         ap[p].npend++;
+        for (int k = 0; k < d; ++k) ap[p].alloc[k] -= req(a, k);
         if (a_pos[a] < ap[p].head) ap[p].head = a_pos[a];
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
             q[qq].npend++;
@@ -235,14 +265,19 @@ public:
 
     void confirm(uint32_t a) {
         t.a_state[a] = ST_ALLOCATED;
-        if (insensitive)   // static order: queue accounting is not needed to order, only to persist
+        if (insensitive) {   // static order: accounting is not needed to order, only to persist
             for (uint32_t qq = t.p_queue[t.a_app[a]]; qq != NONE; qq = t.q_parent[qq])
                 for (int k = 0; k < t.D; ++k) q[qq].alloc[k] += req(a, k);
+            for (int k = 0; k < t.D; ++k) ap[t.a_app[a]].alloc[k] += req(a, k);
+        }
     }
 
-    void finish() {   // persist queue allocations
+    void finish() {   // persist queue and application allocations
         for (uint32_t i = 0; i < t.nq; ++i)
             for (int k = 0; k < t.D; ++k) t.q_alloc[(size_t)k * t.nq + i] = q[i].alloc[k];
+        if (t.p_alloc)
+            for (uint32_t p = 0; p < t.maxP; ++p)
+                if (!ap_asks[p].empty()) for (int k = 0; k < t.D; ++k) t.p_alloc[(size_t)k * t.maxP + p] = ap[p].alloc[k];
     }
 
 private:
@@ -295,7 +330,7 @@ private:
         A.live--;
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) q[qq].live--;
         if (A.live == 0 && A.in_set) {
-            q_set[t.p_queue[p]].erase(AppKey(-A.key_prio, t.p_submit[p], p));
+            q_set[t.p_queue[p]].erase(make_key(p));
             A.in_set = false;
         }
     }
@@ -309,20 +344,20 @@ private:
         AState& A = ap[p];
         set_state(a, ST_TENTATIVE);
         A.npend--;
-        drop_live(a);
-        // advance head, re-key the app if its max pending priority changed
+        drop_live(a);   // may take the app out of its leaf's set
+        // advance head; re-key the app if its max pending priority or (fair leaf) its allocation changed
         const auto& v = ap_asks[p];
         while (A.head < v.size() && (t.a_state[v[A.head]] == ST_ALLOCATED || t.a_state[v[A.head]] == ST_TENTATIVE)) A.head++;
-        if (A.head < v.size()) {
-            int32_t np = t.a_prio[v[A.head]];
-            if (np != A.key_prio) {
-                if (A.in_set) {
-                    auto& S = q_set[t.p_queue[p]];
-                    S.erase(AppKey(-A.key_prio, t.p_submit[p], p));
-                    S.insert(AppKey(-np, t.p_submit[p], p));
-                }
-                A.key_prio = np;
-            }
+        const bool fair = t.q_sort[t.p_queue[p]] == 1;
+        const int32_t np = A.head < v.size() ? t.a_prio[v[A.head]] : A.key_prio;
+        if (np != A.key_prio || fair) {
+            auto& S = q_set[t.p_queue[p]];
+            if (A.in_set) S.erase(make_key(p));
+            A.key_prio = np;
+            for (int k = 0; k < d; ++k) A.alloc[k] += req(a, k);
+            if (A.in_set) S.insert(make_key(p));
+        } else {
+            for (int k = 0; k < d; ++k) A.alloc[k] += req(a, k);
         }
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
             QState& Q = q[qq];
@@ -377,7 +412,7 @@ private:
             headroom(qi, hr);
             auto& S = q_set[qi];
             for (auto it = S.begin(); it != S.end();) {
-                uint32_t p = std::get<2>(*it);
+                uint32_t p = it->app;
                 ++it;   // advance first: the body may erase the current element
                 AState& A = ap[p];
                 const auto& v = ap_asks[p];

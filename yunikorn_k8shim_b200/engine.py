@@ -20,7 +20,7 @@ YK_ERR_CUDA = -2
 EXPORTS = [
     "yk_abi_version", "yk_create", "yk_destroy", "yk_nodes_upsert", "yk_nodes_remove", "yk_queues_set",
     "yk_apps_upsert", "yk_apps_remove", "yk_asks_upsert", "yk_asks_remove", "yk_release", "yk_cycle",
-    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_set_exchange", "yk_stats",
+    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_preemption_search", "yk_set_exchange", "yk_stats",
     "yk_stats_reset", "yk_strerror", "yk_last_error",
 ]
 
@@ -241,6 +241,22 @@ class Engine:
         idx = _arr(idx, np.uint32)
         out = np.zeros(idx.size, dtype=np.float64)
         self._ck(self._lib.yk_node_scores(self._h, C.c_uint32(idx.size), _p(idx), _p(out)))
+        return out
+
+    def preemption_search(self, ask, node, victim_req_lists, start):
+        """victim_req_lists: per query an [n_victims][D] array of what each victim gives back -> index per query"""
+        ask, node, start = _arr(ask, np.uint32), _arr(node, np.uint32), _arr(start, np.uint32)
+        off = np.zeros(len(ask) + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(v) for v in victim_req_lists])
+        flat = np.zeros((self.D, max(int(off[-1]), 1)), dtype=np.int64)
+        pos = 0
+        for v in victim_req_lists:
+            v = np.asarray(v, dtype=np.int64).reshape(-1, self.D)
+            flat[:, pos:pos + len(v)] = v.T
+            pos += len(v)
+        flat = np.ascontiguousarray(flat[:, :max(int(off[-1]), 1)])
+        out = np.zeros(len(ask), dtype=np.int32)
+        self._ck(self._lib.yk_preemption_search(self._h, C.c_uint32(len(ask)), _p(ask), _p(node), _p(off), _p(flat), _p(start), _p(out)))
         return out
 
     def set_exchange(self, fn):

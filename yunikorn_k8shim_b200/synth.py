@@ -244,7 +244,7 @@ def perf(n_nodes=10_000, n_apps=400, tasks=125, masks=False, policy=POLICY_FAIR,
 
 
 def hier(n_nodes=50_000, n_parents=8, leaves_per_parent=8, apps_per_leaf=5, tasks=625, masks=False,
-         policy=POLICY_FAIR, seed=4, quota_frac=1.2, priorities=False, big_nodes=False) -> Snapshot:
+         policy=POLICY_FAIR, seed=4, quota_frac=1.2, priorities=False, big_nodes=False, leaf_sort=SORT_FIFO) -> Snapshot:
     """BASELINE config 4: 3-level queue tree (root -> parents -> leaves), guaranteed + max per leaf, fifo apps
     in the leaves, fair (DRF) parents; demand is `quota_frac` x some leaf maxima so the headroom checks bite.
     Default sizes: 50k nodes, 64 leaves x 5 apps x 625 tasks = 200k asks."""
@@ -286,7 +286,7 @@ def hier(n_nodes=50_000, n_parents=8, leaves_per_parent=8, apps_per_leaf=5, task
         base.node_total[:, 1] = 1 << 50
         base.node_total[:, 2] = 1 << 30
         base.node_avail[:] = base.node_total
-    queues = (qp, guar, mx, np.zeros((Q, D), dtype=np.int64), np.zeros(Q, dtype=np.uint8))
+    queues = (qp, guar, mx, np.zeros((Q, D), dtype=np.int64), np.full(Q, leaf_sort, dtype=np.uint8))
     s = _finish(f"hier-{n_nodes}x{base.n_asks}-q{Q}", D, policy, base.node_total, base.node_avail, base.node_taint,
                 base.node_label, base.node_id, queues, app_queue, base.ask_app, base.ask_req, base.ask_tol,
                 base.ask_need, base.ask_deny, ask_prio=prio, meta={"config": 4, "seed": seed})
