@@ -358,7 +358,7 @@ struct Engine {
         ++st.queue_sorts;
         std::vector<int> sorted;
         for (int c : Q.children) if (queues[(size_t)c].pending_asks > 0) sorted.push_back(c);
-        std::stable_sort(sorted.begin(), sorted.end(), [&](int l, int r) {
+        auto child_less = [&](int l, int r) {
             int c = yko_comp_usage_ratio_separately(D, queues[(size_t)l].alloc.data(), s->q_guaranteed + (size_t)l * D,
                                                     queues[(size_t)r].alloc.data(), s->q_guaranteed + (size_t)r * D);
             if (c != 0) return c < 0;
@@ -369,7 +369,11 @@ struct Engine {
             for (int k = 0; k < D; ++k) diff[k] = -diff[k];
             if (strictly_gt_zero(D, diff)) return false;
             return l < r;
-        });
+        };
+        // stable insertion sort from index order: what Go's sort.SliceStable does for n <= 20 [EXT]; written out so
+        // that the engine's orderer can use the very same algorithm (the tie-break on pending is only a partial order)
+        for (size_t a = 1; a < sorted.size(); ++a)
+            for (size_t b = a; b > 0 && child_less(sorted[b], sorted[b - 1]); --b) std::swap(sorted[b], sorted[b - 1]);
         for (int c : sorted) {
             if (try_queue(c, out, room)) return true;
             if (stop) return false;

@@ -94,6 +94,8 @@ public:
     std::vector<QState> q;
     std::vector<std::vector<uint32_t>> q_children, q_apps;
     std::vector<std::set<AppKey>> q_set;
+    std::vector<std::vector<uint32_t>> q_sorted, q_changed;   // per parent: cached child order, children to re-position
+    std::vector<uint8_t> q_sorted_ok;
     std::vector<AState> ap;
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
@@ -124,6 +126,7 @@ public:
         q_children.assign(t.nq, {});
         q_apps.assign(t.nq, {});
         q_set.assign(t.nq, {});
+        q_sorted.assign(t.nq, {}); q_changed.assign(t.nq, {}); q_sorted_ok.assign(t.nq, 0);
         for (uint32_t i = 0; i < t.nq; ++i) {
             for (int k = 0; k < d; ++k) { q[i].alloc[k] = t.q_alloc[(size_t)k * t.nq + i]; q[i].pending[k] = 0; }
             if (i > 0) q_children[t.q_parent[i]].push_back(i);
@@ -237,6 +240,8 @@ public:
         for (auto it = journal.rbegin(); it != journal.rend(); ++it) t.a_state[it->first] = it->second;
         journal.clear();
         q = sq; ap = sap; q_set = sset; slow_list.resize(slow_mark);
+        std::fill(q_sorted_ok.begin(), q_sorted_ok.end(), 0);
+        for (auto& v : q_changed) v.clear();
         std::vector<uint32_t> replay;
         while (replay.size() < j && step(j, j, replay)) {}
         const uint32_t a = select(0);   // == batch[j] by construction
@@ -364,6 +369,7 @@ private:
             Q.npend--;
             for (int k = 0; k < d; ++k) { Q.alloc[k] += req(a, k); Q.pending[k] -= req(a, k); }
             Q.shares_ok = false;
+            if (t.q_parent[qq] != NONE) q_changed[t.q_parent[qq]].push_back(qq);
         }
     }
 
@@ -431,24 +437,48 @@ private:
             }
             return NONE;
         }
-        // parent: children with pending asks, stable-sorted from index order by the fair comparator
-        uint32_t sorted[256]; int n = 0;
-        std::vector<uint32_t> big;
-        const auto& ch = q_children[qi];
-        uint32_t* s = sorted;
-        if (ch.size() > 256) { big.resize(ch.size()); s = big.data(); }
-        for (uint32_t c : ch) if (q[c].npend > 0) s[n++] = c;
-        std::stable_sort(s, s + n, [&](uint32_t l, uint32_t r) {
+        // parent: children with pending asks in the order a stable insertion sort from index order gives under the
+        // fair comparator (= yunikorn-core sortQueues, Go sort.SliceStable for n <= 20).  The sorted list is cached per
+        // parent: between two passes only the child on the allocated path changed, so it is taken out and put back;
+        // whenever a comparison ties on the shares (where the pending tie-break is only a partial order and the result
+        // could depend on the algorithm) the list is rebuilt with the full insertion sort instead.
+        std::vector<uint32_t>& srt = q_sorted[qi];
+        bool tie = false;
+        auto less = [&](uint32_t l, uint32_t r) {
             int c = cmp_shares(l, r);
             if (c != 0) return c < 0;
+            tie = true;
             int64_t diff[8];
             for (int k = 0; k < d; ++k) diff[k] = q[l].pending[k] - q[r].pending[k];
             if (strictly_gt_zero(diff, d)) return true;
             for (int k = 0; k < d; ++k) diff[k] = -diff[k];
             if (strictly_gt_zero(diff, d)) return false;
             return l < r;
-        });
-        for (int i = 0; i < n; ++i) {
+        };
+        bool rebuild = !q_sorted_ok[qi];
+        if (!rebuild) {
+            for (uint32_t c : q_changed[qi]) {   // re-position the children whose key moved since the last pass
+                auto it = std::find(srt.begin(), srt.end(), c);
+                if (it != srt.end()) srt.erase(it);
+                if (q[c].npend <= 0) continue;
+                size_t pos = 0;
+                while (pos < srt.size() && !less(c, srt[pos])) ++pos;
+                srt.insert(srt.begin() + pos, c);
+            }
+            if (tie) rebuild = true;
+        }
+        if (rebuild) {
+            srt.clear();
+            for (uint32_t c : q_children[qi]) if (q[c].npend > 0) srt.push_back(c);
+            for (size_t a = 1; a < srt.size(); ++a)
+                for (size_t b = a; b > 0 && less(srt[b], srt[b - 1]); --b) std::swap(srt[b], srt[b - 1]);
+            // a list built while shares tie stays "not ok" so that it is rebuilt until the tie is gone
+            q_sorted_ok[qi] = !tie;
+        }
+        q_changed[qi].clear();
+        const size_t n = srt.size();
+        const uint32_t* s = srt.data();
+        for (size_t i = 0; i < n; ++i) {
             uint32_t a = select(s[i]);
             if (a != NONE) return a;
         }
