@@ -125,7 +125,8 @@ typedef struct {
     double last_sweep_ms;
     uint64_t last_sweep_pairs;
     /* host wall-clock split of yk_cycle: 0 table upload + initial device sort, 1 orderer begin_cycle,
-       2 orderer fill/rewind, 3 waiting for device results, 4 ordered commit, 5 order merge, 6 other */
+       2 orderer fill/rewind, 3 waiting for device results, 4 ordered commit, 5 order merge + state push, 6 launch,
+       7 orderer + launch time spent on the helper thread (overlapped with the commit) */
     double host_ms[8];
     /* commit counters: 0 bitmap words scanned, 1 re-scored candidates examined, 2 asks won by a re-scored node,
        3 re-keys of an already re-scored node */

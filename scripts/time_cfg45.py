@@ -13,4 +13,4 @@ for snap in (synth.hier(), synth.gangs()):
         ok = np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
         print(f"{snap.name} batch={batch} ok={ok} n={len(ask)} cycle={dt*1e3:.1f}ms oracle={t_or*1e3:.1f}ms sweep={st['sweep_ms']:.2f}ms "
               f"commit={st['commit_ms']:.2f}ms batches={st['batches']} evals={st['evaluations']:.3e} "
-              f"host_ms={[round(x,1) for x in st['host_ms'][:7]]} dbg={st['dbg']} d2h={st['d2h_bytes']/1e6:.0f}MB", flush=True)
+              f"host_ms={[round(x,1) for x in st['host_ms'][:8]]} dbg={st['dbg']} d2h={st['d2h_bytes']/1e6:.0f}MB", flush=True)

@@ -24,7 +24,8 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
     std::vector<uint32_t> b;
     uint32_t n = 0;
     auto same_gang = [&](uint32_t x, uint32_t y) { return a_gang[x] != yk::NONE && a_gang[x] == a_gang[y] && a_app[x] == a_app[y]; };
-    while (o.fill(batch, (size_t)-1, b) > 0) {
+    yk::Orderer::Snap snap;
+    while (o.fill(batch, (size_t)-1, b, snap) > 0) {
         // the "device": an ask fails if fail[] says so; a gang fails whole if any member does
         std::vector<uint8_t> bad(b.size(), 0);
         for (size_t i = 0; i < b.size();) {
@@ -39,7 +40,7 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
         if (!o.insensitive)
             for (size_t i = 0; i < b.size(); ++i)
                 if (bad[i]) { first_bad = i; consumed = i + 1; while (consumed < b.size() && same_gang(b[i], b[consumed])) ++consumed; break; }
-        if (first_bad < b.size()) o.rewind(b, first_bad);
+        if (first_bad < b.size()) o.rewind(snap, nullptr, b, first_bad);
         for (size_t i = 0; i < consumed; ++i) {
             uint32_t a = b[i];
             if (bad[i]) { if (o.insensitive) o.fail_in_place(a); continue; }

@@ -129,3 +129,23 @@ def test_fair_leaf_application_sort(shim, oracle, batch):
     assert np.array_equal(state, want["state"])
     fifo = oracle.run(synth.hier(40, 2, 2, 4, 30, priorities=True, big_nodes=True, seed=13))
     assert not np.array_equal(fifo["ask"][:len(want["ask"])], want["ask"]), "fair must differ from fifo on this fixture"
+
+
+@pytest.mark.parametrize("batch", [3, 17, 100000])
+def test_orderer_on_fuzz_snapshots(shim, oracle, batch):
+    """All features at once (synth.fuzz): the fake device answers "no node" exactly for the asks the oracle ended
+    NOFIT; the orderer must then reproduce the oracle's ask order and per-ask states, through rewinds and gangs."""
+    checked = 0
+    for seed in range(60):
+        s = synth.fuzz(seed)
+        want = oracle.run(s)
+        if batch == 3 and (s.ask_gang >= 0).any():
+            sizes = np.bincount(s.ask_gang[s.ask_gang >= 0])
+            if sizes.max() > batch:
+                continue                      # gang larger than the batch: documented error path, tested elsewhere
+        fail = (want["state"] == 2).astype(np.uint8)
+        got, state, ins, _ = run_orderer(shim, s, fail=fail, batch=batch)
+        assert np.array_equal(got, want["ask"]), (seed, batch)
+        assert np.array_equal(state, want["state"]), (seed, batch)
+        checked += 1
+    assert checked > 20

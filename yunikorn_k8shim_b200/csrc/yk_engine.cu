@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -126,6 +129,60 @@ struct DirtyList {
     }
 };
 
+// A helper thread that fills and launches the NEXT batch while the caller's thread commits the current one
+// (the orderer state is only touched by one of the two at a time: fork before the commit, join after it).
+struct Worker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, busy = false, quit = false;
+    int device = 0;
+    void start(int dev) {
+        device = dev;
+        th = std::thread([this] {
+            cudaSetDevice(device);
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                has_job = false;
+                lk.unlock();
+                job();
+                lk.lock();
+                busy = false;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f); has_job = true; busy = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return !busy; });
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m); quit = true; cv.notify_all(); }
+        th.join();
+    }
+};
+
+// One in-flight batch: its asks, device / pinned buffers and read-back events.  Two slots let the sweep and the
+// read-back of batch k+1 run while the host commits batch k (both against the same epoch view, see run loop).
+struct Slot {
+    std::vector<uint32_t> asks;
+    yk::Orderer::Snap snap;
+    Dev<uint32_t> d_batch, d_fit, d_first;
+    Pin<uint32_t> h_batch, h_fit, h_first;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
+    int B = 0, W = 0, chunk = 0, nchunks = 0, rows = 0;
+};
+
 }  // namespace
 
 struct yk_engine {
@@ -169,12 +226,15 @@ struct yk_engine {
     Dev<uint64_t> d_key_in, d_key_out; Dev<uint32_t> d_val_in, d_val_out;
     Dev<uint8_t> d_cub; size_t cub_bytes = 0;
     Dev<int64_t> d_scap; Dev<uint64_t> d_staint, d_slabel; Dev<uint32_t> d_snode;
-    Dev<uint32_t> d_batch, d_fit, d_first; Dev<int> d_flag;
+    Dev<int> d_flag;
+    Slot slot[2];
+    Worker worker;
+    yk_stats_t wst{};                        // counters written by the worker thread, merged at join
     Dev<uint32_t> d_dirty_nodes; Dev<int64_t> d_dirty_vals; Dev<double> d_scores;
     size_t Wmax = 0;
 
     // pinned staging
-    Pin<uint32_t> h_batch, h_fit, h_first, h_snode, h_dirty_nodes; Pin<uint64_t> h_skey; Pin<int64_t> h_dirty_vals;
+    Pin<uint32_t> h_snode, h_dirty_nodes; Pin<uint64_t> h_skey; Pin<int64_t> h_dirty_vals;
     Pin<int> h_flag; Pin<double> h_scores;
 
     // commit scratch
@@ -185,7 +245,10 @@ struct yk_engine {
     std::vector<uint32_t> dirty_list;
     Pin<uint32_t> h_order[2]; int cur = 0;   // node order (ascending (score, NodeID)), double-buffered
     Dev<uint32_t> d_order;
-    std::vector<cudaEvent_t> ev_chunk;
+    int64_t dirty_ub[YK_MAX_D];              // per dimension: upper bound of `available` over the touched nodes
+    int front = 0;                           // every sorted position below word `front` is dirty (per epoch)
+    int epochW = 0;                          // words per fit row in the current epoch
+    uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
     DirtyList dirty;
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
     std::vector<int64_t> hot; int hs = 0;    // per node [avail[D], total[D], taint, label] contiguous: the commit's working copy
@@ -344,84 +407,180 @@ int initial_order(yk_engine* e) {
     return YK_OK;
 }
 
-// Device phase + ordered commit for one batch.  result[i] = node or YK_NONE; consumed = how many entries of
-// the batch were decided (stops after the first failure unless the batch is placement-insensitive).
-int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive, std::vector<uint32_t>& result,
-              size_t& consumed) {
-    const int D = e->D;
-    const int B = (int)batch.size();
+// ---- epochs -------------------------------------------------------------------------------------------
+// An epoch is a run of batches swept against ONE sorted view (node order + cap columns as of the epoch start).
+// Exactness does not need the view to be fresh: a node not touched since the epoch began has exactly the state
+// the view holds, and every touched node is masked out of the bitmaps and handled from the working copy
+// (DESIGN.md "ordered commit").  So the order is merged, the availability pushed to the device and the view
+// regathered only when the touched set has grown enough to slow the commit down -- and because the sweeps of one
+// epoch do not depend on each other's commits, the next batch's sweep and read-back overlap the current commit.
+int begin_epoch(yk_engine* e) {
     const int nlive = (int)e->nlive;
-    result.assign((size_t)B, YK_NONE);
-    consumed = 0;
-    if (nlive == 0) {   // no nodes: nothing fits
-        consumed = insensitive ? (size_t)B : 1;
-        return YK_OK;
-    }
+    for (uint32_t n : e->dirty_list) e->is_dirty[n] = 0;
+    e->dirty_list.clear();
+    e->dirty.clear();
+    e->front = 0;
+    for (int k = 0; k < YK_MAX_D; ++k) e->dirty_ub[k] = INT64_MIN;
+    if (nlive == 0) { e->epochW = 0; return YK_OK; }
     const int Np = (int)round_up((size_t)nlive, NODE_TILE);
-    const int W = Np / 32;
+    e->epochW = Np / 32;
+    e->dirty_words.assign((size_t)e->epochW, 0);
     cudaStream_t s = e->stream;
-    double t0 = now_ms();
-    uint32_t* order = e->h_order[e->cur].p;
+    CK(cudaMemcpyAsync(e->d_order.p, e->h_order[e->cur].p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyHostToDevice, s));
+    e->st.h2d_bytes += sizeof(uint32_t) * (size_t)nlive;
+    yk_gather_kernel<<<(Np + 255) / 256, 256, 0, s>>>(e->D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
+                                                     e->d_flags.p, e->d_order.p, nlive, Np, e->d_scap.p, e->d_staint.p,
+                                                     e->d_slabel.p, e->d_snode.p);
+    CK(cudaGetLastError());
+    e->st.other_launches += 1;
+    return YK_OK;
+}
 
-    memcpy(e->h_batch.p, batch.data(), sizeof(uint32_t) * (size_t)B);
-    CK(cudaMemcpyAsync(e->d_batch.p, e->h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_order.p, order, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyHostToDevice, s));
-    e->st.h2d_bytes += sizeof(uint32_t) * ((size_t)B + (size_t)nlive);
+// new node order = merge(previous order minus the touched nodes, touched nodes by new key); touched availability
+// goes back to the column-major host table and to the device table.  `reorder` false = end of cycle (state only).
+int end_epoch(yk_engine* e, bool reorder) {
+    const int D = e->D, nlive = (int)e->nlive;
+    const int nd = (int)e->dirty_list.size();
+    if (!nd) return YK_OK;
+    const double t0 = now_ms();
+    cudaStream_t s = e->stream;
+    DirtyList& dirty = e->dirty;
+    if (reorder) {
+        const uint32_t* order = e->h_order[e->cur].p;
+        uint32_t* out = e->h_order[e->cur ^ 1].p;
+        int o = 0, p = 0;
+        uint32_t si = 0, j = 0;
+        auto dirty_end = [&]() { return si >= dirty.seq.size(); };
+        auto dirty_cur = [&]() -> const DirtyRef& { return dirty.pool[dirty.seq[si]].v[j]; };
+        auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
+        int removed = 0;   // touched nodes passed over in the old order so far
+        while (true) {
+            while (p < nlive && e->is_dirty[order[p]]) { ++p; ++removed; }
+            if (p >= nlive) break;
+            if (dirty_end() && removed == nd) {
+                // every touched node has been taken out and put back: the rest of the order is unchanged
+                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
+                o += nlive - p;
+                p = nlive;
+                break;
+            }
+            const uint32_t n = order[p];
+            const DirtyRef c{e->hkey[n], e->n_rank[n], n};
+            while (!dirty_end() && dirty_cur() < c) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
+            e->pos_of[n] = (uint32_t)o;
+            out[o++] = n;
+            ++p;
+        }
+        while (!dirty_end()) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
+        e->cur ^= 1;
+    }
+    // staging is reused: the previous epoch's upload must have been consumed
+    CK(cudaStreamSynchronize(s));
+    for (int i0 = 0; i0 < nd; i0 += (int)e->h_dirty_nodes.n) {
+        const int cnt = std::min<int>(nd - i0, (int)e->h_dirty_nodes.n);
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t n = e->dirty_list[(size_t)(i0 + i)];
+            e->h_dirty_nodes[(size_t)i] = n;
+            for (int k = 0; k < D; ++k) {
+                const int64_t v = e->hot[(size_t)n * e->hs + k];
+                e->h_dirty_vals[(size_t)k * cnt + i] = v;
+                e->n_avail[(size_t)k * e->maxN + n] = v;   // column-major host table stays authoritative between cycles
+            }
+        }
+        CK(cudaMemcpyAsync(e->d_dirty_nodes.p, e->h_dirty_nodes.p, 4 * (size_t)cnt, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(e->d_dirty_vals.p, e->h_dirty_vals.p, 8 * (size_t)cnt * D, cudaMemcpyHostToDevice, s));
+        yk_apply_avail_kernel<<<(cnt + 255) / 256, 256, 0, s>>>(D, e->d_avail.p, e->maxN, e->d_dirty_nodes.p, e->d_dirty_vals.p, cnt);
+        CK(cudaGetLastError());
+        e->st.h2d_bytes += (size_t)cnt * (4 + 8 * D);
+        e->st.other_launches += 1;
+        if (i0 + cnt < nd) CK(cudaStreamSynchronize(s));
+    }
+    e->st.host_ms[5] += now_ms() - t0;
+    return YK_OK;
+}
 
+// Launch the device phase of one batch (already filled into sl.asks): sweep of this rank's rows against the epoch
+// view, multi-GPU exchange, chunked read-back with one event per chunk.  Returns without waiting.
+int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
+    const int D = e->D;
+    const int B = (int)sl.asks.size();
+    const int nlive = (int)e->nlive;
+    sl.B = B; sl.W = e->epochW; sl.rows = 0; sl.nchunks = 0;
+    if (B == 0 || nlive == 0) return YK_OK;
+    const double t0 = now_ms();
+    const int W = e->epochW, Np = W * 32;
+    cudaStream_t s = e->stream;
+    memcpy(sl.h_batch.p, sl.asks.data(), sizeof(uint32_t) * (size_t)B);
+    CK(cudaMemcpyAsync(sl.d_batch.p, sl.h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
+    st.h2d_bytes += sizeof(uint32_t) * (size_t)B;
     // this rank's shard of the batch rows (world == 1: all of them)
     const int world = std::max<int>(1, (int)e->cfg.world);
     const int rows_per = (B + world - 1) / world;
     const int row0 = std::min(B, (int)e->cfg.rank * rows_per);
     const int rows = std::min(B, row0 + rows_per) - row0;
     const int Bpad = rows_per * world;
-    CK(cudaMemsetAsync(e->d_first.p, 0xFF, sizeof(uint32_t) * (size_t)Bpad, s));
-
-    yk_gather_kernel<<<(Np + 255) / 256, 256, 0, s>>>(D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
-                                                     e->d_flags.p, e->d_order.p, nlive, Np, e->d_scap.p, e->d_staint.p,
-                                                     e->d_slabel.p, e->d_snode.p);
-    CK(cudaEventRecord(e->ev1, s));
+    sl.rows = rows;
+    CK(cudaMemsetAsync(sl.d_first.p, 0xFF, sizeof(uint32_t) * (size_t)Bpad, s));
+    CK(cudaEventRecord(sl.ev_s0, s));
     if (rows > 0) {
         YkSweepArgs a{};
         a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
         a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
-        a.lda = e->maxA; a.batch = e->d_batch.p; a.row0 = row0; a.rows = rows;
-        a.fit = e->d_fit.p; a.first = e->d_first.p; a.W = W;
+        a.lda = e->maxA; a.batch = sl.d_batch.p; a.row0 = row0; a.rows = rows;
+        a.fit = sl.d_fit.p; a.first = sl.d_first.p; a.W = W;
         launch_sweep(D, a, s, e->slots);
-        e->st.sweep_launches += 1;
-        e->st.evaluations += (uint64_t)rows * (uint64_t)nlive;
+        st.sweep_launches += 1;
+        st.evaluations += (uint64_t)rows * (uint64_t)nlive;
     }
-    CK(cudaEventRecord(e->ev2, s));
+    CK(cudaEventRecord(sl.ev_s1, s));
     CK(cudaGetLastError());
-    e->st.other_launches += 1;
     if (world > 1) {
         if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but no exchange function set (yk_set_exchange)");
-        if (e->xfn(e->xctx, e->d_fit.p, (uint64_t)W * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0 ||
-            e->xfn(e->xctx, e->d_first.p, 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
+        if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)W * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0 ||
+            e->xfn(e->xctx, sl.d_first.p, 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
             return e->fail(YK_ERR_COMM, "exchange callback failed");
     }
-
     // read-back in row chunks so the ordered commit overlaps the transfer
-    const int chunk = std::max(128, (B + (int)e->ev_chunk.size() - 1) / (int)e->ev_chunk.size());
-    const int nchunks = (B + chunk - 1) / chunk;
-    CK(cudaMemcpyAsync(e->h_first.p, e->d_first.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
-    for (int c = 0; c < nchunks; ++c) {
-        const size_t r0 = (size_t)c * chunk, r1 = std::min<size_t>((size_t)B, r0 + chunk);
-        CK(cudaMemcpyAsync(e->h_fit.p + r0 * W, e->d_fit.p + r0 * W, sizeof(uint32_t) * (r1 - r0) * W, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(e->ev_chunk[(size_t)c], s));
+    sl.chunk = std::max(128, (B + (int)sl.ev.size() - 1) / (int)sl.ev.size());
+    sl.nchunks = (B + sl.chunk - 1) / sl.chunk;
+    CK(cudaMemcpyAsync(sl.h_first.p, sl.d_first.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
+    for (int c = 0; c < sl.nchunks; ++c) {
+        const size_t r0 = (size_t)c * sl.chunk, r1 = std::min<size_t>((size_t)B, r0 + sl.chunk);
+        CK(cudaMemcpyAsync(sl.h_fit.p + r0 * W, sl.d_fit.p + r0 * W, sizeof(uint32_t) * (r1 - r0) * W, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(sl.ev[(size_t)c], s));
     }
-    e->st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B;
-    e->st.batches++;
+    st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B;
+    st.batches++;
+    st.host_ms[6] += now_ms() - t0;
+    return YK_OK;
+}
 
-    // ---------------- ordered commit (host), overlapped with the read-back ----------------
-    e->dirty_words.assign((size_t)W, 0);
-    for (uint32_t n : e->dirty_list) e->is_dirty[n] = 0;
-    e->dirty_list.clear();
+// wait until everything issued for the slot has landed (used before its buffers are reused or it is dropped)
+int drain(yk_engine* e, Slot& sl) {
+    if (sl.B > 0 && sl.nchunks > 0) CK(cudaEventSynchronize(sl.ev[(size_t)sl.nchunks - 1]));
+    return YK_OK;
+}
+
+// Ordered commit of one batch from its (arriving) bitmaps.  result[i] = node or YK_NONE; consumed = how many
+// entries were decided (stops after the first failed ask / gang unless the order is placement-insensitive).
+int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& result, size_t& consumed) {
+    const int D = e->D;
+    const int B = sl.B;
+    const std::vector<uint32_t>& batch = sl.asks;
+    result.assign((size_t)B, YK_NONE);
+    consumed = 0;
+    if (e->nlive == 0 || sl.nchunks == 0) {   // no nodes: nothing fits
+        consumed = insensitive ? (size_t)B : std::min<size_t>(1, (size_t)B);
+        if (!insensitive && B > 0 && e->a_gang[batch[0]] != YK_NONE)
+            while (consumed < (size_t)B && e->a_gang[batch[consumed]] == e->a_gang[batch[0]] && e->a_app[batch[consumed]] == e->a_app[batch[0]]) ++consumed;
+        return YK_OK;
+    }
+    const int W = sl.W;
+    const uint32_t* order = e->h_order[e->cur].p;
     DirtyList& dirty = e->dirty;
-    dirty.clear();
-    int front = 0;   // every position below word `front` is dirty
-    const uint32_t* fit = e->h_fit.p;
+    int& front = e->front;
+    const uint32_t* fit = sl.h_fit.p;
     double t_wait = 0, t1 = now_ms();
-    e->st.host_ms[6] += t1 - t0;
     int next_chunk = 0;
     bool stop = false;
     // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
@@ -433,9 +592,9 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
                e->a_app[batch[(size_t)x]] == e->a_app[batch[(size_t)y]];
     };
     for (int i = 0; i < B && !stop; ++i) {
-        while (i >= next_chunk * chunk) {
+        while (i >= next_chunk * sl.chunk) {
             const double tw = now_ms();
-            CK(cudaEventSynchronize(e->ev_chunk[(size_t)next_chunk]));
+            CK(cudaEventSynchronize(sl.ev[(size_t)next_chunk]));
             t_wait += now_ms() - tw;
             ++next_chunk;
         }
@@ -445,12 +604,12 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
         const uint32_t* row = fit + (size_t)i * W;
         if (i + 12 < B) {   // rows arrive by DMA and are cache-cold: pull the line the scan will start at
             const uint32_t* nrow = fit + (size_t)(i + 12) * W;
-            const uint32_t nf = e->h_first[(size_t)(i + 12)];
+            const uint32_t nf = sl.h_first[(size_t)(i + 12)];
             __builtin_prefetch(nrow + std::max<int>(front, nf == YK_NONE ? 0 : (int)(nf >> 5)));
         }
-        // (A) best clean node: first set bit of row & ~dirty in sorted order
+        // (A) best untouched node: first set bit of row & ~dirty in sorted order
         uint32_t posA = YK_NONE;
-        const uint32_t f = e->h_first[(size_t)i];
+        const uint32_t f = sl.h_first[(size_t)i];
         if (f != YK_NONE) {
             while (front < W && e->dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
             for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
@@ -464,21 +623,34 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
             const uint32_t nA = order[posA];
             bound = DirtyRef{e->hkey[nA], e->n_rank[nA], nA};
         }
-        // (B) best re-scored node among those committed to earlier in this batch
+        // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the request
+        // exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran over the
+        // whole list without a fit leaves the bound exact (it saw every touched node), which is what keeps a full
+        // cluster cheap: the first failing ask pays for the walk, the following ones are pruned.
         uint32_t chosen = YK_NONE;
-        if (f != YK_NONE) {
+        bool may_fit = f != YK_NONE && dirty.count > 0;
+        if (may_fit)
+            for (int k = 0; k < D; ++k)
+                if (e->a_req[(size_t)k * e->maxA + ask] > std::max<int64_t>(e->dirty_ub[k], 0)) { may_fit = false; break; }
+        if (may_fit) {
+            int64_t seen[YK_MAX_D];
+            for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
+            bool whole = true;
             for (uint32_t si = 0; si < dirty.seq.size() && chosen == YK_NONE; ++si) {
                 const DirtyList::Bucket& bk = dirty.pool[dirty.seq[si]];
-                if (!(bk.v[0] < bound)) break;
+                if (!(bk.v[0] < bound)) { whole = false; break; }
                 for (uint32_t j = 0; j < bk.n; ++j) {
                     const DirtyRef& d = bk.v[j];
-                    if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); break; }
+                    if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); whole = false; break; }
                     ++e->st.dbg[1];
                     // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
                     // lines were just DMA-written and are cold
-                    if (fits_now(e, d.node, ask)) { chosen = d.node; break; }
+                    if (fits_now(e, d.node, ask)) { chosen = d.node; whole = false; break; }
+                    const int64_t* hh = e->hot.data() + (size_t)d.node * e->hs;
+                    for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
                 }
             }
+            if (whole && chosen == YK_NONE) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];
         }
         if (chosen != YK_NONE) ++e->st.dbg[2];   // a re-scored node won
         if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
@@ -492,7 +664,10 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
                     int64_t* hh = e->hot.data() + (size_t)n * e->hs;
                     for (int k = 0; k < D; ++k) hh[k] = it->old_avail[k];
                     e->hkey[n] = it->old_key;
-                    if (it->was_dirty) dirty.insert(DirtyRef{it->old_key, e->n_rank[n], n});
+                    if (it->was_dirty) {
+                        dirty.insert(DirtyRef{it->old_key, e->n_rank[n], n});
+                        for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], hh[k]);   // availability came back
+                    }
                     else {
                         e->is_dirty[n] = 0;
                         e->dirty_list.pop_back();
@@ -527,16 +702,17 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
         e->hkey[chosen] = nk;
         dirty.insert(DirtyRef{nk, e->n_rank[chosen], chosen});
         if (!e->is_dirty[chosen]) {
+            for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], h[k]);
             e->is_dirty[chosen] = 1;
             e->dirty_list.push_back(chosen);
             const uint32_t pos = e->pos_of[chosen];
             e->dirty_words[pos >> 5] |= 1u << (pos & 31);
         }
     }
-    // all read-back must have landed before the staging buffers are reused
+    // all read-back must have landed before the slot's buffers are reused
     {
         const double tw = now_ms();
-        CK(cudaEventSynchronize(e->ev_chunk[(size_t)nchunks - 1]));
+        { int rcd = drain(e, sl); if (rcd) return rcd; }
         t_wait += now_ms() - tw;
     }
     const double t2 = now_ms();
@@ -544,59 +720,10 @@ int run_batch(yk_engine* e, const std::vector<uint32_t>& batch, bool insensitive
     e->st.host_ms[4] += (t2 - t1) - t_wait;
     e->st.commit_ms += (t2 - t1) - t_wait;
     float ms_sweep = 0;
-    cudaEventElapsedTime(&ms_sweep, e->ev1, e->ev2);
+    cudaEventElapsedTime(&ms_sweep, sl.ev_s0, sl.ev_s1);
     e->st.sweep_ms += ms_sweep;
     e->st.last_sweep_ms = ms_sweep;
-    e->st.last_sweep_pairs = (uint64_t)rows * (uint64_t)nlive;
-
-    // new node order = merge(previous order minus the touched nodes, touched nodes by new key)
-    const int nd = (int)e->dirty_list.size();
-    if (nd) {
-        uint32_t* out = e->h_order[e->cur ^ 1].p;
-        int o = 0, p = 0;
-        uint32_t si = 0, j = 0;
-        auto dirty_end = [&]() { return si >= dirty.seq.size(); };
-        auto dirty_cur = [&]() -> const DirtyRef& { return dirty.pool[dirty.seq[si]].v[j]; };
-        auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
-        int removed = 0;   // touched nodes passed over in the old order so far
-        while (true) {
-            while (p < nlive && e->is_dirty[order[p]]) { ++p; ++removed; }
-            if (p >= nlive) break;
-            if (dirty_end() && removed == nd) {
-                // every touched node has been taken out and put back: the rest of the order is unchanged
-                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
-                o += nlive - p;
-                p = nlive;
-                break;
-            }
-            const uint32_t n = order[p];
-            const DirtyRef c{e->hkey[n], e->n_rank[n], n};
-            while (!dirty_end() && dirty_cur() < c) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
-            e->pos_of[n] = (uint32_t)o;
-            out[o++] = n;
-            ++p;
-        }
-        while (!dirty_end()) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
-        e->cur ^= 1;
-
-        // push the new availability of the touched nodes back to the device table
-        for (int i = 0; i < nd; ++i) {
-            const uint32_t n = e->dirty_list[(size_t)i];
-            e->h_dirty_nodes[(size_t)i] = n;
-            for (int k = 0; k < D; ++k) {
-                const int64_t v = e->hot[(size_t)n * e->hs + k];
-                e->h_dirty_vals[(size_t)k * nd + i] = v;
-                e->n_avail[(size_t)k * e->maxN + n] = v;   // column-major host table stays authoritative between cycles
-            }
-        }
-        CK(cudaMemcpyAsync(e->d_dirty_nodes.p, e->h_dirty_nodes.p, 4 * (size_t)nd, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(e->d_dirty_vals.p, e->h_dirty_vals.p, 8 * (size_t)nd * D, cudaMemcpyHostToDevice, s));
-        yk_apply_avail_kernel<<<(nd + 255) / 256, 256, 0, s>>>(D, e->d_avail.p, e->maxN, e->d_dirty_nodes.p, e->d_dirty_vals.p, nd);
-        e->st.h2d_bytes += (size_t)nd * (4 + 8 * D);
-        e->st.other_launches += 1;
-        // the staging buffers are rewritten only after the next batch's read-back events, which are later in the stream
-    }
-    e->st.host_ms[5] += now_ms() - t2;
+    e->st.last_sweep_pairs = (uint64_t)sl.rows * (uint64_t)e->nlive;
     return YK_OK;
 }
 
@@ -624,11 +751,16 @@ const char* yk_last_error(yk_engine* e) { return e ? e->err.c_str() : "null engi
 
 void yk_destroy(yk_engine* e) {
     if (!e) return;
+    e->worker.stop();
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
-    for (auto ev : e->ev_chunk) if (ev) cudaEventDestroy(ev);
+    for (Slot& sl : e->slot) {
+        for (auto ev : sl.ev) if (ev) cudaEventDestroy(ev);
+        if (sl.ev_s0) cudaEventDestroy(sl.ev_s0);
+        if (sl.ev_s1) cudaEventDestroy(sl.ev_s1);
+    }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -671,13 +803,20 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     }
     T(e->d_scap.alloc(Npmax * D)); T(e->d_staint.alloc(Npmax)); T(e->d_slabel.alloc(Npmax)); T(e->d_snode.alloc(Npmax));
     const size_t Bpad = Bm + std::max<uint32_t>(cfg->world, 1);   // rows rounded up to a multiple of world
-    T(e->d_batch.alloc(Bm)); T(e->d_fit.alloc(Bpad * e->Wmax)); T(e->d_first.alloc(Bpad)); T(e->d_flag.alloc(1));
+    T(e->d_flag.alloc(1));
     T(e->h_order[0].alloc(N)); T(e->h_order[1].alloc(N)); T(e->d_order.alloc(N));
-    e->ev_chunk.assign(16, nullptr);
-    for (auto& ev : e->ev_chunk) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    T(e->d_dirty_nodes.alloc(Bm)); T(e->d_dirty_vals.alloc(Bm * D)); T(e->d_scores.alloc(N));
-    T(e->h_batch.alloc(Bm)); T(e->h_fit.alloc(Bm * e->Wmax)); T(e->h_first.alloc(Bm)); T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
-    T(e->h_dirty_nodes.alloc(Bm)); T(e->h_dirty_vals.alloc(Bm * D)); T(e->h_flag.alloc(1)); T(e->h_scores.alloc(N));
+    for (Slot& sl : e->slot) {
+        T(sl.d_batch.alloc(Bm)); T(sl.d_fit.alloc(Bpad * e->Wmax)); T(sl.d_first.alloc(Bpad));
+        T(sl.h_batch.alloc(Bm)); T(sl.h_fit.alloc(Bm * e->Wmax)); T(sl.h_first.alloc(Bm));
+        sl.ev.assign(16, nullptr);
+        for (auto& ev : sl.ev) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        T(cudaEventCreate(&sl.ev_s0)); T(cudaEventCreate(&sl.ev_s1));
+    }
+    e->epoch_limit = std::max<uint32_t>(2 * e->batch, 4096);
+    if (ok) { int dev = 0; cudaGetDevice(&dev); e->worker.start(dev); }
+    T(e->d_dirty_nodes.alloc(N)); T(e->d_dirty_vals.alloc(N * D)); T(e->d_scores.alloc(N));
+    T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
+    T(e->h_dirty_nodes.alloc(N)); T(e->h_dirty_vals.alloc(N * D)); T(e->h_flag.alloc(1)); T(e->h_scores.alloc(N));
     if (ok) {   // does this binary carry an image the device can run?
         cudaFuncAttributes fa;
         T(cudaFuncGetAttributes(&fa, yk_key_kernel));
@@ -882,34 +1021,72 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     e->ord.begin_cycle(pending);
     e->st.host_ms[1] += now_ms() - t_a;
 
-    std::vector<uint32_t> batch, result;
+    rc = begin_epoch(e);
+    if (rc) return rc;
+    std::vector<uint32_t> result;
     uint32_t n = 0;
     size_t bsz = e->batch;
-    while (n < max_bindings) {
+    const bool ins = e->ord.insensitive;
+    // fill + launch one batch into a slot; B == 0 afterwards means the orderer has nothing (more) to offer
+    auto next_batch = [&](Slot& sl, size_t cap_user, yk_stats_t& st) -> int {
+        sl.asks.clear(); sl.B = 0; sl.nchunks = 0;
+        if (cap_user == 0) return YK_OK;
         const double t_f = now_ms();
-        const size_t got = e->ord.fill(bsz, max_bindings - n, batch);
-        e->st.host_ms[2] += now_ms() - t_f;
+        e->ord.fill(bsz, cap_user, sl.asks, sl.snap);
+        st.host_ms[2] += now_ms() - t_f;
         if (e->ord.oversize_gang) {
-            if (bsz < e->batch) { bsz = e->batch; continue; }
-            return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
+            if (bsz < e->batch) { bsz = e->batch; e->ord.fill(bsz, cap_user, sl.asks, sl.snap); }
+            if (e->ord.oversize_gang)
+                return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
         }
-        if (got == 0) break;
-        const bool ins = e->ord.insensitive;
+        return produce(e, sl, st);
+    };
+    auto merge_worker_stats = [&]() {
+        yk_stats_t& w = e->wst;
+        e->st.h2d_bytes += w.h2d_bytes; e->st.d2h_bytes += w.d2h_bytes; e->st.batches += w.batches;
+        e->st.sweep_launches += w.sweep_launches; e->st.evaluations += w.evaluations; e->st.other_launches += w.other_launches;
+        e->st.host_ms[7] += w.host_ms[2] + w.host_ms[6];   // orderer + launch time hidden behind the commit
+        w = yk_stats_t{};
+    };
+    int cur = 0;
+    rc = next_batch(e->slot[0], max_bindings, e->st);
+    if (rc) return rc;
+    while (e->slot[cur].B > 0) {
+        Slot& A = e->slot[cur];
+        Slot& Nx = e->slot[cur ^ 1];
+        // speculate the next batch on the same epoch view unless this batch may fill the epoch
+        Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
+        const bool room = e->dirty_list.size() + (size_t)A.B < (size_t)e->epoch_limit;
+        const size_t left = (size_t)max_bindings - n;
+        bool forked = false;
+        int rc_next = YK_OK;
+        if (room && left > (size_t)A.B) {
+            const size_t cap = left - (size_t)A.B;
+            e->worker.submit([&, cap] { rc_next = next_batch(Nx, cap, e->wst); });
+            forked = true;
+        }
         size_t consumed = 0;
-        rc = run_batch(e, batch, ins, result, consumed);
+        rc = commit(e, A, ins, result, consumed);
+        if (forked) { e->worker.wait(); merge_worker_stats(); }
         if (rc) return rc;
+        if (rc_next) return rc_next;
         bool failed = false;
         if (!ins && consumed > 0 && result[consumed - 1] == YK_NONE) {
             const double t_r = now_ms();
             size_t j = consumed - 1;   // first entry of the failed ask / gang
-            while (j > 0 && e->a_gang[batch[j]] != YK_NONE && e->a_gang[batch[j - 1]] == e->a_gang[batch[j]] &&
-                   e->a_app[batch[j - 1]] == e->a_app[batch[j]] && result[j - 1] == YK_NONE) --j;
-            e->ord.rewind(batch, j);
+            while (j > 0 && e->a_gang[A.asks[j]] != YK_NONE && e->a_gang[A.asks[j - 1]] == e->a_gang[A.asks[j]] &&
+                   e->a_app[A.asks[j - 1]] == e->a_app[A.asks[j]] && result[j - 1] == YK_NONE) --j;
+            e->ord.rewind(A.snap, Nx.B > 0 ? &Nx.snap : nullptr, A.asks, j);
             e->st.host_ms[2] += now_ms() - t_r;
             failed = true;
+            if (Nx.B > 0) {   // the speculated batch was built on an order that did not happen: drop it
+                rc = drain(e, Nx);
+                if (rc) return rc;
+                Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
+            }
         }
         for (size_t i = 0; i < consumed; ++i) {
-            const uint32_t a = batch[i];
+            const uint32_t a = A.asks[i];
             if (result[i] == YK_NONE) {
                 if (ins) e->ord.fail_in_place(a);
                 e->st.nofit++;
@@ -923,7 +1100,25 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         }
         // after a failure in a placement-sensitive order, probe with short batches until placements resume
         bsz = failed ? std::max<size_t>(64, bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
+        if (Nx.B == 0 && n < max_bindings) {
+            // nothing in flight: the epoch may end here (merge order, refresh the device view) before the next batch
+            if (e->dirty_list.size() * 2 >= (size_t)e->epoch_limit || failed) {
+                rc = end_epoch(e, true);
+                if (rc) return rc;
+                rc = begin_epoch(e);
+                if (rc) return rc;
+            }
+            rc = next_batch(Nx, (size_t)max_bindings - n, e->st);
+            if (rc) return rc;
+        }
+        cur ^= 1;
     }
+    rc = end_epoch(e, false);   // leave host and device node tables current for the next call
+    if (rc) return rc;
+    for (uint32_t nn : e->dirty_list) e->is_dirty[nn] = 0;
+    e->dirty_list.clear();
+    e->dirty.clear();
+    CK(cudaStreamSynchronize(e->stream));
     e->ord.finish();
     for (uint32_t a : e->ord.slow_list) {
         if (slow && n_slow && *n_slow < slow_cap) slow[(*n_slow)++] = a;

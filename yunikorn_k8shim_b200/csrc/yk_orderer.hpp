@@ -96,6 +96,7 @@ public:
     std::vector<std::set<AppKey>> q_set;
     std::vector<std::vector<uint32_t>> q_sorted, q_changed;   // per parent: cached child order, children to re-position
     std::vector<uint8_t> q_sorted_ok;
+    std::vector<uint8_t> q_has_quota;                          // some queue on the chain root..q has a max set
     std::vector<AState> ap;
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
@@ -105,12 +106,16 @@ public:
     uint64_t slow_seen = 0;
     std::vector<uint32_t> slow_list;
 
-    // ---- snapshot for rewind ----
-    std::vector<QState> sq;
-    std::vector<AState> sap;
-    std::vector<std::set<AppKey>> sset;
-    std::vector<std::pair<uint32_t, uint8_t>> journal;   // (ask, previous state)
-    size_t slow_mark = 0;
+    // ---- snapshot for rewind: one per in-flight batch ----
+    struct Snap {
+        std::vector<QState> q;
+        std::vector<AState> ap;
+        std::vector<std::set<AppKey>> sets;
+        std::vector<std::pair<uint32_t, uint8_t>> journal;   // (ask, previous state) written while the batch was filled
+        size_t slow_mark = 0;
+        bool valid = false;
+    };
+    std::vector<std::pair<uint32_t, uint8_t>>* jr = nullptr;   // where set_state logs (the batch being filled)
 
     int D() const { return t.D; }
     static bool strictly_gt_zero(const int64_t* v, int d) {
@@ -127,9 +132,13 @@ public:
         q_apps.assign(t.nq, {});
         q_set.assign(t.nq, {});
         q_sorted.assign(t.nq, {}); q_changed.assign(t.nq, {}); q_sorted_ok.assign(t.nq, 0);
+        q_has_quota.assign(t.nq, 0);
         for (uint32_t i = 0; i < t.nq; ++i) {
             for (int k = 0; k < d; ++k) { q[i].alloc[k] = t.q_alloc[(size_t)k * t.nq + i]; q[i].pending[k] = 0; }
             if (i > 0) q_children[t.q_parent[i]].push_back(i);
+            bool own = false;
+            for (int k = 0; k < d; ++k) if (t.q_max[(size_t)k * t.nq + i] != UNSET) own = true;
+            q_has_quota[i] = own || (i > 0 && q_has_quota[t.q_parent[i]]);   // parent[i] < i: already computed
         }
         ap.assign(t.maxP, AState());
         if (ap_asks.size() < t.maxP) ap_asks.resize(t.maxP);
@@ -211,9 +220,10 @@ public:
 
     // Next asks in pass order, assuming every one is placed: at most cap_batch of them, and never past
     // cap_user bindings (max_bindings).  A gang is never split: it goes whole into this batch or the next.
-    size_t fill(size_t cap_batch, size_t cap_user, std::vector<uint32_t>& batch) {
+    size_t fill(size_t cap_batch, size_t cap_user, std::vector<uint32_t>& batch, Snap& snap) {
         oversize_gang = false;
         batch.clear();
+        snap.valid = false;
         if (insensitive) {
             while (static_next < static_order.size()) {
                 const uint32_t a = static_order[static_next];
@@ -228,24 +238,41 @@ public:
             }
             return batch.size();
         }
-        journal.clear(); slow_mark = slow_list.size();
-        sq = q; sap = ap; sset = q_set;   // rewind is only ever needed for placement-sensitive orders
+        snap.journal.clear(); snap.slow_mark = slow_list.size();
+        snap.q = q; snap.ap = ap; snap.sets = q_set; snap.valid = true;   // only placement-sensitive orders ever rewind
+        jr = &snap.journal;
         while (step(cap_batch, cap_user, batch)) {}
+        jr = nullptr;
         return batch.size();
     }
 
     // The device placed batch[0..j) and found no node for the ask (or gang) starting at batch[j]: restore the
     // state before the batch, replay the first j decisions, mark the failed ask / gang.
-    void rewind(const std::vector<uint32_t>& batch, size_t j) {
-        for (auto it = journal.rbegin(); it != journal.rend(); ++it) t.a_state[it->first] = it->second;
-        journal.clear();
-        q = sq; ap = sap; q_set = sset; slow_list.resize(slow_mark);
+    // `later` = the snapshot of a batch filled after this one (speculatively, already in flight) or null: it is undone too.
+    void rewind(Snap& snap, Snap* later, const std::vector<uint32_t>& batch, size_t j) {
+        if (later && later->valid) {
+            for (auto it = later->journal.rbegin(); it != later->journal.rend(); ++it) t.a_state[it->first] = it->second;
+            later->journal.clear();
+            later->valid = false;
+        }
+        for (auto it = snap.journal.rbegin(); it != snap.journal.rend(); ++it) t.a_state[it->first] = it->second;
+        snap.journal.clear();
+        q = snap.q; ap = snap.ap; q_set = snap.sets; slow_list.resize(snap.slow_mark);
+        snap.valid = false;
+        jr = nullptr;
         std::fill(q_sorted_ok.begin(), q_sorted_ok.end(), 0);
         for (auto& v : q_changed) v.clear();
         std::vector<uint32_t> replay;
-        while (replay.size() < j && step(j, j, replay)) {}
-        const uint32_t a = select(0);   // == batch[j] by construction
-        (void)batch;
+        while (replay.size() < j && step(j, (size_t)-1, replay)) {}
+        // passes that add nothing (a gang sunk by its queue-side checks) may sit between entry j-1 and entry j
+        uint32_t a = select(0);
+        for (int guard = 0; a != NONE && a != batch[j] && guard < (1 << 20); ++guard) {
+            const size_t before = replay.size();
+            step((size_t)-1, (size_t)-1, replay);
+            if (replay.size() != before) break;   // cannot happen: the decisions are deterministic
+            a = select(0);
+        }
+        if (a == NONE) return;
         if (t.a_gang[a] == NONE) { mark_dead(a, ST_NOFIT); return; }
         std::vector<uint32_t> mem;
         gang_members(a, mem);
@@ -302,8 +329,9 @@ private:
         std::vector<uint32_t> mem;
         gang_members(a, mem);
         if (batch.size() + mem.size() > cap_user) return false;                 // max_bindings: the cycle ends here
-        if (batch.size() + mem.size() > cap_batch) { if (batch.empty()) oversize_gang = true; return false; }
-        // host-side checks of every member, with the headroom shrinking as earlier members are counted
+        // host-side checks of every member, with the headroom shrinking as earlier members are counted.  They come
+        // BEFORE the batch-capacity test: a gang sunk here needs no room, and the decision must not depend on how the
+        // engine happens to cut its batches (rewind replays with a different capacity).
         int64_t hr[8];
         headroom(t.p_queue[t.a_app[a]], hr);
         uint8_t cause = 0;
@@ -321,12 +349,13 @@ private:
             for (uint32_t m : mem) { if (cause == ST_SLOWPATH && (t.a_flags[m] & 1u)) slow_list.push_back(m); mark_dead(m, cause); }
             return true;   // nothing added, but the pass moved on
         }
+        if (batch.size() + mem.size() > cap_batch) { if (batch.empty()) oversize_gang = true; return false; }
         for (uint32_t m : mem) { tentative(m); batch.push_back(m); }
         return true;
     }
 
     void set_state(uint32_t a, uint8_t st) {
-        journal.emplace_back(a, t.a_state[a]);
+        if (jr) jr->emplace_back(a, t.a_state[a]);
         t.a_state[a] = st;
     }
     void drop_live(uint32_t a) {
@@ -381,7 +410,12 @@ private:
             int64_t v = Q.alloc[k], g = t.q_guar[(size_t)k * t.nq + i];
             Q.shares[k] = (v == 0) ? 0.0 : (g <= 0 ? (double)v : (double)v / (double)g);
         }
-        std::sort(Q.shares, Q.shares + d);
+        for (int a = 1; a < d; ++a) {   // d <= 8: insertion sort
+            const double v = Q.shares[a];
+            int b = a;
+            for (; b > 0 && Q.shares[b - 1] > v; --b) Q.shares[b] = Q.shares[b - 1];
+            Q.shares[b] = v;
+        }
         Q.shares_ok = true;
     }
     int cmp_shares(uint32_t l, uint32_t r) {
@@ -395,6 +429,7 @@ private:
 
     void headroom(uint32_t leaf, int64_t* hr) {
         const int d = t.D;
+        if (!q_has_quota[leaf]) { for (int k = 0; k < d; ++k) hr[k] = UNSET; return; }
         uint32_t chain[64]; int n = 0;
         for (uint32_t qq = leaf; qq != NONE && n < 64; qq = t.q_parent[qq]) chain[n++] = qq;
         for (int k = 0; k < d; ++k) hr[k] = UNSET;
@@ -445,31 +480,42 @@ private:
         std::vector<uint32_t>& srt = q_sorted[qi];
         bool tie = false;
         auto less = [&](uint32_t l, uint32_t r) {
-            int c = cmp_shares(l, r);
-            if (c != 0) return c < 0;
+            const QState& L = q[l];
+            const QState& R = q[r];
+            const double a = L.shares[d - 1], b = R.shares[d - 1];   // dominant shares decide almost always
+            if (a != b) return a < b;
+            for (int k = d - 2; k >= 0; --k) if (L.shares[k] != R.shares[k]) return L.shares[k] < R.shares[k];
             tie = true;
             int64_t diff[8];
-            for (int k = 0; k < d; ++k) diff[k] = q[l].pending[k] - q[r].pending[k];
+            for (int k = 0; k < d; ++k) diff[k] = L.pending[k] - R.pending[k];
             if (strictly_gt_zero(diff, d)) return true;
             for (int k = 0; k < d; ++k) diff[k] = -diff[k];
             if (strictly_gt_zero(diff, d)) return false;
             return l < r;
         };
         bool rebuild = !q_sorted_ok[qi];
+        for (uint32_t c : q_changed[qi]) shares_of(c);
         if (!rebuild) {
             for (uint32_t c : q_changed[qi]) {   // re-position the children whose key moved since the last pass
                 auto it = std::find(srt.begin(), srt.end(), c);
                 if (it != srt.end()) srt.erase(it);
                 if (q[c].npend <= 0) continue;
-                size_t pos = 0;
-                while (pos < srt.size() && !less(c, srt[pos])) ++pos;
-                srt.insert(srt.begin() + pos, c);
+                size_t lo = 0, hi = srt.size();   // first position whose element sorts after c (binary search: the
+                while (lo < hi) {                 // others are in order; any tie met on the way forces the rebuild)
+                    const size_t mid = (lo + hi) / 2;
+                    if (less(c, srt[mid])) hi = mid; else lo = mid + 1;
+                }
+                // equal share vectors sit next to each other: the search may not have compared c with its equals
+                auto same = [&](uint32_t x) { return memcmp(q[c].shares, q[x].shares, sizeof(double) * (size_t)d) == 0; };
+                if ((lo > 0 && same(srt[lo - 1])) || (lo < srt.size() && same(srt[lo]))) tie = true;
+                srt.insert(srt.begin() + lo, c);
             }
             if (tie) rebuild = true;
         }
         if (rebuild) {
+            tie = false;
             srt.clear();
-            for (uint32_t c : q_children[qi]) if (q[c].npend > 0) srt.push_back(c);
+            for (uint32_t c : q_children[qi]) if (q[c].npend > 0) { shares_of(c); srt.push_back(c); }
             for (size_t a = 1; a < srt.size(); ++a)
                 for (size_t b = a; b > 0 && less(srt[b], srt[b - 1]); --b) std::swap(srt[b], srt[b - 1]);
             // a list built while shares tie stays "not ok" so that it is rebuilt until the tie is gone

@@ -317,3 +317,84 @@ def gangs(n_nodes=10_000, n_gangs=2000, members=10, seed=5, policy=POLICY_FAIR, 
     return _finish(f"gangs-{n_nodes}x{n_gangs}x{members}", D, policy, base.node_total, base.node_avail, base.node_taint,
                    base.node_label, base.node_id, _single_queue(D), np.ones(n_gangs, dtype=np.int32), app, req, z,
                    z.copy(), z.copy(), ask_gang=app.copy(), meta={"config": 5, "seed": seed})
+
+
+def fuzz(seed: int, n_nodes=None, n_asks=None) -> Snapshot:
+    """Small snapshot mixing every feature of the path at once (used by the randomized parity tests): random queue
+    tree with guarantees and quotas, fifo and fair leaves, priorities, gangs, taints / selectors, pod.Spec.NodeName,
+    slow-path asks, zero requests, unschedulable / reserved / over-committed nodes, either node-sort policy."""
+    r = _Rng(seed * 2654435761 + 17)
+    D = 4
+    N = int(n_nodes or (3 + r.below(1, 40)[0]))
+    n_par = int(1 + r.below(1, 3)[0])
+    n_leaf_per = int(1 + r.below(1, 3)[0])
+    L = n_par * n_leaf_per
+    Q = 1 + n_par + L
+    qp = np.empty(Q, dtype=np.int32)
+    qp[0] = -1
+    qp[1:1 + n_par] = 0
+    qp[1 + n_par:] = 1 + np.repeat(np.arange(n_par, dtype=np.int32), n_leaf_per)
+    apps_per_leaf = int(1 + r.below(1, 3)[0])
+    P = L * apps_per_leaf
+    app_queue = 1 + n_par + np.repeat(np.arange(L, dtype=np.int32), apps_per_leaf)
+    A = int(n_asks or (5 + r.below(1, 150)[0]))
+    ask_app = np.sort(r.below(A, P)).astype(np.int32)
+    cpu = (16 + r.below(N, 25)) * 1000
+    mem = (64 + r.below(N, 129)) * GI
+    tot = np.stack([cpu, mem, 8 + r.below(N, 30), np.zeros(N, dtype=np.int64)], axis=1)
+    avail = tot.copy()
+    frac = r.uniform(N) * 0.9 * (r.uniform(N) < 0.4)
+    avail[:, 0] -= (tot[:, 0] * frac).astype(np.int64) // 10 * 10
+    avail[:, 1] -= (tot[:, 1] * frac).astype(np.int64) // MI * MI
+    avail[:, 2] -= (tot[:, 2] * frac * 0.5).astype(np.int64)
+    over = r.uniform(N) < 0.05
+    avail[over, 0] = -3000                                  # over-committed: FitIn clamps at 0
+    flags = np.full(N, NODE_SCHEDULABLE, dtype=np.uint32)
+    flags[r.uniform(N) < 0.07] = 0
+    flags[r.uniform(N) < 0.05] |= NODE_RESERVED
+    ids = [f"n{int(x)}" for x in (r.below(N, 1000) * 1000 + np.arange(N))]   # unique, not in index order
+    taint = np.where(r.uniform(N) < 0.3, np.uint64(1) << r.below(N, 4).astype(np.uint64), np.uint64(0)).astype(np.uint64)
+    label = (np.uint64(1) << r.below(N, 3).astype(np.uint64)) | (np.uint64(1) << (3 + r.below(N, 2)).astype(np.uint64))
+    cls = r.below(A, 5)
+    cpus = np.array([10, 250, 1000, 4000, 0], dtype=np.int64)
+    mems = np.array([1_000_000, 256 * MI, 2 * GI, 16 * GI, 0], dtype=np.int64)
+    req = np.zeros((A, D), dtype=np.int64)
+    req[:, 0] = cpus[cls]
+    req[:, 1] = mems[cls]
+    req[:, 2] = (cls != 4).astype(np.int64)                  # class 4 = nothing requested at all: invalid
+    tol = np.where(r.uniform(A) < 0.6, np.uint64(0xF), (np.uint64(1) << r.below(A, 4).astype(np.uint64))).astype(np.uint64)
+    need = np.where(r.uniform(A) < 0.3, np.uint64(1) << r.below(A, 3).astype(np.uint64), np.uint64(0)).astype(np.uint64)
+    deny = np.where(r.uniform(A) < 0.15, np.uint64(1) << (3 + r.below(A, 2)).astype(np.uint64), np.uint64(0)).astype(np.uint64)
+    prio = (r.below(A, 3) - 1).astype(np.int32) * 10 * (r.uniform(1)[0] < 0.5)
+    ask_node = np.where(r.uniform(A) < 0.04, r.below(A, N), -1).astype(np.int32)
+    aflags = (r.uniform(A) < 0.04).astype(np.uint32)
+    gang = np.full(A, -1, dtype=np.int32)
+    if r.uniform(1)[0] < 0.6:                               # gangs: runs of 2..4 consecutive asks of one application
+        i = 0
+        g = 0
+        while i < A:
+            ln = int(2 + r.below(1, 3)[0])
+            j = i
+            while j < A and j - i < ln and ask_app[j] == ask_app[i]:
+                j += 1
+            if j - i >= 2 and r.uniform(1)[0] < 0.35:
+                gang[i:j] = g
+                g += 1
+            i = max(j, i + 1)
+    guar = np.full((Q, D), -1, dtype=np.int64)
+    mx = np.full((Q, D), -1, dtype=np.int64)
+    for q in range(1, Q):
+        if r.uniform(1)[0] < 0.7:
+            guar[q, 0] = int(1000 * (1 + r.below(1, 40)[0]))
+            guar[q, 1] = int(GI * (1 + r.below(1, 200)[0]))
+        if r.uniform(1)[0] < 0.35:
+            mx[q, 0] = int(1000 * (1 + r.below(1, 60)[0]))
+        if r.uniform(1)[0] < 0.2:
+            mx[q, 2] = int(1 + r.below(1, 40)[0])
+    qsort = np.zeros(Q, dtype=np.uint8)
+    qsort[1 + n_par:] = (r.uniform(L) < 0.3).astype(np.uint8)
+    policy = int(r.below(1, 2)[0])
+    return _finish(f"fuzz-{seed}", D, policy, tot, avail, taint, label, ids,
+                   (qp, guar, mx, np.zeros((Q, D), dtype=np.int64), qsort), app_queue, ask_app, req, tol, need, deny,
+                   ask_prio=prio, ask_node=ask_node, ask_flags=aflags, ask_gang=gang, node_flags=flags,
+                   meta={"seed": seed})
