@@ -9,7 +9,7 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
                            const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app, const uint32_t* a_flags, const uint32_t* a_gang,
                            const uint32_t* p_queue, const int64_t* p_submit, const uint32_t* q_parent,
                            const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
-                           const uint8_t* fail /*[nA] 1 = device finds no node*/, uint32_t batch,
+                           const uint8_t* fail /*[nA] 1 = device finds no node*/, uint32_t batch, int speculate,
                            uint32_t* out_order, uint32_t* n_out, uint8_t* state_out, int* insensitive_out) {
     yk::Orderer o;
     std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1);
@@ -24,9 +24,30 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
     std::vector<uint32_t> b;
     uint32_t n = 0;
     auto same_gang = [&](uint32_t x, uint32_t y) { return a_gang[x] != yk::NONE && a_gang[x] == a_gang[y] && a_app[x] == a_app[y]; };
-    yk::Orderer::Snap snap;
-    while (o.fill(batch, (size_t)-1, b, snap) > 0) {
-        // the "device": an ask fails if fail[] says so; a gang fails whole if any member does
+    // the "device + commit": an ask fails if fail[] says so; a gang fails whole if any member does.
+    // Mirrors yk_cycle's control flow: two slots, the next batch is filled (speculatively) BEFORE the current one is
+    // decided; a failure in a placement-sensitive order rewinds both and drops the speculated batch.
+    struct Slot { std::vector<uint32_t> asks; yk::Orderer::Snap snap; };
+    Slot slot[2];
+    size_t bsz = batch;
+    const bool ins = o.insensitive;
+    auto next_batch = [&](Slot& sl) -> int {
+        sl.asks.clear();
+        o.fill(bsz, (size_t)-1, sl.asks, sl.snap);
+        if (o.oversize_gang) {
+            if (bsz < batch) { bsz = batch; o.fill(bsz, (size_t)-1, sl.asks, sl.snap); }
+            if (o.oversize_gang) return -1;
+        }
+        return 0;
+    };
+    int cur = 0;
+    if (next_batch(slot[0])) return -1;
+    while (!slot[cur].asks.empty()) {
+        Slot& A = slot[cur];
+        Slot& Nx = slot[cur ^ 1];
+        Nx.asks.clear();
+        if (speculate && next_batch(Nx)) return -1;
+        const std::vector<uint32_t>& b = A.asks;
         std::vector<uint8_t> bad(b.size(), 0);
         for (size_t i = 0; i < b.size();) {
             size_t j = i + 1;
@@ -37,16 +58,24 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
             i = j;
         }
         size_t consumed = b.size(), first_bad = b.size();
-        if (!o.insensitive)
+        if (!ins)
             for (size_t i = 0; i < b.size(); ++i)
                 if (bad[i]) { first_bad = i; consumed = i + 1; while (consumed < b.size() && same_gang(b[i], b[consumed])) ++consumed; break; }
-        if (first_bad < b.size()) o.rewind(snap, nullptr, b, first_bad);
+        bool failed = false;
+        if (first_bad < b.size()) {
+            o.rewind(A.snap, Nx.asks.empty() ? nullptr : &Nx.snap, b, first_bad);
+            Nx.asks.clear();
+            failed = true;
+        }
         for (size_t i = 0; i < consumed; ++i) {
             uint32_t a = b[i];
-            if (bad[i]) { if (o.insensitive) o.fail_in_place(a); continue; }
+            if (bad[i]) { if (ins) o.fail_in_place(a); continue; }
             o.confirm(a);
             out_order[n++] = a;
         }
+        bsz = failed ? std::max<size_t>(1, bsz / 4) : std::min<size_t>(batch, bsz * 2);
+        if (Nx.asks.empty() && next_batch(Nx)) return -1;
+        cur ^= 1;
     }
     if (o.oversize_gang) return -1;
     o.finish();

@@ -25,7 +25,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def run_orderer(shim, s, fail=None, batch=256):
+def run_orderer(shim, s, fail=None, batch=256, speculate=1):
     A, P, Q, D = s.n_asks, s.n_apps, s.n_queues, s.D
     req = np.ascontiguousarray(s.ask_req.T)
     par = s.q_parent.astype(np.int64).copy()
@@ -44,7 +44,7 @@ def run_orderer(shim, s, fail=None, batch=256):
     gang = gang.astype(np.uint32)
     rc = shim.orderer_run(C.c_int(D), C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(req), _p(s.ask_prio), _p(s.ask_create),
                      _p(app), _p(flags), _p(gang), _p(queue), _p(s.app_submit), _p(par), _p(guar), _p(mx), _p(alloc), _p(s.q_sort),
-                     _p(fail), C.c_uint32(batch), _p(out), C.byref(n), _p(state), C.byref(ins))
+                     _p(fail), C.c_uint32(batch), C.c_int(speculate), _p(out), C.byref(n), _p(state), C.byref(ins))
     assert rc == 0
     return out[:n.value].copy(), state, bool(ins.value), alloc.T.copy()
 
@@ -144,8 +144,9 @@ def test_orderer_on_fuzz_snapshots(shim, oracle, batch):
             if sizes.max() > batch:
                 continue                      # gang larger than the batch: documented error path, tested elsewhere
         fail = (want["state"] == 2).astype(np.uint8)
-        got, state, ins, _ = run_orderer(shim, s, fail=fail, batch=batch)
-        assert np.array_equal(got, want["ask"]), (seed, batch)
-        assert np.array_equal(state, want["state"]), (seed, batch)
+        for spec in (0, 1):     # with and without the engine's speculative fill of the next batch
+            got, state, ins, _ = run_orderer(shim, s, fail=fail, batch=batch, speculate=spec)
+            assert np.array_equal(got, want["ask"]), (seed, batch, spec)
+            assert np.array_equal(state, want["state"]), (seed, batch, spec)
         checked += 1
     assert checked > 20

@@ -18,6 +18,7 @@
 #include <functional>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -249,6 +250,7 @@ struct yk_engine {
     int front = 0;                           // every sorted position below word `front` is dirty (per epoch)
     int epochW = 0;                          // words per fit row in the current epoch
     uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
+    bool no_spec = false;                    // debugging: never launch batch k+1 before batch k is committed
     DirtyList dirty;
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
     std::vector<int64_t> hot; int hs = 0;    // per node [avail[D], total[D], taint, label] contiguous: the commit's working copy
@@ -778,7 +780,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->cfg = *cfg;
     e->D = (int)cfg->D;
     e->maxN = cfg->max_nodes; e->maxA = cfg->max_asks; e->maxP = cfg->max_apps; e->maxQ = cfg->max_queues;
-    e->batch = cfg->batch ? cfg->batch : 2048;
+    e->batch = cfg->batch ? cfg->batch : 4096;
     for (int k = 0; k < 8; ++k) e->w.w[k] = k < e->D ? cfg->weights[k] : 0.0;
     const int D = e->D;
     const size_t N = e->maxN, A = e->maxA, Bm = e->batch;
@@ -813,6 +815,8 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
         T(cudaEventCreate(&sl.ev_s0)); T(cudaEventCreate(&sl.ev_s1));
     }
     e->epoch_limit = std::max<uint32_t>(2 * e->batch, 4096);
+    if (const char* v = getenv("YK_EPOCH_NODES")) e->epoch_limit = (uint32_t)std::max(1, atoi(v));   // tuning / debugging knob
+    e->no_spec = getenv("YK_NO_SPECULATION") != nullptr;
     if (ok) { int dev = 0; cudaGetDevice(&dev); e->worker.start(dev); }
     T(e->d_dirty_nodes.alloc(N)); T(e->d_dirty_vals.alloc(N * D)); T(e->d_scores.alloc(N));
     T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
@@ -1060,7 +1064,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         const size_t left = (size_t)max_bindings - n;
         bool forked = false;
         int rc_next = YK_OK;
-        if (room && left > (size_t)A.B) {
+        if (room && !e->no_spec && left > (size_t)A.B) {
             const size_t cap = left - (size_t)A.B;
             e->worker.submit([&, cap] { rc_next = next_batch(Nx, cap, e->wst); });
             forked = true;
@@ -1099,7 +1103,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
             e->st.allocations++;
         }
         // after a failure in a placement-sensitive order, probe with short batches until placements resume
-        bsz = failed ? std::max<size_t>(64, bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
+        bsz = failed ? std::max<size_t>(std::min<size_t>(64, e->batch), bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
         if (Nx.B == 0 && n < max_bindings) {
             // nothing in flight: the epoch may end here (merge order, refresh the device view) before the next batch
             if (e->dirty_list.size() * 2 >= (size_t)e->epoch_limit || failed) {
