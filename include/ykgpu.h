@@ -131,6 +131,9 @@ typedef struct {
     /* commit counters: 0 bitmap words scanned, 1 re-scored candidates examined, 2 asks won by a re-scored node,
        3 re-keys of an already re-scored node */
     uint64_t dbg[4];
+    /* with YK_PROFILE_COMMIT set: TSC cycles in the commit loop -- 0 clean scan, 1 re-scored walk, 2 choose + undo log
+       + erase, 3 subtract + float64 re-score, 4 re-insert + bookkeeping, 5 asks counted */
+    uint64_t prof[6];
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

@@ -24,6 +24,7 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <x86intrin.h>
 
 #include "yk_kernels.cuh"
 #include "yk_orderer.hpp"
@@ -63,6 +64,8 @@ struct Pin {
     ~Pin() { free(); }
 };
 
+inline unsigned long long yk_tsc() { unsigned aux; unsigned long long t = __rdtscp(&aux); _mm_lfence(); return t; }
+
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -70,37 +73,60 @@ double now_ms() {
 
 struct DirtyRef {
     uint64_t key; uint32_t rank; uint32_t node;
-    bool operator<(const DirtyRef& o) const {
-        if (key != o.key) return key < o.key;
-        return rank < o.rank;
-    }
+    // (key, rank) order as ONE 128-bit unsigned compare: branch-free (ranks are unique, so the node bits never decide)
+    unsigned __int128 word() const { return ((unsigned __int128)key << 64) | ((uint64_t)rank << 32) | node; }
+    bool operator<(const DirtyRef& o) const { return word() < o.word(); }
 };
+// first index in v[0,n) whose entry is not less than x -- branchless (conditional moves): the keys are effectively
+// random, so every probe of a branching binary search is a coin-flip misprediction
+inline uint32_t lower_bound_idx(const DirtyRef* v, uint32_t n, const DirtyRef& x) {
+    if (n == 0) return 0;
+    const unsigned __int128 xw = x.word();
+    const DirtyRef* base = v;
+    uint32_t len = n;
+    while (len > 1) {
+        const uint32_t half = len >> 1;
+        base += (base[half - 1].word() < xw) ? half : 0;
+        len -= half;
+    }
+    return (uint32_t)(base - v) + ((base->word() < xw) ? 1u : 0u);
+}
 
 // Sorted list of the nodes re-scored in the current batch: buckets of <= CAP entries (sqrt decomposition);
 // insert / erase are a binary search over bucket heads plus a short memmove, iteration is sequential.
 struct DirtyList {
-    static constexpr uint32_t CAP = 48;
+#ifndef YK_DIRTY_CAP
+#define YK_DIRTY_CAP 48
+#endif
+    static constexpr uint32_t CAP = YK_DIRTY_CAP;
     struct Bucket { uint32_t n; DirtyRef v[CAP]; };
     std::vector<Bucket> pool;
-    std::vector<uint32_t> seq;    // bucket ids in key order
+    std::vector<uint32_t> seq;     // bucket ids in key order
+    std::vector<DirtyRef> heads;   // heads[i] = first entry of bucket seq[i], contiguous so the locate() search stays in L1
     uint32_t used = 0, count = 0;
-    void clear() { seq.clear(); used = 0; count = 0; }
+    void clear() { seq.clear(); heads.clear(); used = 0; count = 0; }
     uint32_t fresh() {
         if (used == pool.size()) pool.emplace_back();
         pool[used].n = 0;
         return used++;
     }
-    // index in seq of the bucket that should hold x
+    // index in seq of the bucket that should hold x: last bucket whose head <= x, else 0
     uint32_t locate(const DirtyRef& x) const {
-        uint32_t lo = 0, hi = (uint32_t)seq.size();   // last bucket whose head <= x, else 0
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) / 2;
-            if (x < pool[seq[mid]].v[0]) hi = mid; else lo = mid;
+        // number of heads <= x, minus one (clamped at 0): upper bound via the lower bound of the next value
+        const uint32_t n = (uint32_t)heads.size();
+        if (n <= 1) return 0;
+        const unsigned __int128 xw = x.word();
+        const DirtyRef* base = heads.data();
+        uint32_t len = n;
+        while (len > 1) {   // branchless: last position whose head is <= x
+            const uint32_t half = len >> 1;
+            base += (base[half].word() <= xw) ? half : 0;
+            len -= half;
         }
-        return lo;
+        return (uint32_t)(base - heads.data());
     }
     void insert(const DirtyRef& x) {
-        if (seq.empty()) seq.push_back(fresh());
+        if (seq.empty()) { seq.push_back(fresh()); heads.push_back(x); }
         uint32_t si = locate(x);
         Bucket* b = &pool[seq[si]];
         if (b->n == CAP) {   // split
@@ -111,22 +137,25 @@ struct DirtyList {
             memcpy(c->v, b->v + CAP / 2, sizeof(DirtyRef) * (CAP / 2));
             b->n = CAP / 2;
             seq.insert(seq.begin() + si + 1, nb);
+            heads.insert(heads.begin() + si + 1, c->v[0]);
             if (!(x < c->v[0])) { ++si; b = c; }
         }
-        uint32_t pos = (uint32_t)(std::lower_bound(b->v, b->v + b->n, x) - b->v);
+        uint32_t pos = lower_bound_idx(b->v, b->n, x);
         memmove(b->v + pos + 1, b->v + pos, sizeof(DirtyRef) * (b->n - pos));
         b->v[pos] = x;
         b->n++;
         count++;
+        if (pos == 0) heads[si] = x;
     }
     void erase(const DirtyRef& x) {
         uint32_t si = locate(x);
         Bucket* b = &pool[seq[si]];
-        uint32_t pos = (uint32_t)(std::lower_bound(b->v, b->v + b->n, x) - b->v);
+        uint32_t pos = lower_bound_idx(b->v, b->n, x);
         memmove(b->v + pos, b->v + pos + 1, sizeof(DirtyRef) * (b->n - pos - 1));
         b->n--;
         count--;
-        if (b->n == 0) seq.erase(seq.begin() + si);
+        if (b->n == 0) { seq.erase(seq.begin() + si); heads.erase(heads.begin() + si); }
+        else if (pos == 0) heads[si] = b->v[0];
     }
 };
 
@@ -239,10 +268,7 @@ struct yk_engine {
     Pin<int> h_flag; Pin<double> h_scores;
 
     // commit scratch
-    std::vector<uint32_t> pos_of;
     std::vector<uint32_t> dirty_words;
-    std::vector<uint64_t> hkey;      // per node: current sort key (monotone bits of the float64 score)
-    std::vector<uint8_t> is_dirty;
     std::vector<uint32_t> dirty_list;
     Pin<uint32_t> h_order[2]; int cur = 0;   // node order (ascending (score, NodeID)), double-buffered
     Dev<uint32_t> d_order;
@@ -250,10 +276,11 @@ struct yk_engine {
     int front = 0;                           // every sorted position below word `front` is dirty (per epoch)
     int epochW = 0;                          // words per fit row in the current epoch
     uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
+    bool prof = false;                       // YK_PROFILE_COMMIT: TSC split of the commit loop into st.dbg2[]
     bool no_spec = false;                    // debugging: never launch batch k+1 before batch k is committed
     DirtyList dirty;
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
-    std::vector<int64_t> hot; int hs = 0;    // per node [avail[D], total[D], taint, label] contiguous: the commit's working copy
+    std::vector<int64_t> hot; int hs = 0;    // per node working record of the commit (see NodeView)
 
     yk::Orderer ord;
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
@@ -369,6 +396,20 @@ inline bool fits_now(const yk_engine* e, uint32_t node, uint32_t ask) {
     return true;
 }
 
+// The commit's per-node working record lives in one contiguous slice of e->hot (two cache lines at D = 4):
+//   [0,D) available  [D,2D) total  [2D] taint  [2D+1] label  [2D+2] current sort key  [2D+3] rank<<32 | dirty<<31 | position
+struct NodeView {
+    int64_t* h; int D;
+    uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[2 * D + 2]); }
+    uint32_t rank() const { return (uint32_t)((uint64_t)h[2 * D + 3] >> 32); }
+    uint32_t pos() const { return (uint32_t)((uint64_t)h[2 * D + 3]) & 0x7FFFFFFFu; }
+    bool dirty() const { return (((uint64_t)h[2 * D + 3]) >> 31) & 1u; }
+    void set_meta(uint32_t rank, uint32_t pos) { h[2 * D + 3] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
+    void set_pos(uint32_t pos) { h[2 * D + 3] = (int64_t)((((uint64_t)h[2 * D + 3]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
+    void set_dirty(bool d) { h[2 * D + 3] = (int64_t)((((uint64_t)h[2 * D + 3]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
+};
+inline NodeView node_view(yk_engine* e, uint32_t n) { return NodeView{e->hot.data() + (size_t)n * e->hs, e->D}; }
+
 // Initial node order of a cycle, computed on the device: float64 score per node (yk_key_kernel), stable radix
 // sort by key over NodeID-rank order = ascending (score, NodeID).  Later batches keep it current by merging.
 int initial_order(yk_engine* e) {
@@ -395,16 +436,25 @@ int initial_order(yk_engine* e) {
     e->st.sort_ms += ms;
     e->cur = 0;
     const uint32_t* ord = e->h_order[0].p;
-    e->hs = 2 * e->D + 2;
+    e->hs = 2 * e->D + 4;
     e->hot.resize((size_t)e->n_hi * e->hs);
+    // working copy of the node table, built in index order (sequential reads of the column-major host tables)
+    const int D = e->D;
+    for (int k = 0; k < D; ++k) {
+        const int64_t* av = e->n_avail.p + (size_t)k * e->maxN;
+        const int64_t* to = e->n_total.p + (size_t)k * e->maxN;
+        int64_t* h = e->hot.data();
+        for (uint32_t n = 0; n < e->n_hi; ++n) { h[(size_t)n * e->hs + k] = av[n]; h[(size_t)n * e->hs + D + k] = to[n]; }
+    }
+    for (uint32_t n = 0; n < e->n_hi; ++n) {
+        int64_t* h = e->hot.data() + (size_t)n * e->hs;
+        h[2 * D] = (int64_t)e->n_taint[n];
+        h[2 * D + 1] = (int64_t)e->n_label[n];
+    }
     for (int p = 0; p < nlive; ++p) {
         const uint32_t n = ord[p];
-        e->hkey[n] = e->h_skey[(size_t)p];
-        e->pos_of[n] = (uint32_t)p;
-        int64_t* h = e->hot.data() + (size_t)n * e->hs;
-        for (int k = 0; k < e->D; ++k) { h[k] = e->n_avail[(size_t)k * e->maxN + n]; h[e->D + k] = e->n_total[(size_t)k * e->maxN + n]; }
-        h[2 * e->D] = (int64_t)e->n_taint[n];
-        h[2 * e->D + 1] = (int64_t)e->n_label[n];
+        node_view(e, n).key() = e->h_skey[(size_t)p];
+        node_view(e, n).set_meta(e->n_rank[n], (uint32_t)p);
     }
     return YK_OK;
 }
@@ -418,7 +468,7 @@ int initial_order(yk_engine* e) {
 // epoch do not depend on each other's commits, the next batch's sweep and read-back overlap the current commit.
 int begin_epoch(yk_engine* e) {
     const int nlive = (int)e->nlive;
-    for (uint32_t n : e->dirty_list) e->is_dirty[n] = 0;
+    for (uint32_t n : e->dirty_list) node_view(e, n).set_dirty(false);
     e->dirty_list.clear();
     e->dirty.clear();
     e->front = 0;
@@ -457,7 +507,7 @@ int end_epoch(yk_engine* e, bool reorder) {
         auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
         int removed = 0;   // touched nodes passed over in the old order so far
         while (true) {
-            while (p < nlive && e->is_dirty[order[p]]) { ++p; ++removed; }
+            while (p < nlive && node_view(e, order[p]).dirty()) { ++p; ++removed; }
             if (p >= nlive) break;
             if (dirty_end() && removed == nd) {
                 // every touched node has been taken out and put back: the rest of the order is unchanged
@@ -467,13 +517,13 @@ int end_epoch(yk_engine* e, bool reorder) {
                 break;
             }
             const uint32_t n = order[p];
-            const DirtyRef c{e->hkey[n], e->n_rank[n], n};
-            while (!dirty_end() && dirty_cur() < c) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
-            e->pos_of[n] = (uint32_t)o;
+            const DirtyRef c{node_view(e, n).key(), node_view(e, n).rank(), n};
+            while (!dirty_end() && dirty_cur() < c) { node_view(e, dirty_cur().node).set_pos((uint32_t)o); out[o++] = dirty_cur().node; dirty_next(); }
+            node_view(e, n).set_pos((uint32_t)o);
             out[o++] = n;
             ++p;
         }
-        while (!dirty_end()) { e->pos_of[dirty_cur().node] = (uint32_t)o; out[o++] = dirty_cur().node; dirty_next(); }
+        while (!dirty_end()) { node_view(e, dirty_cur().node).set_pos((uint32_t)o); out[o++] = dirty_cur().node; dirty_next(); }
         e->cur ^= 1;
     }
     // staging is reused: the previous epoch's upload must have been consumed
@@ -600,6 +650,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             t_wait += now_ms() - tw;
             ++next_chunk;
         }
+        unsigned long long tc0 = e->prof ? yk_tsc() : 0;
         const uint32_t ask = batch[(size_t)i];
         const bool in_gang = e->a_gang[ask] != YK_NONE;
         if (in_gang && (i == 0 || !same_gang(i - 1, i))) { gang_begin = i; undo.clear(); }
@@ -623,8 +674,9 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         DirtyRef bound{~0ull, ~0u, YK_NONE};
         if (posA != YK_NONE) {
             const uint32_t nA = order[posA];
-            bound = DirtyRef{e->hkey[nA], e->n_rank[nA], nA};
+            bound = DirtyRef{node_view(e, nA).key(), node_view(e, nA).rank(), nA};
         }
+        unsigned long long tc1 = e->prof ? yk_tsc() : 0;
         // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the request
         // exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran over the
         // whole list without a fit leaves the bound exact (it saw every touched node), which is what keeps a full
@@ -639,8 +691,8 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
             bool whole = true;
             for (uint32_t si = 0; si < dirty.seq.size() && chosen == YK_NONE; ++si) {
+                if (!(dirty.heads[si] < bound)) { whole = false; break; }
                 const DirtyList::Bucket& bk = dirty.pool[dirty.seq[si]];
-                if (!(bk.v[0] < bound)) { whole = false; break; }
                 for (uint32_t j = 0; j < bk.n; ++j) {
                     const DirtyRef& d = bk.v[j];
                     if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); whole = false; break; }
@@ -654,6 +706,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             }
             if (whole && chosen == YK_NONE) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];
         }
+        unsigned long long tc2 = e->prof ? yk_tsc() : 0;
         if (chosen != YK_NONE) ++e->st.dbg[2];   // a re-scored node won
         if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
         consumed = (size_t)i + 1;
@@ -662,18 +715,18 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
                 // roll the gang back: undo its commits newest-first, void its results, skip its remaining members
                 for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
                     const uint32_t n = it->node;
-                    dirty.erase(DirtyRef{e->hkey[n], e->n_rank[n], n});
+                    dirty.erase(DirtyRef{node_view(e, n).key(), node_view(e, n).rank(), n});
                     int64_t* hh = e->hot.data() + (size_t)n * e->hs;
                     for (int k = 0; k < D; ++k) hh[k] = it->old_avail[k];
-                    e->hkey[n] = it->old_key;
+                    node_view(e, n).key() = it->old_key;
                     if (it->was_dirty) {
-                        dirty.insert(DirtyRef{it->old_key, e->n_rank[n], n});
+                        dirty.insert(DirtyRef{it->old_key, node_view(e, n).rank(), n});
                         for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], hh[k]);   // availability came back
                     }
                     else {
-                        e->is_dirty[n] = 0;
+                        node_view(e, n).set_dirty(false);
                         e->dirty_list.pop_back();
-                        const uint32_t pos = e->pos_of[n];
+                        const uint32_t pos = node_view(e, n).pos();
                         e->dirty_words[pos >> 5] &= ~(1u << (pos & 31));
                         front = std::min(front, (int)(pos >> 5));
                     }
@@ -692,23 +745,29 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         // commit: available -= request, re-score, move inside the dirty order
         int64_t* h = e->hot.data() + (size_t)chosen * e->hs;
         if (in_gang) {
-            Undo u; u.node = chosen; u.old_key = e->hkey[chosen]; u.was_dirty = e->is_dirty[chosen] != 0;
+            Undo u; u.node = chosen; u.old_key = node_view(e, chosen).key(); u.was_dirty = node_view(e, chosen).dirty() != 0;
             for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
             undo.push_back(u);
         }
-        if (e->is_dirty[chosen]) { dirty.erase(DirtyRef{e->hkey[chosen], e->n_rank[chosen], chosen}); ++e->st.dbg[3]; }
+        if (node_view(e, chosen).dirty()) { dirty.erase(DirtyRef{node_view(e, chosen).key(), node_view(e, chosen).rank(), chosen}); ++e->st.dbg[3]; }
+        unsigned long long tc3 = e->prof ? yk_tsc() : 0;
         for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
         const double sc = yk_node_score(D, e->cfg.policy, e->w.w, h + D, h, 1);
         const uint64_t nk = yk_key_bits(sc);
         if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
-        e->hkey[chosen] = nk;
-        dirty.insert(DirtyRef{nk, e->n_rank[chosen], chosen});
-        if (!e->is_dirty[chosen]) {
+        unsigned long long tc4 = e->prof ? yk_tsc() : 0;
+        node_view(e, chosen).key() = nk;
+        dirty.insert(DirtyRef{nk, node_view(e, chosen).rank(), chosen});
+        if (!node_view(e, chosen).dirty()) {
             for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], h[k]);
-            e->is_dirty[chosen] = 1;
+            node_view(e, chosen).set_dirty(true);
             e->dirty_list.push_back(chosen);
-            const uint32_t pos = e->pos_of[chosen];
+            const uint32_t pos = node_view(e, chosen).pos();
             e->dirty_words[pos >> 5] |= 1u << (pos & 31);
+        }
+        if (e->prof) {
+            const unsigned long long tc5 = yk_tsc();
+            e->st.prof[0] += tc1 - tc0; e->st.prof[1] += tc2 - tc1; e->st.prof[2] += tc3 - tc2; e->st.prof[3] += tc4 - tc3; e->st.prof[4] += tc5 - tc4; e->st.prof[5] += 1;
         }
     }
     // all read-back must have landed before the slot's buffers are reused
@@ -817,6 +876,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->epoch_limit = std::max<uint32_t>(2 * e->batch, 4096);
     if (const char* v = getenv("YK_EPOCH_NODES")) e->epoch_limit = (uint32_t)std::max(1, atoi(v));   // tuning / debugging knob
     e->no_spec = getenv("YK_NO_SPECULATION") != nullptr;
+    e->prof = getenv("YK_PROFILE_COMMIT") != nullptr;
     if (ok) { int dev = 0; cudaGetDevice(&dev); e->worker.start(dev); }
     T(e->d_dirty_nodes.alloc(N)); T(e->d_dirty_vals.alloc(N * D)); T(e->d_scores.alloc(N));
     T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
@@ -837,7 +897,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->p_alloc.assign((size_t)e->maxP * D, 0);
     // default queue tree: root only would have no leaf for apps; root + one leaf "root.default"
     e->nq = 0;
-    e->pos_of.assign(N, 0); e->hkey.assign(N, 0); e->is_dirty.assign(N, 0);
+    
     *out = e;
     return YK_OK;
 }
@@ -1119,7 +1179,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     }
     rc = end_epoch(e, false);   // leave host and device node tables current for the next call
     if (rc) return rc;
-    for (uint32_t nn : e->dirty_list) e->is_dirty[nn] = 0;
+    for (uint32_t nn : e->dirty_list) node_view(e, nn).set_dirty(false);
     e->dirty_list.clear();
     e->dirty.clear();
     CK(cudaStreamSynchronize(e->stream));

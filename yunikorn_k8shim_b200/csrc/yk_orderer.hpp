@@ -157,19 +157,22 @@ public:
             };
             if (!std::is_sorted(v.begin(), v.end(), less)) std::sort(v.begin(), v.end(), less);
             AState& A = ap[p];
+            int64_t psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int64_t nlive = 0;
             for (uint32_t i = 0; i < v.size(); ++i) {
                 uint32_t a = v[i];
                 a_pos[a] = i;
                 if (!have_prio) { prio0 = t.a_prio[a]; have_prio = true; }
                 else if (t.a_prio[a] != prio0) one_prio = false;
-                A.npend++;
-                const bool dead = t.a_state[a] != ST_PENDING;   // INVALID asks are marked by the engine at upsert
-                if (!dead) A.live++;
-                for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
-                    q[qq].npend++;
-                    if (!dead) q[qq].live++;
-                    for (int k = 0; k < d; ++k) q[qq].pending[k] += req(a, k);
-                }
+                if (t.a_state[a] == ST_PENDING) ++nlive;
+                for (int k = 0; k < d; ++k) psum[k] += req(a, k);
+            }
+            A.npend = (int64_t)v.size();
+            A.live = nlive;
+            for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {   // once per application, not per ask
+                q[qq].npend += (int64_t)v.size();
+                q[qq].live += nlive;
+                for (int k = 0; k < d; ++k) q[qq].pending[k] += psum[k];
             }
             q_apps[t.p_queue[p]].push_back(p);
             A.key_prio = t.a_prio[v[0]];

@@ -38,12 +38,13 @@ class Stats(C.Structure):
                 ("other_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("sweep_ms", C.c_double), ("sort_ms", C.c_double), ("commit_ms", C.c_double), ("total_ms", C.c_double),
                 ("last_sweep_ms", C.c_double), ("last_sweep_pairs", C.c_uint64),
-                ("host_ms", C.c_double * 8), ("dbg", C.c_uint64 * 4)]
+                ("host_ms", C.c_double * 8), ("dbg", C.c_uint64 * 4), ("prof", C.c_uint64 * 6)]
 
     def as_dict(self):
         d = {f: getattr(self, f) for f, _ in self._fields_}
         d["host_ms"] = list(d["host_ms"])
         d["dbg"] = list(d["dbg"])
+        d["prof"] = list(d["prof"])
         return d
 
 
