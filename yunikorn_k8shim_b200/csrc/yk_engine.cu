@@ -206,8 +206,8 @@ struct Worker {
 struct Slot {
     std::vector<uint32_t> asks;
     yk::Orderer::Snap snap;
-    Dev<uint32_t> d_batch, d_fit, d_first;
-    Pin<uint32_t> h_batch, h_fit, h_first;
+    Dev<uint32_t> d_batch, d_fit;
+    Pin<uint32_t> h_batch, h_fit;
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
     int B = 0, W = 0, chunk = 0, nchunks = 0, rows = 0;
@@ -560,7 +560,7 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     sl.B = B; sl.W = e->epochW; sl.rows = 0; sl.nchunks = 0;
     if (B == 0 || nlive == 0) return YK_OK;
     const double t0 = now_ms();
-    const int W = e->epochW, Np = W * 32;
+    const int W = e->epochW, Np = W * 32, WS = W + 1;
     cudaStream_t s = e->stream;
     memcpy(sl.h_batch.p, sl.asks.data(), sizeof(uint32_t) * (size_t)B);
     CK(cudaMemcpyAsync(sl.d_batch.p, sl.h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
@@ -572,14 +572,15 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     const int rows = std::min(B, row0 + rows_per) - row0;
     const int Bpad = rows_per * world;
     sl.rows = rows;
-    CK(cudaMemsetAsync(sl.d_first.p, 0xFF, sizeof(uint32_t) * (size_t)Bpad, s));
+    // the last word of every row (first-fit position) starts at YK_NONE
+    CK(cudaMemset2DAsync(sl.d_fit.p + W, sizeof(uint32_t) * (size_t)WS, 0xFF, sizeof(uint32_t), (size_t)Bpad, s));
     CK(cudaEventRecord(sl.ev_s0, s));
     if (rows > 0) {
         YkSweepArgs a{};
         a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
         a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
         a.lda = e->maxA; a.batch = sl.d_batch.p; a.row0 = row0; a.rows = rows;
-        a.fit = sl.d_fit.p; a.first = sl.d_first.p; a.W = W;
+        a.fit = sl.d_fit.p; a.W = W; a.WS = WS;
         launch_sweep(D, a, s, e->slots);
         st.sweep_launches += 1;
         st.evaluations += (uint64_t)rows * (uint64_t)nlive;
@@ -588,20 +589,18 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     CK(cudaGetLastError());
     if (world > 1) {
         if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but no exchange function set (yk_set_exchange)");
-        if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)W * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0 ||
-            e->xfn(e->xctx, sl.d_first.p, 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
+        if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)WS * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
             return e->fail(YK_ERR_COMM, "exchange callback failed");
     }
     // read-back in row chunks so the ordered commit overlaps the transfer
     sl.chunk = std::max(128, (B + (int)sl.ev.size() - 1) / (int)sl.ev.size());
     sl.nchunks = (B + sl.chunk - 1) / sl.chunk;
-    CK(cudaMemcpyAsync(sl.h_first.p, sl.d_first.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, s));
     for (int c = 0; c < sl.nchunks; ++c) {
         const size_t r0 = (size_t)c * sl.chunk, r1 = std::min<size_t>((size_t)B, r0 + sl.chunk);
-        CK(cudaMemcpyAsync(sl.h_fit.p + r0 * W, sl.d_fit.p + r0 * W, sizeof(uint32_t) * (r1 - r0) * W, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(sl.h_fit.p + r0 * WS, sl.d_fit.p + r0 * WS, sizeof(uint32_t) * (r1 - r0) * WS, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(sl.ev[(size_t)c], s));
     }
-    st.d2h_bytes += sizeof(uint32_t) * (size_t)B * W + 4 * (size_t)B;
+    st.d2h_bytes += sizeof(uint32_t) * (size_t)B * WS;
     st.batches++;
     st.host_ms[6] += now_ms() - t0;
     return YK_OK;
@@ -627,7 +626,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             while (consumed < (size_t)B && e->a_gang[batch[consumed]] == e->a_gang[batch[0]] && e->a_app[batch[consumed]] == e->a_app[batch[0]]) ++consumed;
         return YK_OK;
     }
-    const int W = sl.W;
+    const int W = sl.W, WS = W + 1;
     const uint32_t* order = e->h_order[e->cur].p;
     DirtyList& dirty = e->dirty;
     int& front = e->front;
@@ -654,15 +653,17 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         const uint32_t ask = batch[(size_t)i];
         const bool in_gang = e->a_gang[ask] != YK_NONE;
         if (in_gang && (i == 0 || !same_gang(i - 1, i))) { gang_begin = i; undo.clear(); }
-        const uint32_t* row = fit + (size_t)i * W;
-        if (i + 12 < B) {   // rows arrive by DMA and are cache-cold: pull the line the scan will start at
-            const uint32_t* nrow = fit + (size_t)(i + 12) * W;
-            const uint32_t nf = sl.h_first[(size_t)(i + 12)];
-            __builtin_prefetch(nrow + std::max<int>(front, nf == YK_NONE ? 0 : (int)(nf >> 5)));
+        const uint32_t* row = fit + (size_t)i * WS;
+        if (i + 12 < std::min(B, next_chunk * sl.chunk)) {   // rows arrive by DMA and are cache-cold: pull the line the
+            const uint32_t* nrow = fit + (size_t)(i + 12) * WS;   // scan will start at (only rows that have landed)
+            __builtin_prefetch(nrow + W);                        // its first-fit word now ...
+            const uint32_t* mrow = fit + (size_t)(i + 6) * WS;   // ... and, for a row whose first-fit word was pulled
+            const uint32_t nf = mrow[W];                         // six asks ago, the line the scan will start at
+            __builtin_prefetch(mrow + std::max<int>(front, nf == YK_NONE ? 0 : (int)(nf >> 5)));
         }
         // (A) best untouched node: first set bit of row & ~dirty in sorted order
         uint32_t posA = YK_NONE;
-        const uint32_t f = sl.h_first[(size_t)i];
+        const uint32_t f = row[W];
         if (f != YK_NONE) {
             while (front < W && e->dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
             for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
@@ -867,8 +868,8 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->d_flag.alloc(1));
     T(e->h_order[0].alloc(N)); T(e->h_order[1].alloc(N)); T(e->d_order.alloc(N));
     for (Slot& sl : e->slot) {
-        T(sl.d_batch.alloc(Bm)); T(sl.d_fit.alloc(Bpad * e->Wmax)); T(sl.d_first.alloc(Bpad));
-        T(sl.h_batch.alloc(Bm)); T(sl.h_fit.alloc(Bm * e->Wmax)); T(sl.h_first.alloc(Bm));
+        T(sl.d_batch.alloc(Bm)); T(sl.d_fit.alloc(Bpad * (e->Wmax + 1)));
+        T(sl.h_batch.alloc(Bm)); T(sl.h_fit.alloc(Bm * (e->Wmax + 1)));
         sl.ev.assign(16, nullptr);
         for (auto& ev : sl.ev) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         T(cudaEventCreate(&sl.ev_s0)); T(cudaEventCreate(&sl.ev_s1));

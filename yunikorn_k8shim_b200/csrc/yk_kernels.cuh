@@ -6,8 +6,8 @@
 //   ask table  (ask-index space, resident):   req[D][lda] i64, tol/need/deny[lda] u64, node[lda] u32
 //   sorted view (rebuilt per batch):          cap[D][Np] i64, taint/label[Np] u64, node[Np] u32, key[Np] u64
 //                                             position p = p-th node in ascending (score, NodeID) order
-//   outputs per batch:                        fit[B][W] u32 bitmap (bit p of row i = ask i fits sorted node p),
-//                                             first[B] u32 = lowest set position = the frozen-snapshot argmin
+//   outputs per batch:                        fit[B][W+1] u32: W bitmap words (bit p of row i = ask i fits sorted node p)
+//                                             + 1 word = lowest set position = the frozen-snapshot argmin
 //
 // The sweep is integer compare + reduce: no tensor cores (not a contraction).  The node tile lives in
 // registers and is reused across the whole ask chunk; the ask chunk is staged once in shared memory and
@@ -99,9 +99,9 @@ struct YkSweepArgs {
     int row0, rows;           // this launch handles batch rows [row0, row0+rows)
     int per;                  // rows per CTA along grid.y (multiple of 32)
     // outputs
-    uint32_t* fit;            // [B][W]
-    uint32_t* first;          // [B], pre-set to YK_NONE_U32
-    int W;                    // words per row = Np/32
+    uint32_t* fit;            // [B][WS]: W bitmap words, then word W = first fit position (pre-set to YK_NONE_U32)
+    int W;                    // bitmap words per row = Np/32
+    int WS;                   // row stride in words (W + 1): one row = one exchange / read-back unit
 };
 
 // One (ask, 32 x NPT nodes) step.  MASKS / WANT are warp-uniform properties of the ask (staged in shared
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
             // lane l picks up the NPT bitmap words of ask (ab + l) for this warp's positions
             const int i = ab + lane;
             if (i < na) {
-                uint32_t* row = p.fit + (size_t)(a0 + i) * p.W;
+                uint32_t* row = p.fit + (size_t)(a0 + i) * p.WS;
                 uint32_t best = YK_NONE_U32;
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
         }
         __syncthreads();
         for (int i = tid; i < na; i += YK_SWEEP_THREADS)
-            if (sh_first[i] != YK_NONE_U32) atomicMin(&p.first[a0 + i], sh_first[i]);
+            if (sh_first[i] != YK_NONE_U32) atomicMin(&p.fit[(size_t)(a0 + i) * p.WS + p.W], sh_first[i]);
     }
 }
 
