@@ -150,3 +150,14 @@ def test_orderer_on_fuzz_snapshots(shim, oracle, batch):
             assert np.array_equal(state, want["state"]), (seed, batch, spec)
         checked += 1
     assert checked > 20
+
+
+def test_dirty_index_model_check(tmp_path):
+    """csrc/yk_dirty.hpp (the commit's ordered set of re-scored nodes) against std::set under random
+    insert / erase / walk / erase-at-cursor sequences, including duplicate keys and range splits."""
+    out = str(tmp_path / "dirty_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, os.path.join(HERE, "host", "dirty_shim.cpp")])
+    lib = C.CDLL(out)
+    for seed in range(120):
+        for nk, ops, kr in ((1, 200, 5), (10, 500, 3), (1000, 3000, 50), (5000, 12000, 100000), (64, 1000, 2)):
+            assert lib.dirty_model_check(C.c_uint64(seed), nk, ops, kr) == 0, (seed, nk, ops, kr)

@@ -27,6 +27,7 @@
 #include <x86intrin.h>
 
 #include "yk_kernels.cuh"
+#include "yk_dirty.hpp"
 #include "yk_orderer.hpp"
 
 namespace {
@@ -71,93 +72,8 @@ double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-struct DirtyRef {
-    uint64_t key; uint32_t rank; uint32_t node;
-    // (key, rank) order as ONE 128-bit unsigned compare: branch-free (ranks are unique, so the node bits never decide)
-    unsigned __int128 word() const { return ((unsigned __int128)key << 64) | ((uint64_t)rank << 32) | node; }
-    bool operator<(const DirtyRef& o) const { return word() < o.word(); }
-};
-// first index in v[0,n) whose entry is not less than x -- branchless (conditional moves): the keys are effectively
-// random, so every probe of a branching binary search is a coin-flip misprediction
-inline uint32_t lower_bound_idx(const DirtyRef* v, uint32_t n, const DirtyRef& x) {
-    if (n == 0) return 0;
-    const unsigned __int128 xw = x.word();
-    const DirtyRef* base = v;
-    uint32_t len = n;
-    while (len > 1) {
-        const uint32_t half = len >> 1;
-        base += (base[half - 1].word() < xw) ? half : 0;
-        len -= half;
-    }
-    return (uint32_t)(base - v) + ((base->word() < xw) ? 1u : 0u);
-}
-
-// Sorted list of the nodes re-scored in the current batch: buckets of <= CAP entries (sqrt decomposition);
-// insert / erase are a binary search over bucket heads plus a short memmove, iteration is sequential.
-struct DirtyList {
-#ifndef YK_DIRTY_CAP
-#define YK_DIRTY_CAP 48
-#endif
-    static constexpr uint32_t CAP = YK_DIRTY_CAP;
-    struct Bucket { uint32_t n; DirtyRef v[CAP]; };
-    std::vector<Bucket> pool;
-    std::vector<uint32_t> seq;     // bucket ids in key order
-    std::vector<DirtyRef> heads;   // heads[i] = first entry of bucket seq[i], contiguous so the locate() search stays in L1
-    uint32_t used = 0, count = 0;
-    void clear() { seq.clear(); heads.clear(); used = 0; count = 0; }
-    uint32_t fresh() {
-        if (used == pool.size()) pool.emplace_back();
-        pool[used].n = 0;
-        return used++;
-    }
-    // index in seq of the bucket that should hold x: last bucket whose head <= x, else 0
-    uint32_t locate(const DirtyRef& x) const {
-        // number of heads <= x, minus one (clamped at 0): upper bound via the lower bound of the next value
-        const uint32_t n = (uint32_t)heads.size();
-        if (n <= 1) return 0;
-        const unsigned __int128 xw = x.word();
-        const DirtyRef* base = heads.data();
-        uint32_t len = n;
-        while (len > 1) {   // branchless: last position whose head is <= x
-            const uint32_t half = len >> 1;
-            base += (base[half].word() <= xw) ? half : 0;
-            len -= half;
-        }
-        return (uint32_t)(base - heads.data());
-    }
-    void insert(const DirtyRef& x) {
-        if (seq.empty()) { seq.push_back(fresh()); heads.push_back(x); }
-        uint32_t si = locate(x);
-        Bucket* b = &pool[seq[si]];
-        if (b->n == CAP) {   // split
-            uint32_t nb = fresh();
-            b = &pool[seq[si]];
-            Bucket* c = &pool[nb];
-            c->n = CAP / 2;
-            memcpy(c->v, b->v + CAP / 2, sizeof(DirtyRef) * (CAP / 2));
-            b->n = CAP / 2;
-            seq.insert(seq.begin() + si + 1, nb);
-            heads.insert(heads.begin() + si + 1, c->v[0]);
-            if (!(x < c->v[0])) { ++si; b = c; }
-        }
-        uint32_t pos = lower_bound_idx(b->v, b->n, x);
-        memmove(b->v + pos + 1, b->v + pos, sizeof(DirtyRef) * (b->n - pos));
-        b->v[pos] = x;
-        b->n++;
-        count++;
-        if (pos == 0) heads[si] = x;
-    }
-    void erase(const DirtyRef& x) {
-        uint32_t si = locate(x);
-        Bucket* b = &pool[seq[si]];
-        uint32_t pos = lower_bound_idx(b->v, b->n, x);
-        memmove(b->v + pos, b->v + pos + 1, sizeof(DirtyRef) * (b->n - pos - 1));
-        b->n--;
-        count--;
-        if (b->n == 0) { seq.erase(seq.begin() + si); heads.erase(heads.begin() + si); }
-        else if (pos == 0) heads[si] = b->v[0];
-    }
-};
+using yk::DirtyRef;
+using yk::DirtyIndex;
 
 // A helper thread that fills and launches the NEXT batch while the caller's thread commits the current one
 // (the orderer state is only touched by one of the two at a time: fork before the commit, join after it).
@@ -278,7 +194,8 @@ struct yk_engine {
     uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
     bool prof = false;                       // YK_PROFILE_COMMIT: TSC split of the commit loop into st.dbg2[]
     bool no_spec = false;                    // debugging: never launch batch k+1 before batch k is committed
-    DirtyList dirty;
+    DirtyIndex dirty;
+    std::vector<DirtyRef> dirty_sorted;      // scratch: the touched nodes in order, for the epoch-end merge
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
     std::vector<int64_t> hot; int hs = 0;    // per node working record of the commit (see NodeView)
 
@@ -496,20 +413,20 @@ int end_epoch(yk_engine* e, bool reorder) {
     if (!nd) return YK_OK;
     const double t0 = now_ms();
     cudaStream_t s = e->stream;
-    DirtyList& dirty = e->dirty;
+    DirtyIndex& dirty = e->dirty;
     if (reorder) {
         const uint32_t* order = e->h_order[e->cur].p;
         uint32_t* out = e->h_order[e->cur ^ 1].p;
         int o = 0, p = 0;
-        uint32_t si = 0, j = 0;
-        auto dirty_end = [&]() { return si >= dirty.seq.size(); };
-        auto dirty_cur = [&]() -> const DirtyRef& { return dirty.pool[dirty.seq[si]].v[j]; };
-        auto dirty_next = [&]() { if (++j >= dirty.pool[dirty.seq[si]].n) { ++si; j = 0; } };
+        std::vector<DirtyRef>& ds = e->dirty_sorted;
+        ds.clear();
+        dirty.for_each([&](const DirtyRef& r) { ds.push_back(r); });
+        size_t j = 0;
         int removed = 0;   // touched nodes passed over in the old order so far
         while (true) {
             while (p < nlive && node_view(e, order[p]).dirty()) { ++p; ++removed; }
             if (p >= nlive) break;
-            if (dirty_end() && removed == nd) {
+            if (j >= ds.size() && removed == nd) {
                 // every touched node has been taken out and put back: the rest of the order is unchanged
                 memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
                 o += nlive - p;
@@ -517,13 +434,13 @@ int end_epoch(yk_engine* e, bool reorder) {
                 break;
             }
             const uint32_t n = order[p];
-            const DirtyRef c{node_view(e, n).key(), node_view(e, n).rank(), n};
-            while (!dirty_end() && dirty_cur() < c) { node_view(e, dirty_cur().node).set_pos((uint32_t)o); out[o++] = dirty_cur().node; dirty_next(); }
+            const DirtyRef c(node_view(e, n).key(), node_view(e, n).rank(), n);
+            while (j < ds.size() && ds[j] < c) { node_view(e, ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
             node_view(e, n).set_pos((uint32_t)o);
             out[o++] = n;
             ++p;
         }
-        while (!dirty_end()) { node_view(e, dirty_cur().node).set_pos((uint32_t)o); out[o++] = dirty_cur().node; dirty_next(); }
+        while (j < ds.size()) { node_view(e, ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
         e->cur ^= 1;
     }
     // staging is reused: the previous epoch's upload must have been consumed
@@ -628,7 +545,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
     }
     const int W = sl.W, WS = W + 1;
     const uint32_t* order = e->h_order[e->cur].p;
-    DirtyList& dirty = e->dirty;
+    DirtyIndex& dirty = e->dirty;
     int& front = e->front;
     const uint32_t* fit = sl.h_fit.p;
     double t_wait = 0, t1 = now_ms();
@@ -672,10 +589,10 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
                 if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
             }
         }
-        DirtyRef bound{~0ull, ~0u, YK_NONE};
+        DirtyRef bound(~0ull, ~0u, YK_NONE);
         if (posA != YK_NONE) {
             const uint32_t nA = order[posA];
-            bound = DirtyRef{node_view(e, nA).key(), node_view(e, nA).rank(), nA};
+            bound = DirtyRef(node_view(e, nA).key(), node_view(e, nA).rank(), nA);
         }
         unsigned long long tc1 = e->prof ? yk_tsc() : 0;
         // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the request
@@ -683,45 +600,41 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         // whole list without a fit leaves the bound exact (it saw every touched node), which is what keeps a full
         // cluster cheap: the first failing ask pays for the walk, the following ones are pruned.
         uint32_t chosen = YK_NONE;
-        bool may_fit = f != YK_NONE && dirty.count > 0;
+        DirtyIndex::Cursor cur;
+        bool at_cursor = false;   // `chosen` is the entry the cursor stands on (it can be taken out without a search)
+        bool may_fit = f != YK_NONE && dirty.size() > 0;
         if (may_fit)
             for (int k = 0; k < D; ++k)
                 if (e->a_req[(size_t)k * e->maxA + ask] > std::max<int64_t>(e->dirty_ub[k], 0)) { may_fit = false; break; }
         if (may_fit) {
             int64_t seen[YK_MAX_D];
             for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
-            bool whole = true;
-            for (uint32_t si = 0; si < dirty.seq.size() && chosen == YK_NONE; ++si) {
-                if (!(dirty.heads[si] < bound)) { whole = false; break; }
-                const DirtyList::Bucket& bk = dirty.pool[dirty.seq[si]];
-                for (uint32_t j = 0; j < bk.n; ++j) {
-                    const DirtyRef& d = bk.v[j];
-                    if (!(d < bound)) { si = (uint32_t)dirty.seq.size(); whole = false; break; }
-                    ++e->st.dbg[1];
-                    // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
-                    // lines were just DMA-written and are cold
-                    if (fits_now(e, d.node, ask)) { chosen = d.node; whole = false; break; }
-                    const int64_t* hh = e->hot.data() + (size_t)d.node * e->hs;
-                    for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
-                }
+            const DirtyRef* d = dirty.first(cur);
+            for (; d && *d < bound; d = dirty.next(cur)) {
+                ++e->st.dbg[1];
+                // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
+                // lines were just DMA-written and are cold
+                if (fits_now(e, d->node(), ask)) { chosen = d->node(); at_cursor = true; break; }
+                const int64_t* hh = e->hot.data() + (size_t)d->node() * e->hs;
+                for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
             }
-            if (whole && chosen == YK_NONE) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];
+            if (d == nullptr) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];   // saw every touched node: exact
         }
         unsigned long long tc2 = e->prof ? yk_tsc() : 0;
         if (chosen != YK_NONE) ++e->st.dbg[2];   // a re-scored node won
-        if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node;
+        if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node();
         consumed = (size_t)i + 1;
         if (chosen == YK_NONE) {
             if (in_gang) {
                 // roll the gang back: undo its commits newest-first, void its results, skip its remaining members
                 for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
                     const uint32_t n = it->node;
-                    dirty.erase(DirtyRef{node_view(e, n).key(), node_view(e, n).rank(), n});
+                    dirty.erase(DirtyRef(node_view(e, n).key(), node_view(e, n).rank(), n));
                     int64_t* hh = e->hot.data() + (size_t)n * e->hs;
                     for (int k = 0; k < D; ++k) hh[k] = it->old_avail[k];
                     node_view(e, n).key() = it->old_key;
                     if (it->was_dirty) {
-                        dirty.insert(DirtyRef{it->old_key, node_view(e, n).rank(), n});
+                        dirty.insert(DirtyRef(it->old_key, node_view(e, n).rank(), n));
                         for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], hh[k]);   // availability came back
                     }
                     else {
@@ -750,7 +663,11 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
             undo.push_back(u);
         }
-        if (node_view(e, chosen).dirty()) { dirty.erase(DirtyRef{node_view(e, chosen).key(), node_view(e, chosen).rank(), chosen}); ++e->st.dbg[3]; }
+        if (node_view(e, chosen).dirty()) {
+            if (at_cursor) dirty.erase_at(cur);
+            else dirty.erase(DirtyRef(node_view(e, chosen).key(), node_view(e, chosen).rank(), chosen));
+            ++e->st.dbg[3];
+        }
         unsigned long long tc3 = e->prof ? yk_tsc() : 0;
         for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
         const double sc = yk_node_score(D, e->cfg.policy, e->w.w, h + D, h, 1);
@@ -758,7 +675,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
         unsigned long long tc4 = e->prof ? yk_tsc() : 0;
         node_view(e, chosen).key() = nk;
-        dirty.insert(DirtyRef{nk, node_view(e, chosen).rank(), chosen});
+        dirty.insert(DirtyRef(nk, node_view(e, chosen).rank(), chosen));
         if (!node_view(e, chosen).dirty()) {
             for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], h[k]);
             node_view(e, chosen).set_dirty(true);
