@@ -175,6 +175,7 @@ struct yk_engine {
     Dev<int> d_flag;
     Slot slot[2];
     Worker worker;
+    std::vector<uint32_t> pending;           // asks of the current cycle
     yk_stats_t wst{};                        // counters written by the worker thread, merged at join
     Dev<uint32_t> d_dirty_nodes; Dev<int64_t> d_dirty_vals; Dev<double> d_scores;
     size_t Wmax = 0;
@@ -192,6 +193,7 @@ struct yk_engine {
     int front = 0;                           // every sorted position below word `front` is dirty (per epoch)
     int epochW = 0;                          // words per fit row in the current epoch
     uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
+    uint32_t epoch_floor = 8192, epoch_env = 0;
     bool prof = false;                       // YK_PROFILE_COMMIT: TSC split of the commit loop into st.dbg2[]
     bool no_spec = false;                    // debugging: never launch batch k+1 before batch k is committed
     DirtyIndex dirty;
@@ -791,8 +793,8 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
         for (auto& ev : sl.ev) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         T(cudaEventCreate(&sl.ev_s0)); T(cudaEventCreate(&sl.ev_s1));
     }
-    e->epoch_limit = std::max<uint32_t>(2 * e->batch, 4096);
-    if (const char* v = getenv("YK_EPOCH_NODES")) e->epoch_limit = (uint32_t)std::max(1, atoi(v));   // tuning / debugging knob
+    e->epoch_floor = std::max<uint32_t>(2 * e->batch, 4096);
+    if (const char* v = getenv("YK_EPOCH_NODES")) e->epoch_env = (uint32_t)std::max(1, atoi(v));   // tuning / debugging knob
     e->no_spec = getenv("YK_NO_SPECULATION") != nullptr;
     e->prof = getenv("YK_PROFILE_COMMIT") != nullptr;
     if (ok) { int dev = 0; cudaGetDevice(&dev); e->worker.start(dev); }
@@ -977,32 +979,41 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     if (n_slow) *n_slow = 0;
     if (e->nq == 0) return e->fail(YK_ERR_STATE, "yk_cycle: no queues configured (yk_queues_set)");
     const double t_start = now_ms();
+    // the orderer's per-cycle setup (host only) runs on the helper thread while this thread uploads stale tables and
+    // gets the initial node order from the device
+    std::vector<uint32_t>& pending = e->pending;
+    double begin_ms = 0;
+    e->worker.submit([&] {
+        const double t_b = now_ms();
+        pending.clear();
+        pending.reserve(e->a_hi);
+        for (uint32_t a = 0; a < e->a_hi; ++a) {
+            uint8_t& st = e->a_state[a];
+            if (st == yk::ST_ABSENT || st == yk::ST_ALLOCATED) continue;
+            st = yk::ST_PENDING;   // failed / skipped asks are tried again every cycle, like the reference
+            if (!e->p_present[e->a_app[a]]) continue;
+            pending.push_back(a);
+        }
+        yk::Tables& t = e->ord.t;
+        t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
+        t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
+        t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
+        t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
+        t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
+        t.q_sort = e->q_sort.data();
+        e->ord.begin_cycle(pending);
+        begin_ms = now_ms() - t_b;
+    });
     int rc = upload_tables(e);
-    if (rc) return rc;
-    rc = initial_order(e);
-    if (rc) return rc;
-    double t_a = now_ms();
+    if (!rc) rc = initial_order(e);
+    const double t_a = now_ms();
+    e->worker.wait();
     e->st.host_ms[0] += t_a - t_start;
-
-    std::vector<uint32_t> pending;
-    pending.reserve(e->a_hi);
-    for (uint32_t a = 0; a < e->a_hi; ++a) {
-        uint8_t& s = e->a_state[a];
-        if (s == yk::ST_ABSENT || s == yk::ST_ALLOCATED) continue;
-        s = yk::ST_PENDING;   // failed / skipped asks are tried again every cycle, like the reference
-        if (!e->p_present[e->a_app[a]]) continue;
-        pending.push_back(a);
-    }
-    yk::Tables& t = e->ord.t;
-    t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
-    t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
-    t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
-    t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
-    t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
-    t.q_sort = e->q_sort.data();
-    e->ord.begin_cycle(pending);
-    e->st.host_ms[1] += now_ms() - t_a;
-
+    e->st.host_ms[1] += begin_ms;
+    if (rc) return rc;
+    // epoch length: long enough that order merges / view refreshes (and the pipeline bubble they cost) stay rare on big
+    // clusters, short enough that the touched set does not slow the walk: 5/8 of the nodes, at least two batches
+    e->epoch_limit = e->epoch_env ? e->epoch_env : std::max<uint32_t>(e->epoch_floor, (uint32_t)((uint64_t)e->nlive * 5 / 8));
     rc = begin_epoch(e);
     if (rc) return rc;
     std::vector<uint32_t> result;
