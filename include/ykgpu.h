@@ -104,15 +104,11 @@ typedef struct {
     double weights[YK_MAX_D];    /* node-sort resource weights; core default vcore=1, memory=1 */
     uint32_t max_nodes, max_asks, max_apps, max_queues;
     int32_t device;              /* CUDA ordinal, -1 = current device */
-    uint32_t commit_mode;        /* 0 = default; see YK_COMMIT_* */
+    uint32_t reserved0;          /* must be 0 */
     /* multi-GPU (one process per GPU): asks of every batch are split in `world` contiguous shards, this
        engine sweeps shard `rank`; the caller wires the exchange with yk_set_exchange.  world<=1: single GPU */
     uint32_t rank, world;
 } yk_config;
-
-#define YK_COMMIT_DEFAULT 0u
-#define YK_COMMIT_HOST 1u        /* ordered commit on the host from the device bitmaps */
-#define YK_COMMIT_DEVICE 2u      /* ordered commit kernel on the device */
 
 typedef struct { uint32_t ask; uint32_t node; } yk_binding;
 

@@ -155,3 +155,55 @@ def test_device_score_and_evaluate_match_oracle(oracle):
             for n in range(0, s.n_nodes, 11):
                 got, exp = e.evaluate(a, n), oracle.predicate(s, a, n)
                 assert (got == 0) == (exp == 0) and (got == exp or {got, exp} <= {4, 8}), (a, n, got, exp)
+
+
+def _sub_snapshot(s, keep_nodes, keep_asks):
+    """oracle-side view of a snapshot after some nodes / asks were removed (indices are preserved by the engine,
+    so the oracle gets the same arrays with the removed nodes unschedulable+full and the removed asks slow-path)"""
+    import copy
+    t = copy.deepcopy(s)
+    gone_n = np.setdiff1d(np.arange(s.n_nodes), keep_nodes)
+    t.node_flags[gone_n] = 0
+    gone_a = np.setdiff1d(np.arange(s.n_asks), keep_asks)
+    t.ask_flags[gone_a] = 1
+    return t
+
+
+def test_remove_nodes_and_asks_then_cycle(oracle):
+    s = synth.perf(120, 6, 40, masks=True, seed=41)
+    rng = np.random.default_rng(2)
+    keep_n = np.sort(rng.choice(s.n_nodes, 90, replace=False))
+    keep_a = np.sort(rng.choice(s.n_asks, 200, replace=False))
+    want = oracle.run(_sub_snapshot(s, keep_n, keep_a))
+    with Engine.for_snapshot(s, batch=64) as e:
+        e.nodes_remove(np.setdiff1d(np.arange(s.n_nodes), keep_n))
+        e.asks_remove(np.setdiff1d(np.arange(s.n_asks), keep_a))
+        ask, node, _ = e.cycle(s.n_asks)
+        assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
+        assert set(node.tolist()) <= set(keep_n.tolist())
+        # removed asks report ABSENT, removed nodes are gone from evaluation
+        assert set(e.ask_states(np.setdiff1d(np.arange(s.n_asks), keep_a)).tolist()) == {255}
+        assert e.evaluate(int(keep_a[0]), int(np.setdiff1d(np.arange(s.n_nodes), keep_n)[0])) == 9
+
+
+def test_node_update_between_cycles(oracle):
+    """capacity / availability updates (SchedulerAPI.UpdateNode UPDATE, cordon) arriving between two cycles"""
+    import copy
+    s = synth.perf(60, 4, 60, seed=43)
+    first = oracle.run(s, max_bindings=100)
+    with Engine.for_snapshot(s, batch=32) as e:
+        ask, node, _ = e.cycle(100)
+        assert np.array_equal(ask, first["ask"]) and np.array_equal(node, first["node"])
+        # the world after cycle 1, then: node 5 cordoned, node 7 grows
+        t = copy.deepcopy(s)
+        t.node_avail = e.nodes_available(np.arange(s.n_nodes))
+        t.node_flags[5] = 0
+        t.node_total[7, 0] += 16000
+        t.node_avail[7, 0] += 16000
+        e.nodes_upsert([5, 7], t.node_total[[5, 7]], t.node_avail[[5, 7]], t.node_taint[[5, 7]], t.node_label[[5, 7]],
+                       s.node_rank()[[5, 7]], t.node_flags[[5, 7]])
+        t.ask_flags[first["ask"]] = 1                      # already bound: the oracle must leave them alone
+        want = oracle.run(t)
+        ask2, node2, _ = e.cycle(s.n_asks)
+        assert np.array_equal(ask2, want["ask"]) and np.array_equal(node2, want["node"])
+        assert 5 not in set(node2.tolist())

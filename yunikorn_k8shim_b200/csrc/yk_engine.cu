@@ -1129,11 +1129,7 @@ int yk_ask_states(yk_engine* e, uint32_t n, const uint32_t* idx, uint8_t* out) {
     if (n && (!idx || !out)) return e->fail(YK_ERR_ARG, "yk_ask_states: null array");
     for (uint32_t i = 0; i < n; ++i) {
         if (idx[i] >= e->maxA) return e->fail(YK_ERR_ARG, "yk_ask_states: index beyond max_asks");
-        uint8_t s = e->a_state[idx[i]];
-        if (s == yk::ST_PENDING && idx[i] < e->a_hi) {
-            // an ask whose request is not strictly positive is reported as such once a cycle has seen it
-        }
-        out[i] = s;
+        out[i] = e->a_state[idx[i]];
     }
     return YK_OK;
 }

@@ -29,7 +29,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("D", C.c_uint32), ("policy", C.c_uint32), ("batch", C.c_uint32),
                 ("weights", C.c_double * 8),
                 ("max_nodes", C.c_uint32), ("max_asks", C.c_uint32), ("max_apps", C.c_uint32), ("max_queues", C.c_uint32),
-                ("device", C.c_int32), ("commit_mode", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
+                ("device", C.c_int32), ("reserved0", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -108,7 +108,7 @@ class Engine:
     """One yk_engine.  Method names and arguments mirror include/ykgpu.h one to one."""
 
     def __init__(self, D=4, policy=0, weights=None, max_nodes=1024, max_asks=4096, max_apps=64, max_queues=8,
-                 batch=0, device=-1, commit_mode=0, rank=0, world=1):
+                 batch=0, device=-1, rank=0, world=1):
         self._lib = load_library()
         cfg = Config()
         cfg.abi_version = self._lib.yk_abi_version()
@@ -123,7 +123,7 @@ class Engine:
         for i in range(8):
             cfg.weights[i] = float(w[i])
         cfg.max_nodes, cfg.max_asks, cfg.max_apps, cfg.max_queues = max_nodes, max_asks, max_apps, max_queues
-        cfg.device, cfg.commit_mode, cfg.rank, cfg.world = device, commit_mode, rank, world
+        cfg.device, cfg.reserved0, cfg.rank, cfg.world = device, 0, rank, world
         self.D = D
         self._h = C.c_void_p()
         rc = self._lib.yk_create(C.byref(cfg), C.byref(self._h))
