@@ -118,6 +118,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--masks", action="store_true", help="config 3 (taints + nodeAffinity bitmasks) instead of config 2")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE config to run instead of the headline config 2 (4 = 50k nodes / 200k pods, DRF queues; 5 = gangs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -135,7 +137,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    snap = synth.perf(N_NODES, N_APPS, TASKS, masks=args.masks)
+    if args.config == 4:
+        snap = synth.hier()
+    elif args.config == 5:
+        snap = synth.gangs()
+    else:
+        snap = synth.perf(N_NODES, N_APPS, TASKS, masks=args.masks or args.config == 3)
     N, A, D = snap.n_nodes, snap.n_asks, snap.D
     eng = Engine(D=D, policy=snap.policy, weights=snap.weights, max_nodes=N, max_asks=A, max_apps=snap.n_apps,
                  max_queues=snap.n_queues, batch=args.batch, device=local_rank, rank=rank, world=world)
@@ -232,8 +239,10 @@ def main():
             "metric": METRIC, "value": n / tot, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int64+u64 (fit, masks), f64 (node score)", "data": "synthetic",
-            "config": {"workload": ("config3: 10k nodes / 50k pods + taints + nodeAffinity bitmasks" if args.masks else
-                                    "config2: 10k nodes / 50k pending pods, D=4, no affinity") + ", fair node sort, 1 leaf queue, 400 apps x 125",
+            "config": {"workload": {4: "config4: 50k nodes / 200k pods, 73 queues (DRF parents, quotas), fifo leaves",
+                                    5: "config5: 10k nodes / 2000 gangs x 10, all-or-nothing"}.get(args.config) or
+                                   (("config3: 10k nodes / 50k pods + taints + nodeAffinity bitmasks" if (args.masks or args.config == 3) else
+                                     "config2: 10k nodes / 50k pending pods, D=4, no affinity") + ", fair node sort, 1 leaf queue, 400 apps x 125"),
                        "batch": st["evaluations"] // max(launches, 1) // N, "l2": "flushed between steps (256 MiB write)",
                        "parallelism": f"ask-sharded x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": n_e / tot_e, "unit": UNIT, "ms_per_step": tot_e / args.steps * 1e3,

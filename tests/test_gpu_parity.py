@@ -207,3 +207,30 @@ def test_node_update_between_cycles(oracle):
         ask2, node2, _ = e.cycle(s.n_asks)
         assert np.array_equal(ask2, want["ask"]) and np.array_equal(node2, want["node"])
         assert 5 not in set(node2.tolist())
+
+
+def test_error_paths_and_empty_cluster():
+    from yunikorn_k8shim_b200 import YkError
+    s = synth.perf(10, 2, 10)
+    # no nodes at all: every ask ends NOFIT, no crash
+    e = Engine(D=s.D, max_nodes=16, max_asks=64, max_apps=4, max_queues=4)
+    e.queues_set(s.q_parent, s.q_guaranteed, s.q_max, s.q_alloc, s.q_sort)
+    e.apps_upsert(np.arange(s.n_apps), s.app_queue, s.app_submit)
+    e.asks_upsert(np.arange(s.n_asks), s.ask_req, s.ask_app, s.ask_create)
+    ask, node, _ = e.cycle(100)
+    assert len(ask) == 0 and set(e.ask_states(np.arange(s.n_asks)).tolist()) == {2}
+    # argument errors come back as codes, never as a crash
+    with pytest.raises(YkError) as ei:
+        e.nodes_upsert([99], s.node_total[:1], s.node_avail[:1], name_rank=[0])
+    assert ei.value.code == -1
+    with pytest.raises(YkError):
+        e.asks_upsert([0], s.ask_req[:1], [3], [0])            # unknown application
+    with pytest.raises(YkError):
+        e.release([0])                                          # holds no allocation
+    # a node whose weighted totals are zero scores 0 (types absent from total are skipped): still schedulable order
+    tot, av = s.node_total[:2].copy(), s.node_avail[:2].copy()
+    tot[0, 0], av[0, 0] = 0, 0
+    tot[0, 1], av[0, 1] = 0, 0
+    e.nodes_upsert([0, 1], tot, av, name_rank=[0, 1])
+    assert e.node_scores([0])[0] == 0.0
+    e.close()
