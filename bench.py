@@ -146,9 +146,10 @@ def main():
     N, A, D = snap.n_nodes, snap.n_asks, snap.D
     eng = Engine(D=D, policy=snap.policy, weights=snap.weights, max_nodes=N, max_asks=A, max_apps=snap.n_apps,
                  max_queues=snap.n_queues, batch=args.batch, device=local_rank, rank=rank, world=world)
+    exchange = None
     if world > 1:
         from yunikorn_k8shim_b200 import multigpu
-        multigpu.attach(eng, dist)
+        exchange = multigpu.attach(eng, dist)
     eng.queues_set(snap.q_parent, snap.q_guaranteed, snap.q_max, snap.q_alloc, snap.q_sort)
     eng.apps_upsert(np.arange(snap.n_apps), snap.app_queue, snap.app_submit)
 
@@ -244,7 +245,7 @@ def main():
                                    (("config3: 10k nodes / 50k pods + taints + nodeAffinity bitmasks" if (args.masks or args.config == 3) else
                                      "config2: 10k nodes / 50k pending pods, D=4, no affinity") + ", fair node sort, 1 leaf queue, 400 apps x 125"),
                        "batch": st["evaluations"] // max(launches, 1) // N, "l2": "flushed between steps (256 MiB write)",
-                       "parallelism": f"ask-sharded x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"ask-sharded x{world}, exchange={exchange}" if world > 1 else "single GPU"},
             "e2e": {"value": n_e / tot_e, "unit": UNIT, "ms_per_step": tot_e / args.steps * 1e3,
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"] // args.steps), "d2h_bytes_per_step": int(st_e["d2h_bytes"] // args.steps),
                     "abi_h2d_payload": h2d_step, "abi_d2h_payload": d2h_step},
@@ -278,6 +279,9 @@ def main():
                                                        and np.array_equal(ask_e, r["ask"]) and np.array_equal(node_e, r["node"]))
             out["bindings_hash"] = f"{oc.bindings_hash(ask, node):#x}"
         print(json.dumps(out))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()      # peers may still be signalling into this engine's sync block
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -195,6 +195,16 @@ typedef int (*yk_allgather_fn)(void* ctx, void* device_buf, uint64_t row_bytes, 
                                uint32_t n_rows, uint32_t total_rows, void* cuda_stream);
 int yk_set_exchange(yk_engine* e, yk_allgather_fn fn, void* ctx);
 
+/* Peer-to-peer exchange (preferred over yk_set_exchange when all ranks sit on one NVLink / NVSwitch node): every
+ * rank exports its fit buffers and sync block as CUDA IPC handles, imports every other rank's, and from then on the
+ * sweep kernel stores its rows straight into all ranks' buffers -- the all-gather is fused into the sweep, ordered by
+ * sequence flags in peer memory, with no collective launch and no host involvement.  Call yk_peer_export on every
+ * rank, exchange the blobs (any transport), call yk_peer_import once per other rank, then yk_peer_enable. */
+typedef struct { unsigned char blob[3][64]; } yk_peer_handles;   /* cudaIpcMemHandle_t x {slot 0, slot 1, sync} */
+int yk_peer_export(yk_engine* e, yk_peer_handles* out);
+int yk_peer_import(yk_engine* e, uint32_t peer_rank, const yk_peer_handles* in);
+int yk_peer_enable(yk_engine* e);
+
 int yk_stats(yk_engine* e, yk_stats_t* out);
 int yk_stats_reset(yk_engine* e);
 const char* yk_strerror(int status);

@@ -13,14 +13,15 @@ for snap, batch in ((synth.perf(900, 20, 100, masks=True), 256), (synth.hier(300
                     (synth.gangs(60, 40, 5, fill=1.4), 64), (synth.perf(masks=True), 4096)):
     want = oc.run(snap)
     with Engine.for_snapshot(snap, batch=batch, device=lr, rank=rank, world=world) as e:
-        multigpu.attach(e, dist)
+        mode = multigpu.attach(e, dist)
         torch.cuda.synchronize(); dist.barrier()
         t = time.time(); ask, node, _ = e.cycle(snap.n_asks); dt = time.time() - t
         st = e.stats()
+        torch.cuda.synchronize(); dist.barrier()   # peers may still be signalling into this engine's sync block
     ok = np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
     agree = multigpu.check_agreement(dist, ask, node, device="cuda")
     ok_all = ok_all and ok and agree
-    print(f"rank {rank}/{world} {snap.name}: identical_to_oracle={ok} replicas_agree={agree} cycle={dt*1e3:.1f} ms "
+    print(f"rank {rank}/{world} [{mode}] {snap.name}: identical_to_oracle={ok} replicas_agree={agree} cycle={dt*1e3:.1f} ms "
           f"evaluations(local)={st['evaluations']} sweep_ms={st['sweep_ms']:.2f}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)

@@ -124,9 +124,11 @@ struct Slot {
     yk::Orderer::Snap snap;
     Dev<uint32_t> d_batch, d_fit;
     Pin<uint32_t> h_batch, h_fit;
+    Pin<int> h_err;                 // P2P: copy of the device error word after the flag waits
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
     int B = 0, W = 0, chunk = 0, nchunks = 0, rows = 0;
+    uint32_t last_value = 0;        // P2P: sequence value signalled when this slot's previous content was published
 };
 
 }  // namespace
@@ -203,6 +205,13 @@ struct yk_engine {
 
     yk::Orderer ord;
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
+    // peer-to-peer exchange (see yk_peer_export): peers' slot buffers and sync blocks, mapped through CUDA IPC
+    bool p2p = false;
+    uint32_t seq = 0;
+    Dev<uint32_t> d_sync;                    // [32]: ready[slot][rank] at slot*8+rank, consumed[slot][rank] at 16+slot*8+rank
+    uint32_t* peer_fit[2][8] = {};
+    uint32_t* peer_sync[8] = {};
+    bool peer_open[8] = {};
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -492,7 +501,19 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     const int Bpad = rows_per * world;
     sl.rows = rows;
     // the last word of every row (first-fit position) starts at YK_NONE
-    CK(cudaMemset2DAsync(sl.d_fit.p + W, sizeof(uint32_t) * (size_t)WS, 0xFF, sizeof(uint32_t), (size_t)Bpad, s));
+    const int slot_id = (int)(&sl - e->slot);
+    const bool p2p = world > 1 && e->p2p;
+    uint32_t value = 0;
+    const long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a dead peer becomes YK_ERR_COMM, not a hang
+    if (p2p) {
+        // the slot's previous content must have been consumed by every rank before anybody overwrites it
+        value = ++e->seq;
+        yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, world, 16 + slot_id * 8, sl.last_value, e->d_flag.p, spin_limit);
+        sl.last_value = value;
+    } else {
+        // the last word of every row (first-fit position) starts at YK_NONE
+        CK(cudaMemset2DAsync(sl.d_fit.p + W, sizeof(uint32_t) * (size_t)WS, 0xFF, sizeof(uint32_t), (size_t)Bpad, s));
+    }
     CK(cudaEventRecord(sl.ev_s0, s));
     if (rows > 0) {
         YkSweepArgs a{};
@@ -500,14 +521,24 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
         a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
         a.lda = e->maxA; a.batch = sl.d_batch.p; a.row0 = row0; a.rows = rows;
         a.fit = sl.d_fit.p; a.W = W; a.WS = WS;
+        a.n_peer = p2p ? world : 0;
+        for (int g = 0; g < 8; ++g) a.fit_peer[g] = p2p && g < world ? e->peer_fit[slot_id][g] : nullptr;
         launch_sweep(D, a, s, e->slots);
         st.sweep_launches += 1;
         st.evaluations += (uint64_t)rows * (uint64_t)nlive;
     }
     CK(cudaEventRecord(sl.ev_s1, s));
     CK(cudaGetLastError());
-    if (world > 1) {
-        if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but no exchange function set (yk_set_exchange)");
+    if (p2p) {
+        YkPeerSync ps{};
+        for (int g = 0; g < world; ++g) ps.sync[g] = e->peer_sync[g];
+        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, slot_id * 8 + (int)e->cfg.rank, value);            // my rows are in place
+        yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, world, slot_id * 8, value, e->d_flag.p, spin_limit);   // everybody's are
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(sl.h_err.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        st.other_launches += 3;
+    } else if (world > 1) {
+        if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but neither a peer-to-peer nor a callback exchange is set up");
         if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)WS * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
             return e->fail(YK_ERR_COMM, "exchange callback failed");
     }
@@ -518,6 +549,16 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
         const size_t r0 = (size_t)c * sl.chunk, r1 = std::min<size_t>((size_t)B, r0 + sl.chunk);
         CK(cudaMemcpyAsync(sl.h_fit.p + r0 * WS, sl.d_fit.p + r0 * WS, sizeof(uint32_t) * (r1 - r0) * WS, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(sl.ev[(size_t)c], s));
+    }
+    if (p2p) {
+        // consumed: wipe the slot (every word back to 0xFFFFFFFF, so first-fit words start at YK_NONE whatever the next
+        // row layout is) and tell every rank it may publish into it again
+        CK(cudaMemsetAsync(sl.d_fit.p, 0xFF, sl.d_fit.n * sizeof(uint32_t), s));
+        YkPeerSync ps{};
+        for (int g = 0; g < world; ++g) ps.sync[g] = e->peer_sync[g];
+        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, 16 + slot_id * 8 + (int)e->cfg.rank, value);
+        CK(cudaGetLastError());
+        st.other_launches += 1;
     }
     st.d2h_bytes += sizeof(uint32_t) * (size_t)B * WS;
     st.batches++;
@@ -567,6 +608,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
             CK(cudaEventSynchronize(sl.ev[(size_t)next_chunk]));
             t_wait += now_ms() - tw;
             ++next_chunk;
+            if (e->p2p && sl.h_err[0]) return e->fail(YK_ERR_COMM, "peer-to-peer exchange timed out waiting for another rank");
         }
         unsigned long long tc0 = e->prof ? yk_tsc() : 0;
         const uint32_t ask = batch[(size_t)i];
@@ -734,6 +776,9 @@ void yk_destroy(yk_engine* e) {
     if (!e) return;
     e->worker.stop();
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int g = 0; g < 8; ++g)
+        if (e->peer_open[g]) { cudaIpcCloseMemHandle(e->peer_fit[0][g]); cudaIpcCloseMemHandle(e->peer_fit[1][g]); cudaIpcCloseMemHandle(e->peer_sync[g]); }
+    if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
@@ -788,10 +833,15 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->h_order[0].alloc(N)); T(e->h_order[1].alloc(N)); T(e->d_order.alloc(N));
     for (Slot& sl : e->slot) {
         T(sl.d_batch.alloc(Bm)); T(sl.d_fit.alloc(Bpad * (e->Wmax + 1)));
-        T(sl.h_batch.alloc(Bm)); T(sl.h_fit.alloc(Bm * (e->Wmax + 1)));
+        T(sl.h_batch.alloc(Bm)); T(sl.h_fit.alloc(Bm * (e->Wmax + 1))); T(sl.h_err.alloc(1));
         sl.ev.assign(16, nullptr);
         for (auto& ev : sl.ev) T(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         T(cudaEventCreate(&sl.ev_s0)); T(cudaEventCreate(&sl.ev_s1));
+    }
+    T(e->d_sync.alloc(32));
+    if (ok) {
+        T(cudaMemset(e->d_sync.p, 0, 32 * sizeof(uint32_t)));
+        for (Slot& sl : e->slot) T(cudaMemset(sl.d_fit.p, 0xFF, sl.d_fit.n * sizeof(uint32_t)));
     }
     e->epoch_floor = std::max<uint32_t>(2 * e->batch, 4096);
     if (const char* v = getenv("YK_EPOCH_NODES")) e->epoch_env = (uint32_t)std::max(1, atoi(v));   // tuning / debugging knob
@@ -1223,6 +1273,44 @@ int yk_set_exchange(yk_engine* e, yk_allgather_fn fn, void* ctx) {
     if (!e) return YK_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     e->xfn = fn; e->xctx = ctx;
+    return YK_OK;
+}
+
+int yk_peer_export(yk_engine* e, yk_peer_handles* out) {
+    if (!e || !out) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->blob[0], e->slot[0].d_fit.p));
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->blob[1], e->slot[1].d_fit.p));
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)out->blob[2], e->d_sync.p));
+    return YK_OK;
+}
+
+int yk_peer_import(yk_engine* e, uint32_t peer, const yk_peer_handles* in) {
+    if (!e || !in) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (peer >= 8 || peer >= e->cfg.world || peer == e->cfg.rank) return e->fail(YK_ERR_ARG, "yk_peer_import: bad peer rank");
+    if (e->peer_open[peer]) return e->fail(YK_ERR_STATE, "yk_peer_import: peer already imported");
+    cudaIpcMemHandle_t h[3];
+    memcpy(h, in->blob, sizeof(h));
+    void* p0 = nullptr; void* p1 = nullptr; void* p2 = nullptr;
+    CK(cudaIpcOpenMemHandle(&p0, h[0], cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&p1, h[1], cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&p2, h[2], cudaIpcMemLazyEnablePeerAccess));
+    e->peer_fit[0][peer] = (uint32_t*)p0; e->peer_fit[1][peer] = (uint32_t*)p1; e->peer_sync[peer] = (uint32_t*)p2;
+    e->peer_open[peer] = true;
+    return YK_OK;
+}
+
+int yk_peer_enable(yk_engine* e) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    const uint32_t world = e->cfg.world, rank = e->cfg.rank;
+    if (world < 2 || world > 8) return e->fail(YK_ERR_ARG, "yk_peer_enable: world must be 2..8");
+    for (uint32_t p = 0; p < world; ++p)
+        if (p != rank && !e->peer_open[p]) return e->fail(YK_ERR_STATE, "yk_peer_enable: a peer has not been imported");
+    e->peer_fit[0][rank] = e->slot[0].d_fit.p; e->peer_fit[1][rank] = e->slot[1].d_fit.p; e->peer_sync[rank] = e->d_sync.p;
+    e->p2p = true;
     return YK_OK;
 }
 

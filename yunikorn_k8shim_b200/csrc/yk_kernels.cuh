@@ -102,6 +102,11 @@ struct YkSweepArgs {
     uint32_t* fit;            // [B][WS]: W bitmap words, then word W = first fit position (pre-set to YK_NONE_U32)
     int W;                    // bitmap words per row = Np/32
     int WS;                   // row stride in words (W + 1): one row = one exchange / read-back unit
+    // multi-GPU, peer-to-peer: every rank's fit buffer for this slot (IPC-mapped over NVLink, own pointer included).
+    // n_peer == 0: single GPU (or NCCL exchange): write `fit` only.  Otherwise the kernel stores its rows straight into
+    // every rank's buffer -- the all-gather is fused into the sweep, tile by tile, no separate collective launch.
+    uint32_t* fit_peer[8];
+    int n_peer;
 };
 
 // One (ask, 32 x NPT nodes) step.  MASKS / WANT are warp-uniform properties of the ask (staged in shared
@@ -217,13 +222,14 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
             // lane l picks up the NPT bitmap words of ask (ab + l) for this warp's positions
             const int i = ab + lane;
             if (i < na) {
-                uint32_t* row = p.fit + (size_t)(a0 + i) * p.WS;
+                const size_t roff = (size_t)(a0 + i) * p.WS;
                 uint32_t best = YK_NONE_U32;
 #pragma unroll
                 for (int j = NPT - 1; j >= 0; --j) {
                     const uint32_t w = sh_word[warp][j][lane];
                     const int widx = word0 + j * (YK_SWEEP_THREADS / 32);
-                    row[widx] = w;
+                    if (p.n_peer == 0) p.fit[roff + widx] = w;
+                    else for (int g = 0; g < p.n_peer; ++g) p.fit_peer[g][roff + widx] = w;   // peer stores over NVLink
                     if (w) best = (uint32_t)widx * 32u + (uint32_t)(__ffs((int)w) - 1);
                 }
                 if (best != YK_NONE_U32) atomicMin(&sh_first[i], best);
@@ -232,7 +238,11 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
         }
         __syncthreads();
         for (int i = tid; i < na; i += YK_SWEEP_THREADS)
-            if (sh_first[i] != YK_NONE_U32) atomicMin(&p.fit[(size_t)(a0 + i) * p.WS + p.W], sh_first[i]);
+            if (sh_first[i] != YK_NONE_U32) {
+                const size_t foff = (size_t)(a0 + i) * p.WS + p.W;
+                if (p.n_peer == 0) atomicMin(&p.fit[foff], sh_first[i]);
+                else for (int g = 0; g < p.n_peer; ++g) atomicMin_system(&p.fit_peer[g][foff], sh_first[i]);
+            }
     }
 }
 
@@ -319,6 +329,31 @@ __global__ void yk_preempt_kernel(int D, const int64_t* __restrict__ total, cons
         if (m) answer = (int32_t)(base - v0) + (__ffs((int)m) - 1);
     }
     if (lane == 0) out[q] = answer;
+}
+
+// ---- peer-to-peer flags (multi-GPU): "rows ready" / "slot consumed" sequence numbers in every rank's sync block ----
+struct YkPeerSync { uint32_t* sync[8]; };
+
+// one thread per rank: publish `value` at word `offset` of every rank's sync block (after all earlier writes of this
+// stream -- the sweep's peer stores -- are visible system-wide)
+__global__ void yk_p2p_signal_kernel(YkPeerSync ps, int world, int offset, uint32_t value) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    __threadfence_system();
+    volatile uint32_t* q = ps.sync[g] + offset;
+    *q = value;
+}
+// one thread per rank: spin until word base+g of MY sync block has reached `value` (sequence compare), bounded
+__global__ void yk_p2p_wait_kernel(volatile uint32_t* my_sync, int world, int base, uint32_t value, int* err,
+                                   long long max_cycles) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    const long long t0 = clock64();
+    while ((int32_t)(my_sync[base + g] - value) < 0) {
+        if (clock64() - t0 > max_cycles) { atomicExch(err, 2); break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // scatter new availability for a list of nodes (after the ordered commit)

@@ -20,7 +20,8 @@ YK_ERR_CUDA = -2
 EXPORTS = [
     "yk_abi_version", "yk_create", "yk_destroy", "yk_nodes_upsert", "yk_nodes_remove", "yk_queues_set",
     "yk_apps_upsert", "yk_apps_remove", "yk_asks_upsert", "yk_asks_remove", "yk_release", "yk_cycle",
-    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_preemption_search", "yk_set_exchange", "yk_stats",
+    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_preemption_search", "yk_set_exchange",
+    "yk_peer_export", "yk_peer_import", "yk_peer_enable", "yk_stats",
     "yk_stats_reset", "yk_strerror", "yk_last_error",
 ]
 
@@ -264,6 +265,18 @@ class Engine:
         cb = ALLGATHER_FN(fn) if fn is not None else C.cast(None, ALLGATHER_FN)
         self._keep.append(cb)
         self._ck(self._lib.yk_set_exchange(self._h, cb, None))
+
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * 192)()
+        self._ck(self._lib.yk_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_import(self, peer_rank: int, blob: bytes):
+        buf = (C.c_ubyte * 192).from_buffer_copy(blob)
+        self._ck(self._lib.yk_peer_import(self._h, C.c_uint32(peer_rank), buf))
+
+    def peer_enable(self):
+        self._ck(self._lib.yk_peer_enable(self._h))
 
     def stats(self) -> dict:
         s = Stats()
