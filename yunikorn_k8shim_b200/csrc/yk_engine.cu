@@ -531,12 +531,15 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     CK(cudaGetLastError());
     if (p2p) {
         YkPeerSync ps{};
-        for (int g = 0; g < world; ++g) ps.sync[g] = e->peer_sync[g];
+        YkPeerFit pf{};
+        for (int g = 0; g < world; ++g) { ps.sync[g] = e->peer_sync[g]; pf.fit[g] = e->peer_fit[slot_id][g]; }
+        if (rows > 0)
+            yk_p2p_first_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sl.d_fit.p, pf, world, (int)e->cfg.rank, row0, rows, W, WS);
         yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, slot_id * 8 + (int)e->cfg.rank, value);            // my rows are in place
         yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, world, slot_id * 8, value, e->d_flag.p, spin_limit);   // everybody's are
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(sl.h_err.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        st.other_launches += 3;
+        st.other_launches += 4;
     } else if (world > 1) {
         if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but neither a peer-to-peer nor a callback exchange is set up");
         if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)WS * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)

@@ -109,6 +109,8 @@ struct YkSweepArgs {
     int n_peer;
 };
 
+struct YkPeerFit { uint32_t* fit[8]; };
+
 // One (ask, 32 x NPT nodes) step.  MASKS / WANT are warp-uniform properties of the ask (staged in shared
 // memory as `kind`): an ask without tolerations, selectors or a node name needs no mask work at all -- a node
 // passes its mask test iff it carries no taint, which is a per-node constant hoisted out of the loop.
@@ -142,8 +144,8 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
     __shared__ uint64_t sh_mask[AC][3];
     __shared__ uint32_t sh_node[AC];
     __shared__ uint32_t sh_kind[AC];
-    __shared__ uint32_t sh_first[AC];
-    __shared__ uint32_t sh_word[YK_SWEEP_THREADS / 32][NPT][32];
+    constexpr int TW = YK_SWEEP_THREADS / 32 * NPT;   // bitmap words this CTA produces per ask (its node tile / 32)
+    __shared__ uint32_t sh_word[32][TW];              // [ask in group][word in tile]: a row's words sit together
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -163,9 +165,9 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
         nidx[j] = __ldg(p.s_node + pos);
         taintfree[j] = ntaint[j] == 0ull;
     }
-    const int word0 = blockIdx.x * (YK_SWEEP_THREADS * NPT / 32) + warp;
+    const int tile_word0 = blockIdx.x * TW;   // first bitmap word of this CTA's tile
 
-    // this CTA's rows: [r_begin, r_end), multiples of 32 except at the very end
+    // this CTA's rows: [r_begin, r_end)
     const int r_begin = p.row0 + (int)blockIdx.y * p.per;
     const int r_end = min(p.row0 + p.rows, r_begin + p.per);
 
@@ -190,7 +192,6 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
                 kind = 1u;
             }
             sh_kind[i] = kind;
-            sh_first[i] = YK_NONE_U32;
         }
         __syncthreads();
 
@@ -212,38 +213,46 @@ __global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkS
                     if (kind & 2u) yk_pair_step<D, NPT, true, true>(cap, ntaint, nlabel, nidx, taintfree, rq, tol, need, deny, want, word);
                     else yk_pair_step<D, NPT, true, false>(cap, ntaint, nlabel, nidx, taintfree, rq, tol, need, deny, want, word);
                 }
-                // park the ballot words in shared memory (LSU pipe) instead of select-chains on the ALU pipe
+                // park the ballot words in shared memory (LSU pipe) instead of select-chains on the ALU pipe; word
+                // j of warp w is tile word w + j*8, so the TW words of one ask end up contiguous
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < NPT; ++j) sh_word[warp][j][l] = word[j];
+                    for (int j = 0; j < NPT; ++j) sh_word[l][warp + j * (YK_SWEEP_THREADS / 32)] = word[j];
                 }
             }
-            __syncwarp();
-            // lane l picks up the NPT bitmap words of ask (ab + l) for this warp's positions
-            const int i = ab + lane;
-            if (i < na) {
-                const size_t roff = (size_t)(a0 + i) * p.WS;
-                uint32_t best = YK_NONE_U32;
-#pragma unroll
-                for (int j = NPT - 1; j >= 0; --j) {
-                    const uint32_t w = sh_word[warp][j][lane];
-                    const int widx = word0 + j * (YK_SWEEP_THREADS / 32);
-                    if (p.n_peer == 0) p.fit[roff + widx] = w;
-                    else for (int g = 0; g < p.n_peer; ++g) p.fit_peer[g][roff + widx] = w;   // peer stores over NVLink
-                    if (w) best = (uint32_t)widx * 32u + (uint32_t)(__ffs((int)w) - 1);
+            __syncthreads();
+            // cooperative store: TW consecutive threads write the TW consecutive words of one row (64-byte segments
+            // at TW = 16) -- to the local buffer, or straight into every rank's buffer over NVLink
+            for (int t = tid; t < nl * TW; t += YK_SWEEP_THREADS) {
+                const int l = t / TW, wv = t % TW;
+                const uint32_t w = sh_word[l][wv];
+                const size_t off = (size_t)(a0 + ab + l) * p.WS + (size_t)(tile_word0 + wv);
+                if (p.n_peer == 0) p.fit[off] = w;
+                else for (int g = 0; g < p.n_peer; ++g) p.fit_peer[g][off] = w;
+                if (wv == 0) {   // one thread per row: first fit position inside this tile, folded into the row's last word
+                    uint32_t best = YK_NONE_U32;
+                    for (int x = 0; x < TW; ++x) {
+                        const uint32_t wx = sh_word[l][x];
+                        if (wx) { best = (uint32_t)(tile_word0 + x) * 32u + (uint32_t)(__ffs((int)wx) - 1); break; }
+                    }
+                    // always the LOCAL buffer: the owner of the rows publishes the final value to the peers afterwards
+                    if (best != YK_NONE_U32) atomicMin(&p.fit[(size_t)(a0 + ab + l) * p.WS + p.W], best);
                 }
-                if (best != YK_NONE_U32) atomicMin(&sh_first[i], best);
             }
-            __syncwarp();
+            __syncthreads();
         }
-        __syncthreads();
-        for (int i = tid; i < na; i += YK_SWEEP_THREADS)
-            if (sh_first[i] != YK_NONE_U32) {
-                const size_t foff = (size_t)(a0 + i) * p.WS + p.W;
-                if (p.n_peer == 0) atomicMin(&p.fit[foff], sh_first[i]);
-                else for (int g = 0; g < p.n_peer; ++g) atomicMin_system(&p.fit_peer[g][foff], sh_first[i]);
-            }
     }
+}
+
+// multi-GPU, peer-to-peer: after the sweep the first-fit words of this rank's rows are final in the local buffer;
+// copy them into every other rank's buffer (the bitmap words went there directly from the sweep)
+__global__ void yk_p2p_first_kernel(const uint32_t* __restrict__ local, YkPeerFit pf, int n_peer, int self, int row0,
+                                    int rows, int W, int WS) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const size_t off = (size_t)(row0 + i) * WS + W;
+    const uint32_t v = local[off];
+    for (int g = 0; g < n_peer; ++g) if (g != self) pf.fit[g][off] = v;
 }
 
 // ---- one (ask,node) answer in the reference's step order, on the device --------------------------------
