@@ -309,32 +309,39 @@ void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s, int slots) {
 // Full (ask,node) predicate on the commit's working copy, for nodes already committed to in this batch
 // (such nodes are schedulable and unreserved: they were chosen before).  Same steps as the sweep kernel.
 inline bool fits_now(const yk_engine* e, uint32_t node, uint32_t ask) {
+    // everything this needs sits in the first 64 bytes of the node's record at D = 4 (see NodeView)
     const int64_t* h = e->hot.data() + (size_t)node * e->hs;
     const int D = e->D;
-    const uint64_t taint = (uint64_t)h[2 * D], label = (uint64_t)h[2 * D + 1];
+    const uint64_t taint = (uint64_t)h[2], label = (uint64_t)h[3];
     if ((taint & ~e->a_tol[ask]) | (~label & e->a_need[ask]) | (label & e->a_deny[ask])) return false;
     if (e->a_node[ask] != YK_NONE && e->a_node[ask] != node) return false;
-    for (int k = 0; k < D; ++k) {
-        int64_t a = h[k], t = h[D + k];
-        if (a < 0) a = 0;
-        if (t < 0) t = 0;
-        const int64_t r = e->a_req[(size_t)k * e->maxA + ask];
-        if (r > a || r > t) return false;
-    }
+    for (int k = 0; k < D; ++k)
+        if (e->a_req[(size_t)k * e->maxA + ask] > h[4 + k]) return false;   // cap = min(max(0,total), max(0,available))
     return true;
 }
 
-// The commit's per-node working record lives in one contiguous slice of e->hot (two cache lines at D = 4):
-//   [0,D) available  [D,2D) total  [2D] taint  [2D+1] label  [2D+2] current sort key  [2D+3] rank<<32 | dirty<<31 | position
+// The commit's per-node working record lives in one contiguous slice of e->hot (hs = 4 + 3D words):
+//   [0] current sort key   [1] rank<<32 | dirty<<31 | position   [2] taint   [3] label
+//   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
+//   [4+D,4+2D) available   [4+2D,4+3D) total            -- only read when the node is actually committed to
 struct NodeView {
     int64_t* h; int D;
-    uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[2 * D + 2]); }
-    uint32_t rank() const { return (uint32_t)((uint64_t)h[2 * D + 3] >> 32); }
-    uint32_t pos() const { return (uint32_t)((uint64_t)h[2 * D + 3]) & 0x7FFFFFFFu; }
-    bool dirty() const { return (((uint64_t)h[2 * D + 3]) >> 31) & 1u; }
-    void set_meta(uint32_t rank, uint32_t pos) { h[2 * D + 3] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
-    void set_pos(uint32_t pos) { h[2 * D + 3] = (int64_t)((((uint64_t)h[2 * D + 3]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
-    void set_dirty(bool d) { h[2 * D + 3] = (int64_t)((((uint64_t)h[2 * D + 3]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
+    uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[0]); }
+    uint32_t rank() const { return (uint32_t)((uint64_t)h[1] >> 32); }
+    uint32_t pos() const { return (uint32_t)((uint64_t)h[1]) & 0x7FFFFFFFu; }
+    bool dirty() const { return (((uint64_t)h[1]) >> 31) & 1u; }
+    void set_meta(uint32_t rank, uint32_t pos) { h[1] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
+    void set_pos(uint32_t pos) { h[1] = (int64_t)((((uint64_t)h[1]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
+    void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
+    int64_t* cap() { return h + 4; }
+    int64_t* avail() { return h + 4 + D; }
+    int64_t* total() { return h + 4 + 2 * D; }
+    void recap() {   // after `available` changed
+        for (int k = 0; k < D; ++k) {
+            const int64_t a = avail()[k] < 0 ? 0 : avail()[k], t = total()[k] < 0 ? 0 : total()[k];
+            cap()[k] = a < t ? a : t;
+        }
+    }
 };
 inline NodeView node_view(yk_engine* e, uint32_t n) { return NodeView{e->hot.data() + (size_t)n * e->hs, e->D}; }
 
@@ -364,7 +371,7 @@ int initial_order(yk_engine* e) {
     e->st.sort_ms += ms;
     e->cur = 0;
     const uint32_t* ord = e->h_order[0].p;
-    e->hs = 2 * e->D + 4;
+    e->hs = 4 + 3 * e->D;
     e->hot.resize((size_t)e->n_hi * e->hs);
     // working copy of the node table, built in index order (sequential reads of the column-major host tables)
     const int D = e->D;
@@ -372,12 +379,13 @@ int initial_order(yk_engine* e) {
         const int64_t* av = e->n_avail.p + (size_t)k * e->maxN;
         const int64_t* to = e->n_total.p + (size_t)k * e->maxN;
         int64_t* h = e->hot.data();
-        for (uint32_t n = 0; n < e->n_hi; ++n) { h[(size_t)n * e->hs + k] = av[n]; h[(size_t)n * e->hs + D + k] = to[n]; }
+        for (uint32_t n = 0; n < e->n_hi; ++n) { h[(size_t)n * e->hs + 4 + D + k] = av[n]; h[(size_t)n * e->hs + 4 + 2 * D + k] = to[n]; }
     }
     for (uint32_t n = 0; n < e->n_hi; ++n) {
-        int64_t* h = e->hot.data() + (size_t)n * e->hs;
-        h[2 * D] = (int64_t)e->n_taint[n];
-        h[2 * D + 1] = (int64_t)e->n_label[n];
+        NodeView v = node_view(e, n);
+        v.h[2] = (int64_t)e->n_taint[n];
+        v.h[3] = (int64_t)e->n_label[n];
+        v.recap();
     }
     for (int p = 0; p < nlive; ++p) {
         const uint32_t n = ord[p];
@@ -462,7 +470,7 @@ int end_epoch(yk_engine* e, bool reorder) {
             const uint32_t n = e->dirty_list[(size_t)(i0 + i)];
             e->h_dirty_nodes[(size_t)i] = n;
             for (int k = 0; k < D; ++k) {
-                const int64_t v = e->hot[(size_t)n * e->hs + k];
+                const int64_t v = node_view(e, n).avail()[k];
                 e->h_dirty_vals[(size_t)k * cnt + i] = v;
                 e->n_avail[(size_t)k * e->maxN + n] = v;   // column-major host table stays authoritative between cycles
             }
@@ -662,7 +670,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
                 // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
                 // lines were just DMA-written and are cold
                 if (fits_now(e, d->node(), ask)) { chosen = d->node(); at_cursor = true; break; }
-                const int64_t* hh = e->hot.data() + (size_t)d->node() * e->hs;
+                const int64_t* hh = e->hot.data() + (size_t)d->node() * e->hs + 4;   // cap
                 for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
             }
             if (d == nullptr) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];   // saw every touched node: exact
@@ -677,8 +685,10 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
                 for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
                     const uint32_t n = it->node;
                     dirty.erase(DirtyRef(node_view(e, n).key(), node_view(e, n).rank(), n));
-                    int64_t* hh = e->hot.data() + (size_t)n * e->hs;
-                    for (int k = 0; k < D; ++k) hh[k] = it->old_avail[k];
+                    NodeView un = node_view(e, n);
+                    int64_t* hh = un.cap();
+                    for (int k = 0; k < D; ++k) un.avail()[k] = it->old_avail[k];
+                    un.recap();
                     node_view(e, n).key() = it->old_key;
                     if (it->was_dirty) {
                         dirty.insert(DirtyRef(it->old_key, node_view(e, n).rank(), n));
@@ -704,7 +714,8 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         }
         result[(size_t)i] = chosen;
         // commit: available -= request, re-score, move inside the dirty order
-        int64_t* h = e->hot.data() + (size_t)chosen * e->hs;
+        NodeView cv = node_view(e, chosen);
+        int64_t* h = cv.avail();
         if (in_gang) {
             Undo u; u.node = chosen; u.old_key = node_view(e, chosen).key(); u.was_dirty = node_view(e, chosen).dirty() != 0;
             for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
@@ -717,14 +728,15 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         }
         unsigned long long tc3 = e->prof ? yk_tsc() : 0;
         for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
-        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, h + D, h, 1);
+        cv.recap();
+        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, cv.total(), h, 1);
         const uint64_t nk = yk_key_bits(sc);
         if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
         unsigned long long tc4 = e->prof ? yk_tsc() : 0;
         node_view(e, chosen).key() = nk;
         dirty.insert(DirtyRef(nk, node_view(e, chosen).rank(), chosen));
         if (!node_view(e, chosen).dirty()) {
-            for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], h[k]);
+            for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], cv.cap()[k]);
             node_view(e, chosen).set_dirty(true);
             e->dirty_list.push_back(chosen);
             const uint32_t pos = node_view(e, chosen).pos();
