@@ -1,0 +1,168 @@
+// Host-only emulation of yk_cycle for the CPU test suite: the REAL ordering engine (csrc/yk_orderer.hpp) and the REAL
+// ordered commit (csrc/yk_commit.hpp: epochs, touched-node index, gang roll-back, order merge) driven through the same
+// control flow as csrc/yk_engine.cu (two slots, speculative next batch, rewind, epoch ends) -- only the device part is
+// replaced: the fit rows are computed here by a plain CPU loop over the epoch's sorted view (test infrastructure,
+// never part of the product).  What this cannot cover is the CUDA kernels and the stream plumbing: those are the
+// `-m gpu` tests.
+#include "../../yunikorn_k8shim_b200/csrc/yk_commit.hpp"
+#include "../../yunikorn_k8shim_b200/csrc/yk_orderer.hpp"
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+namespace {
+struct Slot { std::vector<uint32_t> asks; yk::Orderer::Snap snap; std::vector<uint32_t> fit; };
+}
+
+extern "C" int engine_host_run(
+    int D, uint32_t policy, const double* weights,
+    uint32_t nN, const int64_t* n_total /*[D][nN]*/, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
+    const uint32_t* n_flags, const uint32_t* n_rank,
+    uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req /*[D][nA]*/, const uint64_t* a_tol, const uint64_t* a_need,
+    const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
+    const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
+    const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+    uint32_t batch, uint32_t epoch_limit, int speculate, uint32_t max_bindings,
+    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out /*[D][nN]*/) {
+    // ---- orderer ----
+    yk::Orderer o;
+    std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1);
+    std::vector<int64_t> p_alloc((size_t)D * nP, 0);
+    o.t.D = D; o.t.maxA = nA; o.t.maxP = nP; o.t.nq = nQ;
+    o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags; o.t.a_gang = a_gang;
+    o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
+    o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.p_alloc = p_alloc.data(); o.t.q_sort = q_sort;
+    std::vector<uint32_t> pending(nA);
+    for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
+    o.begin_cycle(pending);
+    const bool ins = o.insensitive;
+
+    // ---- committer + initial order (what yk_key_kernel + the stable radix sort produce) ----
+    yk::Committer cm;
+    cm.t.D = D; cm.t.policy = policy; cm.t.w = weights; cm.t.lda = nA;
+    cm.t.a_req = a_req; cm.t.a_tol = a_tol; cm.t.a_need = a_need; cm.t.a_deny = a_deny; cm.t.a_node = a_node; cm.t.a_gang = a_gang; cm.t.a_app = a_app;
+    cm.build(nN, n_avail, n_total, nN, n_taint, n_label);
+    const int nlive = (int)nN;
+    std::vector<uint32_t> order[2];
+    order[0].resize(nN); order[1].resize(nN);
+    int cur = 0;
+    {
+        std::vector<yk::DirtyRef> ks(nN);
+        for (uint32_t n = 0; n < nN; ++n) {
+            const double sc = yk_node_score(D, policy, weights, n_total + n, n_avail + n, nN);
+            ks[n] = yk::DirtyRef(yk_key_bits(sc), n_rank[n], n);
+        }
+        std::sort(ks.begin(), ks.end());
+        for (uint32_t p = 0; p < nN; ++p) {
+            const uint32_t n = ks[p].node();
+            order[0][p] = n;
+            cm.node(n).key() = ks[p].key();
+            cm.node(n).set_meta(n_rank[n], p);
+        }
+    }
+    // ---- the epoch's sorted view (what yk_gather_kernel builds) and the CPU stand-in for the sweep ----
+    const int W = nlive ? (nlive + 511) / 512 * 16 : 0;   // same rounding as the engine: tiles of 512 positions
+    const int WS = W + 1;
+    std::vector<int64_t> v_cap;   // [pos][D]
+    std::vector<uint64_t> v_taint, v_label;
+    std::vector<uint32_t> v_node;
+    auto refresh_view = [&]() {
+        v_cap.assign((size_t)W * 32 * D, -1); v_taint.assign((size_t)W * 32, ~0ull); v_label.assign((size_t)W * 32, 0); v_node.assign((size_t)W * 32, yk::CNONE);
+        for (int p = 0; p < nlive; ++p) {
+            const uint32_t n = order[cur][p];
+            const bool usable = (n_flags[n] & 1u) && !(n_flags[n] & 2u);
+            yk::NodeView nv = cm.node(n);
+            for (int k = 0; k < D; ++k) {   // same fold as yk_gather_kernel, from the commit's current availability
+                const int64_t a = std::max<int64_t>(0, nv.avail()[k]), t = std::max<int64_t>(0, nv.total()[k]);
+                v_cap[(size_t)p * D + k] = usable ? std::min(a, t) : -1;
+            }
+            v_taint[p] = n_taint[n]; v_label[p] = n_label[n]; v_node[p] = n;
+        }
+        cm.begin_epoch(W);
+    };
+    auto sweep = [&](Slot& sl) {
+        sl.fit.assign(sl.asks.size() * (size_t)WS, 0);
+        for (size_t i = 0; i < sl.asks.size(); ++i) {
+            const uint32_t a = sl.asks[i];
+            uint32_t* row = sl.fit.data() + i * WS;
+            row[W] = yk::CNONE;
+            for (int p = 0; p < W * 32; ++p) {
+                bool ok = true;
+                for (int k = 0; k < D; ++k) ok = ok && a_req[(size_t)k * nA + a] <= v_cap[(size_t)p * D + k];
+                ok = ok && !((v_taint[p] & ~a_tol[a]) | (~v_label[p] & a_need[a]) | (v_label[p] & a_deny[a]));
+                ok = ok && (a_node[a] == yk::CNONE || a_node[a] == v_node[p]);
+                if (ok) { row[p >> 5] |= 1u << (p & 31); if (row[W] == yk::CNONE) row[W] = (uint32_t)p; }
+            }
+        }
+    };
+    refresh_view();
+
+    Slot slot[2];
+    size_t bsz = batch;
+    uint32_t n = 0;
+    int rc_over = 0;
+    auto next_batch = [&](Slot& sl, size_t cap_user) {
+        sl.asks.clear();
+        if (cap_user == 0) return;
+        o.fill(bsz, cap_user, sl.asks, sl.snap);
+        if (o.oversize_gang) {
+            if (bsz < batch) { bsz = batch; o.fill(bsz, cap_user, sl.asks, sl.snap); }
+            if (o.oversize_gang) { rc_over = -1; return; }
+        }
+        sweep(sl);
+    };
+    std::vector<uint32_t> result;
+    next_batch(slot[0], max_bindings);
+    if (rc_over) return rc_over;
+    int sc = 0;
+    while (!slot[sc].asks.empty()) {
+        Slot& A = slot[sc];
+        Slot& Nx = slot[sc ^ 1];
+        Nx.asks.clear();
+        const bool room = cm.dirty_list.size() + A.asks.size() < (size_t)epoch_limit;
+        const size_t left = (size_t)max_bindings - n;
+        if (speculate && room && left > A.asks.size()) { next_batch(Nx, left - A.asks.size()); if (rc_over) return rc_over; }
+        size_t consumed = 0;
+        if (nlive == 0) {
+            result.assign(A.asks.size(), yk::CNONE);
+            consumed = ins ? A.asks.size() : std::min<size_t>(1, A.asks.size());
+            if (!ins && !A.asks.empty() && a_gang[A.asks[0]] != yk::CNONE)
+                while (consumed < A.asks.size() && cm.same_gang(A.asks[0], A.asks[consumed])) ++consumed;
+        } else {
+            const int rc = cm.commit_batch(A.asks, A.fit.data(), order[cur].data(), ins, result, consumed, [&](int) { return (int)A.asks.size(); });
+            if (rc) return rc;
+        }
+        bool failed = false;
+        if (!ins && consumed > 0 && result[consumed - 1] == yk::CNONE) {
+            size_t j = consumed - 1;
+            while (j > 0 && a_gang[A.asks[j]] != yk::CNONE && a_gang[A.asks[j - 1]] == a_gang[A.asks[j]] &&
+                   a_app[A.asks[j - 1]] == a_app[A.asks[j]] && result[j - 1] == yk::CNONE) --j;
+            o.rewind(A.snap, Nx.asks.empty() ? nullptr : &Nx.snap, A.asks, j);
+            failed = true;
+            Nx.asks.clear();
+        }
+        for (size_t i = 0; i < consumed; ++i) {
+            const uint32_t a = A.asks[i];
+            if (result[i] == yk::CNONE) { if (ins) o.fail_in_place(a); continue; }
+            o.confirm(a);
+            out_ask[n] = a; out_node[n] = result[i]; ++n;
+        }
+        bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
+        if (Nx.asks.empty() && n < max_bindings) {
+            if (cm.dirty_list.size() * 2 >= (size_t)epoch_limit || failed) {
+                if (!cm.dirty_list.empty()) { cm.merge_order(order[cur].data(), order[cur ^ 1].data(), nlive); cur ^= 1; }
+                refresh_view();
+            }
+            next_batch(Nx, (size_t)max_bindings - n);
+            if (rc_over) return rc_over;
+        }
+        sc ^= 1;
+    }
+    o.finish();
+    *n_out = n;
+    for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
+    for (uint32_t nn = 0; nn < nN; ++nn)
+        for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = cm.node(nn).avail()[k];
+    return 0;
+}

@@ -52,3 +52,20 @@ def test_engine_matches_oracle_on_fuzz(oracle, batch):
         assert np.array_equal(node, want["node"]), (seed, batch)
         assert np.array_equal(states, want["state"]), (seed, batch)
         assert np.array_equal(avail, want["avail"]), (seed, batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("policy", [synth.POLICY_FAIR, synth.POLICY_BINPACKING])
+def test_engine_gang_rollback_stress(oracle, policy):
+    """placed-then-undone gangs interleaved with plain asks (synth.poisoned_gangs), one long epoch"""
+    from yunikorn_k8shim_b200 import Engine
+    for seed in range(20):
+        s = synth.poisoned_gangs(seed, policy=policy)
+        want = oracle.run(s)
+        for batch in (16, 1024):
+            with Engine.for_snapshot(s, batch=batch) as e:
+                ask, node, _ = e.cycle(s.n_asks)
+                avail = e.nodes_available(np.arange(s.n_nodes))
+            assert np.array_equal(ask, want["ask"]), (seed, batch)
+            assert np.array_equal(node, want["node"]), (seed, batch)
+            assert np.array_equal(avail, want["avail"]), (seed, batch)

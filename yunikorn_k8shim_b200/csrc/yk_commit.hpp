@@ -1,0 +1,328 @@
+// yk_commit.hpp -- the ordered commit: turns the fit bitmaps of a batch into bindings that are identical to what the
+// reference's one-allocation-per-pass loop would produce (DESIGN.md "ordered commit").  Host code, no CUDA: the engine
+// (yk_engine.cu) feeds it rows as they arrive from the device; tests/host/engine_shim.cpp feeds it rows computed on
+// the CPU so that this logic -- epochs, the touched-node index, gang roll-back -- is exercised by the CPU test suite.
+//
+// Invariant it relies on: within an epoch a node that has not been committed to still has exactly the state the sorted
+// view (and therefore the bitmaps) was built from.  For ask i:
+//   (A) best untouched candidate = first set bit of fit[i] & ~touched, in sorted (score, NodeID) order;
+//   (B) best touched candidate   = first entry of the touched-node index (ordered by CURRENT (score, NodeID)) that sorts
+//       before (A) and passes the full predicate on the working copy;
+//   the ask takes (B) if it exists, else (A); the node's availability drops, it is re-scored and re-indexed.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#if defined(__x86_64__)
+#include <x86intrin.h>
+#endif
+
+#include "yk_dirty.hpp"
+#include "yk_score.h"
+
+namespace yk {
+
+constexpr uint32_t CNONE = 0xFFFFFFFFu;
+constexpr int CMAX_D = 8;
+
+// views of the engine's host tables that the commit reads
+struct CommitTables {
+    int D = 0;
+    uint32_t policy = 0;
+    const double* w = nullptr;       // [D] node-sort weights
+    size_t lda = 0;                  // ask tables are column-major with this stride
+    const int64_t* a_req = nullptr;  // [D][lda]
+    const uint64_t* a_tol = nullptr;
+    const uint64_t* a_need = nullptr;
+    const uint64_t* a_deny = nullptr;
+    const uint32_t* a_node = nullptr;
+    const uint32_t* a_gang = nullptr;
+    const uint32_t* a_app = nullptr;
+};
+
+// The per-node working record lives in one contiguous slice of `hot` (hs = 4 + 3D words):
+//   [0] current sort key   [1] rank<<32 | touched<<31 | position   [2] taint   [3] label
+//   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
+//   [4+D,4+2D) available   [4+2D,4+3D) total            -- only read when the node is actually committed to
+struct NodeView {
+    int64_t* h; int D;
+    uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[0]); }
+    uint32_t rank() const { return (uint32_t)((uint64_t)h[1] >> 32); }
+    uint32_t pos() const { return (uint32_t)((uint64_t)h[1]) & 0x7FFFFFFFu; }
+    bool dirty() const { return (((uint64_t)h[1]) >> 31) & 1u; }
+    void set_meta(uint32_t rank, uint32_t pos) { h[1] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
+    void set_pos(uint32_t pos) { h[1] = (int64_t)((((uint64_t)h[1]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
+    void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
+    int64_t* cap() { return h + 4; }
+    int64_t* avail() { return h + 4 + D; }
+    int64_t* total() { return h + 4 + 2 * D; }
+    void recap() {   // after `available` changed
+        for (int k = 0; k < D; ++k) {
+            const int64_t a = avail()[k] < 0 ? 0 : avail()[k], t = total()[k] < 0 ? 0 : total()[k];
+            cap()[k] = a < t ? a : t;
+        }
+    }
+};
+
+inline unsigned long long commit_tsc() {
+#if defined(__x86_64__)
+    unsigned aux;
+    unsigned long long t = __rdtscp(&aux);
+    _mm_lfence();
+    return t;
+#else
+    return 0;
+#endif
+}
+
+class Committer {
+public:
+    CommitTables t;
+    std::vector<int64_t> hot;            // working copy of the node table (see NodeView)
+    int hs = 0;
+    DirtyIndex dirty;                    // nodes touched in this epoch, ordered by their CURRENT (score, NodeID)
+    std::vector<DirtyRef> dirty_sorted;  // scratch for the epoch-end merge
+    std::vector<uint32_t> dirty_words;   // bit p = the node at sorted position p has been touched in this epoch
+    std::vector<uint32_t> dirty_list;    // the touched nodes, in first-touch order
+    int64_t dirty_ub[CMAX_D];            // per dimension: upper bound of cap over the touched nodes
+    int front = 0;                       // every sorted position below word `front` is touched
+    int W = 0;                           // bitmap words per row in this epoch
+    bool profile = false;
+    uint64_t dbg[4] = {0, 0, 0, 0};      // words scanned, touched candidates examined, asks won by a touched node, re-keys
+    uint64_t prof[6] = {0, 0, 0, 0, 0, 0};
+
+    NodeView node(uint32_t n) { return NodeView{hot.data() + (size_t)n * hs, t.D}; }
+
+    // (re)build the working copy from the engine's column-major host tables (stride ldn), n_hi node slots
+    void build(uint32_t n_hi, const int64_t* n_avail, const int64_t* n_total, size_t ldn, const uint64_t* n_taint,
+               const uint64_t* n_label) {
+        const int D = t.D;
+        hs = 4 + 3 * D;
+        hot.resize((size_t)n_hi * hs);
+        for (int k = 0; k < D; ++k) {   // index order: sequential reads of the column-major tables
+            const int64_t* av = n_avail + (size_t)k * ldn;
+            const int64_t* to = n_total + (size_t)k * ldn;
+            int64_t* h = hot.data();
+            for (uint32_t n = 0; n < n_hi; ++n) { h[(size_t)n * hs + 4 + D + k] = av[n]; h[(size_t)n * hs + 4 + 2 * D + k] = to[n]; }
+        }
+        for (uint32_t n = 0; n < n_hi; ++n) {
+            NodeView v = node(n);
+            v.h[2] = (int64_t)n_taint[n];
+            v.h[3] = (int64_t)n_label[n];
+            v.recap();
+        }
+    }
+
+    // a new epoch starts on a fresh view of `words` bitmap words per row: nothing is touched
+    void begin_epoch(int words) {
+        for (uint32_t n : dirty_list) node(n).set_dirty(false);
+        dirty_list.clear();
+        dirty.clear();
+        front = 0;
+        W = words;
+        dirty_words.assign((size_t)words, 0);
+        for (int k = 0; k < CMAX_D; ++k) dirty_ub[k] = INT64_MIN;
+    }
+
+    // full (ask,node) predicate on the working copy, for touched nodes (they were chosen before: schedulable, unreserved).
+    // Same steps as the sweep kernel; everything it reads sits in the first 64 bytes of the record at D = 4.
+    bool fits_now(uint32_t n, uint32_t ask) const {
+        const int64_t* h = hot.data() + (size_t)n * hs;
+        const uint64_t taint = (uint64_t)h[2], label = (uint64_t)h[3];
+        if ((taint & ~t.a_tol[ask]) | (~label & t.a_need[ask]) | (label & t.a_deny[ask])) return false;
+        if (t.a_node[ask] != CNONE && t.a_node[ask] != n) return false;
+        for (int k = 0; k < t.D; ++k)
+            if (t.a_req[(size_t)k * t.lda + ask] > h[4 + k]) return false;
+        return true;
+    }
+
+    bool same_gang(uint32_t x, uint32_t y) const {
+        return t.a_gang[x] != CNONE && t.a_gang[x] == t.a_gang[y] && t.a_app[x] == t.a_app[y];
+    }
+
+    // Ordered commit of one batch.  fit = rows of WS = W+1 words (W bitmap words, then the first-fit position);
+    // order = sorted position -> node for this epoch; wait(i) blocks until row i has landed and returns how many rows
+    // have (>= i+1), or a negative status.  result[i] = node or CNONE; consumed = entries decided (the loop stops
+    // after the first failed ask / gang unless the order is placement-insensitive).  Returns 0, or wait()'s error,
+    // or -5 when a re-score is NaN.
+    template <typename WaitFn>
+    int commit_batch(const std::vector<uint32_t>& batch, const uint32_t* fit, const uint32_t* order, bool insensitive,
+                     std::vector<uint32_t>& result, size_t& consumed, WaitFn&& wait) {
+        const int D = t.D;
+        const int B = (int)batch.size();
+        const int WS = W + 1;
+        result.assign((size_t)B, CNONE);
+        consumed = 0;
+        int landed = 0;
+        bool stop = false;
+        // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
+        struct Undo { uint32_t node; uint64_t old_key; bool was_dirty; int64_t old_avail[CMAX_D]; };
+        std::vector<Undo> undo;
+        int gang_begin = -1;
+        for (int i = 0; i < B && !stop; ++i) {
+            if (i >= landed) {
+                const int rc = wait(i);
+                if (rc < 0) return rc;
+                landed = rc;
+            }
+            const unsigned long long tc0 = profile ? commit_tsc() : 0;
+            const uint32_t ask = batch[(size_t)i];
+            const bool in_gang = t.a_gang[ask] != CNONE;
+            if (in_gang && (i == 0 || !same_gang(batch[(size_t)i - 1], ask))) { gang_begin = i; undo.clear(); }
+            const uint32_t* row = fit + (size_t)i * WS;
+            if (i + 12 < std::min(B, landed)) {                       // rows arrive by DMA and are cache-cold: pull
+                const uint32_t* nrow = fit + (size_t)(i + 12) * WS;   // the first-fit word of a row that has landed now
+                __builtin_prefetch(nrow + W);                        // ... and, for the row whose first-fit word was
+                const uint32_t* mrow = fit + (size_t)(i + 6) * WS;   // pulled six asks ago, the line its scan starts at
+                const uint32_t nf = mrow[W];
+                __builtin_prefetch(mrow + std::max<int>(front, nf == CNONE ? 0 : (int)(nf >> 5)));
+            }
+            // (A) best untouched node: first set bit of row & ~touched in sorted order
+            uint32_t posA = CNONE;
+            const uint32_t f = row[W];
+            if (f != CNONE) {
+                while (front < W && dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
+                for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
+                    ++dbg[0];
+                    const uint32_t m = row[wd] & ~dirty_words[(size_t)wd];
+                    if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
+                }
+            }
+            DirtyRef bound(~0ull, ~0u, CNONE);
+            if (posA != CNONE) {
+                const uint32_t nA = order[posA];
+                bound = DirtyRef(node(nA).key(), node(nA).rank(), nA);
+            }
+            const unsigned long long tc1 = profile ? commit_tsc() : 0;
+            // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the
+            // request exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran
+            // over the whole index without a fit leaves the bound exact (it saw every touched node), which keeps a full
+            // cluster cheap: the first failing ask pays for the walk, the following ones are pruned.
+            uint32_t chosen = CNONE;
+            DirtyIndex::Cursor cur;
+            bool at_cursor = false;   // `chosen` is the entry the cursor stands on (taken out without a search)
+            bool may_fit = f != CNONE && dirty.size() > 0;
+            if (may_fit)
+                for (int k = 0; k < D; ++k)
+                    if (t.a_req[(size_t)k * t.lda + ask] > std::max<int64_t>(dirty_ub[k], 0)) { may_fit = false; break; }
+            if (may_fit) {
+                int64_t seen[CMAX_D];
+                for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
+                const DirtyRef* d = dirty.first(cur);
+                for (; d && *d < bound; d = dirty.next(cur)) {
+                    ++dbg[1];
+                    // re-evaluated from the (cache-resident) working copy rather than from the bitmap row, whose lines
+                    // were just DMA-written and are cold
+                    if (fits_now(d->node(), ask)) { chosen = d->node(); at_cursor = true; break; }
+                    const int64_t* hh = hot.data() + (size_t)d->node() * hs + 4;   // cap
+                    for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
+                }
+                if (d == nullptr) for (int k = 0; k < D; ++k) dirty_ub[k] = seen[k];   // saw every touched node: exact
+            }
+            const unsigned long long tc2 = profile ? commit_tsc() : 0;
+            if (chosen != CNONE) ++dbg[2];
+            if (chosen == CNONE && posA != CNONE) chosen = bound.node();
+            consumed = (size_t)i + 1;
+            if (chosen == CNONE) {
+                if (in_gang) {
+                    // roll the gang back: undo its commits newest-first, void its results, skip its remaining members
+                    for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
+                        const uint32_t n = it->node;
+                        NodeView un = node(n);
+                        dirty.erase(DirtyRef(un.key(), un.rank(), n));
+                        for (int k = 0; k < D; ++k) un.avail()[k] = it->old_avail[k];
+                        un.recap();
+                        un.key() = it->old_key;
+                        if (it->was_dirty) {
+                            dirty.insert(DirtyRef(it->old_key, un.rank(), n));
+                            for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], un.cap()[k]);   // it came back
+                        } else {
+                            un.set_dirty(false);
+                            dirty_list.pop_back();
+                            const uint32_t pos = un.pos();
+                            dirty_words[pos >> 5] &= ~(1u << (pos & 31));
+                            front = std::min(front, (int)(pos >> 5));
+                        }
+                    }
+                    undo.clear();
+                    int g1 = i + 1;
+                    while (g1 < B && same_gang(ask, batch[(size_t)g1])) ++g1;
+                    for (int x = gang_begin; x < g1; ++x) result[(size_t)x] = CNONE;
+                    consumed = (size_t)g1;
+                    i = g1 - 1;
+                }
+                if (!insensitive) stop = true;
+                continue;
+            }
+            result[(size_t)i] = chosen;
+            // commit: available -= request, re-score, move inside the touched order
+            NodeView cv = node(chosen);
+            int64_t* h = cv.avail();
+            if (in_gang) {
+                Undo u; u.node = chosen; u.old_key = cv.key(); u.was_dirty = cv.dirty();
+                for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
+                undo.push_back(u);
+            }
+            if (cv.dirty()) {
+                if (at_cursor) dirty.erase_at(cur);
+                else dirty.erase(DirtyRef(cv.key(), cv.rank(), chosen));
+                ++dbg[3];
+            }
+            const unsigned long long tc3 = profile ? commit_tsc() : 0;
+            for (int k = 0; k < D; ++k) h[k] -= t.a_req[(size_t)k * t.lda + ask];
+            cv.recap();
+            const double sc = yk_node_score(D, t.policy, t.w, cv.total(), h, 1);
+            const uint64_t nk = yk_key_bits(sc);
+            if (nk == YK_KEY_NAN) return -5;
+            const unsigned long long tc4 = profile ? commit_tsc() : 0;
+            cv.key() = nk;
+            dirty.insert(DirtyRef(nk, cv.rank(), chosen));
+            if (!cv.dirty()) {
+                for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], cv.cap()[k]);
+                cv.set_dirty(true);
+                dirty_list.push_back(chosen);
+                const uint32_t pos = cv.pos();
+                dirty_words[pos >> 5] |= 1u << (pos & 31);
+            }
+            if (profile) {
+                const unsigned long long tc5 = commit_tsc();
+                prof[0] += tc1 - tc0; prof[1] += tc2 - tc1; prof[2] += tc3 - tc2; prof[3] += tc4 - tc3; prof[4] += tc5 - tc4; prof[5] += 1;
+            }
+        }
+        return 0;
+    }
+
+    // Epoch end: new node order = merge(previous order minus the touched nodes, touched nodes by new key).  Writes
+    // `out`, refreshes every moved node's position.  Returns the number of touched nodes.
+    int merge_order(const uint32_t* order, uint32_t* out, int nlive) {
+        const int nd = (int)dirty_list.size();
+        int o = 0, p = 0;
+        std::vector<DirtyRef>& ds = dirty_sorted;
+        ds.clear();
+        dirty.for_each([&](const DirtyRef& r) { ds.push_back(r); });
+        size_t j = 0;
+        int removed = 0;   // touched nodes passed over in the old order so far
+        while (true) {
+            while (p < nlive && node(order[p]).dirty()) { ++p; ++removed; }
+            if (p >= nlive) break;
+            if (j >= ds.size() && removed == nd) {
+                // every touched node has been taken out and put back: the rest of the order is unchanged
+                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
+                o += nlive - p;
+                p = nlive;
+                break;
+            }
+            const uint32_t n = order[p];
+            const DirtyRef c(node(n).key(), node(n).rank(), n);
+            while (j < ds.size() && ds[j] < c) { node(ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
+            node(n).set_pos((uint32_t)o);
+            out[o++] = n;
+            ++p;
+        }
+        while (j < ds.size()) { node(ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
+        return nd;
+    }
+};
+
+}  // namespace yk

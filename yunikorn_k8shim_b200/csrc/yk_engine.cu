@@ -27,7 +27,7 @@
 #include <x86intrin.h>
 
 #include "yk_kernels.cuh"
-#include "yk_dirty.hpp"
+#include "yk_commit.hpp"
 #include "yk_orderer.hpp"
 
 namespace {
@@ -65,15 +65,11 @@ struct Pin {
     ~Pin() { free(); }
 };
 
-inline unsigned long long yk_tsc() { unsigned aux; unsigned long long t = __rdtscp(&aux); _mm_lfence(); return t; }
 
 double now_ms() {
     using namespace std::chrono;
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
-
-using yk::DirtyRef;
-using yk::DirtyIndex;
 
 // A helper thread that fills and launches the NEXT batch while the caller's thread commits the current one
 // (the orderer state is only touched by one of the two at a time: fork before the commit, join after it).
@@ -186,22 +182,16 @@ struct yk_engine {
     Pin<uint32_t> h_snode, h_dirty_nodes; Pin<uint64_t> h_skey; Pin<int64_t> h_dirty_vals;
     Pin<int> h_flag; Pin<double> h_scores;
 
-    // commit scratch
-    std::vector<uint32_t> dirty_words;
-    std::vector<uint32_t> dirty_list;
+    // ordered commit (host logic, csrc/yk_commit.hpp): working copy of the nodes, touched-node index, epoch state
+    yk::Committer cm;
     Pin<uint32_t> h_order[2]; int cur = 0;   // node order (ascending (score, NodeID)), double-buffered
     Dev<uint32_t> d_order;
-    int64_t dirty_ub[YK_MAX_D];              // per dimension: upper bound of `available` over the touched nodes
-    int front = 0;                           // every sorted position below word `front` is dirty (per epoch)
     int epochW = 0;                          // words per fit row in the current epoch
     uint32_t epoch_limit = 8192;             // an epoch ends before its touched-node count would pass this
     uint32_t epoch_floor = 8192, epoch_env = 0;
     bool prof = false;                       // YK_PROFILE_COMMIT: TSC split of the commit loop into st.dbg2[]
     bool no_spec = false;                    // debugging: never launch batch k+1 before batch k is committed
-    DirtyIndex dirty;
-    std::vector<DirtyRef> dirty_sorted;      // scratch: the touched nodes in order, for the epoch-end merge
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
-    std::vector<int64_t> hot; int hs = 0;    // per node working record of the commit (see NodeView)
 
     yk::Orderer ord;
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
@@ -306,45 +296,6 @@ void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s, int slots) {
     }
 }
 
-// Full (ask,node) predicate on the commit's working copy, for nodes already committed to in this batch
-// (such nodes are schedulable and unreserved: they were chosen before).  Same steps as the sweep kernel.
-inline bool fits_now(const yk_engine* e, uint32_t node, uint32_t ask) {
-    // everything this needs sits in the first 64 bytes of the node's record at D = 4 (see NodeView)
-    const int64_t* h = e->hot.data() + (size_t)node * e->hs;
-    const int D = e->D;
-    const uint64_t taint = (uint64_t)h[2], label = (uint64_t)h[3];
-    if ((taint & ~e->a_tol[ask]) | (~label & e->a_need[ask]) | (label & e->a_deny[ask])) return false;
-    if (e->a_node[ask] != YK_NONE && e->a_node[ask] != node) return false;
-    for (int k = 0; k < D; ++k)
-        if (e->a_req[(size_t)k * e->maxA + ask] > h[4 + k]) return false;   // cap = min(max(0,total), max(0,available))
-    return true;
-}
-
-// The commit's per-node working record lives in one contiguous slice of e->hot (hs = 4 + 3D words):
-//   [0] current sort key   [1] rank<<32 | dirty<<31 | position   [2] taint   [3] label
-//   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
-//   [4+D,4+2D) available   [4+2D,4+3D) total            -- only read when the node is actually committed to
-struct NodeView {
-    int64_t* h; int D;
-    uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[0]); }
-    uint32_t rank() const { return (uint32_t)((uint64_t)h[1] >> 32); }
-    uint32_t pos() const { return (uint32_t)((uint64_t)h[1]) & 0x7FFFFFFFu; }
-    bool dirty() const { return (((uint64_t)h[1]) >> 31) & 1u; }
-    void set_meta(uint32_t rank, uint32_t pos) { h[1] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
-    void set_pos(uint32_t pos) { h[1] = (int64_t)((((uint64_t)h[1]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
-    void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
-    int64_t* cap() { return h + 4; }
-    int64_t* avail() { return h + 4 + D; }
-    int64_t* total() { return h + 4 + 2 * D; }
-    void recap() {   // after `available` changed
-        for (int k = 0; k < D; ++k) {
-            const int64_t a = avail()[k] < 0 ? 0 : avail()[k], t = total()[k] < 0 ? 0 : total()[k];
-            cap()[k] = a < t ? a : t;
-        }
-    }
-};
-inline NodeView node_view(yk_engine* e, uint32_t n) { return NodeView{e->hot.data() + (size_t)n * e->hs, e->D}; }
-
 // Initial node order of a cycle, computed on the device: float64 score per node (yk_key_kernel), stable radix
 // sort by key over NodeID-rank order = ascending (score, NodeID).  Later batches keep it current by merging.
 int initial_order(yk_engine* e) {
@@ -371,26 +322,17 @@ int initial_order(yk_engine* e) {
     e->st.sort_ms += ms;
     e->cur = 0;
     const uint32_t* ord = e->h_order[0].p;
-    e->hs = 4 + 3 * e->D;
-    e->hot.resize((size_t)e->n_hi * e->hs);
-    // working copy of the node table, built in index order (sequential reads of the column-major host tables)
-    const int D = e->D;
-    for (int k = 0; k < D; ++k) {
-        const int64_t* av = e->n_avail.p + (size_t)k * e->maxN;
-        const int64_t* to = e->n_total.p + (size_t)k * e->maxN;
-        int64_t* h = e->hot.data();
-        for (uint32_t n = 0; n < e->n_hi; ++n) { h[(size_t)n * e->hs + 4 + D + k] = av[n]; h[(size_t)n * e->hs + 4 + 2 * D + k] = to[n]; }
-    }
-    for (uint32_t n = 0; n < e->n_hi; ++n) {
-        NodeView v = node_view(e, n);
-        v.h[2] = (int64_t)e->n_taint[n];
-        v.h[3] = (int64_t)e->n_label[n];
-        v.recap();
-    }
+    // the commit's working copy of the node table, and each live node's key / rank / position in the order
+    yk::CommitTables& ct = e->cm.t;
+    ct.D = e->D; ct.policy = e->cfg.policy; ct.w = e->w.w; ct.lda = e->maxA;
+    ct.a_req = e->a_req.p; ct.a_tol = e->a_tol.p; ct.a_need = e->a_need.p; ct.a_deny = e->a_deny.p; ct.a_node = e->a_node.p;
+    ct.a_gang = e->a_gang.data(); ct.a_app = e->a_app.data();
+    e->cm.profile = e->prof;
+    e->cm.build(e->n_hi, e->n_avail.p, e->n_total.p, e->maxN, e->n_taint.p, e->n_label.p);
     for (int p = 0; p < nlive; ++p) {
         const uint32_t n = ord[p];
-        node_view(e, n).key() = e->h_skey[(size_t)p];
-        node_view(e, n).set_meta(e->n_rank[n], (uint32_t)p);
+        e->cm.node(n).key() = e->h_skey[(size_t)p];
+        e->cm.node(n).set_meta(e->n_rank[n], (uint32_t)p);
     }
     return YK_OK;
 }
@@ -404,15 +346,10 @@ int initial_order(yk_engine* e) {
 // epoch do not depend on each other's commits, the next batch's sweep and read-back overlap the current commit.
 int begin_epoch(yk_engine* e) {
     const int nlive = (int)e->nlive;
-    for (uint32_t n : e->dirty_list) node_view(e, n).set_dirty(false);
-    e->dirty_list.clear();
-    e->dirty.clear();
-    e->front = 0;
-    for (int k = 0; k < YK_MAX_D; ++k) e->dirty_ub[k] = INT64_MIN;
-    if (nlive == 0) { e->epochW = 0; return YK_OK; }
     const int Np = (int)round_up((size_t)nlive, NODE_TILE);
-    e->epochW = Np / 32;
-    e->dirty_words.assign((size_t)e->epochW, 0);
+    e->epochW = nlive ? Np / 32 : 0;
+    e->cm.begin_epoch(e->epochW);
+    if (nlive == 0) return YK_OK;
     cudaStream_t s = e->stream;
     CK(cudaMemcpyAsync(e->d_order.p, e->h_order[e->cur].p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyHostToDevice, s));
     e->st.h2d_bytes += sizeof(uint32_t) * (size_t)nlive;
@@ -428,38 +365,12 @@ int begin_epoch(yk_engine* e) {
 // goes back to the column-major host table and to the device table.  `reorder` false = end of cycle (state only).
 int end_epoch(yk_engine* e, bool reorder) {
     const int D = e->D, nlive = (int)e->nlive;
-    const int nd = (int)e->dirty_list.size();
+    const int nd = (int)e->cm.dirty_list.size();
     if (!nd) return YK_OK;
     const double t0 = now_ms();
     cudaStream_t s = e->stream;
-    DirtyIndex& dirty = e->dirty;
     if (reorder) {
-        const uint32_t* order = e->h_order[e->cur].p;
-        uint32_t* out = e->h_order[e->cur ^ 1].p;
-        int o = 0, p = 0;
-        std::vector<DirtyRef>& ds = e->dirty_sorted;
-        ds.clear();
-        dirty.for_each([&](const DirtyRef& r) { ds.push_back(r); });
-        size_t j = 0;
-        int removed = 0;   // touched nodes passed over in the old order so far
-        while (true) {
-            while (p < nlive && node_view(e, order[p]).dirty()) { ++p; ++removed; }
-            if (p >= nlive) break;
-            if (j >= ds.size() && removed == nd) {
-                // every touched node has been taken out and put back: the rest of the order is unchanged
-                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
-                o += nlive - p;
-                p = nlive;
-                break;
-            }
-            const uint32_t n = order[p];
-            const DirtyRef c(node_view(e, n).key(), node_view(e, n).rank(), n);
-            while (j < ds.size() && ds[j] < c) { node_view(e, ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
-            node_view(e, n).set_pos((uint32_t)o);
-            out[o++] = n;
-            ++p;
-        }
-        while (j < ds.size()) { node_view(e, ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
+        e->cm.merge_order(e->h_order[e->cur].p, e->h_order[e->cur ^ 1].p, nlive);
         e->cur ^= 1;
     }
     // staging is reused: the previous epoch's upload must have been consumed
@@ -467,10 +378,10 @@ int end_epoch(yk_engine* e, bool reorder) {
     for (int i0 = 0; i0 < nd; i0 += (int)e->h_dirty_nodes.n) {
         const int cnt = std::min<int>(nd - i0, (int)e->h_dirty_nodes.n);
         for (int i = 0; i < cnt; ++i) {
-            const uint32_t n = e->dirty_list[(size_t)(i0 + i)];
+            const uint32_t n = e->cm.dirty_list[(size_t)(i0 + i)];
             e->h_dirty_nodes[(size_t)i] = n;
             for (int k = 0; k < D; ++k) {
-                const int64_t v = node_view(e, n).avail()[k];
+                const int64_t v = e->cm.node(n).avail()[k];
                 e->h_dirty_vals[(size_t)k * cnt + i] = v;
                 e->n_avail[(size_t)k * e->maxN + n] = v;   // column-major host table stays authoritative between cycles
             }
@@ -583,10 +494,9 @@ int drain(yk_engine* e, Slot& sl) {
     return YK_OK;
 }
 
-// Ordered commit of one batch from its (arriving) bitmaps.  result[i] = node or YK_NONE; consumed = how many
-// entries were decided (stops after the first failed ask / gang unless the order is placement-insensitive).
+// Ordered commit of one batch from its (arriving) bitmaps: the logic is yk::Committer::commit_batch; this wrapper
+// supplies the rows as the read-back chunks land and keeps the timing / counters.
 int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& result, size_t& consumed) {
-    const int D = e->D;
     const int B = sl.B;
     const std::vector<uint32_t>& batch = sl.asks;
     result.assign((size_t)B, YK_NONE);
@@ -594,159 +504,29 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
     if (e->nlive == 0 || sl.nchunks == 0) {   // no nodes: nothing fits
         consumed = insensitive ? (size_t)B : std::min<size_t>(1, (size_t)B);
         if (!insensitive && B > 0 && e->a_gang[batch[0]] != YK_NONE)
-            while (consumed < (size_t)B && e->a_gang[batch[consumed]] == e->a_gang[batch[0]] && e->a_app[batch[consumed]] == e->a_app[batch[0]]) ++consumed;
+            while (consumed < (size_t)B && e->cm.same_gang(batch[0], batch[consumed])) ++consumed;
         return YK_OK;
     }
-    const int W = sl.W, WS = W + 1;
-    const uint32_t* order = e->h_order[e->cur].p;
-    DirtyIndex& dirty = e->dirty;
-    int& front = e->front;
-    const uint32_t* fit = sl.h_fit.p;
-    double t_wait = 0, t1 = now_ms();
-    int next_chunk = 0;
-    bool stop = false;
-    // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
-    struct Undo { uint32_t node; uint64_t old_key; bool was_dirty; int64_t old_avail[YK_MAX_D]; };
-    std::vector<Undo> undo;
-    int gang_begin = -1;
-    auto same_gang = [&](int x, int y) {
-        return e->a_gang[batch[(size_t)x]] != YK_NONE && e->a_gang[batch[(size_t)x]] == e->a_gang[batch[(size_t)y]] &&
-               e->a_app[batch[(size_t)x]] == e->a_app[batch[(size_t)y]];
-    };
-    for (int i = 0; i < B && !stop; ++i) {
-        while (i >= next_chunk * sl.chunk) {
+    double t_wait = 0;
+    const double t1 = now_ms();
+    int next_chunk = 0, wait_rc = YK_OK;
+    auto wait = [&](int row) -> int {   // block until the chunk holding `row` has landed; -> rows landed so far
+        while (row >= next_chunk * sl.chunk) {
             const double tw = now_ms();
-            CK(cudaEventSynchronize(sl.ev[(size_t)next_chunk]));
+            const cudaError_t ce = cudaEventSynchronize(sl.ev[(size_t)next_chunk]);
             t_wait += now_ms() - tw;
+            if (ce != cudaSuccess) { wait_rc = e->cuda_fail(ce, "cudaEventSynchronize(read-back chunk)"); return -1; }
             ++next_chunk;
-            if (e->p2p && sl.h_err[0]) return e->fail(YK_ERR_COMM, "peer-to-peer exchange timed out waiting for another rank");
-        }
-        unsigned long long tc0 = e->prof ? yk_tsc() : 0;
-        const uint32_t ask = batch[(size_t)i];
-        const bool in_gang = e->a_gang[ask] != YK_NONE;
-        if (in_gang && (i == 0 || !same_gang(i - 1, i))) { gang_begin = i; undo.clear(); }
-        const uint32_t* row = fit + (size_t)i * WS;
-        if (i + 12 < std::min(B, next_chunk * sl.chunk)) {   // rows arrive by DMA and are cache-cold: pull the line the
-            const uint32_t* nrow = fit + (size_t)(i + 12) * WS;   // scan will start at (only rows that have landed)
-            __builtin_prefetch(nrow + W);                        // its first-fit word now ...
-            const uint32_t* mrow = fit + (size_t)(i + 6) * WS;   // ... and, for a row whose first-fit word was pulled
-            const uint32_t nf = mrow[W];                         // six asks ago, the line the scan will start at
-            __builtin_prefetch(mrow + std::max<int>(front, nf == YK_NONE ? 0 : (int)(nf >> 5)));
-        }
-        // (A) best untouched node: first set bit of row & ~dirty in sorted order
-        uint32_t posA = YK_NONE;
-        const uint32_t f = row[W];
-        if (f != YK_NONE) {
-            while (front < W && e->dirty_words[(size_t)front] == 0xFFFFFFFFu) ++front;
-            for (int wd = std::max((int)(f >> 5), front); wd < W; ++wd) {
-                ++e->st.dbg[0];
-                const uint32_t m = row[wd] & ~e->dirty_words[(size_t)wd];
-                if (m) { posA = (uint32_t)wd * 32u + (uint32_t)__builtin_ctz(m); break; }
+            if (e->p2p && sl.h_err[0]) {
+                wait_rc = e->fail(YK_ERR_COMM, "peer-to-peer exchange timed out waiting for another rank");
+                return -1;
             }
         }
-        DirtyRef bound(~0ull, ~0u, YK_NONE);
-        if (posA != YK_NONE) {
-            const uint32_t nA = order[posA];
-            bound = DirtyRef(node_view(e, nA).key(), node_view(e, nA).rank(), nA);
-        }
-        unsigned long long tc1 = e->prof ? yk_tsc() : 0;
-        // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the request
-        // exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran over the
-        // whole list without a fit leaves the bound exact (it saw every touched node), which is what keeps a full
-        // cluster cheap: the first failing ask pays for the walk, the following ones are pruned.
-        uint32_t chosen = YK_NONE;
-        DirtyIndex::Cursor cur;
-        bool at_cursor = false;   // `chosen` is the entry the cursor stands on (it can be taken out without a search)
-        bool may_fit = f != YK_NONE && dirty.size() > 0;
-        if (may_fit)
-            for (int k = 0; k < D; ++k)
-                if (e->a_req[(size_t)k * e->maxA + ask] > std::max<int64_t>(e->dirty_ub[k], 0)) { may_fit = false; break; }
-        if (may_fit) {
-            int64_t seen[YK_MAX_D];
-            for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
-            const DirtyRef* d = dirty.first(cur);
-            for (; d && *d < bound; d = dirty.next(cur)) {
-                ++e->st.dbg[1];
-                // re-evaluated from the (cache-resident) tables rather than from the bitmap row, whose
-                // lines were just DMA-written and are cold
-                if (fits_now(e, d->node(), ask)) { chosen = d->node(); at_cursor = true; break; }
-                const int64_t* hh = e->hot.data() + (size_t)d->node() * e->hs + 4;   // cap
-                for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
-            }
-            if (d == nullptr) for (int k = 0; k < D; ++k) e->dirty_ub[k] = seen[k];   // saw every touched node: exact
-        }
-        unsigned long long tc2 = e->prof ? yk_tsc() : 0;
-        if (chosen != YK_NONE) ++e->st.dbg[2];   // a re-scored node won
-        if (chosen == YK_NONE && posA != YK_NONE) chosen = bound.node();
-        consumed = (size_t)i + 1;
-        if (chosen == YK_NONE) {
-            if (in_gang) {
-                // roll the gang back: undo its commits newest-first, void its results, skip its remaining members
-                for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
-                    const uint32_t n = it->node;
-                    dirty.erase(DirtyRef(node_view(e, n).key(), node_view(e, n).rank(), n));
-                    NodeView un = node_view(e, n);
-                    int64_t* hh = un.cap();
-                    for (int k = 0; k < D; ++k) un.avail()[k] = it->old_avail[k];
-                    un.recap();
-                    node_view(e, n).key() = it->old_key;
-                    if (it->was_dirty) {
-                        dirty.insert(DirtyRef(it->old_key, node_view(e, n).rank(), n));
-                        for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], hh[k]);   // availability came back
-                    }
-                    else {
-                        node_view(e, n).set_dirty(false);
-                        e->dirty_list.pop_back();
-                        const uint32_t pos = node_view(e, n).pos();
-                        e->dirty_words[pos >> 5] &= ~(1u << (pos & 31));
-                        front = std::min(front, (int)(pos >> 5));
-                    }
-                }
-                undo.clear();
-                int g1 = i + 1;
-                while (g1 < B && same_gang(i, g1)) ++g1;
-                for (int x = gang_begin; x < g1; ++x) result[(size_t)x] = YK_NONE;
-                consumed = (size_t)g1;
-                i = g1 - 1;
-            }
-            if (!insensitive) stop = true;
-            continue;
-        }
-        result[(size_t)i] = chosen;
-        // commit: available -= request, re-score, move inside the dirty order
-        NodeView cv = node_view(e, chosen);
-        int64_t* h = cv.avail();
-        if (in_gang) {
-            Undo u; u.node = chosen; u.old_key = node_view(e, chosen).key(); u.was_dirty = node_view(e, chosen).dirty() != 0;
-            for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
-            undo.push_back(u);
-        }
-        if (node_view(e, chosen).dirty()) {
-            if (at_cursor) dirty.erase_at(cur);
-            else dirty.erase(DirtyRef(node_view(e, chosen).key(), node_view(e, chosen).rank(), chosen));
-            ++e->st.dbg[3];
-        }
-        unsigned long long tc3 = e->prof ? yk_tsc() : 0;
-        for (int k = 0; k < D; ++k) h[k] -= e->a_req[(size_t)k * e->maxA + ask];
-        cv.recap();
-        const double sc = yk_node_score(D, e->cfg.policy, e->w.w, cv.total(), h, 1);
-        const uint64_t nk = yk_key_bits(sc);
-        if (nk == YK_KEY_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
-        unsigned long long tc4 = e->prof ? yk_tsc() : 0;
-        node_view(e, chosen).key() = nk;
-        dirty.insert(DirtyRef(nk, node_view(e, chosen).rank(), chosen));
-        if (!node_view(e, chosen).dirty()) {
-            for (int k = 0; k < D; ++k) e->dirty_ub[k] = std::max(e->dirty_ub[k], cv.cap()[k]);
-            node_view(e, chosen).set_dirty(true);
-            e->dirty_list.push_back(chosen);
-            const uint32_t pos = node_view(e, chosen).pos();
-            e->dirty_words[pos >> 5] |= 1u << (pos & 31);
-        }
-        if (e->prof) {
-            const unsigned long long tc5 = yk_tsc();
-            e->st.prof[0] += tc1 - tc0; e->st.prof[1] += tc2 - tc1; e->st.prof[2] += tc3 - tc2; e->st.prof[3] += tc4 - tc3; e->st.prof[4] += tc5 - tc4; e->st.prof[5] += 1;
-        }
-    }
+        return std::min(B, next_chunk * sl.chunk);
+    };
+    const int rc = e->cm.commit_batch(batch, sl.h_fit.p, e->h_order[e->cur].p, insensitive, result, consumed, wait);
+    if (rc == -5) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
+    if (rc < 0) return wait_rc ? wait_rc : e->fail(YK_ERR_CUDA, "commit aborted");
     // all read-back must have landed before the slot's buffers are reused
     {
         const double tw = now_ms();
@@ -1114,7 +894,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         Slot& Nx = e->slot[cur ^ 1];
         // speculate the next batch on the same epoch view unless this batch may fill the epoch
         Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
-        const bool room = e->dirty_list.size() + (size_t)A.B < (size_t)e->epoch_limit;
+        const bool room = e->cm.dirty_list.size() + (size_t)A.B < (size_t)e->epoch_limit;
         const size_t left = (size_t)max_bindings - n;
         bool forked = false;
         int rc_next = YK_OK;
@@ -1160,7 +940,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, e->batch), bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
         if (Nx.B == 0 && n < max_bindings) {
             // nothing in flight: the epoch may end here (merge order, refresh the device view) before the next batch
-            if (e->dirty_list.size() * 2 >= (size_t)e->epoch_limit || failed) {
+            if (e->cm.dirty_list.size() * 2 >= (size_t)e->epoch_limit || failed) {
                 rc = end_epoch(e, true);
                 if (rc) return rc;
                 rc = begin_epoch(e);
@@ -1173,9 +953,9 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     }
     rc = end_epoch(e, false);   // leave host and device node tables current for the next call
     if (rc) return rc;
-    for (uint32_t nn : e->dirty_list) node_view(e, nn).set_dirty(false);
-    e->dirty_list.clear();
-    e->dirty.clear();
+    e->cm.begin_epoch(e->epochW);   // nothing touched any more
+    for (int k = 0; k < 4; ++k) { e->st.dbg[k] += e->cm.dbg[k]; e->cm.dbg[k] = 0; }
+    for (int k = 0; k < 6; ++k) { e->st.prof[k] += e->cm.prof[k]; e->cm.prof[k] = 0; }
     CK(cudaStreamSynchronize(e->stream));
     e->ord.finish();
     for (uint32_t a : e->ord.slow_list) {

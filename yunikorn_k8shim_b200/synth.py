@@ -319,6 +319,22 @@ def gangs(n_nodes=10_000, n_gangs=2000, members=10, seed=5, policy=POLICY_FAIR, 
                    z.copy(), z.copy(), ask_gang=app.copy(), meta={"config": 5, "seed": seed})
 
 
+def poisoned_gangs(seed: int, n_nodes=64, n_gangs=80, members=4, policy=POLICY_FAIR) -> Snapshot:
+    """Roll-back stress: an under-committed gangs() cluster where ~30% of the gangs have a LAST member no node can
+    hold (so the gang is placed, then undone) and half of the healthy gangs are dissolved into plain asks, so single
+    asks keep landing on nodes that roll-backs have just handed back."""
+    s = gangs(n_nodes, n_gangs, members, seed=seed, fill=0.7, policy=policy)
+    rng = np.random.default_rng(seed)
+    bad = rng.random(n_gangs) < 0.3
+    last = np.arange(n_gangs) * members + members - 1
+    s.ask_req[last[bad], 2] = 1 << 31
+    plain = (~bad) & (rng.random(n_gangs) < 0.5)
+    for g in np.nonzero(plain)[0]:
+        s.ask_gang[g * members:(g + 1) * members] = -1
+    s.name = f"poisoned-gangs-{seed}"
+    return s
+
+
 def fuzz(seed: int, n_nodes=None, n_asks=None) -> Snapshot:
     """Small snapshot mixing every feature of the path at once (used by the randomized parity tests): random queue
     tree with guarantees and quotas, fifo and fair leaves, priorities, gangs, taints / selectors, pod.Spec.NodeName,
