@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
                     help="BASELINE config to run instead of the headline config 2 (4 = 50k nodes / 200k pods, DRF queues; 5 = gangs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-row-sharing", action="store_true",
+                    help="sweep one row per ask even when asks have identical predicate inputs (YK_FLAG_NO_ROW_SHARING)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -144,14 +146,18 @@ def main():
     else:
         snap = synth.perf(N_NODES, N_APPS, TASKS, masks=args.masks or args.config == 3)
     N, A, D = snap.n_nodes, snap.n_asks, snap.D
-    eng = Engine(D=D, policy=snap.policy, weights=snap.weights, max_nodes=N, max_asks=A, max_apps=snap.n_apps,
-                 max_queues=snap.n_queues, batch=args.batch, device=local_rank, rank=rank, world=world)
-    exchange = None
-    if world > 1:
-        from yunikorn_k8shim_b200 import multigpu
-        exchange = multigpu.attach(eng, dist)
-    eng.queues_set(snap.q_parent, snap.q_guaranteed, snap.q_max, snap.q_alloc, snap.q_sort)
-    eng.apps_upsert(np.arange(snap.n_apps), snap.app_queue, snap.app_submit)
+    def make_engine(share_rows):
+        e = Engine(D=D, policy=snap.policy, weights=snap.weights, max_nodes=N, max_asks=A, max_apps=snap.n_apps,
+                   max_queues=snap.n_queues, batch=args.batch, device=local_rank, rank=rank, world=world, share_rows=share_rows)
+        x = None
+        if world > 1:
+            from yunikorn_k8shim_b200 import multigpu
+            x = multigpu.attach(e, dist)
+        e.queues_set(snap.q_parent, snap.q_guaranteed, snap.q_max, snap.q_alloc, snap.q_sort)
+        e.apps_upsert(np.arange(snap.n_apps), snap.app_queue, snap.app_submit)
+        return e, x
+
+    eng, exchange = make_engine(not args.no_row_sharing)
 
     # host buffers in the ABI's layout (column-major), prepared once outside the timed region
     idxN, idxA = np.arange(N, dtype=np.uint32), np.arange(A, dtype=np.uint32)
@@ -161,7 +167,7 @@ def main():
     h2d_step = N * (16 * D + 8 + 8 + 4 + 4) + A * (8 * D + 8 * 3 + 4)
     d2h_step = A * 8
 
-    def upsert_all():
+    def upsert_all(eng):
         eng.nodes_upsert(idxN, totalT, availT, snap.node_taint, snap.node_label, rank_arr, snap.node_flags)
         eng.asks_upsert(idxA, reqT, snap.ask_app, snap.ask_create, snap.ask_tol, snap.ask_need, snap.ask_deny,
                         snap.ask_prio, snap.ask_node, snap.ask_flags, snap.ask_gang)
@@ -177,21 +183,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def one_step(e2e: bool):
+    def one_step(eng, eng_alloc, e2e: bool):
         """returns (seconds, n_bindings, ask, node)"""
         if e2e:
             if eng_alloc[0] is not None:
                 eng.release(eng_alloc[0])
             l2_flush(); barrier()
             t0 = time.perf_counter()
-            upsert_all()
+            upsert_all(eng)
             ask, node, _ = eng.cycle(A)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         else:
             if eng_alloc[0] is not None:
                 eng.release(eng_alloc[0])
-            upsert_all()
+            upsert_all(eng)
             eng.evaluate(0, 0)              # forces the table upload: inputs resident in HBM before timing
             l2_flush(); barrier()
             t0 = time.perf_counter()
@@ -203,14 +209,14 @@ def main():
 
     eng_alloc = [None]
     for _ in range(args.warmup):
-        one_step(False)
-        one_step(True)
+        one_step(eng, eng_alloc, False)
+        one_step(eng, eng_alloc, True)
 
-    def timed(e2e):
+    def timed(e2e, eng=eng, eng_alloc=eng_alloc, steps=args.steps):
         eng.stats_reset()
         tot, n = 0.0, 0
-        for _ in range(args.steps):
-            dt, k, ask, node = one_step(e2e)
+        for _ in range(steps):
+            dt, k, ask, node = one_step(eng, eng_alloc, e2e)
             tot += dt
             n += k
         if world > 1:
@@ -224,18 +230,39 @@ def main():
         tot_e, n_e, ask_e, node_e, st_e = timed(True)
     clocks = cs.summary()
 
-    if rank == 0:
-        hbm, hbm_src = peaks()
+    def sweep_roofline(st, hbm, hbm_src):
         launches = st["sweep_launches"]
         pairs_per_launch = st["evaluations"] / max(launches, 1)
-        asks_per_launch = pairs_per_launch / N
-        alg_bytes = pairs_per_launch * B_NODE + asks_per_launch * B_ASK
+        rows_per_launch = pairs_per_launch / N
+        alg_bytes = pairs_per_launch * B_NODE + rows_per_launch * B_ASK
         ms_launch = st["sweep_ms"] / max(launches, 1)
         achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        if os.path.exists(tp):   # the ncu capture is of full launches (one row per ask): only comparable to those
+            prof = json.load(open(tp))
+            if abs(prof.get("rows_per_launch", 3846) - rows_per_launch) < 0.25 * rows_per_launch:
+                traffic = prof.get("dram_bytes_per_launch")
+        return {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": traffic, "peak_source": hbm_src, "kernel": "yk_sweep_kernel",
+                "ms_per_launch": ms_launch, "pairs_per_launch": pairs_per_launch, "rows_per_launch": rows_per_launch,
+                "launches_per_step": launches / args.steps}
+
+    # the same workload once more with one row per ask (row sharing off): what the sweep kernel does at full load
+    unshared = None
+    if world == 1 and not args.no_row_sharing and st["rows_swept"] * 2 < st["asks_swept"]:
+        eng2, _ = make_engine(False)
+        alloc2 = [None]
+        for _ in range(3):
+            one_step(eng2, alloc2, False)
+        steps2 = max(3, min(args.steps, 5))
+        tot2, n2, _, _, st2 = timed(False, eng2, alloc2, steps2)
+        unshared = (tot2, n2, st2, steps2)
+        eng2.close()
+
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        roof = sweep_roofline(st, hbm, hbm_src)
         out = {
             "metric": METRIC, "value": n / tot, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -244,23 +271,35 @@ def main():
                                     5: "config5: 10k nodes / 2000 gangs x 10, all-or-nothing"}.get(args.config) or
                                    (("config3: 10k nodes / 50k pods + taints + nodeAffinity bitmasks" if (args.masks or args.config == 3) else
                                      "config2: 10k nodes / 50k pending pods, D=4, no affinity") + ", fair node sort, 1 leaf queue, 400 apps x 125"),
-                       "batch": st["evaluations"] // max(launches, 1) // N, "l2": "flushed between steps (256 MiB write)",
+                       "batch": int(st["asks_swept"] // max(st["batches"], 1)),
+                       "row_sharing": (not args.no_row_sharing), "l2": "flushed between steps (256 MiB write)",
                        "parallelism": f"ask-sharded x{world}, exchange={exchange}" if world > 1 else "single GPU"},
             "e2e": {"value": n_e / tot_e, "unit": UNIT, "ms_per_step": tot_e / args.steps * 1e3,
                     "h2d_bytes_per_step": int(st_e["h2d_bytes"] // args.steps), "d2h_bytes_per_step": int(st_e["d2h_bytes"] // args.steps),
                     "abi_h2d_payload": h2d_step, "abi_d2h_payload": d2h_step},
             "gpu_launches": int(st["sweep_launches"] + st["other_launches"]),
-            "evaluations_per_s": st["evaluations"] / tot,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": hbm_src, "kernel": "yk_sweep_kernel",
-                         "ms_per_launch": ms_launch, "pairs_per_launch": pairs_per_launch,
-                         "note": "algorithmic bytes follow SURVEY 8(d)'s streaming model (64 B per evaluation); the kernel keeps the "
-                                 "node tile in registers and the ask chunk in shared memory, so real DRAM traffic is far below it and "
-                                 "frac > 1 is expected: the kernel is bound by integer-compare issue rate, not HBM (DESIGN.md)"},
+            "evaluations_per_s": st["evaluations"] / tot,                       # (row,node) pairs the kernel really evaluated
+            "evaluations_represented_per_s": st["asks_swept"] * N / tot,        # (ask,node) pairs those rows stand for
+            "rows_swept_per_step": st["rows_swept"] / args.steps, "asks_swept_per_step": st["asks_swept"] / args.steps,
+            "roofline": dict(roof, note=(
+                "algorithmic bytes follow SURVEY 8(d)'s streaming model (64 B per evaluation); the kernel keeps the node tile "
+                "in registers and the ask chunk in shared memory, so real DRAM traffic is far below it and frac > 1 is "
+                "possible: the kernel is bound by integer-compare issue rate, not HBM (DESIGN.md)."
+                + (" Row sharing is on: asks with identical predicate inputs share one swept row, so the launches in this "
+                   "timed region are small (rows_per_launch) and latency-bound; roofline_one_row_per_ask is the same "
+                   "kernel on the same workload with sharing off." if unshared else ""))),
             "phase_ms_per_step": {"sweep": st["sweep_ms"] / args.steps, "key_sort_gather": st["sort_ms"] / args.steps,
                                   "ordered_commit": st["commit_ms"] / args.steps, "cycle_total": st["total_ms"] / args.steps},
             "clocks": clocks,
         }
+        if unshared:
+            tot2, n2, st2, steps2 = unshared
+            r2 = sweep_roofline(dict(st2, sweep_launches=st2["sweep_launches"]), hbm, hbm_src)
+            r2["launches_per_step"] = st2["sweep_launches"] / steps2
+            out["roofline_one_row_per_ask"] = r2
+            out["one_row_per_ask"] = {"value": n2 / tot2, "unit": UNIT, "ms_per_step": tot2 / steps2 * 1e3, "steps": steps2,
+                                      "evaluations_per_s": st2["evaluations"] / tot2,
+                                      "d2h_bytes_per_step": int(st2["d2h_bytes"] // steps2)}
         if not args.no_cpu_baseline:
             from oracle import oracle_ctypes as oc
             oc.run(snap)

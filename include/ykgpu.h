@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define YK_ABI_VERSION 1
+#define YK_ABI_VERSION 2
 #define YK_MAX_D 8
 #define YK_NONE 0xFFFFFFFFu          /* "no node" / "no gang" index */
 
@@ -94,6 +94,10 @@ typedef enum {
 #define YK_FAIL_RESOURCES 8
 #define YK_FAIL_ABSENT 9         /* pod or node not in the cache (context.go:686-694) */
 
+/* yk_config.flags */
+#define YK_FLAG_NO_ROW_SHARING 1u   /* sweep one row per ask even when asks of a batch have identical predicate inputs
+                                      (requests, tolerations, label masks, node name); default: one row per distinct set */
+
 typedef struct yk_engine yk_engine;
 
 typedef struct {
@@ -104,7 +108,7 @@ typedef struct {
     double weights[YK_MAX_D];    /* node-sort resource weights; core default vcore=1, memory=1 */
     uint32_t max_nodes, max_asks, max_apps, max_queues;
     int32_t device;              /* CUDA ordinal, -1 = current device */
-    uint32_t reserved0;          /* must be 0 */
+    uint32_t flags;              /* YK_FLAG_* (0 = defaults) */
     /* multi-GPU (one process per GPU): asks of every batch are split in `world` contiguous shards, this
        engine sweeps shard `rank`; the caller wires the exchange with yk_set_exchange.  world<=1: single GPU */
     uint32_t rank, world;
@@ -130,6 +134,8 @@ typedef struct {
     /* with YK_PROFILE_COMMIT set: TSC cycles in the commit loop -- 0 clean scan, 1 re-scored walk, 2 choose + undo log
        + erase, 3 subtract + float64 re-score, 4 re-insert + bookkeeping, 5 asks counted */
     uint64_t prof[6];
+    /* row sharing: asks that went through a sweep batch, and the rows (distinct predicate signatures) actually swept */
+    uint64_t asks_swept, rows_swept;
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

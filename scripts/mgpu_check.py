@@ -10,7 +10,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok_all = True
 for snap, batch in ((synth.perf(900, 20, 100, masks=True), 256), (synth.hier(300, 3, 4, 2, 40, priorities=True), 128),
-                    (synth.gangs(60, 40, 5, fill=1.4), 64), (synth.perf(masks=True), 4096)):
+                    (synth.gangs(60, 40, 5, fill=1.4), 64), (synth.perf(masks=True), 4096),
+                    (synth.perf(), 4096), (synth.perf(900, 20, 100), 64), (synth.poisoned_gangs(3), 16)):   # shared rows: fewer rows than ranks
     want = oc.run(snap)
     with Engine.for_snapshot(snap, batch=batch, device=lr, rank=rank, world=world) as e:
         mode = multigpu.attach(e, dist)

@@ -12,7 +12,7 @@
 #include <vector>
 
 namespace {
-struct Slot { std::vector<uint32_t> asks; yk::Orderer::Snap snap; std::vector<uint32_t> fit; };
+struct Slot { std::vector<uint32_t> asks, reps, row_of; yk::Orderer::Snap snap; std::vector<uint32_t> fit; };
 }
 
 extern "C" int engine_host_run(
@@ -23,8 +23,8 @@ extern "C" int engine_host_run(
     const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
     const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
     const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
-    uint32_t batch, uint32_t epoch_limit, int speculate, uint32_t max_bindings,
-    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out /*[D][nN]*/) {
+    uint32_t batch, uint32_t epoch_limit, int speculate, int share_rows, uint32_t max_bindings,
+    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out /*[D][nN]*/, uint64_t* rows_out) {
     // ---- orderer ----
     yk::Orderer o;
     std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1);
@@ -81,10 +81,16 @@ extern "C" int engine_host_run(
         }
         cm.begin_epoch(W);
     };
+    std::vector<uint64_t> a_sig(nA);
+    for (uint32_t a = 0; a < nA; ++a) a_sig[a] = yk::ask_signature(cm.t, a);   // the engine does this in yk_asks_upsert
+    yk::RowShare share;
+    uint64_t rows_swept = 0;
     auto sweep = [&](Slot& sl) {
-        sl.fit.assign(sl.asks.size() * (size_t)WS, 0);
-        for (size_t i = 0; i < sl.asks.size(); ++i) {
-            const uint32_t a = sl.asks[i];
+        share.build(cm.t, a_sig.data(), sl.asks, share_rows != 0, sl.reps, sl.row_of);   // as produce() does
+        rows_swept += sl.reps.size();
+        sl.fit.assign(sl.reps.size() * (size_t)WS, 0);
+        for (size_t i = 0; i < sl.reps.size(); ++i) {
+            const uint32_t a = sl.reps[i];
             uint32_t* row = sl.fit.data() + i * WS;
             row[W] = yk::CNONE;
             for (int p = 0; p < W * 32; ++p) {
@@ -130,7 +136,7 @@ extern "C" int engine_host_run(
             if (!ins && !A.asks.empty() && a_gang[A.asks[0]] != yk::CNONE)
                 while (consumed < A.asks.size() && cm.same_gang(A.asks[0], A.asks[consumed])) ++consumed;
         } else {
-            const int rc = cm.commit_batch(A.asks, A.fit.data(), order[cur].data(), ins, result, consumed, [&](int) { return (int)A.asks.size(); });
+            const int rc = cm.commit_batch(A.asks, A.row_of.data(), A.fit.data(), order[cur].data(), ins, result, consumed, [&](int) { return (int)A.reps.size(); });
             if (rc) return rc;
         }
         bool failed = false;
@@ -161,6 +167,7 @@ extern "C" int engine_host_run(
     }
     o.finish();
     *n_out = n;
+    if (rows_out) *rows_out = rows_swept;
     for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
     for (uint32_t nn = 0; nn < nN; ++nn)
         for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = cm.node(nn).avail()[k];

@@ -33,7 +33,7 @@ def _u32(x):
     return x.astype(np.uint32)
 
 
-def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindings=None):
+def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindings=None, share_rows=1, rows=None):
     N, A, P, Q, D = s.n_nodes, s.n_asks, s.n_apps, s.n_queues, s.D
     if epoch_limit is None:
         epoch_limit = max(2 * batch, N * 5 // 8)
@@ -56,14 +56,17 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
     n = C.c_uint32(0)
     state = np.zeros(max(A, 1), dtype=np.uint8)
     avail = np.zeros((D, max(N, 1)), dtype=np.int64)
+    nrows = C.c_uint64(0)
     rc = shim.engine_host_run(
         C.c_int(D), C.c_uint32(s.policy), _p(k["w"]),
         C.c_uint32(N), _p(k["total"]), _p(k["avail"]), _p(k["taint"]), _p(k["label"]), _p(k["nflags"]), _p(k["rank"]),
         C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(k["req"]), _p(k["tol"]), _p(k["need"]), _p(k["deny"]), _p(k["anode"]),
         _p(k["prio"]), _p(k["create"]), _p(k["app"]), _p(k["aflags"]), _p(k["gang"]), _p(k["queue"]), _p(k["submit"]),
         _p(k["par"]), _p(k["guar"]), _p(k["mx"]), _p(k["alloc"]), _p(k["sort"]),
-        C.c_uint32(batch), C.c_uint32(epoch_limit), C.c_int(speculate), C.c_uint32(max_bindings),
-        _p(out_ask), _p(out_node), C.byref(n), _p(state), _p(avail))
+        C.c_uint32(batch), C.c_uint32(epoch_limit), C.c_int(speculate), C.c_int(share_rows), C.c_uint32(max_bindings),
+        _p(out_ask), _p(out_node), C.byref(n), _p(state), _p(avail), C.byref(nrows))
+    if rows is not None:
+        rows.append(nrows.value)
     return rc, out_ask[:n.value].astype(np.int64), out_node[:n.value].astype(np.int64), state[:A], avail[:, :N].T.copy()
 
 
@@ -88,8 +91,8 @@ def test_host_engine_matches_oracle_on_fuzz(shim, oracle, batch):
             rc = run_engine_host(shim, s, batch=batch)[0]
             assert rc == -1                      # documented error: a gang larger than the sweep batch
             continue
-        for spec in (1, 0):
-            check(shim, oracle, s, tag=(seed, batch, spec), batch=batch, speculate=spec)
+        for spec, share in ((1, 1), (0, 1), (1, 0)):
+            check(shim, oracle, s, tag=(seed, batch, spec, share), batch=batch, speculate=spec, share_rows=share)
         checked += 1
     assert checked > 30
 
@@ -150,3 +153,36 @@ def test_overcommitted_gangs(shim, oracle, fill):
             s = synth.gangs(120, 40, 5, seed=seed, fill=fill, policy=policy)
             check(shim, oracle, s, tag=(seed, policy), batch=64, epoch_limit=10 ** 9)
             check(shim, oracle, s, tag=(seed, policy), batch=1000)
+
+
+def test_shared_rows_sweep_one_row_per_signature(shim, oracle):
+    """asks with identical predicate inputs share one swept row: same bindings, far fewer rows; asks that differ in
+    any input (request, toleration, required / forbidden label, node name) never share"""
+    s = synth.perf(300, 20, 40)
+    shared, single = [], []
+    want = check(shim, oracle, s, batch=128, rows=shared)
+    check(shim, oracle, s, batch=128, share_rows=0, rows=single)
+    assert single[0] >= len(want["ask"]) and shared[0] * 4 < single[0]
+    # make every ask distinct in one input at a time: nothing may be shared any more
+    for field in ("req", "tol", "need", "deny", "node"):
+        t = synth.perf(64, 4, 20)
+        i = np.arange(t.n_asks)
+        if field == "req":
+            t.ask_req[:, 3] = i                      # a dimension every node has plenty of
+            t.node_total[:, 3] = t.node_avail[:, 3] = 1 << 40
+        elif field == "tol":
+            t.ask_tol[:] = (i.astype(np.uint64) << np.uint64(8))
+        elif field == "need":
+            t.node_label[:] |= np.uint64((1 << 40) - 1) << np.uint64(8)
+            t.ask_need[:] = (i.astype(np.uint64) << np.uint64(8))
+        elif field == "deny":
+            t.ask_deny[:] = (i.astype(np.uint64) << np.uint64(48))
+        else:
+            t.ask_node[:] = i % t.n_nodes
+            t.ask_req[:, 0] = 1                      # all can fit their node
+        rows = []
+        check(shim, oracle, t, batch=t.n_asks, rows=rows, tag=field)
+        sig = np.column_stack([t.ask_req, t.ask_tol.astype(np.int64), t.ask_need.astype(np.int64), t.ask_deny.astype(np.int64), t.ask_node])
+        distinct = len(np.unique(sig, axis=0))
+        assert distinct >= min(t.n_asks, t.n_nodes), field        # the fixture really separates the asks
+        assert rows[0] >= distinct, (field, rows, distinct)

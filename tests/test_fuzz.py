@@ -34,13 +34,13 @@ def test_fuzz_exercises_the_features(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("batch", [7, 64, 1024])
-def test_engine_matches_oracle_on_fuzz(oracle, batch):
+@pytest.mark.parametrize("batch,share", [(7, True), (64, True), (1024, True), (64, False)])
+def test_engine_matches_oracle_on_fuzz(oracle, batch, share):
     from yunikorn_k8shim_b200 import Engine
     for seed in range(60):
         s = synth.fuzz(seed)
         want = oracle.run(s)
-        with Engine.for_snapshot(s, batch=batch) as e:
+        with Engine.for_snapshot(s, batch=batch, share_rows=share) as e:
             try:
                 ask, node, _ = e.cycle(s.n_asks)
             except Exception as exc:          # a gang larger than a tiny batch is a documented error, not a mismatch

@@ -41,7 +41,13 @@ def test_config3_small(oracle, policy):
 
 
 def test_config2_full(oracle):
-    _check(synth.perf(), oracle, batch=2048)
+    st = _check(synth.perf(), oracle, batch=2048)
+    assert st["rows_swept"] * 50 < st["asks_swept"]      # a few dozen distinct pod shapes: rows are shared
+
+
+def test_config2_full_one_row_per_ask(oracle):
+    st = _check(synth.perf(), oracle, batch=2048, share_rows=False)
+    assert st["rows_swept"] == st["asks_swept"] >= 50_000
 
 
 def test_config3_full(oracle):

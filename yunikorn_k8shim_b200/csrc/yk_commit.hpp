@@ -41,6 +41,74 @@ struct CommitTables {
     const uint32_t* a_app = nullptr;
 };
 
+// ---- shared rows ----------------------------------------------------------------------------------------------
+// What the sweep computes for an ask depends only on (request, tolerations, required / forbidden labels, node name):
+// asks of one deployment / job / task group are identical there.  The batch is therefore swept once per DISTINCT
+// signature: rows[] lists one representative ask per signature (in order of first appearance, so rows land in the
+// order the commit first needs them) and row_of[i] is the row of batch entry i.  The 64-bit signature hash is
+// computed once when an ask is upserted; equality is always confirmed on the full signature.
+inline uint64_t sig_mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    return h ^ (h >> 32);
+}
+inline uint64_t ask_signature(const CommitTables& t, uint32_t a) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+    for (int k = 0; k < t.D; ++k) h = sig_mix(h, (uint64_t)t.a_req[(size_t)k * t.lda + a]);
+    h = sig_mix(h, t.a_tol[a]);
+    h = sig_mix(h, t.a_need[a]);
+    h = sig_mix(h, t.a_deny[a]);
+    return sig_mix(h, t.a_node[a]);
+}
+inline bool same_signature(const CommitTables& t, uint32_t a, uint32_t b) {
+    if (t.a_tol[a] != t.a_tol[b] || t.a_need[a] != t.a_need[b] || t.a_deny[a] != t.a_deny[b] || t.a_node[a] != t.a_node[b]) return false;
+    for (int k = 0; k < t.D; ++k)
+        if (t.a_req[(size_t)k * t.lda + a] != t.a_req[(size_t)k * t.lda + b]) return false;
+    return true;
+}
+
+class RowShare {
+public:
+    // share == false: one row per ask (rows = batch, row_of = identity)
+    void build(const CommitTables& t, const uint64_t* a_sig, const std::vector<uint32_t>& batch, bool share,
+               std::vector<uint32_t>& rows, std::vector<uint32_t>& row_of) {
+        const size_t B = batch.size();
+        rows.clear();
+        row_of.resize(B);
+        if (!share) {
+            rows = batch;
+            for (size_t i = 0; i < B; ++i) row_of[i] = (uint32_t)i;
+            return;
+        }
+        size_t cap = 64;
+        while (cap < 2 * B) cap <<= 1;
+        if (slot_.size() < cap) { slot_.assign(cap, Entry{0, 0, 0}); stamp_ = 0; }
+        if (++stamp_ == 0) { std::fill(slot_.begin(), slot_.end(), Entry{0, 0, 0}); stamp_ = 1; }
+        const size_t mask = slot_.size() - 1;
+        for (size_t i = 0; i < B; ++i) {
+            const uint32_t a = batch[i];
+            const uint64_t h = a_sig[a];
+            size_t x = (size_t)(h ^ (h >> 29)) & mask;
+            while (true) {
+                Entry& e = slot_[x];
+                if (e.stamp != stamp_) {   // free in this batch: a new signature
+                    e.stamp = stamp_; e.sig = h; e.row = (uint32_t)rows.size();
+                    row_of[i] = e.row;
+                    rows.push_back(a);
+                    break;
+                }
+                if (e.sig == h && same_signature(t, rows[e.row], a)) { row_of[i] = e.row; break; }
+                x = (x + 1) & mask;
+            }
+        }
+    }
+
+private:
+    struct Entry { uint64_t sig; uint32_t row; uint32_t stamp; };
+    std::vector<Entry> slot_;
+    uint32_t stamp_ = 0;
+};
+
 // The per-node working record lives in one contiguous slice of `hot` (hs = 4 + 3D words):
 //   [0] current sort key   [1] rank<<32 | touched<<31 | position   [2] taint   [3] label
 //   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
@@ -142,13 +210,13 @@ public:
     }
 
     // Ordered commit of one batch.  fit = rows of WS = W+1 words (W bitmap words, then the first-fit position);
-    // order = sorted position -> node for this epoch; wait(i) blocks until row i has landed and returns how many rows
-    // have (>= i+1), or a negative status.  result[i] = node or CNONE; consumed = entries decided (the loop stops
+    // row_of[i] = the row of batch entry i (see RowShare); order = sorted position -> node for this epoch; wait(r) blocks
+    // until row r has landed and returns how many rows have (>= r+1), or a negative status.  result[i] = node or CNONE; consumed = entries decided (the loop stops
     // after the first failed ask / gang unless the order is placement-insensitive).  Returns 0, or wait()'s error,
     // or -5 when a re-score is NaN.
     template <typename WaitFn>
-    int commit_batch(const std::vector<uint32_t>& batch, const uint32_t* fit, const uint32_t* order, bool insensitive,
-                     std::vector<uint32_t>& result, size_t& consumed, WaitFn&& wait) {
+    int commit_batch(const std::vector<uint32_t>& batch, const uint32_t* row_of, const uint32_t* fit, const uint32_t* order,
+                     bool insensitive, std::vector<uint32_t>& result, size_t& consumed, WaitFn&& wait) {
         const int D = t.D;
         const int B = (int)batch.size();
         const int WS = W + 1;
@@ -161,8 +229,9 @@ public:
         std::vector<Undo> undo;
         int gang_begin = -1;
         for (int i = 0; i < B && !stop; ++i) {
-            if (i >= landed) {
-                const int rc = wait(i);
+            const int ri = (int)row_of[(size_t)i];
+            if (ri >= landed) {
+                const int rc = wait(ri);
                 if (rc < 0) return rc;
                 landed = rc;
             }
@@ -170,13 +239,13 @@ public:
             const uint32_t ask = batch[(size_t)i];
             const bool in_gang = t.a_gang[ask] != CNONE;
             if (in_gang && (i == 0 || !same_gang(batch[(size_t)i - 1], ask))) { gang_begin = i; undo.clear(); }
-            const uint32_t* row = fit + (size_t)i * WS;
-            if (i + 12 < std::min(B, landed)) {                       // rows arrive by DMA and are cache-cold: pull
-                const uint32_t* nrow = fit + (size_t)(i + 12) * WS;   // the first-fit word of a row that has landed now
+            const uint32_t* row = fit + (size_t)ri * WS;
+            if (i + 12 < B && (int)row_of[(size_t)i + 12] < landed) {   // rows arrive by DMA and are cache-cold: pull
+                const uint32_t* nrow = fit + (size_t)row_of[(size_t)i + 12] * WS;   // the first-fit word of a landed row now
                 __builtin_prefetch(nrow + W);                        // ... and, for the row whose first-fit word was
-                const uint32_t* mrow = fit + (size_t)(i + 6) * WS;   // pulled six asks ago, the line its scan starts at
+                const uint32_t* mrow = fit + (size_t)row_of[(size_t)i + 6] * WS;   // pulled six asks ago, the line its scan starts at
                 const uint32_t nf = mrow[W];
-                __builtin_prefetch(mrow + std::max<int>(front, nf == CNONE ? 0 : (int)(nf >> 5)));
+                __builtin_prefetch(mrow + std::min<int>(W, std::max<int>(front, nf == CNONE ? 0 : (int)(nf >> 5))));
             }
             // (A) best untouched node: first set bit of row & ~touched in sorted order
             uint32_t posA = CNONE;

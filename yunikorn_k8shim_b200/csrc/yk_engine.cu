@@ -116,14 +116,16 @@ struct Worker {
 // One in-flight batch: its asks, device / pinned buffers and read-back events.  Two slots let the sweep and the
 // read-back of batch k+1 run while the host commits batch k (both against the same epoch view, see run loop).
 struct Slot {
-    std::vector<uint32_t> asks;
+    std::vector<uint32_t> asks;     // the batch, in commit order
+    std::vector<uint32_t> reps;     // one representative ask per distinct signature = the rows the device sweeps
+    std::vector<uint32_t> row_of;   // batch entry -> row
     yk::Orderer::Snap snap;
     Dev<uint32_t> d_batch, d_fit;
     Pin<uint32_t> h_batch, h_fit;
     Pin<int> h_err;                 // P2P: copy of the device error word after the flag waits
     std::vector<cudaEvent_t> ev;
     cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;
-    int B = 0, W = 0, chunk = 0, nchunks = 0, rows = 0;
+    int B = 0, R = 0, W = 0, chunk = 0, nchunks = 0, rows = 0;   // B asks, R rows (all ranks), rows = this rank's shard
     uint32_t last_value = 0;        // P2P: sequence value signalled when this slot's previous content was published
 };
 
@@ -155,6 +157,9 @@ struct yk_engine {
     Pin<uint32_t> a_node;
     std::vector<int32_t> a_prio;
     std::vector<int64_t> a_create;
+    std::vector<uint64_t> a_sig;    // signature hash of each ask's predicate inputs (yk::ask_signature)
+    yk::RowShare share;
+    bool share_rows = true;
     std::vector<uint32_t> a_app, a_flags, a_gang, a_bound;
     std::vector<uint8_t> a_state;              // yk::ST_*, ST_ABSENT when not present
     uint32_t a_hi = 0;
@@ -404,19 +409,23 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     const int D = e->D;
     const int B = (int)sl.asks.size();
     const int nlive = (int)e->nlive;
-    sl.B = B; sl.W = e->epochW; sl.rows = 0; sl.nchunks = 0;
+    sl.B = B; sl.R = 0; sl.W = e->epochW; sl.rows = 0; sl.nchunks = 0;
     if (B == 0 || nlive == 0) return YK_OK;
     const double t0 = now_ms();
     const int W = e->epochW, Np = W * 32, WS = W + 1;
     cudaStream_t s = e->stream;
-    memcpy(sl.h_batch.p, sl.asks.data(), sizeof(uint32_t) * (size_t)B);
-    CK(cudaMemcpyAsync(sl.d_batch.p, sl.h_batch.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyHostToDevice, s));
-    st.h2d_bytes += sizeof(uint32_t) * (size_t)B;
-    // this rank's shard of the batch rows (world == 1: all of them)
+    // one row per distinct predicate signature in the batch (yk_commit.hpp "shared rows")
+    e->share.build(e->cm.t, e->a_sig.data(), sl.asks, e->share_rows, sl.reps, sl.row_of);
+    const int R = (int)sl.reps.size();
+    sl.R = R;
+    memcpy(sl.h_batch.p, sl.reps.data(), sizeof(uint32_t) * (size_t)R);
+    CK(cudaMemcpyAsync(sl.d_batch.p, sl.h_batch.p, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s));
+    st.h2d_bytes += sizeof(uint32_t) * (size_t)R;
+    // this rank's shard of the rows (world == 1: all of them)
     const int world = std::max<int>(1, (int)e->cfg.world);
-    const int rows_per = (B + world - 1) / world;
-    const int row0 = std::min(B, (int)e->cfg.rank * rows_per);
-    const int rows = std::min(B, row0 + rows_per) - row0;
+    const int rows_per = (R + world - 1) / world;
+    const int row0 = std::min(R, (int)e->cfg.rank * rows_per);
+    const int rows = std::min(R, row0 + rows_per) - row0;
     const int Bpad = rows_per * world;
     sl.rows = rows;
     // the last word of every row (first-fit position) starts at YK_NONE
@@ -465,10 +474,10 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
             return e->fail(YK_ERR_COMM, "exchange callback failed");
     }
     // read-back in row chunks so the ordered commit overlaps the transfer
-    sl.chunk = std::max(128, (B + (int)sl.ev.size() - 1) / (int)sl.ev.size());
-    sl.nchunks = (B + sl.chunk - 1) / sl.chunk;
+    sl.chunk = std::max(128, (R + (int)sl.ev.size() - 1) / (int)sl.ev.size());
+    sl.nchunks = (R + sl.chunk - 1) / sl.chunk;
     for (int c = 0; c < sl.nchunks; ++c) {
-        const size_t r0 = (size_t)c * sl.chunk, r1 = std::min<size_t>((size_t)B, r0 + sl.chunk);
+        const size_t r0 = (size_t)c * sl.chunk, r1 = std::min<size_t>((size_t)R, r0 + sl.chunk);
         CK(cudaMemcpyAsync(sl.h_fit.p + r0 * WS, sl.d_fit.p + r0 * WS, sizeof(uint32_t) * (r1 - r0) * WS, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(sl.ev[(size_t)c], s));
     }
@@ -482,8 +491,10 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
         CK(cudaGetLastError());
         st.other_launches += 1;
     }
-    st.d2h_bytes += sizeof(uint32_t) * (size_t)B * WS;
+    st.d2h_bytes += sizeof(uint32_t) * (size_t)R * WS;
     st.batches++;
+    st.asks_swept += (uint64_t)B;
+    st.rows_swept += (uint64_t)R;
     st.host_ms[6] += now_ms() - t0;
     return YK_OK;
 }
@@ -522,9 +533,9 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
                 return -1;
             }
         }
-        return std::min(B, next_chunk * sl.chunk);
+        return std::min(sl.R, next_chunk * sl.chunk);
     };
-    const int rc = e->cm.commit_batch(batch, sl.h_fit.p, e->h_order[e->cur].p, insensitive, result, consumed, wait);
+    const int rc = e->cm.commit_batch(batch, sl.row_of.data(), sl.h_fit.p, e->h_order[e->cur].p, insensitive, result, consumed, wait);
     if (rc == -5) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
     if (rc < 0) return wait_rc ? wait_rc : e->fail(YK_ERR_CUDA, "commit aborted");
     // all read-back must have landed before the slot's buffers are reused
@@ -597,6 +608,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     yk_engine* e = new (std::nothrow) yk_engine();
     if (!e) return YK_ERR_NOMEM;
     e->cfg = *cfg;
+    e->share_rows = !(cfg->flags & YK_FLAG_NO_ROW_SHARING) && !getenv("YK_NO_ROW_SHARING");
     e->D = (int)cfg->D;
     e->maxN = cfg->max_nodes; e->maxA = cfg->max_asks; e->maxP = cfg->max_apps; e->maxQ = cfg->max_queues;
     e->batch = cfg->batch ? cfg->batch : 4096;
@@ -656,7 +668,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     }
     if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
     e->n_rank.assign(N, 0); e->n_present.assign(N, 0);
-    e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
+    e->a_sig.assign(A, 0); e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
     e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
     e->p_alloc.assign((size_t)e->maxP * D, 0);
@@ -762,6 +774,8 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
             return e->fail(YK_ERR_ARG, "yk_asks_upsert: required_node beyond max_nodes");
         if (e->a_state[idx[i]] == yk::ST_ALLOCATED) return e->fail(YK_ERR_STATE, "yk_asks_upsert: ask holds an allocation (release it first)");
     }
+    yk::CommitTables sv;   // just enough of a view for the signature hash
+    sv.D = e->D; sv.lda = e->maxA; sv.a_req = e->a_req.p; sv.a_tol = e->a_tol.p; sv.a_need = e->a_need.p; sv.a_deny = e->a_deny.p; sv.a_node = e->a_node.p;
     for (uint32_t i = 0; i < a; ++i) {
         const uint32_t x = idx[i];
         for (int k = 0; k < e->D; ++k) e->a_req[(size_t)k * e->maxA + x] = req[(size_t)k * a + i];
@@ -769,6 +783,7 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
         e->a_need[x] = need ? need[i] : 0;
         e->a_deny[x] = deny ? deny[i] : 0;
         e->a_node[x] = required_node ? required_node[i] : YK_NONE;
+        e->a_sig[x] = yk::ask_signature(sv, x);
         e->a_prio[x] = prio ? prio[i] : 0;
         e->a_create[x] = create_seq[i];
         e->a_app[x] = app[i];
@@ -882,6 +897,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     auto merge_worker_stats = [&]() {
         yk_stats_t& w = e->wst;
         e->st.h2d_bytes += w.h2d_bytes; e->st.d2h_bytes += w.d2h_bytes; e->st.batches += w.batches;
+        e->st.asks_swept += w.asks_swept; e->st.rows_swept += w.rows_swept;
         e->st.sweep_launches += w.sweep_launches; e->st.evaluations += w.evaluations; e->st.other_launches += w.other_launches;
         e->st.host_ms[7] += w.host_ms[2] + w.host_ms[6];   // orderer + launch time hidden behind the commit
         w = yk_stats_t{};

@@ -30,7 +30,10 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("D", C.c_uint32), ("policy", C.c_uint32), ("batch", C.c_uint32),
                 ("weights", C.c_double * 8),
                 ("max_nodes", C.c_uint32), ("max_asks", C.c_uint32), ("max_apps", C.c_uint32), ("max_queues", C.c_uint32),
-                ("device", C.c_int32), ("reserved0", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
+                ("device", C.c_int32), ("flags", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32)]
+
+
+FLAG_NO_ROW_SHARING = 1
 
 
 class Stats(C.Structure):
@@ -39,7 +42,8 @@ class Stats(C.Structure):
                 ("other_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("sweep_ms", C.c_double), ("sort_ms", C.c_double), ("commit_ms", C.c_double), ("total_ms", C.c_double),
                 ("last_sweep_ms", C.c_double), ("last_sweep_pairs", C.c_uint64),
-                ("host_ms", C.c_double * 8), ("dbg", C.c_uint64 * 4), ("prof", C.c_uint64 * 6)]
+                ("host_ms", C.c_double * 8), ("dbg", C.c_uint64 * 4), ("prof", C.c_uint64 * 6),
+                ("asks_swept", C.c_uint64), ("rows_swept", C.c_uint64)]
 
     def as_dict(self):
         d = {f: getattr(self, f) for f, _ in self._fields_}
@@ -109,7 +113,7 @@ class Engine:
     """One yk_engine.  Method names and arguments mirror include/ykgpu.h one to one."""
 
     def __init__(self, D=4, policy=0, weights=None, max_nodes=1024, max_asks=4096, max_apps=64, max_queues=8,
-                 batch=0, device=-1, rank=0, world=1):
+                 batch=0, device=-1, rank=0, world=1, share_rows=True):
         self._lib = load_library()
         cfg = Config()
         cfg.abi_version = self._lib.yk_abi_version()
@@ -124,7 +128,7 @@ class Engine:
         for i in range(8):
             cfg.weights[i] = float(w[i])
         cfg.max_nodes, cfg.max_asks, cfg.max_apps, cfg.max_queues = max_nodes, max_asks, max_apps, max_queues
-        cfg.device, cfg.reserved0, cfg.rank, cfg.world = device, 0, rank, world
+        cfg.device, cfg.flags, cfg.rank, cfg.world = device, (0 if share_rows else FLAG_NO_ROW_SHARING), rank, world
         self.D = D
         self._h = C.c_void_p()
         rc = self._lib.yk_create(C.byref(cfg), C.byref(self._h))
