@@ -41,6 +41,6 @@ for share in (True, False, True, False):
         st = eng.stats()
         prev = ask
         if step >= 3:
-            print(f"{mode} share={share} step={step} cycle={dt*1e3:.2f}ms upsert={t_u*1e3:.2f}ms commit={st['commit_ms']:.2f} rows={st['rows_swept']} "
+            print(f"{mode} share={share} step={step} cycle={dt*1e3:.2f}ms total_ms={st["total_ms"]:.2f} upsert={t_u*1e3:.2f}ms commit={st['commit_ms']:.2f} rows={st['rows_swept']} "
                   f"host_ms={[round(x, 2) for x in st['host_ms'][:8]]}")
     eng.close()

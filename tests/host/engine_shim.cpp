@@ -42,11 +42,9 @@ extern "C" int engine_host_run(
     yk::Committer cm;
     cm.t.D = D; cm.t.policy = policy; cm.t.w = weights; cm.t.lda = nA;
     cm.t.a_req = a_req; cm.t.a_tol = a_tol; cm.t.a_need = a_need; cm.t.a_deny = a_deny; cm.t.a_node = a_node; cm.t.a_gang = a_gang; cm.t.a_app = a_app;
-    cm.build(nN, n_avail, n_total, nN, n_taint, n_label);
+    cm.build(nN, n_avail, n_total, nN, n_taint, n_label, n_rank);
     const int nlive = (int)nN;
-    std::vector<uint32_t> order[2];
-    order[0].resize(nN); order[1].resize(nN);
-    int cur = 0;
+    std::vector<uint32_t> order_nodes(nN);   // what the engine uploads for the device's gather
     {
         std::vector<yk::DirtyRef> ks(nN);
         for (uint32_t n = 0; n < nN; ++n) {
@@ -54,12 +52,9 @@ extern "C" int engine_host_run(
             ks[n] = yk::DirtyRef(yk_key_bits(sc), n_rank[n], n);
         }
         std::sort(ks.begin(), ks.end());
-        for (uint32_t p = 0; p < nN; ++p) {
-            const uint32_t n = ks[p].node();
-            order[0][p] = n;
-            cm.node(n).key() = ks[p].key();
-            cm.node(n).set_meta(n_rank[n], p);
-        }
+        std::vector<uint64_t> keys(nN);
+        for (uint32_t p = 0; p < nN; ++p) { order_nodes[p] = ks[p].node(); keys[p] = ks[p].key(); }
+        cm.set_order(order_nodes.data(), keys.data(), nlive);
     }
     // ---- the epoch's sorted view (what yk_gather_kernel builds) and the CPU stand-in for the sweep ----
     const int W = nlive ? (nlive + 511) / 512 * 16 : 0;   // same rounding as the engine: tiles of 512 positions
@@ -70,7 +65,7 @@ extern "C" int engine_host_run(
     auto refresh_view = [&]() {
         v_cap.assign((size_t)W * 32 * D, -1); v_taint.assign((size_t)W * 32, ~0ull); v_label.assign((size_t)W * 32, 0); v_node.assign((size_t)W * 32, yk::CNONE);
         for (int p = 0; p < nlive; ++p) {
-            const uint32_t n = order[cur][p];
+            const uint32_t n = order_nodes[p];
             const bool usable = (n_flags[n] & 1u) && !(n_flags[n] & 2u);
             yk::NodeView nv = cm.node(n);
             for (int k = 0; k < D; ++k) {   // same fold as yk_gather_kernel, from the commit's current availability
@@ -136,7 +131,7 @@ extern "C" int engine_host_run(
             if (!ins && !A.asks.empty() && a_gang[A.asks[0]] != yk::CNONE)
                 while (consumed < A.asks.size() && cm.same_gang(A.asks[0], A.asks[consumed])) ++consumed;
         } else {
-            const int rc = cm.commit_batch(A.asks, A.row_of.data(), A.fit.data(), order[cur].data(), ins, result, consumed, [&](int) { return (int)A.reps.size(); });
+            const int rc = cm.commit_batch(A.asks, A.row_of.data(), A.fit.data(), ins, result, consumed, [&](int) { return (int)A.reps.size(); });
             if (rc) return rc;
         }
         bool failed = false;
@@ -157,7 +152,7 @@ extern "C" int engine_host_run(
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
         if (Nx.asks.empty() && n < max_bindings) {
             if (cm.dirty_list.size() * 2 >= (size_t)epoch_limit || failed) {
-                if (!cm.dirty_list.empty()) { cm.merge_order(order[cur].data(), order[cur ^ 1].data(), nlive); cur ^= 1; }
+                if (!cm.dirty_list.empty()) cm.merge_order(order_nodes.data(), nlive);
                 refresh_view();
             }
             next_batch(Nx, (size_t)max_bindings - n);

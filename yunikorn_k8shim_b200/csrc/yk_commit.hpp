@@ -110,17 +110,15 @@ private:
 };
 
 // The per-node working record lives in one contiguous slice of `hot` (hs = 4 + 3D words):
-//   [0] current sort key   [1] rank<<32 | touched<<31 | position   [2] taint   [3] label
+//   [0] sort key (valid while the node is touched)   [1] rank<<32 | touched<<31   [2] taint   [3] label
 //   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
 //   [4+D,4+2D) available   [4+2D,4+3D) total            -- only read when the node is actually committed to
 struct NodeView {
     int64_t* h; int D;
     uint64_t& key() { return *reinterpret_cast<uint64_t*>(&h[0]); }
     uint32_t rank() const { return (uint32_t)((uint64_t)h[1] >> 32); }
-    uint32_t pos() const { return (uint32_t)((uint64_t)h[1]) & 0x7FFFFFFFu; }
     bool dirty() const { return (((uint64_t)h[1]) >> 31) & 1u; }
-    void set_meta(uint32_t rank, uint32_t pos) { h[1] = (int64_t)(((uint64_t)rank << 32) | (pos & 0x7FFFFFFFu)); }
-    void set_pos(uint32_t pos) { h[1] = (int64_t)((((uint64_t)h[1]) & 0xFFFFFFFF80000000ull) | (pos & 0x7FFFFFFFu)); }
+    void set_rank(uint32_t rank) { h[1] = (int64_t)((uint64_t)rank << 32); }   // also clears the touched flag
     void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
     int64_t* cap() { return h + 4; }
     int64_t* avail() { return h + 4 + D; }
@@ -153,6 +151,8 @@ public:
     std::vector<DirtyRef> dirty_sorted;  // scratch for the epoch-end merge
     std::vector<uint32_t> dirty_words;   // bit p = the node at sorted position p has been touched in this epoch
     std::vector<uint32_t> dirty_list;    // the touched nodes, in first-touch order
+    std::vector<DirtyRef> oref[2];       // node order of the epoch: sorted position -> (key, rank, node); double-buffered
+    int ocur = 0;
     int64_t dirty_ub[CMAX_D];            // per dimension: upper bound of cap over the touched nodes
     int front = 0;                       // every sorted position below word `front` is touched
     int W = 0;                           // bitmap words per row in this epoch
@@ -164,7 +164,7 @@ public:
 
     // (re)build the working copy from the engine's column-major host tables (stride ldn), n_hi node slots
     void build(uint32_t n_hi, const int64_t* n_avail, const int64_t* n_total, size_t ldn, const uint64_t* n_taint,
-               const uint64_t* n_label) {
+               const uint64_t* n_label, const uint32_t* n_rank) {
         const int D = t.D;
         hs = 4 + 3 * D;
         hot.resize((size_t)n_hi * hs);
@@ -176,11 +176,22 @@ public:
         }
         for (uint32_t n = 0; n < n_hi; ++n) {
             NodeView v = node(n);
+            v.h[0] = 0;
+            v.set_rank(n_rank[n]);
             v.h[2] = (int64_t)n_taint[n];
             v.h[3] = (int64_t)n_label[n];
             v.recap();
         }
     }
+
+    // the cycle's initial node order (ascending (score key, NodeID rank)), as the device sort produced it
+    void set_order(const uint32_t* nodes, const uint64_t* keys, int nlive) {
+        ocur = 0;
+        oref[0].resize((size_t)nlive);
+        oref[1].resize((size_t)nlive);
+        for (int p = 0; p < nlive; ++p) oref[0][(size_t)p] = DirtyRef(keys[p], node(nodes[p]).rank(), nodes[p]);
+    }
+    const DirtyRef* order() const { return oref[ocur].data(); }
 
     // a new epoch starts on a fresh view of `words` bitmap words per row: nothing is touched
     void begin_epoch(int words) {
@@ -210,13 +221,14 @@ public:
     }
 
     // Ordered commit of one batch.  fit = rows of WS = W+1 words (W bitmap words, then the first-fit position);
-    // row_of[i] = the row of batch entry i (see RowShare); order = sorted position -> node for this epoch; wait(r) blocks
+    // row_of[i] = the row of batch entry i (see RowShare); wait(r) blocks
     // until row r has landed and returns how many rows have (>= r+1), or a negative status.  result[i] = node or CNONE; consumed = entries decided (the loop stops
     // after the first failed ask / gang unless the order is placement-insensitive).  Returns 0, or wait()'s error,
     // or -5 when a re-score is NaN.
     template <typename WaitFn>
-    int commit_batch(const std::vector<uint32_t>& batch, const uint32_t* row_of, const uint32_t* fit, const uint32_t* order,
+    int commit_batch(const std::vector<uint32_t>& batch, const uint32_t* row_of, const uint32_t* fit,
                      bool insensitive, std::vector<uint32_t>& result, size_t& consumed, WaitFn&& wait) {
+        const DirtyRef* order = oref[ocur].data();
         const int D = t.D;
         const int B = (int)batch.size();
         const int WS = W + 1;
@@ -225,7 +237,7 @@ public:
         int landed = 0;
         bool stop = false;
         // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
-        struct Undo { uint32_t node; uint64_t old_key; bool was_dirty; int64_t old_avail[CMAX_D]; };
+        struct Undo { uint32_t node; uint32_t pos; uint64_t old_key; bool was_dirty; int64_t old_avail[CMAX_D]; };
         std::vector<Undo> undo;
         int gang_begin = -1;
         for (int i = 0; i < B && !stop; ++i) {
@@ -259,10 +271,7 @@ public:
                 }
             }
             DirtyRef bound(~0ull, ~0u, CNONE);
-            if (posA != CNONE) {
-                const uint32_t nA = order[posA];
-                bound = DirtyRef(node(nA).key(), node(nA).rank(), nA);
-            }
+            if (posA != CNONE) bound = order[posA];
             const unsigned long long tc1 = profile ? commit_tsc() : 0;
             // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the
             // request exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran
@@ -309,7 +318,7 @@ public:
                         } else {
                             un.set_dirty(false);
                             dirty_list.pop_back();
-                            const uint32_t pos = un.pos();
+                            const uint32_t pos = it->pos;
                             dirty_words[pos >> 5] &= ~(1u << (pos & 31));
                             front = std::min(front, (int)(pos >> 5));
                         }
@@ -329,7 +338,7 @@ public:
             NodeView cv = node(chosen);
             int64_t* h = cv.avail();
             if (in_gang) {
-                Undo u; u.node = chosen; u.old_key = cv.key(); u.was_dirty = cv.dirty();
+                Undo u; u.node = chosen; u.pos = posA; u.old_key = cv.key(); u.was_dirty = cv.dirty();
                 for (int k = 0; k < D; ++k) u.old_avail[k] = h[k];
                 undo.push_back(u);
             }
@@ -351,7 +360,7 @@ public:
                 for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], cv.cap()[k]);
                 cv.set_dirty(true);
                 dirty_list.push_back(chosen);
-                const uint32_t pos = cv.pos();
+                const uint32_t pos = posA;   // an untouched node can only have come from the clean scan (A)
                 dirty_words[pos >> 5] |= 1u << (pos & 31);
             }
             if (profile) {
@@ -362,34 +371,36 @@ public:
         return 0;
     }
 
-    // Epoch end: new node order = merge(previous order minus the touched nodes, touched nodes by new key).  Writes
-    // `out`, refreshes every moved node's position.  Returns the number of touched nodes.
-    int merge_order(const uint32_t* order, uint32_t* out, int nlive) {
+    // Epoch end: new node order = merge(previous order minus the touched positions, touched nodes by their new keys).
+    // Both inputs are sorted arrays of (key, rank, node) words, so this is one streaming merge; out_nodes receives the
+    // node of every new position (what the device's gather needs).  Returns the number of touched nodes.
+    int merge_order(uint32_t* out_nodes, int nlive) {
         const int nd = (int)dirty_list.size();
-        int o = 0, p = 0;
         std::vector<DirtyRef>& ds = dirty_sorted;
         ds.clear();
         dirty.for_each([&](const DirtyRef& r) { ds.push_back(r); });
+        const DirtyRef* in = oref[ocur].data();
+        DirtyRef* out = oref[ocur ^ 1].data();
+        const size_t nds = ds.size();
         size_t j = 0;
-        int removed = 0;   // touched nodes passed over in the old order so far
-        while (true) {
-            while (p < nlive && node(order[p]).dirty()) { ++p; ++removed; }
-            if (p >= nlive) break;
-            if (j >= ds.size() && removed == nd) {
+        int o = 0, p = 0, removed = 0;   // removed = touched positions passed over in the old order so far
+        while (p < nlive) {
+            if ((dirty_words[(size_t)p >> 5] >> (p & 31)) & 1u) { ++p; ++removed; continue; }
+            if (j >= nds && removed == nd) {
                 // every touched node has been taken out and put back: the rest of the order is unchanged
-                memcpy(out + o, order + p, sizeof(uint32_t) * (size_t)(nlive - p));
+                memcpy(out + o, in + p, sizeof(DirtyRef) * (size_t)(nlive - p));
+                for (int x = p; x < nlive; ++x) out_nodes[o + (x - p)] = in[x].node();
                 o += nlive - p;
                 p = nlive;
                 break;
             }
-            const uint32_t n = order[p];
-            const DirtyRef c(node(n).key(), node(n).rank(), n);
-            while (j < ds.size() && ds[j] < c) { node(ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
-            node(n).set_pos((uint32_t)o);
-            out[o++] = n;
+            const DirtyRef c = in[p];
+            while (j < nds && ds[j] < c) { out[o] = ds[j]; out_nodes[o++] = ds[j].node(); ++j; }
+            out[o] = c; out_nodes[o++] = c.node();
             ++p;
         }
-        while (j < ds.size()) { node(ds[j].node()).set_pos((uint32_t)o); out[o++] = ds[j].node(); ++j; }
+        while (j < nds) { out[o] = ds[j]; out_nodes[o++] = ds[j].node(); ++j; }
+        ocur ^= 1;
         return nd;
     }
 };

@@ -37,102 +37,141 @@ public:
     void insert(const DirtyRef& x) {
         if (lo_.empty()) { lo_.push_back(0); id_.push_back(fresh()); }
         uint32_t r = range_of(x.w);
-        Range* g = &pool_[id_[r]];
-        if (g->n == CAP) {   // split: put in order, move the upper half into a new range right after this one
-            sort_range(*g);
-            const uint32_t nid = fresh();
-            g = &pool_[id_[r]];
-            Range& u = pool_[nid];
-            u.n = CAP - CAP / 2; u.sorted = 1;
-            memcpy(u.v, g->v + CAP / 2, sizeof(DirtyRef) * u.n);
-            g->n = CAP / 2;
-            lo_.insert(lo_.begin() + r + 1, u.v[0].w);
-            id_.insert(id_.begin() + r + 1, nid);
-            if (!(x.w < u.v[0].w)) { ++r; g = &u; }
+        uint32_t s = id_[r];
+        Meta* m = &meta_[s];
+        if (m->n == CAP && m->b > 0) {   // the walk has eaten entries off the front: reclaim that room first
+            DirtyRef* v = body(s);
+            memmove(v, v + m->b, sizeof(DirtyRef) * (m->n - m->b));
+            m->n -= m->b; m->b = 0;
         }
-        // append; the range is put back in order only if and when the walk reaches it
-        if (g->sorted && g->n && x.w < g->v[g->n - 1].w) g->sorted = 0;
-        g->v[g->n++] = x;
+        if (m->n == CAP) {   // split: put in order, move the upper half into a new range right after this one
+            sort_range(s);
+            const uint32_t ns = fresh();   // may move meta_ / body_
+            m = &meta_[s];
+            Meta& u = meta_[ns];
+            u.n = CAP - CAP / 2; u.b = 0; u.sorted = 1;
+            memcpy(body(ns), body(s) + CAP / 2, sizeof(DirtyRef) * u.n);
+            u.max = body(ns)[u.n - 1].w;
+            m->n = CAP / 2;
+            m->max = body(s)[m->n - 1].w;
+            lo_.insert(lo_.begin() + r + 1, body(ns)[0].w);
+            id_.insert(id_.begin() + r + 1, ns);
+            if (!(x.w < body(ns)[0].w)) { ++r; s = ns; m = &u; }
+        }
+        // append; the range is put back in order only if and when the walk reaches it.  Everything decided here comes
+        // from the small per-range records (L1); the range body itself only receives one store.
+        if (m->n > m->b && x.w < m->max) m->sorted = 0; else m->max = x.w;   // max may be stale-high after erases: harmless
+        body(s)[m->n++] = x;
         ++count_;
     }
     // general erase (re-keying an entry the walk did not just stand on, gang roll-back)
     void erase(const DirtyRef& x) {
         const uint32_t r = range_of(x.w);
-        Range& g = pool_[id_[r]];
-        uint32_t i = 0;
-        while (i < g.n && !(g.v[i] == x)) ++i;
-        if (g.sorted) memmove(g.v + i, g.v + i + 1, sizeof(DirtyRef) * (g.n - i - 1));
-        else g.v[i] = g.v[g.n - 1];
-        --g.n;
+        const uint32_t s = id_[r];
+        Meta& m = meta_[s];
+        DirtyRef* v = body(s);
+        uint32_t i = m.b;
+        while (i < m.n && !(v[i] == x)) ++i;
+        if (i == m.b) ++m.b;
+        else {
+            if (m.sorted) memmove(v + i, v + i + 1, sizeof(DirtyRef) * (m.n - i - 1));
+            else v[i] = v[m.n - 1];
+            --m.n;
+        }
         --count_;
-        if (g.n == 0 && lo_.size() > 1) drop_range(r);
+        if (m.n == m.b) { m.n = m.b = 0; m.sorted = 1; if (lo_.size() > 1) drop_range(r); }
     }
 
     // ---- ordered walk from the smallest entry ----
-    struct Cursor { uint32_t r = 0; uint32_t i = 0; };
-    const DirtyRef* first(Cursor& c) { c.r = 0; c.i = 0; return settle(c); }
+    struct Cursor { uint32_t r = 0; uint32_t i = 0; bool enter = true; };
+    const DirtyRef* first(Cursor& c) { c.r = 0; c.i = 0; c.enter = true; return settle(c); }
     const DirtyRef* next(Cursor& c) { ++c.i; return settle(c); }
     // take out the entry the cursor stands on
     void erase_at(const Cursor& c) {
-        Range& g = pool_[id_[c.r]];
-        memmove(g.v + c.i, g.v + c.i + 1, sizeof(DirtyRef) * (g.n - c.i - 1));
-        --g.n;
+        const uint32_t s = id_[c.r];
+        Meta& m = meta_[s];
+        if (c.i == m.b) ++m.b;   // the usual case: the walk takes the smallest entry -- no shifting
+        else {
+            DirtyRef* v = body(s);
+            memmove(v + c.i, v + c.i + 1, sizeof(DirtyRef) * (m.n - c.i - 1));
+            --m.n;
+        }
         --count_;
-        if (g.n == 0 && lo_.size() > 1) drop_range(c.r);
+        if (m.n == m.b) { m.n = m.b = 0; m.sorted = 1; if (lo_.size() > 1) drop_range(c.r); }
     }
 
     template <typename F>
     void for_each(F&& f) {   // all entries, ascending (puts every range in order: epoch end)
         for (uint32_t r = 0; r < lo_.size(); ++r) {
-            Range& g = pool_[id_[r]];
-            sort_range(g);
-            for (uint32_t i = 0; i < g.n; ++i) f(g.v[i]);
+            const uint32_t s = id_[r];
+            sort_range(s);
+            const Meta& m = meta_[s];
+            const DirtyRef* v = body(s);
+            for (uint32_t i = m.b; i < m.n; ++i) f(v[i]);
         }
     }
 
 private:
-    struct Range { uint32_t n; uint32_t sorted; uint64_t pad; DirtyRef v[CAP]; };   // storage inline: no pointer chase
+    struct Meta { unsigned __int128 max; uint32_t n, b, sorted, pad; };   // live entries of the range: body[b, n)
+    DirtyRef* body(uint32_t s) { return body_.data() + (size_t)s * CAP; }
     uint32_t fresh() {
-        if (used_ == pool_.size()) pool_.emplace_back();
-        pool_[used_].n = 0; pool_[used_].sorted = 1;
+        if (used_ == meta_.size()) { meta_.emplace_back(); body_.resize(body_.size() + CAP); }
+        Meta& m = meta_[used_];
+        m.n = 0; m.b = 0; m.sorted = 1; m.max = 0;
         return used_++;
     }
     void drop_range(uint32_t r) {
         lo_.erase(lo_.begin() + r); id_.erase(id_.begin() + r);
         lo_[0] = 0;   // the first range always starts at -inf
     }
-    static void sort_range(Range& g) {
-        if (g.sorted) return;
+    void sort_range(uint32_t s) {
+        Meta& m = meta_[s];
+        if (m.sorted) return;
+        DirtyRef* v = body(s);
         // the range was in order before a few appends: insertion sort is adaptive to that
-        for (uint32_t a = 1; a < g.n; ++a) {
-            const DirtyRef x = g.v[a];
+        for (uint32_t a = m.b + 1; a < m.n; ++a) {
+            const DirtyRef x = v[a];
             uint32_t b = a;
-            for (; b > 0 && x.w < g.v[b - 1].w; --b) g.v[b] = g.v[b - 1];
-            g.v[b] = x;
+            for (; b > m.b && x.w < v[b - 1].w; --b) v[b] = v[b - 1];
+            v[b] = x;
         }
-        g.sorted = 1;
+        m.sorted = 1;
+        m.max = v[m.n - 1].w;
     }
-    uint32_t range_of(unsigned __int128 w) const {   // last range whose lower bound is <= w (branchless)
-        const unsigned __int128* base = lo_.data();
-        uint32_t len = (uint32_t)lo_.size();
-        while (len > 1) {
-            const uint32_t half = len >> 1;
-            base += (base[half] <= w) ? half : 0;
-            len -= half;
+    // last range whose lower bound is <= w.  16-ary counting search: every level issues up to 15 independent
+    // compares (the bounds are sorted, so "how many samples are <= w" IS the child to descend into) instead of the 8-11
+    // dependent load-compare steps of a binary search; two levels cover 256 ranges, three cover 4096.
+    uint32_t range_of(unsigned __int128 w) const {
+        const unsigned __int128* lo = lo_.data();
+        uint32_t base = 0, len = (uint32_t)lo_.size();   // invariant: lo[base] <= w, the answer is in [base, base+len)
+        while (len > 16) {
+            const uint32_t step = (len + 15) >> 4;
+            uint32_t c = 0;
+            for (uint32_t k = 1; k < 16; ++k) {
+                const uint32_t idx = base + k * step;
+                c += (k * step < len && lo[idx] <= w) ? 1u : 0u;
+            }
+            base += c * step;
+            len = std::min(step, len - c * step);
         }
-        return (uint32_t)(base - lo_.data());
+        uint32_t c = 0;
+        for (uint32_t k = 1; k < len; ++k) c += (lo[base + k] <= w) ? 1u : 0u;
+        return base + c;
     }
     const DirtyRef* settle(Cursor& c) {
         while (c.r < lo_.size()) {
-            Range& g = pool_[id_[c.r]];
-            if (c.i < g.n) { sort_range(g); return &g.v[c.i]; }
-            ++c.r; c.i = 0;
+            const uint32_t s = id_[c.r];
+            const Meta& m = meta_[s];
+            if (c.enter) { c.i = m.b; c.enter = false; }
+            if (c.i < m.n) { sort_range(s); return body(s) + c.i; }
+            ++c.r; c.enter = true;
         }
         return nullptr;
     }
     std::vector<unsigned __int128> lo_;   // lower bound of each range, ascending, contiguous (the search stays in L1)
-    std::vector<uint32_t> id_;            // range -> slot in pool_
-    std::vector<Range> pool_;             // range storage, reused across epochs
+    std::vector<uint32_t> id_;            // range -> slot
+    std::vector<Meta> meta_;              // per slot: counts, order flag, largest entry (small: stays in L1)
+    std::vector<DirtyRef> body_;          // per slot: CAP entries; reused across epochs
     uint32_t used_ = 0;
     size_t count_ = 0;
 };

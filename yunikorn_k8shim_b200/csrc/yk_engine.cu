@@ -305,6 +305,11 @@ void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s, int slots) {
 // sort by key over NodeID-rank order = ascending (score, NodeID).  Later batches keep it current by merging.
 int initial_order(yk_engine* e) {
     const int nlive = (int)e->nlive;
+    yk::CommitTables& ct = e->cm.t;
+    ct.D = e->D; ct.policy = e->cfg.policy; ct.w = e->w.w; ct.lda = e->maxA;
+    ct.a_req = e->a_req.p; ct.a_tol = e->a_tol.p; ct.a_need = e->a_need.p; ct.a_deny = e->a_deny.p; ct.a_node = e->a_node.p;
+    ct.a_gang = e->a_gang.data(); ct.a_app = e->a_app.data();
+    e->cm.profile = e->prof;
     if (nlive == 0) return YK_OK;
     cudaStream_t s = e->stream;
     CK(cudaMemsetAsync(e->d_flag.p, 0, sizeof(int), s));
@@ -318,6 +323,8 @@ int initial_order(yk_engine* e) {
     CK(cudaMemcpyAsync(e->h_order[0].p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    // while the device scores and sorts: the commit's working copy of the node table (host only)
+    e->cm.build(e->n_hi, e->n_avail.p, e->n_total.p, e->maxN, e->n_taint.p, e->n_label.p, e->n_rank.data());
     CK(cudaStreamSynchronize(s));
     e->st.d2h_bytes += 12 * (size_t)nlive + 4;
     e->st.other_launches += 11;   // key + cub radix sort (histogram, exclusive sum, 8 onesweep passes for 64-bit keys)
@@ -326,19 +333,7 @@ int initial_order(yk_engine* e) {
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->st.sort_ms += ms;
     e->cur = 0;
-    const uint32_t* ord = e->h_order[0].p;
-    // the commit's working copy of the node table, and each live node's key / rank / position in the order
-    yk::CommitTables& ct = e->cm.t;
-    ct.D = e->D; ct.policy = e->cfg.policy; ct.w = e->w.w; ct.lda = e->maxA;
-    ct.a_req = e->a_req.p; ct.a_tol = e->a_tol.p; ct.a_need = e->a_need.p; ct.a_deny = e->a_deny.p; ct.a_node = e->a_node.p;
-    ct.a_gang = e->a_gang.data(); ct.a_app = e->a_app.data();
-    e->cm.profile = e->prof;
-    e->cm.build(e->n_hi, e->n_avail.p, e->n_total.p, e->maxN, e->n_taint.p, e->n_label.p);
-    for (int p = 0; p < nlive; ++p) {
-        const uint32_t n = ord[p];
-        e->cm.node(n).key() = e->h_skey[(size_t)p];
-        e->cm.node(n).set_meta(e->n_rank[n], (uint32_t)p);
-    }
+    e->cm.set_order(e->h_order[0].p, e->h_skey.p, nlive);   // the cycle's initial order: (key, rank, node) per position
     return YK_OK;
 }
 
@@ -375,7 +370,7 @@ int end_epoch(yk_engine* e, bool reorder) {
     const double t0 = now_ms();
     cudaStream_t s = e->stream;
     if (reorder) {
-        e->cm.merge_order(e->h_order[e->cur].p, e->h_order[e->cur ^ 1].p, nlive);
+        e->cm.merge_order(e->h_order[e->cur ^ 1].p, nlive);
         e->cur ^= 1;
     }
     // staging is reused: the previous epoch's upload must have been consumed
@@ -535,7 +530,7 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
         }
         return std::min(sl.R, next_chunk * sl.chunk);
     };
-    const int rc = e->cm.commit_batch(batch, sl.row_of.data(), sl.h_fit.p, e->h_order[e->cur].p, insensitive, result, consumed, wait);
+    const int rc = e->cm.commit_batch(batch, sl.row_of.data(), sl.h_fit.p, insensitive, result, consumed, wait);
     if (rc == -5) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
     if (rc < 0) return wait_rc ? wait_rc : e->fail(YK_ERR_CUDA, "commit aborted");
     // all read-back must have landed before the slot's buffers are reused

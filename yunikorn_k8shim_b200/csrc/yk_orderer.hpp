@@ -300,14 +300,24 @@ public:
 
     void confirm(uint32_t a) {
         t.a_state[a] = ST_ALLOCATED;
-        if (insensitive) {   // static order: accounting is not needed to order, only to persist
-            for (uint32_t qq = t.p_queue[t.a_app[a]]; qq != NONE; qq = t.q_parent[qq])
-                for (int k = 0; k < t.D; ++k) q[qq].alloc[k] += req(a, k);
-            for (int k = 0; k < t.D; ++k) ap[t.a_app[a]].alloc[k] += req(a, k);
-        }
+        if (insensitive)   // static order: accounting is not needed to order, only to persist; the queue chain gets the
+            for (int k = 0; k < t.D; ++k) ap[t.a_app[a]].alloc[k] += req(a, k);   // application's total once, in finish()
     }
 
     void finish() {   // persist queue and application allocations
+        if (insensitive)
+            for (uint32_t p = 0; p < t.maxP; ++p) {
+                if (ap_asks[p].empty()) continue;
+                int64_t delta[8];
+                bool any = false;
+                for (int k = 0; k < t.D; ++k) {
+                    delta[k] = ap[p].alloc[k] - (t.p_alloc ? t.p_alloc[(size_t)k * t.maxP + p] : 0);
+                    any = any || delta[k] != 0;
+                }
+                if (!any) continue;
+                for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq])
+                    for (int k = 0; k < t.D; ++k) q[qq].alloc[k] += delta[k];
+            }
         for (uint32_t i = 0; i < t.nq; ++i)
             for (int k = 0; k < t.D; ++k) t.q_alloc[(size_t)k * t.nq + i] = q[i].alloc[k];
         if (t.p_alloc)
