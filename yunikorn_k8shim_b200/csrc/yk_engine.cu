@@ -160,6 +160,7 @@ struct yk_engine {
     std::vector<uint64_t> a_sig;    // signature hash of each ask's predicate inputs (yk::ask_signature)
     yk::RowShare share;
     bool share_rows = true;
+    uint64_t split_min_pairs = 1ull << 25;   // multi-GPU: batches with fewer (row,node) pairs are swept whole on every rank
     std::vector<uint32_t> a_app, a_flags, a_gang, a_bound;
     std::vector<uint8_t> a_state;              // yk::ST_*, ST_ABSENT when not present
     uint32_t a_hi = 0;
@@ -416,23 +417,32 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     memcpy(sl.h_batch.p, sl.reps.data(), sizeof(uint32_t) * (size_t)R);
     CK(cudaMemcpyAsync(sl.d_batch.p, sl.h_batch.p, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s));
     st.h2d_bytes += sizeof(uint32_t) * (size_t)R;
-    // this rank's shard of the rows (world == 1: all of them)
-    const int world = std::max<int>(1, (int)e->cfg.world);
+    // this rank's shard of the rows (world == 1: all of them).  A sweep too small to pay for the exchange (shared rows:
+    // a few dozen rows per batch) is not split at all: every rank sweeps every row locally and nothing is exchanged.
+    // All ranks see the same R and nlive, so they take the same branch.
+    const int G = std::max<int>(1, (int)e->cfg.world);
+    const bool split = G > 1 && (uint64_t)R * (uint64_t)nlive >= e->split_min_pairs;
+    const int world = split ? G : 1;
+    const int my_rank = split ? (int)e->cfg.rank : 0;
     const int rows_per = (R + world - 1) / world;
-    const int row0 = std::min(R, (int)e->cfg.rank * rows_per);
+    const int row0 = std::min(R, my_rank * rows_per);
     const int rows = std::min(R, row0 + rows_per) - row0;
     const int Bpad = rows_per * world;
     sl.rows = rows;
     // the last word of every row (first-fit position) starts at YK_NONE
     const int slot_id = (int)(&sl - e->slot);
-    const bool p2p = world > 1 && e->p2p;
+    const bool p2p_on = G > 1 && e->p2p;   // peers can write into this rank's slots
+    const bool p2p = split && p2p_on;      // ... and do, for this batch
     uint32_t value = 0;
     const long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a dead peer becomes YK_ERR_COMM, not a hang
-    if (p2p) {
-        // the slot's previous content must have been consumed by every rank before anybody overwrites it
+    if (p2p_on) {
+        // The slot's previous content must have been consumed by every rank before anybody overwrites it.  Batches that
+        // are not split take part in this hand-shake too (not in the "rows ready" one): ranks are not in lock-step, and
+        // a rank that is ahead must not publish the rows of a later, split batch into a slot this rank still reads.
         value = ++e->seq;
-        yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, world, 16 + slot_id * 8, sl.last_value, e->d_flag.p, spin_limit);
+        yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, G, 16 + slot_id * 8, sl.last_value, e->d_flag.p, spin_limit);
         sl.last_value = value;
+        st.other_launches += 1;
     } else {
         // the last word of every row (first-fit position) starts at YK_NONE
         CK(cudaMemset2DAsync(sl.d_fit.p + W, sizeof(uint32_t) * (size_t)WS, 0xFF, sizeof(uint32_t), (size_t)Bpad, s));
@@ -457,17 +467,17 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
         YkPeerFit pf{};
         for (int g = 0; g < world; ++g) { ps.sync[g] = e->peer_sync[g]; pf.fit[g] = e->peer_fit[slot_id][g]; }
         if (rows > 0)
-            yk_p2p_first_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sl.d_fit.p, pf, world, (int)e->cfg.rank, row0, rows, W, WS);
-        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, slot_id * 8 + (int)e->cfg.rank, value);            // my rows are in place
+            yk_p2p_first_kernel<<<(rows + 255) / 256, 256, 0, s>>>(sl.d_fit.p, pf, world, my_rank, row0, rows, W, WS);
+        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, slot_id * 8 + my_rank, value);            // my rows are in place
         yk_p2p_wait_kernel<<<1, 32, 0, s>>>(e->d_sync.p, world, slot_id * 8, value, e->d_flag.p, spin_limit);   // everybody's are
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(sl.h_err.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        st.other_launches += 4;
+        st.other_launches += 3;
     } else if (world > 1) {
         if (!e->xfn) return e->fail(YK_ERR_COMM, "world > 1 but neither a peer-to-peer nor a callback exchange is set up");
         if (e->xfn(e->xctx, sl.d_fit.p, (uint64_t)WS * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)Bpad, (void*)s) != 0)
             return e->fail(YK_ERR_COMM, "exchange callback failed");
     }
+    if (p2p_on) CK(cudaMemcpyAsync(sl.h_err.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));   // flag waits timed out?
     // read-back in row chunks so the ordered commit overlaps the transfer
     sl.chunk = std::max(128, (R + (int)sl.ev.size() - 1) / (int)sl.ev.size());
     sl.nchunks = (R + sl.chunk - 1) / sl.chunk;
@@ -476,13 +486,13 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
         CK(cudaMemcpyAsync(sl.h_fit.p + r0 * WS, sl.d_fit.p + r0 * WS, sizeof(uint32_t) * (r1 - r0) * WS, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(sl.ev[(size_t)c], s));
     }
-    if (p2p) {
+    if (p2p_on) {
         // consumed: wipe the slot (every word back to 0xFFFFFFFF, so first-fit words start at YK_NONE whatever the next
         // row layout is) and tell every rank it may publish into it again
         CK(cudaMemsetAsync(sl.d_fit.p, 0xFF, sl.d_fit.n * sizeof(uint32_t), s));
         YkPeerSync ps{};
-        for (int g = 0; g < world; ++g) ps.sync[g] = e->peer_sync[g];
-        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, world, 16 + slot_id * 8 + (int)e->cfg.rank, value);
+        for (int g = 0; g < G; ++g) ps.sync[g] = e->peer_sync[g];
+        yk_p2p_signal_kernel<<<1, 32, 0, s>>>(ps, G, 16 + slot_id * 8 + (int)e->cfg.rank, value);
         CK(cudaGetLastError());
         st.other_launches += 1;
     }
@@ -604,6 +614,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     if (!e) return YK_ERR_NOMEM;
     e->cfg = *cfg;
     e->share_rows = !(cfg->flags & YK_FLAG_NO_ROW_SHARING) && !getenv("YK_NO_ROW_SHARING");
+    if (const char* sp = getenv("YK_SPLIT_MIN_PAIRS")) e->split_min_pairs = strtoull(sp, nullptr, 10);
     e->D = (int)cfg->D;
     e->maxN = cfg->max_nodes; e->maxA = cfg->max_asks; e->maxP = cfg->max_apps; e->maxQ = cfg->max_queues;
     e->batch = cfg->batch ? cfg->batch : 4096;
@@ -1116,6 +1127,7 @@ int yk_peer_enable(yk_engine* e) {
     for (uint32_t p = 0; p < world; ++p)
         if (p != rank && !e->peer_open[p]) return e->fail(YK_ERR_STATE, "yk_peer_enable: a peer has not been imported");
     e->peer_fit[0][rank] = e->slot[0].d_fit.p; e->peer_fit[1][rank] = e->slot[1].d_fit.p; e->peer_sync[rank] = e->d_sync.p;
+    for (Slot& sl : e->slot) CK(cudaMemset(sl.d_fit.p, 0xFF, sl.d_fit.n * sizeof(uint32_t)));   // slots start wiped
     e->p2p = true;
     return YK_OK;
 }
