@@ -164,13 +164,20 @@ def main():
     totalT, availT = np.ascontiguousarray(snap.node_total.T), np.ascontiguousarray(snap.node_avail.T)
     reqT = np.ascontiguousarray(snap.ask_req.T)
     rank_arr = snap.node_rank()
+
+    def u32(x):   # -1 -> YK_NONE, as the ABI encodes "no node" / "no gang"
+        a = np.asarray(x, dtype=np.int64).copy()
+        a[a < 0] = 0xFFFFFFFF
+        return a.astype(np.uint32)
+    a_app, a_node, a_gang, a_flags = u32(snap.ask_app), u32(snap.ask_node), u32(snap.ask_gang), u32(snap.ask_flags)
+    a_prio, n_flags = np.ascontiguousarray(snap.ask_prio, dtype=np.int32), np.ascontiguousarray(snap.node_flags, dtype=np.uint32)
     h2d_step = N * (16 * D + 8 + 8 + 4 + 4) + A * (8 * D + 8 * 3 + 4)
     d2h_step = A * 8
 
     def upsert_all(eng):
-        eng.nodes_upsert(idxN, totalT, availT, snap.node_taint, snap.node_label, rank_arr, snap.node_flags)
-        eng.asks_upsert(idxA, reqT, snap.ask_app, snap.ask_create, snap.ask_tol, snap.ask_need, snap.ask_deny,
-                        snap.ask_prio, snap.ask_node, snap.ask_flags, snap.ask_gang)
+        eng.nodes_upsert(idxN, totalT, availT, snap.node_taint, snap.node_label, rank_arr, n_flags)
+        eng.asks_upsert(idxA, reqT, a_app, snap.ask_create, snap.ask_tol, snap.ask_need, snap.ask_deny,
+                        a_prio, a_node, a_flags, a_gang)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 

@@ -20,6 +20,18 @@ extern "C" int dirty_model_check(uint64_t seed, int n_keys, int ops, int key_ran
         } else if (op < 7) {            // general erase of a random live entry
             size_t i = r() % live.size();
             d.erase(live[i]); model.erase(live[i].w); live[i] = live.back(); live.pop_back();
+        } else if (op == 7) {           // seek to a random point, walk a few entries, compare with lower_bound
+            yk::DirtyRef x(r() % (uint64_t)(key_range + 3), (uint32_t)(r() % (uint64_t)(t + 1)), 0);
+            yk::DirtyIndex::Cursor c;
+            const yk::DirtyRef* e = d.seek(c, x);
+            auto it = model.lower_bound(x.w);
+            int k = (int)(r() % 6);
+            for (int s = 0; s <= k; ++s) {
+                if ((e == nullptr) != (it == model.end())) return -6;
+                if (!e) break;
+                if (*it != e->w) return -7;
+                e = d.next(c); ++it;
+            }
         } else {                        // walk k entries from the front, compare with the model, maybe erase where we stand
             yk::DirtyIndex::Cursor c;
             const yk::DirtyRef* e = d.first(c);

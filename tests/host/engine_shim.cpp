@@ -43,6 +43,7 @@ extern "C" int engine_host_run(
     cm.t.D = D; cm.t.policy = policy; cm.t.w = weights; cm.t.lda = nA;
     cm.t.a_req = a_req; cm.t.a_tol = a_tol; cm.t.a_need = a_need; cm.t.a_deny = a_deny; cm.t.a_node = a_node; cm.t.a_gang = a_gang; cm.t.a_app = a_app;
     cm.build(nN, n_avail, n_total, nN, n_taint, n_label, n_rank);
+    cm.set_pending(pending);
     const int nlive = (int)nN;
     std::vector<uint32_t> order_nodes(nN);   // what the engine uploads for the device's gather
     {
@@ -152,7 +153,21 @@ extern "C" int engine_host_run(
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
         if (Nx.asks.empty() && n < max_bindings) {
             if (cm.dirty_list.size() * 2 >= (size_t)epoch_limit || failed) {
-                if (!cm.dirty_list.empty()) cm.merge_order(order_nodes.data(), nlive);
+                if (!cm.dirty_list.empty()) {
+                    cm.merge_order(order_nodes.data(), nlive);
+                    // the merged order must be exactly: every node once, ascending by (CURRENT score key, NodeID rank)
+                    std::vector<uint8_t> seen_node(nN, 0);
+                    for (int p = 0; p < nlive; ++p) {
+                        const yk::DirtyRef r = cm.order()[p];
+                        const uint32_t nn = r.node();
+                        if (nn >= nN || seen_node[nn] || order_nodes[p] != nn) return -7;
+                        seen_node[nn] = 1;
+                        yk::NodeView nv = cm.node(nn);
+                        const double sc = yk_node_score(D, policy, weights, nv.total(), nv.avail(), 1);
+                        if (r.key() != yk_key_bits(sc) || r.rank() != n_rank[nn]) return -8;
+                        if (p > 0 && !(cm.order()[p - 1] < r)) return -9;
+                    }
+                }
                 refresh_view();
             }
             next_batch(Nx, (size_t)max_bindings - n);

@@ -110,7 +110,7 @@ private:
 };
 
 // The per-node working record lives in one contiguous slice of `hot` (hs = 4 + 3D words):
-//   [0] sort key (valid while the node is touched)   [1] rank<<32 | touched<<31   [2] taint   [3] label
+//   [0] sort key (valid while the node is touched)   [1] rank<<32 | touched<<31 | retired<<30   [2] taint   [3] label
 //   [4,4+D) cap = min(max(0,total), max(0,available))   -- first 64 bytes at D = 4: all a predicate re-check touches
 //   [4+D,4+2D) available   [4+2D,4+3D) total            -- only read when the node is actually committed to
 struct NodeView {
@@ -119,7 +119,9 @@ struct NodeView {
     uint32_t rank() const { return (uint32_t)((uint64_t)h[1] >> 32); }
     bool dirty() const { return (((uint64_t)h[1]) >> 31) & 1u; }
     void set_rank(uint32_t rank) { h[1] = (int64_t)((uint64_t)rank << 32); }   // also clears the touched flag
-    void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x80000000ull) | (d ? 0x80000000ull : 0ull)); }
+    bool retired() const { return (((uint64_t)h[1]) >> 30) & 1u; }
+    void set_dirty(bool d) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0xC0000000ull) | (d ? 0x80000000ull : 0ull)); }   // clears `retired` too
+    void set_retired(bool r) { h[1] = (int64_t)((((uint64_t)h[1]) & ~0x40000000ull) | (r ? 0x40000000ull : 0ull)); }
     int64_t* cap() { return h + 4; }
     int64_t* avail() { return h + 4 + D; }
     int64_t* total() { return h + 4 + 2 * D; }
@@ -151,9 +153,23 @@ public:
     std::vector<DirtyRef> dirty_sorted;  // scratch for the epoch-end merge
     std::vector<uint32_t> dirty_words;   // bit p = the node at sorted position p has been touched in this epoch
     std::vector<uint32_t> dirty_list;    // the touched nodes, in first-touch order
+    // Touched nodes that can no longer hold ANY pending ask of the cycle (some dimension is below the smallest request
+    // of the cycle in that dimension) are retired: kept out of the walked index -- a binpacking cycle would otherwise
+    // step over every node it has filled, for every ask -- and put back into the order at the epoch end.
+    std::vector<DirtyRef> retired_refs;
+    int64_t cycle_min_req[CMAX_D];       // per dimension: smallest request among the cycle's pending asks
     std::vector<DirtyRef> oref[2];       // node order of the epoch: sorted position -> (key, rank, node); double-buffered
     int ocur = 0;
     int64_t dirty_ub[CMAX_D];            // per dimension: upper bound of cap over the touched nodes
+    // Per row of the current batch: a frontier in the touched order below which no entry fits that row's signature.
+    // Within an epoch a touched node only loses availability, so "does not fit signature r" is permanent, except for the
+    // nodes a gang roll-back hands back: walks for r start at the frontier instead of the front, after replaying from
+    // ins_log the entries (re)inserted -- by commits and by roll-backs -- since the row last looked.  Without this, a
+    // binpacking cycle walks over every node it has already filled, for every ask.
+    struct RowSkip { DirtyRef skip; uint32_t seen; };
+    std::vector<RowSkip> rskip;
+    std::vector<uint32_t> ins_log;       // nodes (re)inserted into the touched order during this batch
+    bool skip_active = false;
     int front = 0;                       // every sorted position below word `front` is touched
     int W = 0;                           // bitmap words per row in this epoch
     bool profile = false;
@@ -193,8 +209,21 @@ public:
     }
     const DirtyRef* order() const { return oref[ocur].data(); }
 
+    // once per cycle, before the first batch: what the smallest pending request is in every dimension
+    void set_pending(const std::vector<uint32_t>& pending) {
+        for (int k = 0; k < CMAX_D; ++k) cycle_min_req[k] = INT64_MIN;   // nothing is ever below it: retire nothing
+        if (pending.empty()) return;
+        for (int k = 0; k < t.D; ++k) {
+            const int64_t* col = t.a_req + (size_t)k * t.lda;
+            int64_t m = INT64_MAX;
+            for (uint32_t a : pending) m = std::min(m, col[a]);
+            cycle_min_req[k] = m;
+        }
+    }
+
     // a new epoch starts on a fresh view of `words` bitmap words per row: nothing is touched
     void begin_epoch(int words) {
+        retired_refs.clear();
         for (uint32_t n : dirty_list) node(n).set_dirty(false);
         dirty_list.clear();
         dirty.clear();
@@ -234,6 +263,13 @@ public:
         const int WS = W + 1;
         result.assign((size_t)B, CNONE);
         consumed = 0;
+        {
+            uint32_t nrows = 0;
+            for (int i = 0; i < B; ++i) nrows = std::max(nrows, row_of[(size_t)i] + 1);
+            rskip.assign(nrows, RowSkip{DirtyRef(), 0});
+            ins_log.clear();
+            skip_active = false;
+        }
         int landed = 0;
         bool stop = false;
         // all-or-nothing gangs: commits of the gang in progress are logged so they can be undone
@@ -287,16 +323,37 @@ public:
             if (may_fit) {
                 int64_t seen[CMAX_D];
                 for (int k = 0; k < D; ++k) seen[k] = INT64_MIN;
-                const DirtyRef* d = dirty.first(cur);
+                RowSkip& rs = rskip[(size_t)ri];
+                if (skip_active && rs.skip.w != 0) {
+                    if (ins_log.size() - rs.seen > 64) rs.skip = DirtyRef();   // too much to replay: walk from the front again
+                    else
+                        for (size_t j = rs.seen; j < ins_log.size(); ++j) {
+                            const uint32_t n = ins_log[j];
+                            NodeView v = node(n);
+                            if (!v.dirty() || v.retired()) continue;
+                            const DirtyRef now(v.key(), v.rank(), n);
+                            if (now < rs.skip && fits_now(n, ask)) rs.skip = now;
+                        }
+                }
+                rs.seen = (uint32_t)ins_log.size();
+                const bool from_start = rs.skip.w == 0;
+                const DirtyRef* d = from_start ? dirty.first(cur) : dirty.seek(cur, rs.skip);
+                uint32_t misses = 0;
                 for (; d && *d < bound; d = dirty.next(cur)) {
                     ++dbg[1];
                     // re-evaluated from the (cache-resident) working copy rather than from the bitmap row, whose lines
                     // were just DMA-written and are cold
                     if (fits_now(d->node(), ask)) { chosen = d->node(); at_cursor = true; break; }
+                    ++misses;
                     const int64_t* hh = hot.data() + (size_t)d->node() * hs + 4;   // cap
                     for (int k = 0; k < D; ++k) seen[k] = std::max(seen[k], hh[k]);
                 }
-                if (d == nullptr) for (int k = 0; k < D; ++k) dirty_ub[k] = seen[k];   // saw every touched node: exact
+                if (d == nullptr && from_start) for (int k = 0; k < D; ++k) dirty_ub[k] = seen[k];   // saw every touched node: exact
+                if (misses >= 8 || !from_start) {
+                    // everything from the old frontier up to where the walk stopped does not fit this signature
+                    rs.skip = (d && *d < bound) ? *d : bound;
+                    skip_active = true;
+                }
             }
             const unsigned long long tc2 = profile ? commit_tsc() : 0;
             if (chosen != CNONE) ++dbg[2];
@@ -308,12 +365,20 @@ public:
                     for (auto it = undo.rbegin(); it != undo.rend(); ++it) {
                         const uint32_t n = it->node;
                         NodeView un = node(n);
-                        dirty.erase(DirtyRef(un.key(), un.rank(), n));
+                        if (un.retired()) {   // it was taken out of the index when this gang filled it: it is near the back
+                            const DirtyRef r(un.key(), un.rank(), n);
+                            for (size_t x = retired_refs.size(); x-- > 0;)
+                                if (retired_refs[x] == r) { retired_refs.erase(retired_refs.begin() + (long)x); break; }
+                            un.set_retired(false);
+                        } else {
+                            dirty.erase(DirtyRef(un.key(), un.rank(), n));
+                        }
                         for (int k = 0; k < D; ++k) un.avail()[k] = it->old_avail[k];
                         un.recap();
                         un.key() = it->old_key;
                         if (it->was_dirty) {
                             dirty.insert(DirtyRef(it->old_key, un.rank(), n));
+                            if (skip_active) ins_log.push_back(n);   // its availability went back up: frontiers must re-check it
                             for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], un.cap()[k]);   // it came back
                         } else {
                             un.set_dirty(false);
@@ -355,14 +420,22 @@ public:
             if (nk == YK_KEY_NAN) return -5;
             const unsigned long long tc4 = profile ? commit_tsc() : 0;
             cv.key() = nk;
-            dirty.insert(DirtyRef(nk, cv.rank(), chosen));
+            bool spent = false;   // below the cycle's smallest request somewhere: no pending ask can ever use it again
+            for (int k = 0; k < D; ++k) spent = spent || cv.cap()[k] < cycle_min_req[k];
+            if (spent) {
+                retired_refs.push_back(DirtyRef(nk, cv.rank(), chosen));
+            } else {
+                dirty.insert(DirtyRef(nk, cv.rank(), chosen));
+                if (skip_active) ins_log.push_back(chosen);
+            }
             if (!cv.dirty()) {
-                for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], cv.cap()[k]);
+                if (!spent) for (int k = 0; k < D; ++k) dirty_ub[k] = std::max(dirty_ub[k], cv.cap()[k]);
                 cv.set_dirty(true);
                 dirty_list.push_back(chosen);
                 const uint32_t pos = posA;   // an untouched node can only have come from the clean scan (A)
                 dirty_words[pos >> 5] |= 1u << (pos & 31);
             }
+            if (spent) cv.set_retired(true);
             if (profile) {
                 const unsigned long long tc5 = commit_tsc();
                 prof[0] += tc1 - tc0; prof[1] += tc2 - tc1; prof[2] += tc3 - tc2; prof[3] += tc4 - tc3; prof[4] += tc5 - tc4; prof[5] += 1;
@@ -379,6 +452,12 @@ public:
         std::vector<DirtyRef>& ds = dirty_sorted;
         ds.clear();
         dirty.for_each([&](const DirtyRef& r) { ds.push_back(r); });
+        if (!retired_refs.empty()) {   // the retired nodes come back into the order under their final keys
+            std::sort(retired_refs.begin(), retired_refs.end());
+            const size_t mid = ds.size();
+            ds.insert(ds.end(), retired_refs.begin(), retired_refs.end());
+            std::inplace_merge(ds.begin(), ds.begin() + (long)mid, ds.end());
+        }
         const DirtyRef* in = oref[ocur].data();
         DirtyRef* out = oref[ocur ^ 1].data();
         const size_t nds = ds.size();

@@ -86,6 +86,19 @@ public:
     struct Cursor { uint32_t r = 0; uint32_t i = 0; bool enter = true; };
     const DirtyRef* first(Cursor& c) { c.r = 0; c.i = 0; c.enter = true; return settle(c); }
     const DirtyRef* next(Cursor& c) { ++c.i; return settle(c); }
+    // start the walk at the first entry >= x instead (entries before it are known to be of no interest)
+    const DirtyRef* seek(Cursor& c, const DirtyRef& x) {
+        if (lo_.empty()) return nullptr;
+        c.r = range_of(x.w);
+        const uint32_t s = id_[c.r];
+        sort_range(s);
+        const Meta& m = meta_[s];
+        const DirtyRef* v = body(s);
+        uint32_t lo = m.b, hi = m.n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (v[mid].w < x.w) lo = mid + 1; else hi = mid; }
+        c.i = lo; c.enter = false;
+        return settle(c);
+    }
     // take out the entry the cursor stands on
     void erase_at(const Cursor& c) {
         const uint32_t s = id_[c.r];

@@ -564,6 +564,17 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
 }  // namespace
 
 // ======================================= C ABI =======================================
+// idx[] = first, first+1, ... : the bulk-load shape; lets the upserts copy whole columns
+static bool contiguous_run(const uint32_t* idx, uint32_t n) {
+    for (uint32_t i = 1; i < n; ++i) if (idx[i] != idx[0] + i) return false;
+    return n > 0;
+}
+template <typename T>
+static void copy_or_fill(T* dst, const T* src, uint32_t n, T dflt) {
+    if (src) memcpy(dst, src, sizeof(T) * (size_t)n);
+    else std::fill(dst, dst + n, dflt);
+}
+
 extern "C" {
 
 uint32_t yk_abi_version(void) { return YK_ABI_VERSION; }
@@ -691,6 +702,23 @@ int yk_nodes_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const int64_t
     std::lock_guard<std::mutex> g(e->mu);
     if (n && (!idx || !total || !avail || !name_rank)) return e->fail(YK_ERR_ARG, "yk_nodes_upsert: null array");
     for (uint32_t i = 0; i < n; ++i) if (idx[i] >= e->maxN) return e->fail(YK_ERR_ARG, "yk_nodes_upsert: index beyond max_nodes");
+    if (contiguous_run(idx, n)) {   // whole-column copies
+        const uint32_t x0 = idx[0];
+        for (int k = 0; k < e->D; ++k) {
+            memcpy(&e->n_total[(size_t)k * e->maxN + x0], total + (size_t)k * n, sizeof(int64_t) * (size_t)n);
+            memcpy(&e->n_avail[(size_t)k * e->maxN + x0], avail + (size_t)k * n, sizeof(int64_t) * (size_t)n);
+        }
+        copy_or_fill<uint64_t>(&e->n_taint[x0], taint, n, 0);
+        copy_or_fill<uint64_t>(&e->n_label[x0], label, n, 0);
+        copy_or_fill<uint32_t>(&e->n_flags[x0], flags, n, YK_NODE_SCHEDULABLE);
+        for (uint32_t i = 0; i < n && !e->rank_stale; ++i)
+            if (!e->n_present[x0 + i] || e->n_rank[x0 + i] != name_rank[i]) e->rank_stale = true;
+        memcpy(&e->n_rank[x0], name_rank, sizeof(uint32_t) * (size_t)n);
+        std::fill(e->n_present.begin() + x0, e->n_present.begin() + x0 + n, 1);
+        e->n_hi = std::max(e->n_hi, x0 + n);
+        e->nodes_stale = true;
+        return YK_OK;
+    }
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t x = idx[i];
         for (int k = 0; k < e->D; ++k) {
@@ -782,6 +810,25 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
     }
     yk::CommitTables sv;   // just enough of a view for the signature hash
     sv.D = e->D; sv.lda = e->maxA; sv.a_req = e->a_req.p; sv.a_tol = e->a_tol.p; sv.a_need = e->a_need.p; sv.a_deny = e->a_deny.p; sv.a_node = e->a_node.p;
+    if (contiguous_run(idx, a)) {   // whole-column copies, then the signature hashes in one sequential pass
+        const uint32_t x0 = idx[0];
+        for (int k = 0; k < e->D; ++k) memcpy(&e->a_req[(size_t)k * e->maxA + x0], req + (size_t)k * a, sizeof(int64_t) * (size_t)a);
+        copy_or_fill<uint64_t>(&e->a_tol[x0], tol, a, 0);
+        copy_or_fill<uint64_t>(&e->a_need[x0], need, a, 0);
+        copy_or_fill<uint64_t>(&e->a_deny[x0], deny, a, 0);
+        copy_or_fill<uint32_t>(&e->a_node[x0], required_node, a, YK_NONE);
+        copy_or_fill<int32_t>(&e->a_prio[x0], prio, a, 0);
+        memcpy(&e->a_create[x0], create_seq, sizeof(int64_t) * (size_t)a);
+        memcpy(&e->a_app[x0], app, sizeof(uint32_t) * (size_t)a);
+        copy_or_fill<uint32_t>(&e->a_flags[x0], flags, a, 0);
+        copy_or_fill<uint32_t>(&e->a_gang[x0], gang, a, YK_NONE);
+        std::fill(e->a_state.begin() + x0, e->a_state.begin() + x0 + a, (uint8_t)yk::ST_PENDING);
+        std::fill(e->a_bound.begin() + x0, e->a_bound.begin() + x0 + a, YK_NONE);
+        for (uint32_t i = 0; i < a; ++i) e->a_sig[x0 + i] = yk::ask_signature(sv, x0 + i);
+        e->a_hi = std::max(e->a_hi, x0 + a);
+        e->asks_stale = true;
+        return YK_OK;
+    }
     for (uint32_t i = 0; i < a; ++i) {
         const uint32_t x = idx[i];
         for (int k = 0; k < e->D; ++k) e->a_req[(size_t)k * e->maxA + x] = req[(size_t)k * a + i];
@@ -877,6 +924,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
     e->st.host_ms[0] += t_a - t_start;
     e->st.host_ms[1] += begin_ms;
     if (rc) return rc;
+    e->cm.set_pending(pending);   // smallest pending request per dimension: nodes below it are retired from the walk
     // epoch length: long enough that order merges / view refreshes (and the pipeline bubble they cost) stay rare on big
     // clusters, short enough that the touched set does not slow the walk: 5/8 of the nodes, at least two batches
     e->epoch_limit = e->epoch_env ? e->epoch_env : std::max<uint32_t>(e->epoch_floor, (uint32_t)((uint64_t)e->nlive * 5 / 8));

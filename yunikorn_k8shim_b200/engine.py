@@ -199,6 +199,8 @@ class Engine:
         def u32none(x):
             if x is None:
                 return None
+            if isinstance(x, np.ndarray) and x.dtype == np.uint32:   # already in the ABI's encoding (YK_NONE = 0xFFFFFFFF)
+                return _arr(x, np.uint32, n)
             a = np.asarray(x, dtype=np.int64).copy()
             a[a < 0] = YK_NONE
             return _arr(a, np.uint32, n)
