@@ -47,18 +47,24 @@ struct CommitTables {
 // signature: rows[] lists one representative ask per signature (in order of first appearance, so rows land in the
 // order the commit first needs them) and row_of[i] is the row of batch entry i.  The 64-bit signature hash is
 // computed once when an ask is upserted; equality is always confirmed on the full signature.
-inline uint64_t sig_mix(uint64_t h, uint64_t v) {
-    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-    h *= 0xFF51AFD7ED558CCDull;
-    return h ^ (h >> 32);
-}
 inline uint64_t ask_signature(const CommitTables& t, uint32_t a) {
+    // every field gets its own odd multiplier (independent multiplies: no serial chain), folded by xor / rotate, one
+    // final avalanche.  Collisions only cost a full compare: equality is never decided on the hash.
+    static const uint64_t C[12] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0xD6E8FEB86659FD93ull,
+                                   0xFF51AFD7ED558CCDull, 0xC4CEB9FE1A85EC53ull, 0x2545F4914F6CDD1Dull, 0x94D049BB133111EBull,
+                                   0xBF58476D1CE4E5B9ull, 0xA0761D6478BD642Full, 0xE7037ED1A0B428DBull, 0x8EBC6AF09C88C6E3ull};
     uint64_t h = 0x243F6A8885A308D3ull;
-    for (int k = 0; k < t.D; ++k) h = sig_mix(h, (uint64_t)t.a_req[(size_t)k * t.lda + a]);
-    h = sig_mix(h, t.a_tol[a]);
-    h = sig_mix(h, t.a_need[a]);
-    h = sig_mix(h, t.a_deny[a]);
-    return sig_mix(h, t.a_node[a]);
+    for (int k = 0; k < t.D; ++k) {
+        const uint64_t v = (uint64_t)t.a_req[(size_t)k * t.lda + a] * C[k];
+        h ^= (v << (7 * k + 1)) | (v >> (63 - 7 * k));
+    }
+    h ^= t.a_tol[a] * C[8];
+    h ^= (t.a_need[a] * C[9]) >> 3 | (t.a_need[a] * C[9]) << 61;
+    h ^= (t.a_deny[a] * C[10]) >> 17 | (t.a_deny[a] * C[10]) << 47;
+    h ^= ((uint64_t)t.a_node[a] + 1) * C[11];
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    return h ^ (h >> 29);
 }
 inline bool same_signature(const CommitTables& t, uint32_t a, uint32_t b) {
     if (t.a_tol[a] != t.a_tol[b] || t.a_need[a] != t.a_need[b] || t.a_deny[a] != t.a_deny[b] || t.a_node[a] != t.a_node[b]) return false;
