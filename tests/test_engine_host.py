@@ -186,3 +186,21 @@ def test_shared_rows_sweep_one_row_per_signature(shim, oracle):
         distinct = len(np.unique(sig, axis=0))
         assert distinct >= min(t.n_asks, t.n_nodes), field        # the fixture really separates the asks
         assert rows[0] >= distinct, (field, rows, distinct)
+
+
+def test_shared_rows_survive_hash_collisions(shim, oracle):
+    """the signature hash only finds candidates: with every hash equal (share_rows=2 in the harness) rows are still
+    shared exactly between asks whose full signatures are equal, and the bindings do not change"""
+    for seed in (0, 3, 7, 11):
+        s = synth.fuzz(seed)
+        if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > 64:
+            continue
+        good, collide = [], []
+        check(shim, oracle, s, batch=64, rows=good, tag=seed)
+        check(shim, oracle, s, batch=64, share_rows=2, rows=collide, tag=seed)
+        assert good == collide
+    s = synth.perf(300, 20, 40)
+    good, collide = [], []
+    check(shim, oracle, s, batch=128, rows=good)
+    check(shim, oracle, s, batch=128, share_rows=2, rows=collide)
+    assert good == collide
