@@ -313,7 +313,14 @@ public:
                 }
             }
             DirtyRef bound(~0ull, ~0u, CNONE);
-            if (posA != CNONE) bound = order[posA];
+            if (posA != CNONE) {
+                bound = order[posA];
+                // the clean candidate wins about half the time; on big clusters its record is not in cache: start
+                // pulling both lines now, the walk below hides the latency
+                const int64_t* rec = hot.data() + (size_t)bound.node() * hs;
+                __builtin_prefetch(rec);
+                __builtin_prefetch(rec + 8);
+            }
             const unsigned long long tc1 = profile ? commit_tsc() : 0;
             // (B) best re-scored node among those touched earlier in this epoch.  dirty_ub prunes the walk: if the
             // request exceeds what ANY touched node has left on some dimension, none of them can fit.  A walk that ran
