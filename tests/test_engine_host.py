@@ -204,3 +204,16 @@ def test_shared_rows_survive_hash_collisions(shim, oracle):
     check(shim, oracle, s, batch=128, rows=good)
     check(shim, oracle, s, batch=128, share_rows=2, rows=collide)
     assert good == collide
+
+
+def test_cut_cycle_leaves_no_tentative_gang_members(shim, oracle):
+    """placement-insensitive order + gangs + max_bindings: members queued behind the cut must read PENDING again"""
+    s = synth.gangs(200, 40, 5, fill=0.5)
+    full = oracle.run(s)
+    k = (len(full["ask"]) // 2) // 5 * 5 + 5
+    want = oracle.run(s, max_bindings=k)
+    rc, ask, node, state, avail = run_engine_host(shim, s, batch=20, max_bindings=k)
+    assert rc == 0
+    assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
+    assert set(np.unique(state)) <= {0, 1}, np.unique(state)        # pending or allocated, nothing in between
+    assert np.array_equal(state, want["state"])

@@ -102,6 +102,7 @@ public:
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
     bool insensitive = false;
     std::vector<uint32_t> static_order; size_t static_next = 0;
+    std::vector<uint32_t> static_apps, sa_mem; size_t sa_app = 0, sa_pos = 0;   // where extend_static() stands
     bool oversize_gang = false;   // a gang larger than the batch capacity was met: the caller must raise its batch size
     uint64_t slow_seen = 0;
     std::vector<uint32_t> slow_list;
@@ -192,32 +193,39 @@ public:
         }
         static_order.clear();
         static_next = 0;
-        if (insensitive) {   // the whole cycle's pass order is known up front: apps in set order, asks in app order
-            auto cause_of = [&](uint32_t a) -> uint8_t {
-                if (t.a_flags[a] & 1u) return ST_SLOWPATH;
-                int64_t rq[8];
-                for (int k2 = 0; k2 < d; ++k2) rq[k2] = req(a, k2);
-                return strictly_gt_zero(rq, d) ? 0 : ST_INVALID;
-            };
-            std::vector<uint32_t> mem;
-            for (const AppKey& k : q_set[leaf]) {
-                const auto& v = ap_asks[k.app];
-                for (uint32_t a : v) {
-                    if (t.a_state[a] != ST_PENDING) continue;
-                    const uint8_t c = cause_of(a);
-                    if (c) { if (c == ST_SLOWPATH) slow_list.push_back(a); t.a_state[a] = c; continue; }
-                    if (t.a_gang[a] == NONE) { static_order.push_back(a); continue; }
-                    // a gang: all its pending members follow its first member; one bad member sinks the gang
-                    mem.clear();
-                    uint8_t gc = 0;
-                    for (uint32_t m : v)
-                        if (t.a_gang[m] == t.a_gang[a] && t.a_state[m] == ST_PENDING) { mem.push_back(m); if (!gc) gc = cause_of(m); }
-                    for (uint32_t m : mem) {
-                        if (gc) t.a_state[m] = gc; else { t.a_state[m] = ST_TENTATIVE; static_order.push_back(m); }
-                    }
-                }
+        static_apps.clear();
+        sa_app = sa_pos = 0;
+        if (insensitive)   // the whole cycle's pass order is known up front: apps in set order, asks in app order;
+            for (const AppKey& k : q_set[leaf]) static_apps.push_back(k.app);   // it is materialised batch by batch (extend_static)
+    }
+
+    // placement-insensitive cycles: append to static_order until `want` entries are waiting (or nothing is left).
+    // Same walk the reference's passes would do: applications in leaf order, asks in application order; an ask that can
+    // never be tried gets its cause; a gang's pending members follow its first member (marked TENTATIVE so the walk does
+    // not meet them again; confirm / fail_in_place / finish give them their final state), one bad member sinks the gang.
+    void extend_static(size_t want) {
+        const int d = t.D;
+        auto cause_of = [&](uint32_t a) -> uint8_t {
+            if (t.a_flags[a] & 1u) return ST_SLOWPATH;
+            int64_t rq[8];
+            for (int k2 = 0; k2 < d; ++k2) rq[k2] = req(a, k2);
+            return strictly_gt_zero(rq, d) ? 0 : ST_INVALID;
+        };
+        while (static_order.size() - static_next < want && sa_app < static_apps.size()) {
+            const auto& v = ap_asks[static_apps[sa_app]];
+            if (sa_pos >= v.size()) { ++sa_app; sa_pos = 0; continue; }
+            const uint32_t a = v[sa_pos++];
+            if (t.a_state[a] != ST_PENDING) continue;
+            const uint8_t c = cause_of(a);
+            if (c) { if (c == ST_SLOWPATH) slow_list.push_back(a); t.a_state[a] = c; continue; }
+            if (t.a_gang[a] == NONE) { static_order.push_back(a); continue; }
+            sa_mem.clear();
+            uint8_t gc = 0;
+            for (uint32_t m : v)
+                if (t.a_gang[m] == t.a_gang[a] && t.a_state[m] == ST_PENDING) { sa_mem.push_back(m); if (!gc) gc = cause_of(m); }
+            for (uint32_t m : sa_mem) {
+                if (gc) t.a_state[m] = gc; else { t.a_state[m] = ST_TENTATIVE; static_order.push_back(m); }
             }
-            for (uint32_t a : static_order) t.a_state[a] = ST_PENDING;
         }
     }
 
@@ -228,6 +236,7 @@ public:
         batch.clear();
         snap.valid = false;
         if (insensitive) {
+            extend_static(cap_batch == (size_t)-1 ? cap_batch : cap_batch + 1);   // one more than fits: the loop below ends on capacity
             while (static_next < static_order.size()) {
                 const uint32_t a = static_order[static_next];
                 size_t len = 1;
@@ -305,6 +314,9 @@ public:
     }
 
     void finish() {   // persist queue and application allocations
+        if (insensitive)   // gang members queued but never batched (max_bindings cut the cycle) are simply still pending
+            for (size_t i = static_next; i < static_order.size(); ++i)
+                if (t.a_state[static_order[i]] == ST_TENTATIVE) t.a_state[static_order[i]] = ST_PENDING;
         if (insensitive)
             for (uint32_t p = 0; p < t.maxP; ++p) {
                 if (ap_asks[p].empty()) continue;
