@@ -184,3 +184,8 @@ extern "C" int engine_host_run(
         for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = cm.node(nn).avail()[k];
     return 0;
 }
+
+// csrc/yk_score.h compiled for the host (the same code the device runs): for the score known-answer test
+extern "C" double score_host(int D, uint32_t policy, const double* w, const int64_t* total, const int64_t* avail) {
+    return yk_node_score(D, policy, w, total, avail, 1);
+}

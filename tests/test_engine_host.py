@@ -217,3 +217,32 @@ def test_cut_cycle_leaves_no_tentative_gang_members(shim, oracle):
     assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
     assert set(np.unique(state)) <= {0, 1}, np.unique(state)        # pending or allocated, nothing in between
     assert np.array_equal(state, want["state"])
+
+
+def test_score_bits_match_the_oracle(shim, oracle):
+    """csrc/yk_score.h (host build of the code the device runs; it forms usage/W without a divide when W is 1 or 2)
+    against the oracle's plain restatement: identical IEEE-754 bits, including tiny and huge operands"""
+    shim.score_host.restype = C.c_double
+    rng = np.random.default_rng(5)
+    cases = 0
+    for wts in ([1.0, 1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0], [1.0, 1.0, 1.0, 0.0], [0.5, 1.5, 0.0, 0.0], [2.0, 0.0, 0.0, 0.0],
+                [1.0, 1.0, 1.0, 1.0], [0.25, 0.25, 0.5, 1.0]):
+        w = np.array(wts, dtype=np.float64)
+        for _ in range(3000):
+            mag = rng.integers(0, 62, size=4)
+            total = (rng.integers(0, 1 << 62, size=4) >> (62 - mag)).astype(np.int64)
+            total[rng.random(4) < 0.1] = 0
+            avail = (total * rng.random(4)).astype(np.int64)
+            if rng.random() < 0.2:
+                avail = avail - rng.integers(0, 5, size=4)            # slightly negative / over-committed
+            if rng.random() < 0.1:
+                avail = total.copy()                                 # empty node: shares exactly 0
+            if rng.random() < 0.05:
+                avail = total - 1                                    # shares of 1 ulp-ish size
+            for policy in (0, 1):
+                got = shim.score_host(C.c_int(4), C.c_uint32(policy), _p(w), _p(total), _p(avail))
+                want = oracle.node_score(policy, w, total, avail)
+                assert np.float64(got).tobytes() == np.float64(want).tobytes() or (got != got and want != want), \
+                    (wts, total, avail, policy, got, want)
+                cases += 1
+    assert cases > 40000

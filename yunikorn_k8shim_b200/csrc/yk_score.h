@@ -31,7 +31,9 @@ YK_HD double yk_node_score(int D, uint32_t policy, const double* w, const int64_
         usage += share * w[k];
         tw += w[k];
     }
-    double a = (tw == 0.0) ? 0.0 : usage / tw;
+    // usage / tw; for tw = 1 or 2 (the default weights) the quotient is formed without a divide: x / 2 and x * 0.5 are the
+    // same real number, so their correctly rounded doubles are the same bits
+    double a = (tw == 0.0) ? 0.0 : (tw == 2.0 ? usage * 0.5 : (tw == 1.0 ? usage : usage / tw));
     double s = (policy == 1u) ? 1.0 - a : a;
     return s + 0.0;  // -0.0 -> +0.0
 }
