@@ -38,6 +38,13 @@ def test_python_stub_lists_the_same_symbols():
     from yunikorn_k8shim_b200.dictionary import DICT_EXPORTS
     assert sorted(EXPORTS) == declared_functions()
     assert sorted(DICT_EXPORTS) == declared_functions("ykgpu_dict.h")
+    from yunikorn_k8shim_b200.podres import POD_EXPORTS
+    assert sorted(POD_EXPORTS) == declared_functions("ykgpu_pod.h")
+
+
+def test_pod_symbols_are_exported(lib):
+    for name in declared_functions("ykgpu_pod.h"):
+        assert hasattr(lib, name), f"{name} declared in ykgpu_pod.h but not exported by libykgpu.so"
 
 
 def test_dictionary_symbols_are_exported(lib):
