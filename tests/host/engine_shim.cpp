@@ -15,7 +15,11 @@ namespace {
 struct Slot { std::vector<uint32_t> asks, reps, row_of; yk::Orderer::Snap snap; std::vector<uint32_t> fit; };
 }
 
-extern "C" int engine_host_run(
+// exchange callback with the signature of yk_allgather_fn (include/ykgpu.h): all-gather of equal row blocks, in place
+typedef int (*shim_allgather_fn)(void* ctx, void* buf, uint64_t row_bytes, uint32_t first_row, uint32_t n_rows, uint32_t total_rows, void* stream);
+
+static int engine_host_run_impl(
+    uint32_t rank, uint32_t world, shim_allgather_fn xfn, uint64_t split_min_pairs,
     int D, uint32_t policy, const double* weights,
     uint32_t nN, const int64_t* n_total /*[D][nN]*/, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
     const uint32_t* n_flags, const uint32_t* n_rank,
@@ -82,11 +86,18 @@ extern "C" int engine_host_run(
     for (uint32_t a = 0; a < nA; ++a) a_sig[a] = share_rows == 2 ? 42 : yk::ask_signature(cm.t, a);
     yk::RowShare share;
     uint64_t rows_swept = 0;
+    int xrc = 0;
     auto sweep = [&](Slot& sl) {
+        if (sl.asks.empty()) { sl.reps.clear(); sl.row_of.clear(); sl.fit.clear(); return; }   // produce() returns early as well
         share.build(cm.t, a_sig.data(), sl.asks, share_rows != 0, sl.reps, sl.row_of);   // as produce() does
         rows_swept += sl.reps.size();
-        sl.fit.assign(sl.reps.size() * (size_t)WS, 0);
-        for (size_t i = 0; i < sl.reps.size(); ++i) {
+        // this rank's shard of the rows, exactly as produce() cuts it (world == 1 or a small sweep: all of them)
+        const size_t R = sl.reps.size();
+        const bool split = world > 1 && (uint64_t)R * (uint64_t)nlive >= split_min_pairs;
+        const size_t G = split ? world : 1, my = split ? rank : 0;
+        const size_t rows_per = (R + G - 1) / G, row0 = std::min(R, my * rows_per), row1 = std::min(R, row0 + rows_per);
+        sl.fit.assign(rows_per * G * (size_t)WS, 0);
+        for (size_t i = row0; i < row1; ++i) {
             const uint32_t a = sl.reps[i];
             uint32_t* row = sl.fit.data() + i * WS;
             row[W] = yk::CNONE;
@@ -97,6 +108,9 @@ extern "C" int engine_host_run(
                 ok = ok && (a_node[a] == yk::CNONE || a_node[a] == v_node[p]);
                 if (ok) { row[p >> 5] |= 1u << (p & 31); if (row[W] == yk::CNONE) row[W] = (uint32_t)p; }
             }
+        }
+        if (split) {   // the other ranks' rows arrive through the exchange callback (the engine's yk_set_exchange path)
+            if (!xfn || xfn(nullptr, sl.fit.data(), (uint64_t)WS * 4, (uint32_t)row0, (uint32_t)rows_per, (uint32_t)(rows_per * G), nullptr) != 0) xrc = -11;
         }
     };
     refresh_view();
@@ -114,6 +128,7 @@ extern "C" int engine_host_run(
             if (o.oversize_gang) { rc_over = -1; return; }
         }
         sweep(sl);
+        if (xrc) rc_over = xrc;
     };
     std::vector<uint32_t> result;
     next_batch(slot[0], max_bindings);
@@ -183,6 +198,31 @@ extern "C" int engine_host_run(
     for (uint32_t nn = 0; nn < nN; ++nn)
         for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = cm.node(nn).avail()[k];
     return 0;
+}
+
+extern "C" int engine_host_run(int D, uint32_t policy, const double* weights,
+    uint32_t nN, const int64_t* n_total /*[D][nN]*/, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
+    const uint32_t* n_flags, const uint32_t* n_rank,
+    uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req /*[D][nA]*/, const uint64_t* a_tol, const uint64_t* a_need,
+    const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
+    const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
+    const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+    uint32_t batch, uint32_t epoch_limit, int speculate, int share_rows, uint32_t max_bindings,
+    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out /*[D][nN]*/, uint64_t* rows_out) {
+    return engine_host_run_impl(0, 1, nullptr, 0, D, policy, weights, nN, n_total, n_avail, n_taint, n_label, n_flags, n_rank, nA, nP, nQ, a_req, a_tol, a_need, a_deny, a_node, a_prio, a_create, a_app, a_flags, a_gang, p_queue, p_submit, q_parent, q_guar, q_max, q_alloc, q_sort, batch, epoch_limit, speculate, share_rows, max_bindings, out_ask, out_node, n_out, state_out, avail_out, rows_out);
+}
+
+// the same cycle as one of `world` replicas: rows of each batch are cut across the ranks and exchanged through xfn
+extern "C" int engine_host_run_ranked(uint32_t rank, uint32_t world, shim_allgather_fn xfn, uint64_t split_min_pairs, int D, uint32_t policy, const double* weights,
+    uint32_t nN, const int64_t* n_total /*[D][nN]*/, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
+    const uint32_t* n_flags, const uint32_t* n_rank,
+    uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req /*[D][nA]*/, const uint64_t* a_tol, const uint64_t* a_need,
+    const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
+    const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
+    const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+    uint32_t batch, uint32_t epoch_limit, int speculate, int share_rows, uint32_t max_bindings,
+    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out /*[D][nN]*/, uint64_t* rows_out) {
+    return engine_host_run_impl(rank, world, xfn, split_min_pairs, D, policy, weights, nN, n_total, n_avail, n_taint, n_label, n_flags, n_rank, nA, nP, nQ, a_req, a_tol, a_need, a_deny, a_node, a_prio, a_create, a_app, a_flags, a_gang, p_queue, p_submit, q_parent, q_guar, q_max, q_alloc, q_sort, batch, epoch_limit, speculate, share_rows, max_bindings, out_ask, out_node, n_out, state_out, avail_out, rows_out);
 }
 
 // csrc/yk_score.h compiled for the host (the same code the device runs): for the score known-answer test

@@ -73,3 +73,73 @@ def test_shard_rows_covers_every_row_once():
                 seen[first:min(n, first + rows_per)] += 1
                 assert total >= n and total % world == 0
             assert (seen == 1).all()
+
+
+# ---- the whole N>1 host path on CPU: two replicas of the engine's host side (tests/host/engine_shim.cpp: the real
+# orderer and ordered commit, CPU stand-in for the sweep), rows of every batch cut across the ranks exactly as
+# produce() cuts them and exchanged through the same callback type the engine calls (yk_allgather_fn) over gloo ----
+def _replica(rank, world, port, seeds, split_min_pairs, q):
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import test_engine_host as T
+        from yunikorn_k8shim_b200 import synth
+        from yunikorn_k8shim_b200.engine import ALLGATHER_FN
+        from oracle import oracle_ctypes as oc
+        so = os.path.join(os.environ["YK_SHIM_DIR"], f"engine_shim_{rank}.so")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", so,
+                               os.path.join(here, "host", "engine_shim.cpp")])
+        shim = C.CDLL(so)
+        cb = ALLGATHER_FN(multigpu.make_allgather(dist, cuda=False))
+        out = []
+        for seed in seeds:
+            s = synth.fuzz(seed) if seed >= 0 else synth.perf(300, 12, 40, masks=(seed == -2))
+            if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > 64:
+                continue
+            want = oc.run(s)
+            real = shim.engine_host_run
+
+            def ranked(*args):      # same argument list, prefixed with (rank, world, callback, threshold)
+                return shim.engine_host_run_ranked(C.c_uint32(rank), C.c_uint32(world), cb, C.c_uint64(split_min_pairs), *args)
+
+            class Proxy:
+                engine_host_run = staticmethod(ranked)
+            rc, ask, node, state, avail = T.run_engine_host(Proxy, s, batch=64)
+            ok = rc == 0 and np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"]) and \
+                np.array_equal(avail, want["avail"]) and np.array_equal(state, want["state"])
+            agree = multigpu.check_agreement(dist, ask, node)
+            out.append((seed, bool(ok), bool(agree)))
+            assert real is not None
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("split_min_pairs", [0, 20000])
+def test_two_replicas_split_rows_and_commit_identically(tmp_path, split_min_pairs):
+    """split_min_pairs = 0: every batch is cut across the two ranks (rank 1 may own zero rows when rows are shared);
+    20000: small sweeps stay whole on every rank and only the large ones are exchanged -- both must reproduce the
+    oracle's bindings on both ranks, and the replicas must agree."""
+    world = 2
+    os.environ["YK_SHIM_DIR"] = str(tmp_path)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    seeds = [-1, -2, 0, 2, 5, 8, 13, 21, 34]
+    procs = [ctx.Process(target=_replica, args=(r, world, port, seeds, split_min_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(res[0]) == len(res[1]) >= 6
+    for rank in range(world):
+        for seed, ok, agree in res[rank]:
+            assert ok, f"rank {rank}, snapshot {seed}: differs from the oracle"
+            assert agree, f"rank {rank}, snapshot {seed}: replicas disagree"
