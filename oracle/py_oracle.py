@@ -238,7 +238,17 @@ def run(s, max_bindings=-1):
         import functools
         cand = [c for c in children[q] if q_npend[c] > 0]
 
+        def queue_prio(x):            # highest priority among the asks still pending below queue x
+            if not children[x]:
+                pr = [app_prio(p) for p in q_apps[x] if app_npend(p) > 0]
+            else:
+                pr = [queue_prio(c) for c in children[x] if q_npend[c] > 0]
+            return max(pr) if pr else -(1 << 31)
+        qp = {c: queue_prio(c) for c in cand}
+
         def qcmp(l, r):
+            if qp[l] != qp[r]:            # priority first (sortQueuesByPriorityAndFairness), then the shares
+                return -1 if qp[l] > qp[r] else 1
             c = compare_shares(shares(q_alloc[l], [int(x) for x in s.q_guaranteed[l]]),
                                shares(q_alloc[r], [int(x) for x in s.q_guaranteed[r]]))
             if c:

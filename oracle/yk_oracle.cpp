@@ -290,6 +290,19 @@ struct Engine {
         return ap.head < ap.asks.size() ? s->ask_prio[ap.asks[ap.head]] : INT32_MIN;
     }
 
+    // Queue.GetCurrentPriority with default offsets / policies [EXT]: leaf = max over its applications that still have
+    // pending asks; parent = max over its children
+    int queue_priority(int q) {
+        Queue& Q = queues[(size_t)q];
+        int best = INT32_MIN;
+        if (Q.children.empty()) {
+            for (int p : Q.apps) if (apps[(size_t)p].pending_asks > 0) best = std::max(best, app_priority(p));
+        } else {
+            for (int c : Q.children) if (queues[(size_t)c].pending_asks > 0) best = std::max(best, queue_priority(c));
+        }
+        return best;
+    }
+
     // appends the pass's allocation(s) to out (one ask, or a whole gang); returns true if anything was allocated
     bool try_app(int p, const int64_t* hr, std::vector<std::pair<int, int>>& out, int room) {
         bool retry = (mode & YKO_MODE_RETRY_FAILED) != 0;
@@ -358,7 +371,13 @@ struct Engine {
         ++st.queue_sorts;
         std::vector<int> sorted;
         for (int c : Q.children) if (queues[(size_t)c].pending_asks > 0) sorted.push_back(c);
+        // sortQueuesByPriorityAndFairness [EXT yunikorn-core objects/sorters.go; priority sorting is on by default]: the
+        // queue's current priority (highest priority among the asks still pending below it) first, then the shares.
+        // Behaviour pinned by /root/reference/test/e2e/priority_scheduling/priority_scheduling_test.go:70-133.
+        std::vector<int> qprio((size_t)s->n_queues, INT32_MIN);
+        for (int c : sorted) qprio[(size_t)c] = queue_priority(c);
         auto child_less = [&](int l, int r) {
+            if (qprio[(size_t)l] != qprio[(size_t)r]) return qprio[(size_t)l] > qprio[(size_t)r];
             int c = yko_comp_usage_ratio_separately(D, queues[(size_t)l].alloc.data(), s->q_guaranteed + (size_t)l * D,
                                                     queues[(size_t)r].alloc.data(), s->q_guaranteed + (size_t)r * D);
             if (c != 0) return c < 0;

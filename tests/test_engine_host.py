@@ -246,3 +246,23 @@ def test_score_bits_match_the_oracle(shim, oracle):
                     (wts, total, avail, policy, got, want)
                 cases += 1
     assert cases > 40000
+
+
+def test_reference_e2e_scenarios_through_the_host_engine(shim, oracle):
+    """the two behaviour-level known answers the reference's e2e suites give for this path (priority order across
+    sibling queues, binpacking node order; tests/test_oracle_golden.py states them) through the real orderer + commit"""
+    done = []
+    for expect in ("high", "normal", "low"):
+        s = synth.priority_fence(quota_pods=1, done=done)
+        for batch in (1, 64):
+            rc, ask, node, state, avail = run_engine_host(shim, s, batch=batch)
+            assert rc == 0 and [s.meta["apps"][a] for a in ask] == [expect]
+        check(shim, oracle, s, batch=8)
+        done.append(expect)
+    s = synth.priority_fence(quota_pods=3)
+    rc, ask, node, state, avail = run_engine_host(shim, s, batch=2)
+    assert [s.meta["apps"][a] for a in ask] == ["high", "normal", "low"]
+    s = synth.binpacking_e2e()
+    rc, ask, node, state, avail = run_engine_host(shim, s, batch=4)
+    assert [s.node_id[n] for n in node] == ["nodeA"] * 3 + ["nodeB"] * 3
+    check(shim, oracle, s, batch=4)

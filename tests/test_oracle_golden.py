@@ -126,3 +126,35 @@ def test_frozen_oracle_goldens(oracle):
         if "ask" in c:
             assert [int(a) for a in r["ask"]] == c["ask"]
             assert [s.node_id[n] for n in r["node"]] == c["node_id_of_binding"]
+
+
+def test_priority_order_across_sibling_queues_from_priority_scheduling_e2e(oracle):
+    """/root/reference/test/e2e/priority_scheduling/priority_scheduling_test.go:70-133,407-476: low, normal and high
+    priority pods sit in two sibling queues under a parent whose quota admits one pod at a time; whenever room appears
+    the reference starts high, then normal, then low -- regardless of submit order and of which queue they are in."""
+    from oracle import py_oracle
+    from yunikorn_k8shim_b200 import synth
+    done = []
+    for expect in ("high", "normal", "low"):
+        s = synth.priority_fence(quota_pods=1, done=done)
+        for run in (oracle.run, py_oracle.run):
+            r = run(s)
+            assert [s.meta["apps"][a] for a in r["ask"]] == [expect]            # one pod fits the quota: it must be this one
+            assert sorted(int(x) for x in r["state"]) == [1] + [3] * (len(s.meta["apps"]) - 1)   # the others: headroom
+        done.append(expect)
+    # with room for all three the cycle serves them in priority order
+    s = synth.priority_fence(quota_pods=3)
+    for run in (oracle.run, py_oracle.run):
+        assert [s.meta["apps"][a] for a in run(s)["ask"]] == ["high", "normal", "low"]
+
+
+def test_binpacking_node_order_from_bin_packing_e2e(oracle):
+    """/root/reference/test/e2e/bin_packing/bin_packing_test.go:46-200: job A's 3 pods all land on the most utilised
+    node, job B's 3 pods (kept off that node) on the second most utilised one."""
+    from oracle import py_oracle
+    from yunikorn_k8shim_b200 import synth
+    s = synth.binpacking_e2e()
+    for run in (oracle.run, py_oracle.run):
+        r = run(s)
+        assert list(r["ask"]) == [0, 1, 2, 3, 4, 5]
+        assert [s.node_id[n] for n in r["node"]] == ["nodeA"] * 3 + ["nodeB"] * 3

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <set>
 #include <tuple>
 #include <vector>
@@ -54,6 +55,8 @@ public:
         int64_t npend = 0, live = 0;
         double shares[8];
         bool shares_ok = false;
+        int32_t prio = INT32_MIN;   // Queue.GetCurrentPriority: highest priority among the asks still pending below it
+        bool prio_ok = false;
     };
     struct AState {
         uint32_t head = 0;       // first ask not allocated/tentative
@@ -97,6 +100,11 @@ public:
     std::vector<std::vector<uint32_t>> q_sorted, q_changed;   // per parent: cached child order, children to re-position
     std::vector<uint8_t> q_sorted_ok;
     std::vector<uint8_t> q_has_quota;                          // some queue on the chain root..q has a max set
+    // queue priorities (parents sort their children by priority first, then by share: sortQueuesByPriorityAndFairness
+    // [EXT]).  uniform_prio: every pending ask of the cycle has the same priority, so none of this can matter and it is
+    // skipped.  Otherwise every leaf keeps {priority of an application's best pending ask -> how many such applications}.
+    bool uniform_prio = true;
+    std::vector<std::map<int32_t, int>> q_prio_cnt;
     std::vector<AState> ap;
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
@@ -112,6 +120,7 @@ public:
         std::vector<QState> q;
         std::vector<AState> ap;
         std::vector<std::set<AppKey>> sets;
+        std::vector<std::map<int32_t, int>> prio_cnt;
         std::vector<std::pair<uint32_t, uint8_t>> journal;   // (ask, previous state) written while the batch was filled
         size_t slow_mark = 0;
         bool valid = false;
@@ -134,6 +143,7 @@ public:
         q_set.assign(t.nq, {});
         q_sorted.assign(t.nq, {}); q_changed.assign(t.nq, {}); q_sorted_ok.assign(t.nq, 0);
         q_has_quota.assign(t.nq, 0);
+        q_prio_cnt.assign(t.nq, {});
         for (uint32_t i = 0; i < t.nq; ++i) {
             for (int k = 0; k < d; ++k) { q[i].alloc[k] = t.q_alloc[(size_t)k * t.nq + i]; q[i].pending[k] = 0; }
             if (i > 0) q_children[t.q_parent[i]].push_back(i);
@@ -177,6 +187,7 @@ public:
             }
             q_apps[t.p_queue[p]].push_back(p);
             A.key_prio = t.a_prio[v[0]];
+            ++q_prio_cnt[t.p_queue[p]][A.key_prio];
             if (t.p_alloc) for (int k = 0; k < d; ++k) A.alloc[k] = t.p_alloc[(size_t)k * t.maxP + p];
             if (A.live > 0) { q_set[t.p_queue[p]].insert(make_key(p)); A.in_set = true; }
         }
@@ -184,6 +195,7 @@ public:
         int leaves = 0; uint32_t leaf = NONE;
         for (uint32_t i = 0; i < t.nq; ++i)
             if (q_children[i].empty() && q[i].npend > 0) { ++leaves; leaf = i; }
+        uniform_prio = one_prio;
         insensitive = false;
         if (leaves == 1 && one_prio && t.q_sort[leaf] == 0) {
             bool quota = false;
@@ -252,6 +264,7 @@ public:
         }
         snap.journal.clear(); snap.slow_mark = slow_list.size();
         snap.q = q; snap.ap = ap; snap.sets = q_set; snap.valid = true;   // only placement-sensitive orders ever rewind
+        if (!uniform_prio) snap.prio_cnt = q_prio_cnt;
         jr = &snap.journal;
         while (step(cap_batch, cap_user, batch)) {}
         jr = nullptr;
@@ -270,6 +283,7 @@ public:
         for (auto it = snap.journal.rbegin(); it != snap.journal.rend(); ++it) t.a_state[it->first] = it->second;
         snap.journal.clear();
         q = snap.q; ap = snap.ap; q_set = snap.sets; slow_list.resize(snap.slow_mark);
+        if (!uniform_prio) q_prio_cnt = snap.prio_cnt;
         snap.valid = false;
         jr = nullptr;
         std::fill(q_sorted_ok.begin(), q_sorted_ok.end(), 0);
@@ -402,6 +416,7 @@ private:
         uint32_t p = t.a_app[a];
         AState& A = ap[p];
         set_state(a, ST_TENTATIVE);
+        const int32_t prio_before = A.key_prio;   // the application counted under this priority in its leaf (npend > 0)
         A.npend--;
         drop_live(a);   // may take the app out of its leaf's set
         // advance head; re-key the app if its max pending priority or (fair leaf) its allocation changed
@@ -418,13 +433,35 @@ private:
         } else {
             for (int k = 0; k < d; ++k) A.alloc[k] += req(a, k);
         }
+        if (!uniform_prio) {   // the leaf's priority census follows the application's best pending ask
+            auto& M = q_prio_cnt[t.p_queue[p]];
+            auto it = M.find(prio_before);
+            if (it != M.end() && --it->second == 0) M.erase(it);
+            if (A.npend > 0) ++M[A.key_prio];
+        }
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
             QState& Q = q[qq];
             Q.npend--;
             for (int k = 0; k < d; ++k) { Q.alloc[k] += req(a, k); Q.pending[k] -= req(a, k); }
             Q.shares_ok = false;
+            Q.prio_ok = false;
             if (t.q_parent[qq] != NONE) q_changed[t.q_parent[qq]].push_back(qq);
         }
+    }
+
+    int32_t prio_of(uint32_t i) {
+        QState& Q = q[i];
+        if (Q.prio_ok) return Q.prio;
+        int32_t best = INT32_MIN;
+        if (q_children[i].empty()) {
+            const auto& M = q_prio_cnt[i];
+            if (!M.empty()) best = M.rbegin()->first;
+        } else {
+            for (uint32_t c : q_children[i]) if (q[c].npend > 0) best = std::max(best, prio_of(c));
+        }
+        Q.prio = best;
+        Q.prio_ok = true;
+        return best;
     }
 
     void shares_of(uint32_t i) {
@@ -505,6 +542,10 @@ private:
         std::vector<uint32_t>& srt = q_sorted[qi];
         bool tie = false;
         auto less = [&](uint32_t l, uint32_t r) {
+            if (!uniform_prio) {   // priority first, then the shares (sortQueuesByPriorityAndFairness)
+                const int32_t pl = prio_of(l), pr = prio_of(r);
+                if (pl != pr) return pl > pr;
+            }
             const QState& L = q[l];
             const QState& R = q[r];
             const double a = L.shares[d - 1], b = R.shares[d - 1];   // dominant shares decide almost always

@@ -414,3 +414,46 @@ def fuzz(seed: int, n_nodes=None, n_asks=None) -> Snapshot:
                    (qp, guar, mx, np.zeros((Q, D), dtype=np.int64), qsort), app_queue, ask_app, req, tol, need, deny,
                    ask_prio=prio, ask_node=ask_node, ask_flags=aflags, ask_gang=gang, node_flags=flags,
                    meta={"seed": seed})
+
+
+def priority_fence(quota_pods: int = 1, done=()) -> Snapshot:
+    """The scenario of /root/reference/test/e2e/priority_scheduling/priority_scheduling_test.go:70-133
+    (Verify_Static_Queue_App_Scheduling_Order): root -> fence (max = `quota_pods` pods) -> child1, child2; applications
+    low (child1, priority -100), normal (child2, 0), high (child1, +100) submitted in that order, one pod each.  The
+    reference serves them high, normal, low.  `done` lists applications ("high", ...) already finished."""
+    D = 4
+    base = perf(4, 1, 1)
+    qp = np.array([-1, 0, 1, 1], dtype=np.int32)
+    unset = np.full((4, D), -1, dtype=np.int64)
+    qmax = unset.copy()
+    req = np.array([100, 100 * 1000 * 1000, 1, 0], dtype=np.int64)            # rr: one pod's request
+    qmax[1, :3] = req[:3] * quota_pods
+    queues = (qp, unset.copy(), qmax, np.zeros((4, D), dtype=np.int64), np.zeros(4, dtype=np.uint8))
+    apps = [("low", 2, -100), ("normal", 3, 0), ("high", 2, 100)]
+    apps = [a for a in apps if a[0] not in done]
+    z = np.zeros(len(apps), dtype=np.uint64)
+    s = _finish("priority-fence", D, POLICY_FAIR, base.node_total, base.node_avail, base.node_taint, base.node_label, base.node_id,
+                queues, np.array([a[1] for a in apps], dtype=np.int32), np.arange(len(apps), dtype=np.int32),
+                np.tile(req, (len(apps), 1)), z, z.copy(), z.copy(), ask_prio=np.array([a[2] for a in apps], dtype=np.int32))
+    s.meta["apps"] = [a[0] for a in apps]
+    return s
+
+
+def binpacking_e2e() -> Snapshot:
+    """The scenario of /root/reference/test/e2e/bin_packing/bin_packing_test.go:46-200: binpacking node sort; nodeA is the
+    most utilised node, nodeB the second; job A (3 pods) must land on nodeA, job B (3 pods that may not run on nodeA --
+    pod anti-affinity in the reference, a forbidden label bit here) on nodeB."""
+    D = 4
+    total = np.tile(np.array([16000, 64 * GI, 110, 0], dtype=np.int64), (4, 1))
+    avail = total.copy()
+    avail[0, 1] -= 40 * GI            # nodeA: least available memory
+    avail[1, 1] -= 30 * GI            # nodeB
+    avail[2, 1] -= 10 * GI
+    label = np.array([1, 2, 4, 8], dtype=np.uint64)                         # one identity bit per node
+    req = np.tile(np.array([100, 1 * GI, 1, 0], dtype=np.int64), (6, 1))
+    z = np.zeros(6, dtype=np.uint64)
+    deny = z.copy()
+    deny[3:] = 1                                                            # job B: not on nodeA
+    return _finish("binpacking-e2e", D, POLICY_BINPACKING, total, avail, np.zeros(4, dtype=np.uint64), label,
+                   ["nodeA", "nodeB", "nodeC", "nodeD"], _single_queue(D), np.array([1, 1], dtype=np.int32),
+                   np.array([0, 0, 0, 1, 1, 1], dtype=np.int32), req, z, z.copy(), deny)
