@@ -140,7 +140,8 @@ static int engine_host_run_impl(
         Nx.asks.clear();
         const bool room = cm.dirty_list.size() + A.asks.size() < (size_t)epoch_limit;
         const size_t left = (size_t)max_bindings - n;
-        if (speculate && room && left > A.asks.size()) { next_batch(Nx, left - A.asks.size()); if (rc_over) return rc_over; }
+        bool forked = false;
+        if (speculate && room && left > A.asks.size()) { next_batch(Nx, left - A.asks.size()); forked = true; if (rc_over) return rc_over; }
         size_t consumed = 0;
         if (nlive == 0) {
             result.assign(A.asks.size(), yk::CNONE);
@@ -156,7 +157,7 @@ static int engine_host_run_impl(
             size_t j = consumed - 1;
             while (j > 0 && a_gang[A.asks[j]] != yk::CNONE && a_gang[A.asks[j - 1]] == a_gang[A.asks[j]] &&
                    a_app[A.asks[j - 1]] == a_app[A.asks[j]] && result[j - 1] == yk::CNONE) --j;
-            o.rewind(A.snap, Nx.asks.empty() ? nullptr : &Nx.snap, A.asks, j);
+            o.rewind(A.snap, forked ? &Nx.snap : nullptr, A.asks, j);   // also when the speculated batch came out empty
             failed = true;
             Nx.asks.clear();
         }

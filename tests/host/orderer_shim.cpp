@@ -47,6 +47,7 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
         Slot& Nx = slot[cur ^ 1];
         Nx.asks.clear();
         if (speculate && next_batch(Nx)) return -1;
+        const bool forked = speculate != 0;
         const std::vector<uint32_t>& b = A.asks;
         std::vector<uint8_t> bad(b.size(), 0);
         for (size_t i = 0; i < b.size();) {
@@ -63,7 +64,7 @@ extern "C" int orderer_run(int D, uint32_t nA, uint32_t nP, uint32_t nQ, const i
                 if (bad[i]) { first_bad = i; consumed = i + 1; while (consumed < b.size() && same_gang(b[i], b[consumed])) ++consumed; break; }
         bool failed = false;
         if (first_bad < b.size()) {
-            o.rewind(A.snap, Nx.asks.empty() ? nullptr : &Nx.snap, b, first_bad);
+            o.rewind(A.snap, forked ? &Nx.snap : nullptr, b, first_bad);
             Nx.asks.clear();
             failed = true;
         }

@@ -266,3 +266,45 @@ def test_reference_e2e_scenarios_through_the_host_engine(shim, oracle):
     rc, ask, node, state, avail = run_engine_host(shim, s, batch=4)
     assert [s.node_id[n] for n in node] == ["nodeA"] * 3 + ["nodeB"] * 3
     check(shim, oracle, s, batch=4)
+
+
+@pytest.mark.parametrize("prio", [False, True])
+def test_speculated_empty_batch_is_undone_too(shim, oracle, prio):
+    """a cluster far too small for its queues' quotas (tests/test_gpu_parity.py::test_config4_overcommitted_rewinds): near
+    the end every in-flight batch fails at its first ask while the batch speculated behind it comes out EMPTY -- but has
+    marked the remaining asks SKIPPED against a quota that the failing asks never consumed.  Those marks must be rolled
+    back like any other speculated decision (they once were not: the asks ended SKIPPED where the oracle says NOFIT)."""
+    s = synth.hier(6, 3, 3, 2, 60, priorities=prio, seed=22)
+    for batch in (8, 64, 256):
+        for spec in (0, 1):
+            want = check(shim, oracle, s, tag=(batch, spec), batch=batch, speculate=spec)
+    assert (want["state"] == 2).sum() > 100
+
+
+def test_gpu_suite_snapshots_through_the_host_engine(shim, oracle):
+    """every single-cycle snapshot of tests/test_gpu_parity.py (minus the full-size ones), so that a change to the orderer
+    or the commit that would fail on the GPU box already fails here"""
+    cases = []
+    for variant in ("bare", "sized"):
+        for pol in (synth.POLICY_FAIR, synth.POLICY_BINPACKING):
+            cases.append((synth.kwok(100, 10, 50, variant=variant, policy=pol), 128))
+    for b in (64, 1000, 4096):
+        cases.append((synth.perf(700, 20, 100), b))
+    for pol in (synth.POLICY_FAIR, synth.POLICY_BINPACKING):
+        cases.append((synth.perf(900, 20, 100, masks=True, policy=pol), 512))
+        cases.append((synth.gangs(60, 40, 5, fill=1.4, policy=pol), 64))
+    cases.append((synth.perf(8, 10, 200, masks=True), 256))
+    for prio in (False, True):
+        cases.append((synth.hier(300, 3, 4, 2, 40, masks=True, priorities=prio, seed=21), 128))
+    cases.append((synth.hier(200, 2, 3, 3, 30, masks=True, priorities=True, seed=23, leaf_sort=synth.SORT_FAIR), 64))
+    s = synth.hier(30, 2, 3, 2, 24, seed=9)
+    s.ask_gang[:] = np.arange(s.n_asks) // 4
+    cases.append((s, 32))
+    s = synth.perf(5, 2, 10); s.node_flags[:] = 0; cases.append((s, 16))
+    s = synth.perf(5, 2, 10); s.ask_req[::3] = 0; cases.append((s, 16))
+    s = synth.perf(5, 2, 10); s.ask_flags[::2] = 1; cases.append((s, 16))
+    s = synth.perf(9, 2, 10); s.ask_node[:] = 3; cases.append((s, 16))
+    s = synth.perf(9, 2, 10); s.node_flags[4] = synth.NODE_SCHEDULABLE | synth.NODE_RESERVED; s.node_avail[2, 0] = -5000
+    cases.append((s, 16))
+    for s, b in cases:
+        check(shim, oracle, s, tag=(s.name, b), batch=b)

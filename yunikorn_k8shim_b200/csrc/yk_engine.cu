@@ -984,7 +984,8 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
             size_t j = consumed - 1;   // first entry of the failed ask / gang
             while (j > 0 && e->a_gang[A.asks[j]] != YK_NONE && e->a_gang[A.asks[j - 1]] == e->a_gang[A.asks[j]] &&
                    e->a_app[A.asks[j - 1]] == e->a_app[A.asks[j]] && result[j - 1] == YK_NONE) --j;
-            e->ord.rewind(A.snap, Nx.B > 0 ? &Nx.snap : nullptr, A.asks, j);
+            // the speculated fill is undone even when it produced no batch: it may still have marked asks (headroom skips)
+            e->ord.rewind(A.snap, forked ? &Nx.snap : nullptr, A.asks, j);
             e->st.host_ms[2] += now_ms() - t_r;
             failed = true;
             if (Nx.B > 0) {   // the speculated batch was built on an order that did not happen: drop it
