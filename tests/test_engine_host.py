@@ -308,3 +308,28 @@ def test_gpu_suite_snapshots_through_the_host_engine(shim, oracle):
     cases.append((s, 16))
     for s, b in cases:
         check(shim, oracle, s, tag=(s.name, b), batch=b)
+
+
+def test_randomized_queue_trees_through_the_host_engine(shim, oracle):
+    """random queue trees on clusters from far too small to roomy: priorities on/off, fair or fifo leaves, both node
+    policies, masks, gangs -- every run with and without the speculative next batch.  (The overcommitted ones are what
+    exercises rewind after rewind; this family found the 'empty speculated batch' bug once the GPU suite had shown it.)"""
+    import random
+    rng = random.Random(1)
+    runs = 0
+    for it in range(120):
+        nn = rng.choice([3, 6, 10, 25, 80])
+        par, lv, apps, tasks = rng.randrange(1, 4), rng.randrange(1, 4), rng.randrange(1, 4), rng.choice([5, 20, 60])
+        s = synth.hier(nn, par, lv, apps, tasks, masks=rng.random() < 0.3, priorities=rng.random() < 0.7, seed=rng.randrange(1000),
+                       leaf_sort=rng.choice([synth.SORT_FAIR, synth.SORT_FIFO]), policy=rng.choice([synth.POLICY_FAIR, synth.POLICY_BINPACKING]))
+        if rng.random() < 0.3:
+            g = rng.choice([2, 4, 5])
+            if tasks % g == 0:
+                s.ask_gang[:] = np.arange(s.n_asks) // g
+        for b in (8, 64, 256):
+            if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > b:
+                continue
+            for spec in (0, 1):
+                check(shim, oracle, s, tag=(it, s.name, b, spec), batch=b, speculate=spec)
+                runs += 1
+    assert runs > 500
