@@ -279,6 +279,10 @@ def test_speculated_empty_batch_is_undone_too(shim, oracle, prio):
         for spec in (0, 1):
             want = check(shim, oracle, s, tag=(batch, spec), batch=batch, speculate=spec)
     assert (want["state"] == 2).sum() > 100
+    for nodes in (4, 6):          # the same shape over more seeds: about a third of them hit the condition
+        for seed in range(12):
+            s = synth.hier(nodes, 3, 3, 2, 60, priorities=prio, seed=seed)
+            check(shim, oracle, s, tag=(nodes, seed), batch=64, speculate=1)
 
 
 def test_gpu_suite_snapshots_through_the_host_engine(shim, oracle):
