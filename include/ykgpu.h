@@ -154,6 +154,13 @@ int yk_nodes_remove(yk_engine* e, uint32_t n, const uint32_t* idx);
 int yk_queues_set(yk_engine* e, uint32_t q, const uint32_t* parent, const int64_t* guaranteed,
                   const int64_t* max, const int64_t* allocated, const uint8_t* sort);
 
+/* optional queue priority properties of the core's queue configuration [EXT yunikorn-core configs: properties
+ * priority.offset, priority.policy]: a parent sorts its children by their current priority first (highest priority among the
+ * asks pending below the child, plus the child's offset; a child with policy "fence" shows only its offset), then by share.
+ * Both arrays are [q] in yk_queues_set order and may be NULL (= 0 / no fence); yk_queues_set resets them.  Behaviour
+ * checked by the reference in test/e2e/priority_scheduling/priority_scheduling_test.go:70-251. */
+int yk_queues_priority(yk_engine* e, uint32_t q, const int32_t* offset, const uint8_t* fence);
+
 int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t* queue,
                    const int64_t* submit_time);
 int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx);

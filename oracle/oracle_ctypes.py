@@ -26,6 +26,7 @@ class _Snap(C.Structure):
         ("ask_tol", C.c_void_p), ("ask_need", C.c_void_p), ("ask_deny", C.c_void_p),
         ("ask_prio", C.c_void_p), ("ask_create", C.c_void_p), ("ask_node", C.c_void_p),
         ("ask_flags", C.c_void_p), ("ask_gang", C.c_void_p),
+        ("q_prio_offset", C.c_void_p), ("q_prio_fence", C.c_void_p),
     ]
 
 
@@ -81,7 +82,9 @@ def _pack(s):
         n_asks=s.n_asks, ask_app=arr(s.ask_app, np.int32), ask_req=arr(s.ask_req, np.int64),
         ask_tol=arr(s.ask_tol, np.uint64), ask_need=arr(s.ask_need, np.uint64), ask_deny=arr(s.ask_deny, np.uint64),
         ask_prio=arr(s.ask_prio, np.int32), ask_create=arr(s.ask_create, np.int64), ask_node=arr(s.ask_node, np.int32),
-        ask_flags=arr(s.ask_flags, np.uint32), ask_gang=arr(s.ask_gang, np.int32))
+        ask_flags=arr(s.ask_flags, np.uint32), ask_gang=arr(s.ask_gang, np.int32),
+        q_prio_offset=(arr(s.q_prio_offset, np.int32) if getattr(s, "q_prio_offset", None) is not None else None),
+        q_prio_fence=(arr(s.q_prio_fence, np.uint8) if getattr(s, "q_prio_fence", None) is not None else None))
     return st, keep
 
 

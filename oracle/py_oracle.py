@@ -243,7 +243,10 @@ def run(s, max_bindings=-1):
                 pr = [app_prio(p) for p in q_apps[x] if app_npend(p) > 0]
             else:
                 pr = [queue_prio(c) for c in children[x] if q_npend[c] > 0]
-            return max(pr) if pr else -(1 << 31)
+            best = max(pr) if pr else -(1 << 31)
+            off = int(s.q_prio_offset[x]) if getattr(s, "q_prio_offset", None) is not None else 0
+            fence = bool(s.q_prio_fence[x]) if getattr(s, "q_prio_fence", None) is not None else False
+            return max(-(1 << 31), min((1 << 31) - 1, off + (0 if fence else best)))   # priorityValueByPolicy
         qp = {c: queue_prio(c) for c in cand}
 
         def qcmp(l, r):

@@ -300,7 +300,11 @@ struct Engine {
         } else {
             for (int c : Q.children) if (queues[(size_t)c].pending_asks > 0) best = std::max(best, queue_priority(c));
         }
-        return best;
+        // priorityValueByPolicy [EXT]: offset, plus what is pending below unless the queue is a fence; clamped to int32
+        const int64_t off = s->q_prio_offset ? s->q_prio_offset[q] : 0;
+        const bool fence = s->q_prio_fence && s->q_prio_fence[q];
+        const int64_t v = off + (fence ? 0 : (int64_t)best);
+        return (int)std::min<int64_t>(INT32_MAX, std::max<int64_t>(INT32_MIN, v));
     }
 
     // appends the pass's allocation(s) to out (one ask, or a whole gang); returns true if anything was allocated

@@ -82,6 +82,9 @@ typedef struct {
     const int32_t* ask_node;     /* [a] required node index or -1 (pod.Spec.NodeName) */
     const uint32_t* ask_flags;   /* [a] */
     const int32_t* ask_gang;     /* [a] gang id or -1; may be NULL */
+    /* queue priority properties (priority.offset, priority.policy = fence) [EXT yunikorn-core configs]; may be NULL = 0 */
+    const int32_t* q_prio_offset;   /* [q] */
+    const uint8_t* q_prio_fence;    /* [q] 1 = fence: the queue shows its parent only its offset */
 } yko_snapshot;
 
 typedef struct {

@@ -23,6 +23,9 @@ while time.time()-t0 < float(sys.argv[2]):
         if rng.random()<0.3:
             g=rng.choice([2,4,5])
             if tasks%g==0: s.ask_gang[:]=np.arange(s.n_asks)//g
+        if rng.random()<0.4:
+            s.q_prio_offset=np.array([rng.choice([0,0,5,-5,100]) for _ in range(s.n_queues)],dtype=np.int32)
+            s.q_prio_fence=np.array([rng.random()<0.25 for _ in range(s.n_queues)],dtype=np.uint8)
     elif kind<0.75:
         s=synth.fuzz(rng.randrange(100000))
     elif kind<0.9:

@@ -11,6 +11,13 @@
 #include <cstdint>
 #include <vector>
 
+
+// queue priority properties for the next run (priority.offset / priority.policy = fence); NULL = defaults.  Test
+// harness convenience: keeps the long argument lists of the run functions unchanged.
+static const int32_t* g_q_prio_offset = nullptr;
+static const uint8_t* g_q_prio_fence = nullptr;
+extern "C" void host_set_queue_priority(const int32_t* offset, const uint8_t* fence) { g_q_prio_offset = offset; g_q_prio_fence = fence; }
+
 namespace {
 struct Slot { std::vector<uint32_t> asks, reps, row_of; yk::Orderer::Snap snap; std::vector<uint32_t> fit; };
 }
@@ -37,6 +44,7 @@ static int engine_host_run_impl(
     o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags; o.t.a_gang = a_gang;
     o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
     o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.p_alloc = p_alloc.data(); o.t.q_sort = q_sort;
+    o.t.q_prio_offset = g_q_prio_offset; o.t.q_prio_fence = g_q_prio_fence;
     std::vector<uint32_t> pending(nA);
     for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
     o.begin_cycle(pending);

@@ -51,6 +51,12 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
         guar=np.ascontiguousarray(s.q_guaranteed.T), mx=np.ascontiguousarray(s.q_max.T),
         alloc=np.ascontiguousarray(s.q_alloc.T).copy(), sort=np.ascontiguousarray(s.q_sort, dtype=np.uint8))
     k = keep
+    # queue properties priority.offset / priority.policy=fence go through a setter (keeps the argument list short)
+    k["qoff"] = np.ascontiguousarray(s.q_prio_offset, dtype=np.int32) if getattr(s, "q_prio_offset", None) is not None else None
+    k["qfen"] = np.ascontiguousarray(s.q_prio_fence, dtype=np.uint8) if getattr(s, "q_prio_fence", None) is not None else None
+    setter = getattr(shim, "host_set_queue_priority", None)
+    if setter is not None:
+        setter(_p(k["qoff"]) if k["qoff"] is not None else None, _p(k["qfen"]) if k["qfen"] is not None else None)
     out_ask = np.zeros(max(A, 1), dtype=np.uint32)
     out_node = np.zeros(max(A, 1), dtype=np.uint32)
     n = C.c_uint32(0)
@@ -266,6 +272,21 @@ def test_reference_e2e_scenarios_through_the_host_engine(shim, oracle):
     rc, ask, node, state, avail = run_engine_host(shim, s, batch=4)
     assert [s.node_id[n] for n in node] == ["nodeA"] * 3 + ["nodeB"] * 3
     check(shim, oracle, s, batch=4)
+    done = []
+    for expect in ("high", "normal", "low"):                      # the same order from queue offsets (:179-251)
+        s = synth.priority_offsets(quota_pods=1, done=done)
+        for batch in (1, 64):
+            rc, ask, node, state, avail = run_engine_host(shim, s, batch=batch)
+            assert rc == 0 and [s.meta["apps"][a] for a in ask] == [expect]
+        check(shim, oracle, s, batch=8)
+        done.append(expect)
+    from test_oracle_golden import _fence_snapshot
+    for fenced, want in ((False, [2, 3, 0, 1]), (True, [0, 2, 1, 3])):
+        s = _fence_snapshot(fenced)
+        for batch in (1, 3, 64):
+            for spec in (0, 1):
+                rc, ask, node, state, avail = run_engine_host(shim, s, batch=batch, speculate=spec)
+                assert rc == 0 and list(ask) == want, (fenced, batch, spec)
 
 
 @pytest.mark.parametrize("prio", [False, True])
@@ -330,6 +351,9 @@ def test_randomized_queue_trees_through_the_host_engine(shim, oracle):
             g = rng.choice([2, 4, 5])
             if tasks % g == 0:
                 s.ask_gang[:] = np.arange(s.n_asks) // g
+        if rng.random() < 0.4:       # queue priority properties: offsets and fences
+            s.q_prio_offset = np.array([rng.choice([0, 0, 5, -5, 100]) for _ in range(s.n_queues)], dtype=np.int32)
+            s.q_prio_fence = np.array([rng.random() < 0.25 for _ in range(s.n_queues)], dtype=np.uint8)
         for b in (8, 64, 256):
             if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > b:
                 continue

@@ -146,15 +146,42 @@ def test_priority_order_across_sibling_queues_from_priority_scheduling_e2e(oracl
     s = synth.priority_fence(quota_pods=3)
     for run in (oracle.run, py_oracle.run):
         assert [s.meta["apps"][a] for a in run(s)["ask"]] == ["high", "normal", "low"]
-
-
-def test_binpacking_node_order_from_bin_packing_e2e(oracle):
-    """/root/reference/test/e2e/bin_packing/bin_packing_test.go:46-200: job A's 3 pods all land on the most utilised
-    node, job B's 3 pods (kept off that node) on the second most utilised one."""
-    from oracle import py_oracle
-    from yunikorn_k8shim_b200 import synth
-    s = synth.binpacking_e2e()
+    # priority_scheduling_test.go:179-251: the same order when it comes from queue offsets (+100 / 0 / -100) instead of
+    # pod priority classes
+    done = []
+    for expect in ("high", "normal", "low"):
+        s = synth.priority_offsets(quota_pods=1, done=done)
+        for run in (oracle.run, py_oracle.run):
+            assert [s.meta["apps"][a] for a in run(s)["ask"]] == [expect]
+        done.append(expect)
+    s = synth.priority_offsets(quota_pods=3)
     for run in (oracle.run, py_oracle.run):
-        r = run(s)
-        assert list(r["ask"]) == [0, 1, 2, 3, 4, 5]
-        assert [s.node_id[n] for n in r["node"]] == ["nodeA"] * 3 + ["nodeB"] * 3
+        assert [s.meta["apps"][a] for a in run(s)["ask"]] == ["high", "normal", "low"]
+
+
+def _fence_snapshot(fenced):
+    from yunikorn_k8shim_b200 import synth
+    D = 4
+    base = synth.perf(4, 1, 1)
+    qp = np.array([-1, 0, 0], dtype=np.int32)                                # root -> A, B
+    unset = np.full((3, D), -1, dtype=np.int64)
+    queues = (qp, unset.copy(), unset.copy(), np.zeros((3, D), dtype=np.int64), np.zeros(3, dtype=np.uint8))
+    req = np.tile(np.array([100, 100 * 1000 * 1000, 1, 0], dtype=np.int64), (4, 1))
+    z = np.zeros(4, dtype=np.uint64)
+    s = synth._finish("fence", D, synth.POLICY_FAIR, base.node_total, base.node_avail, base.node_taint, base.node_label, base.node_id,
+                      queues, np.array([1, 2], dtype=np.int32), np.array([0, 0, 1, 1], dtype=np.int32), req, z, z.copy(), z.copy(),
+                      ask_prio=np.array([-100, -100, 0, 0], dtype=np.int32))
+    s.q_prio_fence = np.array([0, 1 if fenced else 0, 0], dtype=np.uint8)
+    s.q_prio_offset = np.zeros(3, dtype=np.int32)
+    return s
+
+
+def test_fence_hides_the_priorities_below_it(oracle):
+    """priority.policy = fence [EXT yunikorn-core, restated; unpinned by a reference test]: queue A holds two pods of
+    priority -100, queue B two of priority 0.  Unfenced, B's pods go first (queue priority 0 > -100).  With A fenced its
+    parent sees only A's offset (0): the queues tie on priority and alternate by share, starting with A (index order)."""
+    from oracle import py_oracle
+    for fenced, want in ((False, [2, 3, 0, 1]), (True, [0, 2, 1, 3])):
+        s = _fence_snapshot(fenced)
+        for run in (oracle.run, py_oracle.run):
+            assert list(run(s)["ask"]) == want, fenced

@@ -42,6 +42,9 @@ def run_orderer(shim, s, fail=None, batch=256, speculate=1):
     gang = s.ask_gang.astype(np.int64).copy()
     gang[gang < 0] = 0xFFFFFFFF
     gang = gang.astype(np.uint32)
+    qoff = np.ascontiguousarray(s.q_prio_offset, dtype=np.int32) if getattr(s, "q_prio_offset", None) is not None else None
+    qfen = np.ascontiguousarray(s.q_prio_fence, dtype=np.uint8) if getattr(s, "q_prio_fence", None) is not None else None
+    shim.host_set_queue_priority(_p(qoff) if qoff is not None else None, _p(qfen) if qfen is not None else None)
     rc = shim.orderer_run(C.c_int(D), C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(req), _p(s.ask_prio), _p(s.ask_create),
                      _p(app), _p(flags), _p(gang), _p(queue), _p(s.app_submit), _p(par), _p(guar), _p(mx), _p(alloc), _p(s.q_sort),
                      _p(fail), C.c_uint32(batch), C.c_int(speculate), _p(out), C.byref(n), _p(state), C.byref(ins))

@@ -169,6 +169,7 @@ struct yk_engine {
     std::vector<uint32_t> p_queue; std::vector<int64_t> p_submit, p_alloc; std::vector<uint8_t> p_present;
     uint32_t nq = 0;
     std::vector<uint32_t> q_parent; std::vector<int64_t> q_guar, q_max, q_alloc; std::vector<uint8_t> q_sort;
+    std::vector<int32_t> q_prio_offset; std::vector<uint8_t> q_prio_fence;   // queue properties priority.offset / priority.policy=fence
 
     // ---- device ----
     Dev<int64_t> d_total, d_avail; Dev<uint64_t> d_taint, d_label; Dev<uint32_t> d_flags, d_by_rank;
@@ -764,8 +765,19 @@ int yk_queues_set(yk_engine* e, uint32_t q, const uint32_t* parent, const int64_
     if (allocated) e->q_alloc.assign(allocated, allocated + (size_t)q * D);
     e->q_sort.assign(q, 0);
     if (sort) e->q_sort.assign(sort, sort + q);
+    e->q_prio_offset.assign(q, 0); e->q_prio_fence.assign(q, 0);   // defaults; yk_queues_priority sets them
     for (uint32_t i = 0; i < q; ++i)
         if (e->q_sort[i] > 1) return e->fail(YK_ERR_ARG, "yk_queues_set: unknown application sort policy");
+    return YK_OK;
+}
+
+int yk_queues_priority(yk_engine* e, uint32_t q, const int32_t* offset, const uint8_t* fence) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (q != e->nq) return e->fail(YK_ERR_ARG, "yk_queues_priority: queue count differs from yk_queues_set");
+    e->q_prio_offset.assign(q, 0); e->q_prio_fence.assign(q, 0);
+    if (offset) e->q_prio_offset.assign(offset, offset + q);
+    if (fence) for (uint32_t i = 0; i < q; ++i) e->q_prio_fence[i] = fence[i] ? 1 : 0;
     return YK_OK;
 }
 
@@ -914,6 +926,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
         t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
         t.q_sort = e->q_sort.data();
+        t.q_prio_offset = e->q_prio_offset.data(); t.q_prio_fence = e->q_prio_fence.data();
         e->ord.begin_cycle(pending);
         begin_ms = now_ms() - t_b;
     });

@@ -46,6 +46,8 @@ struct Tables {   // views into the engine's host tables
     int64_t* q_alloc = nullptr;          // [D][nq] persistent allocated (updated at finish())
     int64_t* p_alloc = nullptr;          // [D][maxP] persistent per-application allocated (may be null)
     const uint8_t* q_sort = nullptr;
+    const int32_t* q_prio_offset = nullptr;   // [nq] queue property priority.offset; null = all 0
+    const uint8_t* q_prio_fence = nullptr;    // [nq] 1 = priority.policy fence: the parent sees only the offset; null = none
 };
 
 class Orderer {
@@ -195,7 +197,9 @@ public:
         int leaves = 0; uint32_t leaf = NONE;
         for (uint32_t i = 0; i < t.nq; ++i)
             if (q_children[i].empty() && q[i].npend > 0) { ++leaves; leaf = i; }
-        uniform_prio = one_prio;
+        uniform_prio = one_prio;   // ... and no queue shifts or fences priorities
+        for (uint32_t i = 0; i < t.nq && uniform_prio; ++i)
+            if ((t.q_prio_offset && t.q_prio_offset[i] != 0) || (t.q_prio_fence && t.q_prio_fence[i])) uniform_prio = false;
         insensitive = false;
         if (leaves == 1 && one_prio && t.q_sort[leaf] == 0) {
             bool quota = false;
@@ -459,6 +463,11 @@ private:
         } else {
             for (uint32_t c : q_children[i]) if (q[c].npend > 0) best = std::max(best, prio_of(c));
         }
+        // priorityValueByPolicy [EXT]: the queue's offset, plus what is pending below unless the queue is a fence
+        const int64_t off = t.q_prio_offset ? t.q_prio_offset[i] : 0;
+        const bool fence = t.q_prio_fence && t.q_prio_fence[i];
+        const int64_t v = off + (fence ? 0 : (int64_t)best);
+        best = (int32_t)std::min<int64_t>(INT32_MAX, std::max<int64_t>(INT32_MIN, v));
         Q.prio = best;
         Q.prio_ok = true;
         return best;

@@ -18,7 +18,7 @@ ST_ABSENT = 255
 YK_ERR_CUDA = -2
 
 EXPORTS = [
-    "yk_abi_version", "yk_create", "yk_destroy", "yk_nodes_upsert", "yk_nodes_remove", "yk_queues_set",
+    "yk_abi_version", "yk_create", "yk_destroy", "yk_nodes_upsert", "yk_nodes_remove", "yk_queues_set", "yk_queues_priority",
     "yk_apps_upsert", "yk_apps_remove", "yk_asks_upsert", "yk_asks_remove", "yk_release", "yk_cycle",
     "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_preemption_search", "yk_set_exchange",
     "yk_peer_export", "yk_peer_import", "yk_peer_enable", "yk_stats",
@@ -181,6 +181,13 @@ class Engine:
         al = None if allocated is None else _colmajor(allocated, self.D, q)
         self._ck(self._lib.yk_queues_set(self._h, C.c_uint32(q), _p(par), _p(g), _p(m), _p(al), _p(_arr(sort, np.uint8, q))))
 
+    def queues_priority(self, offset=None, fence=None):
+        """queue properties priority.offset ([Q] int32) / priority.policy == fence ([Q] bool); call after queues_set"""
+        off = _arr(offset, np.int32) if offset is not None else None
+        fen = _arr(np.asarray(fence).astype(np.uint8), np.uint8) if fence is not None else None
+        q = off.size if off is not None else (fen.size if fen is not None else 0)
+        self._ck(self._lib.yk_queues_priority(self._h, C.c_uint32(q), _p(off), _p(fen)))
+
     def apps_upsert(self, idx, queue, submit_time):
         idx = _arr(idx, np.uint32)
         n = idx.size
@@ -296,6 +303,8 @@ class Engine:
     def load_snapshot(self, s):
         N, A, P = s.n_nodes, s.n_asks, s.n_apps
         self.queues_set(s.q_parent, s.q_guaranteed, s.q_max, s.q_alloc, s.q_sort)
+        if getattr(s, "q_prio_offset", None) is not None or getattr(s, "q_prio_fence", None) is not None:
+            self.queues_priority(s.q_prio_offset, s.q_prio_fence)
         self.nodes_upsert(np.arange(N), s.node_total, s.node_avail, s.node_taint, s.node_label, s.node_rank(), s.node_flags)
         self.apps_upsert(np.arange(P), s.app_queue, s.app_submit)
         self.asks_upsert(np.arange(A), s.ask_req, s.ask_app, s.ask_create, s.ask_tol, s.ask_need, s.ask_deny,

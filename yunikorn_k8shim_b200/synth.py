@@ -90,6 +90,8 @@ class Snapshot:
     ask_gang: np.ndarray         # [A] i32
     name: str = ""
     meta: dict = field(default_factory=dict)
+    q_prio_offset: np.ndarray = None   # [Q] i32 queue property priority.offset (None = all 0)
+    q_prio_fence: np.ndarray = None    # [Q] u8  queue property priority.policy == fence (None = none)
 
     @property
     def n_nodes(self): return len(self.node_id)
@@ -457,3 +459,27 @@ def binpacking_e2e() -> Snapshot:
     return _finish("binpacking-e2e", D, POLICY_BINPACKING, total, avail, np.zeros(4, dtype=np.uint64), label,
                    ["nodeA", "nodeB", "nodeC", "nodeD"], _single_queue(D), np.array([1, 1], dtype=np.int32),
                    np.array([0, 0, 0, 1, 1, 1], dtype=np.int32), req, z, z.copy(), deny)
+
+
+def priority_offsets(quota_pods: int = 1, done=()) -> Snapshot:
+    """The scenario of priority_scheduling_test.go:179-251 (Verify_Priority_Offset_Queue_App_Scheduling_Order):
+    root -> priority (fence, max = `quota_pods` pods) -> high (priority.offset +100), normal (0), low (-100); one pod
+    without a priority class in each, submitted low, normal, high.  The reference serves them high, normal, low."""
+    D = 4
+    base = perf(4, 1, 1)
+    qp = np.array([-1, 0, 1, 1, 1], dtype=np.int32)                          # root, priority, high, normal, low
+    unset = np.full((5, D), -1, dtype=np.int64)
+    qmax = unset.copy()
+    req = np.array([100, 100 * 1000 * 1000, 1, 0], dtype=np.int64)
+    qmax[1, :3] = req[:3] * quota_pods
+    queues = (qp, unset.copy(), qmax, np.zeros((5, D), dtype=np.int64), np.zeros(5, dtype=np.uint8))
+    apps = [("low", 4), ("normal", 3), ("high", 2)]
+    apps = [a for a in apps if a[0] not in done]
+    z = np.zeros(len(apps), dtype=np.uint64)
+    s = _finish("priority-offsets", D, POLICY_FAIR, base.node_total, base.node_avail, base.node_taint, base.node_label, base.node_id,
+                queues, np.array([a[1] for a in apps], dtype=np.int32), np.arange(len(apps), dtype=np.int32),
+                np.tile(req, (len(apps), 1)), z, z.copy(), z.copy())
+    s.q_prio_offset = np.array([0, 0, 100, 0, -100], dtype=np.int32)
+    s.q_prio_fence = np.array([0, 1, 0, 0, 0], dtype=np.uint8)
+    s.meta["apps"] = [a[0] for a in apps]
+    return s
