@@ -123,8 +123,11 @@ struct Engine {
         std::vector<int> apps;
         std::vector<int64_t> alloc, pending;
         int64_t pending_asks = 0;
+        int prio = INT32_MIN;     // cached current priority (the core keeps it up to date incrementally, too)
+        bool prio_ok = false;
     };
     std::vector<Queue> queues;
+    bool uniform_prio = false;    // every ask has the same priority and no queue shifts / fences: priorities cannot matter
     struct App {
         std::vector<int> asks;   // sorted (priority desc, create asc, index asc)
         int64_t pending_asks = 0;
@@ -214,6 +217,7 @@ struct Engine {
         for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
             Queue& Q = queues[(size_t)q];
             Q.pending_asks--;
+            Q.prio_ok = false;
             for (int k = 0; k < D; ++k) { Q.alloc[(size_t)k] += r[k]; Q.pending[(size_t)k] -= r[k]; }
         }
         state[(size_t)a] = YKO_ST_ALLOCATED;
@@ -233,6 +237,7 @@ struct Engine {
         for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
             Queue& Q = queues[(size_t)q];
             Q.pending_asks++;
+            Q.prio_ok = false;
             for (int k = 0; k < D; ++k) { Q.alloc[(size_t)k] -= r[k]; Q.pending[(size_t)k] += r[k]; }
         }
         state[(size_t)a] = YKO_ST_PENDING;
@@ -294,6 +299,7 @@ struct Engine {
     // pending asks; parent = max over its children
     int queue_priority(int q) {
         Queue& Q = queues[(size_t)q];
+        if (Q.prio_ok) return Q.prio;
         int best = INT32_MIN;
         if (Q.children.empty()) {
             for (int p : Q.apps) if (apps[(size_t)p].pending_asks > 0) best = std::max(best, app_priority(p));
@@ -304,7 +310,9 @@ struct Engine {
         const int64_t off = s->q_prio_offset ? s->q_prio_offset[q] : 0;
         const bool fence = s->q_prio_fence && s->q_prio_fence[q];
         const int64_t v = off + (fence ? 0 : (int64_t)best);
-        return (int)std::min<int64_t>(INT32_MAX, std::max<int64_t>(INT32_MIN, v));
+        Q.prio = (int)std::min<int64_t>(INT32_MAX, std::max<int64_t>(INT32_MIN, v));
+        Q.prio_ok = true;
+        return Q.prio;
     }
 
     // appends the pass's allocation(s) to out (one ask, or a whole gang); returns true if anything was allocated
@@ -378,10 +386,11 @@ struct Engine {
         // sortQueuesByPriorityAndFairness [EXT yunikorn-core objects/sorters.go; priority sorting is on by default]: the
         // queue's current priority (highest priority among the asks still pending below it) first, then the shares.
         // Behaviour pinned by /root/reference/test/e2e/priority_scheduling/priority_scheduling_test.go:70-133.
-        std::vector<int> qprio((size_t)s->n_queues, INT32_MIN);
-        for (int c : sorted) qprio[(size_t)c] = queue_priority(c);
         auto child_less = [&](int l, int r) {
-            if (qprio[(size_t)l] != qprio[(size_t)r]) return qprio[(size_t)l] > qprio[(size_t)r];
+            if (!uniform_prio) {
+                const int pl = queue_priority(l), pr = queue_priority(r);
+                if (pl != pr) return pl > pr;
+            }
             int c = yko_comp_usage_ratio_separately(D, queues[(size_t)l].alloc.data(), s->q_guaranteed + (size_t)l * D,
                                                     queues[(size_t)r].alloc.data(), s->q_guaranteed + (size_t)r * D);
             if (c != 0) return c < 0;
@@ -487,6 +496,10 @@ int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings, int32_t*
         e.order.insert(NodeRef{sc, e.rank[(size_t)n], n});
     }
 
+    e.uniform_prio = true;
+    for (int a = 1; a < s->n_asks; ++a) if (s->ask_prio[a] != s->ask_prio[0]) { e.uniform_prio = false; break; }
+    for (int q = 0; q < s->n_queues && e.uniform_prio; ++q)
+        if ((s->q_prio_offset && s->q_prio_offset[q] != 0) || (s->q_prio_fence && s->q_prio_fence[q])) e.uniform_prio = false;
     e.queues.resize((size_t)s->n_queues);
     for (int q = 0; q < s->n_queues; ++q) {
         auto& Q = e.queues[(size_t)q];
