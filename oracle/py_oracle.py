@@ -198,9 +198,6 @@ def run(s, max_bindings=-1):
                     g = int(s.ask_gang[a])
                     if g >= 0:
                         members = [m for m in app_asks[p] if int(s.ask_gang[m]) == g and state[m] != ST_ALLOCATED and not dead[m]]
-                        if room is not None and len(members) > room:
-                            stop[0] = True
-                            return None
                         placed, cause = [], 0
                         hrm = headroom(q)           # queue-side checks of all members first, headroom shrinking
                         for m in members:
@@ -213,6 +210,9 @@ def run(s, max_bindings=-1):
                             if cause:
                                 break
                             hrm = [hrm[k] if hrm[k] == UNSET else hrm[k] - req[m][k] for k in range(D)]
+                        if not cause and room is not None and len(members) > room:
+                            stop[0] = True          # passed the queue-side checks but does not fit in max_bindings: the
+                            return None             # cycle ends (a gang sunk above needs no room and does not end it)
                         for m in members:           # then the node walks
                             if cause:
                                 break

@@ -251,7 +251,8 @@ struct Engine {
     // members are placed one after the other in the application's ask order, each exactly like an ordinary
     // ask (headroom re-read after every member, ordered node walk, commit + re-score); if any member cannot
     // be placed every earlier member is rolled back and the whole gang is marked with that member's cause.
-    bool try_gang(int p, int first, std::vector<std::pair<int, int>>& out) {
+    bool stop = false;
+    bool try_gang(int p, int first, std::vector<std::pair<int, int>>& out, int room) {
         const int g = gang_of(first);
         App& ap = apps[(size_t)p];
         std::vector<int> members;
@@ -272,6 +273,9 @@ struct Engine {
                 for (int k = 0; k < D; ++k) if (hr[k] != UNSET) hr[k] -= req(a)[k];
             }
         }
+        // a gang that passed them but has more members than max_bindings leaves room for ends the cycle (one that was
+        // sunk above needs no room and does not)
+        if (!cause && room >= 0 && (int)members.size() > room) { stop = true; return false; }
         // ... then the node walks, member by member
         for (int a : members) {
             if (cause) break;
@@ -327,11 +331,8 @@ struct Engine {
             if (!fit_in_max_undef(hr, req(a))) { state[(size_t)a] = YKO_ST_SKIPPED; done[(size_t)a] = 1; continue; }
             if (!strictly_gt_zero(D, req(a))) { state[(size_t)a] = YKO_ST_INVALID; done[(size_t)a] = 1; continue; }
             if (gang_of(a) >= 0) {
-                int members = 0;
-                for (size_t j = ap.head; j < ap.asks.size(); ++j)
-                    if (gang_of(ap.asks[j]) == gang_of(a) && state[(size_t)ap.asks[j]] != YKO_ST_ALLOCATED && !done[(size_t)ap.asks[j]]) ++members;
-                if (room >= 0 && members > room) { stop = true; return false; }   // gang does not fit in max_bindings: end the cycle
-                if (try_gang(p, a, out)) return true;
+                if (try_gang(p, a, out, room)) return true;
+                if (stop) return false;   // the gang does not fit in max_bindings: end of the cycle
                 continue;
             }
             int n = try_nodes(a);
@@ -341,7 +342,6 @@ struct Engine {
         }
         return false;
     }
-    bool stop = false;
 
     bool try_queue(int q, std::vector<std::pair<int, int>>& out, int room) {
         Queue& Q = queues[(size_t)q];

@@ -42,7 +42,7 @@ while time.time()-t0 < float(sys.argv[2]):
         n+=1
         ok=rc==0 and np.array_equal(ask,want['ask']) and np.array_equal(node,want['node']) and np.array_equal(state,want['state']) and np.array_equal(avail,want['avail'])
         if not ok: bad+=1; print('FAIL',s.name,s.meta,b,spec,ep,share, flush=True)
-    if rng.random()<0.15 and len(want['ask'])>2:
+    if rng.random()<0.4 and len(want['ask'])>2:
         k=rng.randrange(1,len(want['ask']))
         w2=oc.run(s,max_bindings=k)
         b=rng.choice([8,64,300])

@@ -361,3 +361,21 @@ def test_randomized_queue_trees_through_the_host_engine(shim, oracle):
                 check(shim, oracle, s, tag=(it, s.name, b, spec), batch=b, speculate=spec)
                 runs += 1
     assert runs > 500
+
+
+def test_max_bindings_and_a_gang_sunk_by_its_own_members(shim, oracle):
+    """max_bindings ends the cycle at a gang that would need more bindings than are left -- unless the gang is sunk by its
+    queue-side checks (an invalid / slow-path member, no headroom): that gang needs no room, gets its cause, and the
+    cycle goes on.  (Found by scripts/host_campaign.py: the static order of a single-leaf cycle already behaved that way,
+    the oracle and the tree walk stopped at the gang.)"""
+    from oracle import py_oracle
+    s = synth.fuzz(17513)                       # ask 70 is binding #53; then a 3-member gang with an invalid member; then ask 77
+    for k in (53, 54, 55, 60):
+        want = oracle.run(s, max_bindings=k)
+        assert len(want["ask"]) == min(k, len(oracle.run(s)["ask"]))
+        p = py_oracle.run(s, max_bindings=k)
+        assert list(want["ask"]) == p["ask"] and list(want["node"]) == p["node"]
+        for b in (8, 64, 300):
+            for spec in (0, 1):
+                rc, ask, node, state, avail = run_engine_host(shim, s, batch=b, max_bindings=k, speculate=spec)
+                assert rc == 0 and np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"]), (k, b, spec)

@@ -371,9 +371,8 @@ private:
         const int d = t.D;
         std::vector<uint32_t> mem;
         gang_members(a, mem);
-        if (batch.size() + mem.size() > cap_user) return false;                 // max_bindings: the cycle ends here
         // host-side checks of every member, with the headroom shrinking as earlier members are counted.  They come
-        // BEFORE the batch-capacity test: a gang sunk here needs no room, and the decision must not depend on how the
+        // BEFORE the capacity tests (batch size and max_bindings): a gang sunk here needs no room, and the decision must not depend on how the
         // engine happens to cut its batches (rewind replays with a different capacity).
         int64_t hr[8];
         headroom(t.p_queue[t.a_app[a]], hr);
@@ -392,6 +391,7 @@ private:
             for (uint32_t m : mem) { if (cause == ST_SLOWPATH && (t.a_flags[m] & 1u)) slow_list.push_back(m); mark_dead(m, cause); }
             return true;   // nothing added, but the pass moved on
         }
+        if (batch.size() + mem.size() > cap_user) return false;                 // max_bindings: the cycle ends here
         if (batch.size() + mem.size() > cap_batch) { if (batch.empty()) oversize_gang = true; return false; }
         for (uint32_t m : mem) { tentative(m); batch.push_back(m); }
         return true;
