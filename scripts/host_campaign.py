@@ -33,7 +33,12 @@ while time.time()-t0 < float(sys.argv[2]):
     else:
         s=synth.perf(rng.choice([3,10,50,300]),rng.randrange(1,12),rng.choice([5,40,120]),masks=rng.random()<0.5,policy=rng.choice([0,1]),seed=rng.randrange(10000))
         if rng.random()<0.3: s.ask_prio[:]=np.random.default_rng(rng.randrange(1000)).integers(-2,3,size=s.n_asks)
-    want=oc.run(s)
+    if rng.random()<0.15:
+        s=synth.redim(s,rng.choice([1,2,3,5,6,8]),rng.randrange(1000))
+    try:
+        want=oc.run(s)
+    except RuntimeError:
+        continue   # NaN score (zero total on a weighted dimension)
     gmax=np.bincount(s.ask_gang[s.ask_gang>=0]).max() if (s.ask_gang>=0).any() else 0
     for b in rng.sample([1,2,5,8,16,33,64,256,5000],4):
         if gmax>b: continue

@@ -379,3 +379,24 @@ def test_max_bindings_and_a_gang_sunk_by_its_own_members(shim, oracle):
             for spec in (0, 1):
                 rc, ask, node, state, avail = run_engine_host(shim, s, batch=b, max_bindings=k, speculate=spec)
                 assert rc == 0 and np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"]), (k, b, spec)
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 5, 8])
+def test_other_dimension_counts(shim, oracle, D):
+    """the commit's node record and the orderer's accounting are sized by D (1..8): same snapshots, other widths"""
+    from oracle import py_oracle
+    n = 0
+    for seed in range(0, 60, 4):
+        s = synth.redim(synth.fuzz(seed), D, seed)
+        try:
+            want = oracle.run(s)
+        except RuntimeError:
+            continue                              # a zero total on a weighted dimension: NaN score, rejected up front
+        if seed % 12 == 0:
+            p = py_oracle.run(s)
+            assert list(want["ask"]) == p["ask"] and list(want["node"]) == p["node"]
+        if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > 64:
+            continue
+        check(shim, oracle, s, tag=(seed, D), batch=64)
+        n += 1
+    assert n >= 8

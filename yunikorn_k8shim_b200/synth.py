@@ -483,3 +483,32 @@ def priority_offsets(quota_pods: int = 1, done=()) -> Snapshot:
     s.q_prio_fence = np.array([0, 1, 0, 0, 0], dtype=np.uint8)
     s.meta["apps"] = [a[0] for a in apps]
     return s
+
+
+def redim(s: Snapshot, D2: int, seed: int = 0) -> Snapshot:
+    """The same snapshot with D2 resource dimensions (1..8): the first dimensions are kept, extra ones copy random existing
+    columns (quotas: unset), weights are extended with 0 / 0.5 / 1 -- for tests of the code paths that depend on D."""
+    import copy
+    import random
+    rng = random.Random(seed)
+    s = copy.deepcopy(s)
+    D = s.D
+
+    def cols(x, fill):
+        x = np.asarray(x)
+        if D2 <= D:
+            return np.ascontiguousarray(x[:, :D2])
+        extra = np.stack([x[:, rng.randrange(D)] if fill is None else np.full(x.shape[0], fill, dtype=x.dtype)
+                          for _ in range(D2 - D)], axis=1)
+        return np.ascontiguousarray(np.concatenate([x, extra], axis=1))
+    s.node_total, s.node_avail, s.ask_req = cols(s.node_total, None), cols(s.node_avail, None), cols(s.ask_req, None)
+    s.q_guaranteed, s.q_max, s.q_alloc = cols(s.q_guaranteed, -1), cols(s.q_max, -1), cols(s.q_alloc, 0)
+    w = np.zeros(D2)
+    w[:min(D, D2)] = s.weights[:min(D, D2)]
+    if D2 > D and rng.random() < 0.5:
+        w[D:] = rng.choice([0.0, 1.0, 0.5])
+    if w.sum() == 0:
+        w[0] = 1.0
+    s.weights, s.D = w, D2
+    s.name = f"{s.name}-D{D2}"
+    return s
