@@ -400,3 +400,27 @@ def test_other_dimension_counts(shim, oracle, D):
         check(shim, oracle, s, tag=(seed, D), batch=64)
         n += 1
     assert n >= 8
+
+
+def test_extreme_priorities_and_everything_tied(shim, oracle):
+    """identical nodes, identical requests, priorities at the int32 limits (the application key once stored -priority in
+    32 bits: -INT32_MIN wrapped and the application sorted last instead of first), extreme queue offsets"""
+    import random
+    rng = random.Random(4)
+    runs = 0
+    for it in range(60):
+        nn = rng.choice([1, 2, 5, 33, 64, 65])
+        s = synth.hier(nn, rng.randrange(1, 3), rng.randrange(1, 4), rng.randrange(1, 3), rng.choice([4, 16, 50]),
+                       seed=rng.randrange(1000), leaf_sort=rng.choice([synth.SORT_FIFO, synth.SORT_FAIR]),
+                       policy=rng.choice([synth.POLICY_FAIR, synth.POLICY_BINPACKING]), quota_frac=rng.choice([1.0, 3.0]))
+        s.node_total[:] = s.node_total[0]
+        s.node_avail[:] = s.node_total
+        s.ask_req[:] = s.ask_req[0]
+        s.ask_prio[:] = np.array([rng.choice([-(1 << 31), (1 << 31) - 1, 0, 1, -1]) for _ in range(s.n_asks)], dtype=np.int32)
+        if rng.random() < 0.5:
+            s.q_prio_offset = np.array([rng.choice([0, (1 << 31) - 1, -(1 << 31), 7]) for _ in range(s.n_queues)], dtype=np.int32)
+            s.q_prio_fence = np.array([rng.random() < 0.3 for _ in range(s.n_queues)], dtype=np.uint8)
+        for b in (7, 64):
+            check(shim, oracle, s, tag=(it, b), batch=b, speculate=it % 2)
+            runs += 1
+    assert runs == 120

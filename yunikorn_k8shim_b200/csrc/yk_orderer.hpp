@@ -70,7 +70,7 @@ public:
     // application order inside a leaf: (-max pending priority, [fair leaves: allocation shares against the
     // queue's guaranteed resource, largest first], submission time, app index).  fifo leaves keep sh all zero.
     struct AppKey {
-        int32_t negprio; double sh[8]; int64_t submit; uint32_t app;
+        int64_t negprio; double sh[8]; int64_t submit; uint32_t app;   // 64-bit: -INT32_MIN must not wrap
         bool operator<(const AppKey& o) const {
             if (negprio != o.negprio) return negprio < o.negprio;
             for (int k = 0; k < 8; ++k) if (sh[k] != o.sh[k]) return sh[k] < o.sh[k];
@@ -80,7 +80,7 @@ public:
     };
     AppKey make_key(uint32_t p) const {
         AppKey k;
-        k.negprio = -ap[p].key_prio; k.submit = t.p_submit[p]; k.app = p;
+        k.negprio = -(int64_t)ap[p].key_prio; k.submit = t.p_submit[p]; k.app = p;
         for (int i = 0; i < 8; ++i) k.sh[i] = 0.0;
         const uint32_t leaf = t.p_queue[p];
         if (t.q_sort[leaf] == 1) {   // fair
