@@ -111,3 +111,42 @@ def test_masks_give_the_string_level_verdict(seed):
         assert checked > 0
     finally:
         d.close()
+
+
+def test_full_dictionary_flags_slow_path_and_stays_exact():
+    """a vocabulary far larger than 63 requirement bits: pods that no longer get bits are flagged YK_ASK_SLOWPATH (never
+    approximated), and every pod that did get its bits still yields the string-level verdict"""
+    rng = random.Random(3)
+    keys = [f"k{i}" for i in range(14)]
+    saved = (list(KEYS), dict(VALUES))
+    try:
+        KEYS[:] = keys
+        VALUES.clear()
+        VALUES.update({k: [f"v{j}" for j in range(6)] for k in keys})
+        VALUES["cores"], VALUES["tier"] = ["8", "16"], ["1", "2"]
+        nodes = [_rand_node(rng, i) for i in range(10)]
+        pods = [_rand_pod(rng, 10) for _ in range(400)]
+    finally:
+        KEYS[:] = saved[0]
+        VALUES.clear()
+        VALUES.update(saved[1])
+    d = Dictionary()
+    try:
+        for i, nd in enumerate(nodes):
+            d.node(i, nd["name"], nd["labels"], nd["taints"], nd["unschedulable"])
+        masks = [d.pod(node_selector=p.get("node_selector"), affinity_terms=p.get("affinity_terms"),
+                       has_affinity=p.get("has_affinity", False), tolerations=p.get("tolerations"), node_name=p.get("node_name"))
+                 for p in pods]
+        bits = [d.node_bits(i) for i in range(10)]
+        slow = sum(1 for m in masks if m.flags & SLOWPATH)
+        assert 50 < slow < 390
+        for p, m in zip(pods, masks):
+            if m.flags & SLOWPATH:
+                continue
+            for i, nd in enumerate(nodes):
+                lb, tb = bits[i]
+                got = (tb & ~m.tolerated_bits) == 0 and (lb & m.required_bits) == m.required_bits and \
+                    (lb & m.forbidden_bits) == 0 and (m.required_node == NONE or m.required_node == i)
+                assert got == k8s.fits(p, nd), (p, nd)
+    finally:
+        d.close()
