@@ -240,3 +240,22 @@ def test_error_paths_and_empty_cluster():
     e.nodes_upsert([0, 1], tot, av, name_rank=[0, 1])
     assert e.node_scores([0])[0] == 0.0
     e.close()
+
+
+def test_queue_priority_properties(oracle):
+    """yk_queues_priority (priority.offset / priority.policy = fence) through the C ABI: the offsets scenario of
+    priority_scheduling_test.go:179-251, the pod-priority scenario of :70-133, and a fenced queue"""
+    done = []
+    for expect in ("high", "normal", "low"):
+        s = synth.priority_offsets(quota_pods=1, done=done)
+        _check(s, oracle, batch=8)
+        with Engine.for_snapshot(s, batch=8) as e:
+            ask, node, _ = e.cycle(s.n_asks)
+        assert [s.meta["apps"][a] for a in ask] == [expect]
+        done.append(expect)
+    _check(synth.priority_offsets(quota_pods=3), oracle, batch=2)
+    _check(synth.priority_fence(quota_pods=3), oracle, batch=2)
+    s = synth.hier(40, 2, 3, 2, 12, priorities=True, seed=31)
+    s.q_prio_offset = (np.arange(s.n_queues) % 3 * 50 - 50).astype(np.int32)
+    s.q_prio_fence = (np.arange(s.n_queues) % 4 == 1).astype(np.uint8)
+    _check(s, oracle, batch=16)
