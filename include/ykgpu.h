@@ -181,7 +181,12 @@ int yk_release(yk_engine* e, uint32_t n, const uint32_t* ask_idx);
 
 /* One scheduling cycle: runs schedule() passes until no pending ask can be placed or max_bindings is
  * reached.  out[0..*n_out) are the bindings in the reference's commit order.  slow_path_asks (may be NULL)
- * receives up to slow_cap asks flagged YK_ASK_SLOWPATH that were reached in order. */
+ * receives up to slow_cap asks flagged YK_ASK_SLOWPATH that were reached in order.
+ * max_bindings ends the cycle at the first placement it cannot hold (an ask, or a gang that passed its queue-side checks
+ * and has more members than bindings are left); the bindings are exactly the first max_bindings of the uncut cycle's.
+ * The engine looks one batch ahead, so a few asks just behind the cut may already carry a cause (INVALID / SLOWPATH /
+ * SKIPPED / NOFIT) that the uncut order would have given them later; every cycle starts all unallocated asks as pending
+ * again, so this never changes a later binding. */
 int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_out,
              uint32_t* slow_path_asks, uint32_t slow_cap, uint32_t* n_slow);
 
