@@ -183,7 +183,7 @@ int yk_release(yk_engine* e, uint32_t n, const uint32_t* ask_idx);
  * reached.  out[0..*n_out) are the bindings in the reference's commit order.  slow_path_asks (may be NULL)
  * receives up to slow_cap asks flagged YK_ASK_SLOWPATH that were reached in order.
  * max_bindings ends the cycle at the first placement it cannot hold (an ask, or a gang that passed its queue-side checks
- * and has more members than bindings are left); the bindings are exactly the first max_bindings of the uncut cycle's.
+ * and has more members than bindings are left); the bindings are a prefix of the uncut cycle's.
  * The engine looks one batch ahead, so a few asks just behind the cut may already carry a cause (INVALID / SLOWPATH /
  * SKIPPED / NOFIT) that the uncut order would have given them later; every cycle starts all unallocated asks as pending
  * again, so this never changes a later binding. */
