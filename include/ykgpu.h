@@ -161,6 +161,8 @@ int yk_queues_set(yk_engine* e, uint32_t q, const uint32_t* parent, const int64_
  * checked by the reference in test/e2e/priority_scheduling/priority_scheduling_test.go:70-251. */
 int yk_queues_priority(yk_engine* e, uint32_t q, const int32_t* offset, const uint8_t* fence);
 
+/* applications live in LEAF queues (as in the core: placement into a parent queue is rejected there; here an application
+ * whose queue has children is accepted but never scheduled -- the adapter must not produce one) */
 int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t* queue,
                    const int64_t* submit_time);
 int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx);
