@@ -79,3 +79,23 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_ctypes" not in txt and "yk_oracle" not in txt and "py_oracle" not in txt, f
+
+
+def test_python_stub_array_helpers():
+    """engine.py's argument marshalling (no library call): row-major [n][D] and column-major [D][n] inputs both become the
+    ABI's contiguous [D][n] int64; wrong shapes are rejected; typed arrays pass through without a copy"""
+    import numpy as np
+    from yunikorn_k8shim_b200 import engine as E
+    a = np.arange(12, dtype=np.int64).reshape(4, 3)            # [n=4][D=3]
+    c = E._colmajor(a, 3, 4)
+    assert c.shape == (3, 4) and c.flags["C_CONTIGUOUS"] and np.array_equal(c, a.T)
+    c2 = E._colmajor(np.ascontiguousarray(a.T), 3, 4)
+    assert np.array_equal(c2, a.T)
+    with pytest.raises(ValueError):
+        E._colmajor(np.zeros((5, 3), dtype=np.int64), 3, 4)
+    x = np.arange(5, dtype=np.uint32)
+    assert E._arr(x, np.uint32, 5) is x                         # no copy when the dtype already matches
+    assert E._arr([1, 2, 3], np.int32).dtype == np.int32
+    with pytest.raises(ValueError):
+        E._arr(x, np.uint32, 4)
+    assert E._arr(None, np.uint32) is None and E._p(None) is None
