@@ -1,0 +1,230 @@
+// Host emulation of the device-resident ordered commit for the CPU test suite: csrc/yk_lattice.h is single-source -- nvcc
+// turns it into yk_lattice_kernel, g++ turns the SAME code into plain loops -- so the lattice algorithm (bound, element
+// order, acceptance rows, chain, gang snapshots, capacity bound, order patch) is fuzzed against the oracle here without a
+// GPU.  The driver around it is the real ordering engine (csrc/yk_orderer.hpp) and the real meta builder
+// (csrc/yk_lattice_host.hpp).  Test infrastructure: the product only ever runs the kernel.
+//
+// Where the engine hands a batch over to its host commit (status HANDOFF: a gang that cannot be placed from the front of
+// the order), this shim finishes the batch with a plain sequential first-fit over the current order instead.
+#include "../../yunikorn_k8shim_b200/csrc/yk_lattice_host.hpp"
+#include "../../yunikorn_k8shim_b200/csrc/yk_orderer.hpp"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+static const int32_t* g_q_prio_offset = nullptr;
+static const uint8_t* g_q_prio_fence = nullptr;
+extern "C" void host_set_queue_priority(const int32_t* offset, const uint8_t* fence) { g_q_prio_offset = offset; g_q_prio_fence = fence; }
+
+namespace {
+
+template <int D>
+int run_d(uint32_t policy, const double* weights,
+          uint32_t nN, const int64_t* n_total, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
+          const uint32_t* n_flags, const uint32_t* n_rank,
+          uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req, const uint64_t* a_tol, const uint64_t* a_need,
+          const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
+          const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
+          const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+          uint32_t batch, uint32_t max_bindings,
+          uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out, uint64_t* stats_out) {
+    yk::Orderer o;
+    std::vector<uint8_t> state(nA, yk::ST_PENDING), present(nP, 1), npresent(nN, 1);
+    std::vector<int64_t> p_alloc((size_t)D * nP, 0);
+    o.t.D = D; o.t.maxA = nA; o.t.maxP = nP; o.t.nq = nQ;
+    o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags; o.t.a_gang = a_gang;
+    o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
+    o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.p_alloc = p_alloc.data(); o.t.q_sort = q_sort;
+    o.t.q_prio_offset = g_q_prio_offset; o.t.q_prio_fence = g_q_prio_fence;
+    std::vector<uint32_t> pending(nA);
+    for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
+    o.begin_cycle(pending);
+    const bool ins = o.insensitive;
+
+    yk::CommitTables ct;
+    ct.D = D; ct.policy = policy; ct.w = weights; ct.lda = nA;
+    ct.a_req = a_req; ct.a_tol = a_tol; ct.a_need = a_need; ct.a_deny = a_deny; ct.a_node = a_node; ct.a_gang = a_gang; ct.a_app = a_app;
+    const yklt::Eligibility el = yklt::eligible(ct, nN, npresent.data(), n_total, nN, n_rank, pending);
+    if (!el.ok) return 100;
+    std::vector<uint64_t> a_sig(nA);
+    std::vector<uint32_t> a_shape(nA, 0);
+    if (yklt::assign_shapes(ct, pending, a_shape) > (uint32_t)yklt::SHAPE_IDS) return 100;
+    for (uint32_t a = 0; a < nA; ++a) a_sig[a] = yk::ask_signature(ct, a);
+
+    // ---- device state: node records, the order (what yk_key_kernel + the radix sort + yk_lt_init_kernel build) ----
+    const int RS = (2 * D + 3 + 3) / 4 * 4;
+    std::vector<int64_t> rec((size_t)std::max<uint32_t>(nN, 1) * RS, 0);
+    std::vector<yklt::Ent> ord0(std::max<uint32_t>(nN, 1)), ord1(std::max<uint32_t>(nN, 1));
+    for (uint32_t n = 0; n < nN; ++n) {
+        int64_t* r = rec.data() + (size_t)n * RS;
+        for (int k = 0; k < D; ++k) { r[k] = n_avail[(size_t)k * nN + n]; r[D + k] = n_total[(size_t)k * nN + n]; }
+        r[2 * D] = (int64_t)n_taint[n]; r[2 * D + 1] = (int64_t)n_label[n];
+        r[2 * D + 2] = (int64_t)(((uint64_t)n_rank[n] << 32) | n_flags[n]);
+        const double sc = yk_node_score(D, policy, weights, n_total + n, n_avail + n, nN);
+        ord0[n].key = yk_key_bits(sc); ord0[n].rn = ((uint64_t)n_rank[n] << 32) | n;
+        if (ord0[n].key == YK_KEY_NAN) return -5;
+    }
+    auto ent_lt = [](const yklt::Ent& x, const yklt::Ent& y) { return x.key < y.key || (x.key == y.key && x.rn < y.rn); };
+    std::sort(ord0.begin(), ord0.begin() + nN, ent_lt);
+    int cur = 0;
+    int hdr[yklt::H_WORDS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t ub[8];
+    for (int k = 0; k < 8; ++k) ub[k] = INT64_MAX;
+    std::unique_ptr<yklt::Shared<D>> sh(new yklt::Shared<D>());
+
+    yklt::Args la{};
+    la.policy = policy;
+    for (int k = 0; k < 8; ++k) la.w[k] = k < D ? weights[k] : 0.0;
+    la.rec = rec.data(); la.RS = RS; la.ord[0] = ord0.data(); la.ord[1] = ord1.data(); la.cur = &cur; la.nlive = (int)nN;
+    la.a_req = a_req; la.lda = nA; la.a_tol = a_tol; la.a_need = a_need; la.a_deny = a_deny; la.a_node = a_node;
+    la.hdr = hdr; la.ub = ub; la.insensitive = ins ? 1 : 0;
+
+    // the order must stay exactly: every node once, ascending by (CURRENT key, rank)
+    auto order_ok = [&]() -> bool {
+        const yklt::Ent* e = la.ord[cur];
+        std::vector<uint8_t> seen(nN, 0);
+        for (uint32_t p = 0; p < nN; ++p) {
+            const uint32_t n = (uint32_t)e[p].rn;
+            if (n >= nN || seen[n]) return false;
+            seen[n] = 1;
+            const int64_t* r = rec.data() + (size_t)n * RS;
+            if (e[p].key != yk_key_bits(yk_node_score(D, policy, weights, r + D, r, 1)) || (e[p].rn >> 32) != n_rank[n]) return false;
+            if (p > 0 && !ent_lt(e[p - 1], e[p])) return false;
+        }
+        return true;
+    };
+    // plain sequential first fit on the current order (stands in for the engine's host commit after a hand-off)
+    auto resort = [&]() {
+        yklt::Ent* e = la.ord[cur];
+        for (uint32_t p = 0; p < nN; ++p) {
+            const uint32_t n = (uint32_t)e[p].rn;
+            const int64_t* r = rec.data() + (size_t)n * RS;
+            e[p].key = yk_key_bits(yk_node_score(D, policy, weights, r + D, r, 1));
+        }
+        std::sort(e, e + nN, ent_lt);
+    };
+    auto seq_place = [&](uint32_t ask) -> uint32_t {
+        int64_t rq[D];
+        for (int k = 0; k < D; ++k) rq[k] = a_req[(size_t)k * nA + ask];
+        const yklt::Ent* e = la.ord[cur];
+        for (uint32_t p = 0; p < nN; ++p) {
+            const uint32_t n = (uint32_t)e[p].rn;
+            int64_t* r = rec.data() + (size_t)n * RS;
+            const uint32_t fl = (uint32_t)(uint64_t)r[2 * D + 2];
+            if (!yklt::fits<D>((fl & 1u) && !(fl & 2u), r, r + D, rq)) continue;
+            if (!yklt::accepts((uint64_t)r[2 * D], (uint64_t)r[2 * D + 1], n, a_tol[ask], a_need[ask], a_deny[ask], a_node[ask])) continue;
+            for (int k = 0; k < D; ++k) r[k] -= rq[k];
+            resort();
+            return n;
+        }
+        return yk::CNONE;
+    };
+
+    std::vector<uint32_t> asks, meta, result;
+    yk::Orderer::Snap snap;
+    size_t bsz = batch;
+    uint32_t n = 0;
+    uint64_t handoffs = 0, batches = 0;
+    while (n < max_bindings) {
+        o.fill(bsz, (size_t)max_bindings - n, asks, snap);
+        if (o.oversize_gang) {
+            if (bsz < batch) { bsz = batch; o.fill(bsz, (size_t)max_bindings - n, asks, snap); }
+            if (o.oversize_gang) return -1;
+        }
+        if (asks.empty()) break;
+        ++batches;
+        const size_t B = asks.size();
+        yklt::build_meta(ct, a_sig.data(), a_shape.data(), asks, meta);
+        result.assign(B, yk::CNONE);
+        la.asks = asks.data(); la.meta = meta.data(); la.B = (int)B; la.res = result.data();
+        size_t consumed = 0;
+        if (nN == 0) {
+            consumed = ins ? B : 1;
+            if (!ins && a_gang[asks[0]] != yk::CNONE)
+                while (consumed < B && a_gang[asks[consumed]] == a_gang[asks[0]] && a_app[asks[consumed]] == a_app[asks[0]]) ++consumed;
+        } else {
+            yklt::lattice_batch<D>(la, *sh);
+            if (hdr[yklt::H_STATUS] == yklt::ST_NAN) return -5;
+            if (!order_ok()) return -9;
+            consumed = (size_t)hdr[yklt::H_CONSUMED];
+            if (hdr[yklt::H_STATUS] == yklt::ST_HANDOFF) {
+                ++handoffs;
+                bool stop = false;
+                size_t i = consumed;
+                while (i < B && !stop) {
+                    const uint32_t a = asks[i];
+                    if (a_gang[a] == yk::CNONE) {
+                        result[i] = seq_place(a);
+                        if (result[i] == yk::CNONE && !ins) stop = true;
+                        ++i;
+                        continue;
+                    }
+                    size_t g1 = i;
+                    while (g1 < B && a_gang[asks[g1]] == a_gang[a] && a_app[asks[g1]] == a_app[a]) ++g1;
+                    std::vector<int64_t> keep(rec);
+                    bool okg = true;
+                    for (size_t x = i; x < g1 && okg; ++x) { result[x] = seq_place(asks[x]); okg = result[x] != yk::CNONE; }
+                    if (!okg) {
+                        rec = keep; la.rec = rec.data();
+                        resort();
+                        for (size_t x = i; x < g1; ++x) result[x] = yk::CNONE;
+                        if (!ins) stop = true;
+                    }
+                    i = g1;
+                }
+                consumed = i;
+                for (int k = 0; k < 8; ++k) ub[k] = INT64_MAX;   // a roll-back may have handed capacity back
+            }
+        }
+        bool failed = false;
+        if (!ins && consumed > 0 && result[consumed - 1] == yk::CNONE) {
+            size_t j = consumed - 1;
+            while (j > 0 && a_gang[asks[j]] != yk::CNONE && a_gang[asks[j - 1]] == a_gang[asks[j]] &&
+                   a_app[asks[j - 1]] == a_app[asks[j]] && result[j - 1] == yk::CNONE) --j;
+            o.rewind(snap, nullptr, asks, j);
+            failed = true;
+        } else if (!ins && consumed < B) {
+            return -12;   // a placement-sensitive batch may only end early on a failure
+        }
+        for (size_t i = 0; i < consumed; ++i) {
+            const uint32_t a = asks[i];
+            if (result[i] == yk::CNONE) { if (ins) o.fail_in_place(a); continue; }
+            o.confirm(a);
+            out_ask[n] = a; out_node[n] = result[i]; ++n;
+        }
+        if (ins && consumed < B) return -13;
+        bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
+    }
+    o.finish();
+    *n_out = n;
+    for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
+    for (uint32_t nn = 0; nn < nN; ++nn)
+        for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = rec[(size_t)nn * RS + k];
+    if (stats_out) {
+        stats_out[0] = (uint64_t)hdr[yklt::H_SUBRUNS]; stats_out[1] = (uint64_t)hdr[yklt::H_FULLSCANS]; stats_out[2] = (uint64_t)hdr[yklt::H_SORTS];
+        stats_out[3] = (uint64_t)hdr[yklt::H_ELEMS]; stats_out[4] = (uint64_t)hdr[yklt::H_QUICK]; stats_out[5] = (uint64_t)hdr[yklt::H_ESC];
+        stats_out[6] = handoffs; stats_out[7] = batches;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// same argument list as engine_host_run (tests/host/engine_shim.cpp) so that the Python harness is shared; epoch_limit,
+// speculate and share_rows do not apply.  Returns 100 when the snapshot is not eligible for the lattice commit.
+extern "C" int lattice_host_run(int D, uint32_t policy, const double* weights,
+    uint32_t nN, const int64_t* n_total, const int64_t* n_avail, const uint64_t* n_taint, const uint64_t* n_label,
+    const uint32_t* n_flags, const uint32_t* n_rank,
+    uint32_t nA, uint32_t nP, uint32_t nQ, const int64_t* a_req, const uint64_t* a_tol, const uint64_t* a_need,
+    const uint64_t* a_deny, const uint32_t* a_node, const int32_t* a_prio, const int64_t* a_create, const uint32_t* a_app,
+    const uint32_t* a_flags, const uint32_t* a_gang, const uint32_t* p_queue, const int64_t* p_submit,
+    const uint32_t* q_parent, const int64_t* q_guar, const int64_t* q_max, int64_t* q_alloc, const uint8_t* q_sort,
+    uint32_t batch, uint32_t /*epoch_limit*/, int /*speculate*/, int /*share_rows*/, uint32_t max_bindings,
+    uint32_t* out_ask, uint32_t* out_node, uint32_t* n_out, uint8_t* state_out, int64_t* avail_out, uint64_t* stats_out) {
+#define RUN(DD) case DD: return run_d<DD>(policy, weights, nN, n_total, n_avail, n_taint, n_label, n_flags, n_rank, nA, nP, nQ, a_req, a_tol, a_need, a_deny, a_node, a_prio, a_create, a_app, a_flags, a_gang, p_queue, p_submit, q_parent, q_guar, q_max, q_alloc, q_sort, batch, max_bindings, out_ask, out_node, n_out, state_out, avail_out, stats_out);
+    switch (D) { RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) default: return -2; }
+#undef RUN
+}

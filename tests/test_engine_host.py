@@ -33,7 +33,8 @@ def _u32(x):
     return x.astype(np.uint32)
 
 
-def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindings=None, share_rows=1, rows=None):
+def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindings=None, share_rows=1, rows=None,
+                    fn="engine_host_run"):
     N, A, P, Q, D = s.n_nodes, s.n_asks, s.n_apps, s.n_queues, s.D
     if epoch_limit is None:
         epoch_limit = max(2 * batch, N * 5 // 8)
@@ -62,17 +63,17 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
     n = C.c_uint32(0)
     state = np.zeros(max(A, 1), dtype=np.uint8)
     avail = np.zeros((D, max(N, 1)), dtype=np.int64)
-    nrows = C.c_uint64(0)
-    rc = shim.engine_host_run(
+    nrows = np.zeros(8, dtype=np.uint64)   # engine shim: [0] rows swept; lattice shim: its eight counters
+    rc = getattr(shim, fn)(
         C.c_int(D), C.c_uint32(s.policy), _p(k["w"]),
         C.c_uint32(N), _p(k["total"]), _p(k["avail"]), _p(k["taint"]), _p(k["label"]), _p(k["nflags"]), _p(k["rank"]),
         C.c_uint32(A), C.c_uint32(P), C.c_uint32(Q), _p(k["req"]), _p(k["tol"]), _p(k["need"]), _p(k["deny"]), _p(k["anode"]),
         _p(k["prio"]), _p(k["create"]), _p(k["app"]), _p(k["aflags"]), _p(k["gang"]), _p(k["queue"]), _p(k["submit"]),
         _p(k["par"]), _p(k["guar"]), _p(k["mx"]), _p(k["alloc"]), _p(k["sort"]),
         C.c_uint32(batch), C.c_uint32(epoch_limit), C.c_int(speculate), C.c_int(share_rows), C.c_uint32(max_bindings),
-        _p(out_ask), _p(out_node), C.byref(n), _p(state), _p(avail), C.byref(nrows))
+        _p(out_ask), _p(out_node), C.byref(n), _p(state), _p(avail), _p(nrows))
     if rows is not None:
-        rows.append(nrows.value)
+        rows.append(int(nrows[0]) if fn == "engine_host_run" else [int(x) for x in nrows])
     return rc, out_ask[:n.value].astype(np.int64), out_node[:n.value].astype(np.int64), state[:A], avail[:, :N].T.copy()
 
 

@@ -1,0 +1,125 @@
+"""The device-resident ordered commit ("lattice commit", csrc/yk_lattice.h) on the CPU: the header is single-source, so
+tests/host/lattice_shim.cpp compiles the very code of yk_lattice_kernel into plain loops and drives it with the real
+ordering engine.  Bindings, ask states and node availability must equal the oracle's; after every batch the shim also
+checks that the patched node order is exactly "every node once, ascending by (current key, NodeID rank)"."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from yunikorn_k8shim_b200 import synth
+from test_engine_host import run_engine_host
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+INELIGIBLE = 100
+
+
+@pytest.fixture(scope="module")
+def lshim(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("lattice") / "lattice_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-o", out,
+                           os.path.join(HERE, "host", "lattice_shim.cpp")])
+    return C.CDLL(out)
+
+
+def run(lshim, s, stats=None, **kw):
+    rows = []
+    r = run_engine_host(lshim, s, fn="lattice_host_run", rows=rows, **kw)
+    if stats is not None:
+        stats.append(dict(zip(("subruns", "fullscans", "sorts", "elems", "quick", "escalations", "handoffs", "batches"), rows[0])))
+    return r
+
+
+def check(lshim, oracle, s, tag=None, stats=None, **kw):
+    want = oracle.run(s, max_bindings=kw.get("max_bindings") or -1)
+    rc, ask, node, state, avail = run(lshim, s, stats=stats, **kw)
+    if rc == INELIGIBLE:
+        return None
+    assert rc == 0, (tag, rc)
+    assert np.array_equal(ask, want["ask"]), tag
+    assert np.array_equal(node, want["node"]), tag
+    if kw.get("max_bindings") is None:
+        assert np.array_equal(state, want["state"]), tag
+    assert np.array_equal(avail, want["avail"]), tag
+    return want
+
+
+@pytest.mark.parametrize("batch", [7, 64, 1024])
+def test_lattice_matches_oracle_on_fuzz(lshim, oracle, batch):
+    checked = 0
+    for seed in range(120):
+        s = synth.fuzz(seed)
+        if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > batch:
+            continue
+        if check(lshim, oracle, s, tag=(seed, batch), batch=batch) is not None:
+            checked += 1
+    assert checked > 20
+
+
+def test_config_shapes_small(lshim, oracle):
+    for s, batch in ((synth.kwok(60, 6, 30), 64), (synth.kwok(60, 6, 30, variant="bare"), 64),
+                     (synth.perf(300, 20, 40), 128), (synth.perf(300, 20, 40, masks=True), 128),
+                     (synth.perf(1500, 20, 100), 4096), (synth.perf(1500, 20, 100, masks=True), 700),
+                     (synth.hier(400, 3, 3, 2, 40), 96), (synth.hier(400, 2, 3, 2, 40, masks=True, leaf_sort=synth.SORT_FAIR), 96),
+                     (synth.gangs(300, 60, 5), 100)):
+        st = []
+        want = check(lshim, oracle, s, tag=s.name, batch=batch, stats=st)
+        assert want is not None and len(want["ask"]) > 0, s.name
+        assert st[0]["subruns"] > 0
+
+
+def test_binpacking_is_left_to_the_host_commit(lshim):
+    assert run(lshim, synth.perf(50, 2, 10, policy=synth.POLICY_BINPACKING))[0] == INELIGIBLE
+
+
+def test_full_cluster_and_gang_rollbacks(lshim, oracle):
+    """over-committed clusters: certain NOFITs by full scan, the capacity bound that rejects later asks without one, gangs
+    that do not fit (decided on the device when no node takes the first member, handed over otherwise)"""
+    for seed in range(6):
+        for fill in (1.05, 2.0):
+            st = []
+            s = synth.gangs(120, 40, 5, seed=seed, fill=fill)
+            want = check(lshim, oracle, s, tag=(seed, fill), batch=1000, stats=st)
+            assert want is not None and (want["state"] == 2).sum() > 0
+    # a gang whose members differ in what they request never reaches the lattice commit
+    assert run(lshim, synth.poisoned_gangs(3))[0] == INELIGIBLE
+
+
+def test_tiny_requests_stack_on_the_front_nodes(lshim, oracle):
+    """requests much smaller than the key distance between nodes: one node takes many allocations in a row, the extras of
+    the lattice carry the run and the elements have to be sorted"""
+    s = synth.perf(40, 4, 300)
+    s.ask_req[:, 0] = 10
+    s.ask_req[:, 1] = 1_000_000
+    st = []
+    assert check(lshim, oracle, s, batch=4096, stats=st) is not None
+    assert st[0]["sorts"] > 0
+    # requests that do not move the key at all ({pods: 1}: no weighted resource): every element of a node ties with
+    # the next one
+    s = synth.kwok(30, 3, 200, variant="bare")
+    assert check(lshim, oracle, s, batch=4096) is not None
+
+
+def test_max_bindings(lshim, oracle):
+    for seed in (1, 4, 9, 12, 30):
+        s = synth.fuzz(seed)
+        full = oracle.run(s)
+        k = max(1, len(full["ask"]) // 2)
+        want = oracle.run(s, max_bindings=k)
+        rc, ask, node, _, avail = run(lshim, s, batch=8 if not (s.ask_gang >= 0).any() else 64, max_bindings=k)
+        if rc == INELIGIBLE:
+            continue
+        assert rc == 0
+        assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
+        assert np.array_equal(avail, want["avail"])
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 5, 8])
+def test_other_dimension_counts(lshim, oracle, D):
+    for seed in range(12):
+        s = synth.redim(synth.fuzz(seed), D, seed)
+        check(lshim, oracle, s, tag=(seed, D), batch=64)
+    s = synth.redim(synth.perf(200, 8, 40, masks=True), D, 1)
+    assert check(lshim, oracle, s, batch=512) is not None

@@ -1,0 +1,103 @@
+// yk_lattice_host.hpp -- host-side companions of the lattice commit (yk_lattice.h): the per-entry meta words the kernel
+// reads, and the test that decides whether a cycle may use the lattice commit at all.  No CUDA in here: csrc/yk_engine.cu
+// and tests/host/lattice_shim.cpp both include it.
+#pragma once
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "yk_commit.hpp"
+#include "yk_lattice.h"
+
+namespace yklt {
+
+inline bool same_request(const yk::CommitTables& t, uint32_t a, uint32_t b) {
+    for (int k = 0; k < t.D; ++k)
+        if (t.a_req[(size_t)k * t.lda + a] != t.a_req[(size_t)k * t.lda + b]) return false;
+    return true;
+}
+
+// Dense numbers for the distinct request vectors of the cycle's pending asks ("shapes"): a_shape[ask].  Returns how many.
+inline uint32_t assign_shapes(const yk::CommitTables& t, const std::vector<uint32_t>& pending, std::vector<uint32_t>& a_shape) {
+    struct Slot { uint32_t ask; uint32_t id; };
+    size_t cap = 64;
+    while (cap < 4 * pending.size()) cap <<= 1;
+    std::vector<Slot> tab(cap, Slot{yk::CNONE, 0});
+    uint32_t n = 0;
+    for (uint32_t a : pending) {
+        uint64_t h = 0x9E3779B97F4A7C15ull;
+        for (int k = 0; k < t.D; ++k) { h ^= (uint64_t)t.a_req[(size_t)k * t.lda + a] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xD6E8FEB86659FD93ull; }
+        size_t x = (size_t)(h ^ (h >> 29)) & (cap - 1);
+        for (;;) {
+            Slot& s = tab[x];
+            if (s.ask == yk::CNONE) { s.ask = a; s.id = n++; a_shape[a] = s.id; break; }
+            if (same_request(t, s.ask, a)) { a_shape[a] = s.id; break; }
+            x = (x + 1) & (cap - 1);
+        }
+    }
+    return n;
+}
+
+// meta word of every batch entry (M_* flags | shape id << 16, yk_lattice.h); returns the number of runs (maximal stretches
+// of equal requests)
+inline size_t build_meta(const yk::CommitTables& t, const uint64_t* a_sig, const uint32_t* a_shape, const std::vector<uint32_t>& batch,
+                         std::vector<uint32_t>& meta) {
+    const size_t B = batch.size();
+    meta.resize(B);
+    size_t runs = 0;
+    for (size_t i = 0; i < B; ++i) {
+        const uint32_t a = batch[i];
+        uint32_t m = 0;
+        if (i == 0 || !same_request(t, a, batch[i - 1])) { m |= M_RUN | M_SIG; ++runs; }
+        else if (a_sig[a] != a_sig[batch[i - 1]] || !yk::same_signature(t, a, batch[i - 1])) m |= M_SIG;
+        if (t.a_gang[a] != yk::CNONE) {
+            m |= M_GANG;
+            const uint32_t b = i ? batch[i - 1] : a;
+            if (i == 0 || t.a_gang[b] != t.a_gang[a] || t.a_app[b] != t.a_app[a]) m |= M_GSTART;
+        }
+        meta[i] = m | (a_shape[a] << 16);
+    }
+    return runs;
+}
+
+// What the lattice commit relies on (DESIGN.md "lattice commit"):
+//   fair node sort; weights >= 0 and weighted totals >= 0 (a node's key must not decrease when it is allocated to);
+//   NodeID ranks unique (element order is (key, rank, j)); every gang's members request the same vector (a gang never
+//   straddles two runs, so a failed gang is undone inside one sub-run).
+struct Eligibility {
+    bool ok = false;
+    const char* why = "";
+};
+
+inline Eligibility eligible(const yk::CommitTables& t, uint32_t n_hi, const uint8_t* n_present, const int64_t* n_total,
+                            size_t ldn, const uint32_t* n_rank, const std::vector<uint32_t>& pending) {
+    Eligibility e;
+    if (t.policy != 0u) { e.why = "binpacking node sort"; return e; }
+    for (int k = 0; k < t.D; ++k) if (t.w[k] < 0.0 || t.w[k] != t.w[k]) { e.why = "negative node-sort weight"; return e; }
+    {
+        std::vector<uint32_t> ranks;
+        ranks.reserve(n_hi);
+        for (uint32_t n = 0; n < n_hi; ++n) {
+            if (!n_present[n]) continue;
+            ranks.push_back(n_rank[n]);
+            for (int k = 0; k < t.D; ++k)
+                if (t.w[k] != 0.0 && n_total[(size_t)k * ldn + n] < 0) { e.why = "negative total on a weighted resource"; return e; }
+        }
+        std::sort(ranks.begin(), ranks.end());
+        for (size_t i = 1; i < ranks.size(); ++i) if (ranks[i] == ranks[i - 1]) { e.why = "duplicate NodeID ranks"; return e; }
+    }
+    {
+        std::unordered_map<uint64_t, uint32_t> first;   // (app, gang) -> first member seen
+        for (uint32_t a : pending) {
+            if (t.a_gang[a] == yk::CNONE) continue;
+            const uint64_t key = ((uint64_t)t.a_app[a] << 32) | t.a_gang[a];
+            auto it = first.find(key);
+            if (it == first.end()) first.emplace(key, a);
+            else if (!same_request(t, a, it->second)) { e.why = "a gang mixes request vectors"; return e; }
+        }
+    }
+    e.ok = true;
+    return e;
+}
+
+}  // namespace yklt
