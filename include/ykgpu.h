@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define YK_ABI_VERSION 2
+#define YK_ABI_VERSION 3
 #define YK_MAX_D 8
 #define YK_NONE 0xFFFFFFFFu          /* "no node" / "no gang" index */
 
@@ -97,6 +97,11 @@ typedef enum {
 /* yk_config.flags */
 #define YK_FLAG_NO_ROW_SHARING 1u   /* sweep one row per ask even when asks of a batch have identical predicate inputs
                                       (requests, tolerations, label masks, node name); default: one row per distinct set */
+#define YK_FLAG_HOST_COMMIT 2u      /* never use the device-resident ordered commit (yk_lattice_kernel): every cycle takes the
+                                      sweep + host commit path (the default today: measured, the host commit is still ahead) */
+#define YK_FLAG_DEVICE_COMMIT 4u    /* commit on the device (yk_lattice_kernel: exact, no bitmap read-back, no host work per
+                                      ask) whenever the cycle is eligible: fair node sort, non-negative weights, every gang's
+                                      members requesting one vector.  Ineligible cycles take the sweep + host commit path. */
 
 typedef struct yk_engine yk_engine;
 
@@ -136,6 +141,13 @@ typedef struct {
     uint64_t prof[6];
     /* row sharing: asks that went through a sweep batch, and the rows (distinct predicate signatures) actually swept */
     uint64_t asks_swept, rows_swept;
+    /* device-resident ordered commit (yk_lattice_kernel): launches, sub-runs (scan + lattice + chain + patch rounds), asks it
+       decided, lattice elements evaluated, sorts, full-order scans (an ask with no candidate near the front), asks decided by
+       the capacity bound alone, cycles handed over to the host commit (a gang that has to be rolled back), CUDA-event time */
+    uint64_t lattice_launches, lattice_subruns, lattice_asks, lattice_elements, lattice_sorts, lattice_fullscans,
+             lattice_quick, lattice_handoffs;
+    double lattice_ms;
+    uint64_t lattice_cycles;     /* cycles that started on the device commit */
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

@@ -50,9 +50,10 @@ int run_d(uint32_t policy, const double* weights,
     const yklt::Eligibility el = yklt::eligible(ct, nN, npresent.data(), n_total, nN, n_rank, pending);
     if (!el.ok) return 100;
     std::vector<uint64_t> a_sig(nA);
-    std::vector<uint32_t> a_shape(nA, 0);
-    if (yklt::assign_shapes(ct, pending, a_shape) > (uint32_t)yklt::SHAPE_IDS) return 100;
+    std::vector<uint32_t> a_shape(nA, 0), a_sigid(nA, 0);
     for (uint32_t a = 0; a < nA; ++a) a_sig[a] = yk::ask_signature(ct, a);
+    uint32_t n_shapes = 0, n_sigs = 0;
+    yklt::assign_ids(ct, a_sig.data(), pending, a_shape, a_sigid, &n_shapes, &n_sigs);
 
     // ---- device state: node records, the order (what yk_key_kernel + the radix sort + yk_lt_init_kernel build) ----
     const int RS = (2 * D + 3 + 3) / 4 * 4;
@@ -123,7 +124,7 @@ int run_d(uint32_t policy, const double* weights,
         return yk::CNONE;
     };
 
-    std::vector<uint32_t> asks, meta, result;
+    std::vector<uint32_t> asks, meta, shp, sig, result;
     yk::Orderer::Snap snap;
     size_t bsz = batch;
     uint32_t n = 0;
@@ -137,9 +138,10 @@ int run_d(uint32_t policy, const double* weights,
         if (asks.empty()) break;
         ++batches;
         const size_t B = asks.size();
-        yklt::build_meta(ct, a_sig.data(), a_shape.data(), asks, meta);
+        meta.resize(B); shp.resize(B); sig.resize(B);
+        yklt::build_meta(ct, a_shape.data(), a_sigid.data(), asks, meta.data(), shp.data(), sig.data());
         result.assign(B, yk::CNONE);
-        la.asks = asks.data(); la.meta = meta.data(); la.B = (int)B; la.res = result.data();
+        la.asks = asks.data(); la.meta = meta.data(); la.shp = shp.data(); la.sig = sig.data(); la.B = (int)B; la.res = result.data();
         size_t consumed = 0;
         if (nN == 0) {
             consumed = ins ? B : 1;

@@ -54,7 +54,7 @@ def test_dictionary_symbols_are_exported(lib):
 
 def test_abi_version_and_strerror(lib):
     lib.yk_abi_version.restype = ctypes.c_uint32
-    assert lib.yk_abi_version() == 2
+    assert lib.yk_abi_version() == 3
     lib.yk_strerror.restype = ctypes.c_char_p
     assert b"CUDA" in lib.yk_strerror(-2)
     assert lib.yk_strerror(0) == b"ok"

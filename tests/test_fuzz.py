@@ -34,13 +34,14 @@ def test_fuzz_exercises_the_features(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("batch,share", [(7, True), (64, True), (1024, True), (64, False)])
-def test_engine_matches_oracle_on_fuzz(oracle, batch, share):
+@pytest.mark.parametrize("batch,share,commit", [(7, True, "host"), (64, True, "host"), (1024, True, "host"), (64, False, "host"),
+                                                (7, True, "device"), (64, True, "device"), (1024, True, "device")])
+def test_engine_matches_oracle_on_fuzz(oracle, batch, share, commit):
     from yunikorn_k8shim_b200 import Engine
-    for seed in range(60):
+    for seed in range(60 if commit == "host" else 120):
         s = synth.fuzz(seed)
         want = oracle.run(s)
-        with Engine.for_snapshot(s, batch=batch, share_rows=share) as e:
+        with Engine.for_snapshot(s, batch=batch, share_rows=share, commit=commit) as e:
             try:
                 ask, node, _ = e.cycle(s.n_asks)
             except Exception as exc:          # a gang larger than a tiny batch is a documented error, not a mismatch
@@ -62,8 +63,8 @@ def test_engine_gang_rollback_stress(oracle, policy):
     for seed in range(20):
         s = synth.poisoned_gangs(seed, policy=policy)
         want = oracle.run(s)
-        for batch in (16, 1024):
-            with Engine.for_snapshot(s, batch=batch) as e:
+        for batch, commit in ((16, "host"), (1024, "host"), (64, "device")):
+            with Engine.for_snapshot(s, batch=batch, commit=commit) as e:
                 ask, node, _ = e.cycle(s.n_asks)
                 avail = e.nodes_available(np.arange(s.n_nodes))
             assert np.array_equal(ask, want["ask"]), (seed, batch)

@@ -8,19 +8,28 @@ from yunikorn_k8shim_b200 import Engine, synth
 pytestmark = pytest.mark.gpu
 
 
-def _check(snap, oracle, **kw):
-    want = oracle.run(snap)
+def _run(snap, want, **kw):
     with Engine.for_snapshot(snap, **kw) as e:
         ask, node, _ = e.cycle(snap.n_asks)
         avail = e.nodes_available(np.arange(snap.n_nodes))
         states = e.ask_states(np.arange(snap.n_asks))
         st = e.stats()
-    assert len(ask) == len(want["ask"])
-    assert np.array_equal(ask, want["ask"]), "ask order differs"
-    assert np.array_equal(node, want["node"]), "node choice differs"
-    assert np.array_equal(avail, want["avail"])
-    assert np.array_equal(states, want["state"])
-    assert st["sweep_launches"] > 0 and st["evaluations"] > 0
+    assert len(ask) == len(want["ask"]), kw
+    assert np.array_equal(ask, want["ask"]), ("ask order differs", kw)
+    assert np.array_equal(node, want["node"]), ("node choice differs", kw)
+    assert np.array_equal(avail, want["avail"]), kw
+    assert np.array_equal(states, want["state"]), kw
+    return st
+
+
+def _check(snap, oracle, **kw):
+    """both commits: the device-resident one (wherever the cycle is eligible for it) and sweep + host commit"""
+    want = oracle.run(snap)
+    dev = _run(snap, want, commit="device", **kw)
+    assert dev["sweep_launches"] + dev["lattice_launches"] > 0 or snap.n_nodes == 0
+    st = _run(snap, want, commit="host", **kw)
+    assert st["sweep_launches"] > 0 and st["evaluations"] > 0 and st["lattice_launches"] == 0
+    st["device"] = dev
     return st
 
 
@@ -43,6 +52,11 @@ def test_config3_small(oracle, policy):
 def test_config2_full(oracle):
     st = _check(synth.perf(), oracle, batch=2048)
     assert st["rows_swept"] * 50 < st["asks_swept"]      # a few dozen distinct pod shapes: rows are shared
+    dev = st["device"]                                    # the device commit took the whole cycle: no sweep, no hand-over
+    assert dev["lattice_asks"] == 50_000 and dev["sweep_launches"] == 0 and dev["lattice_handoffs"] == 0
+    assert dev["lattice_subruns"] < 1000
+
+
 
 
 def test_config2_full_one_row_per_ask(oracle):
@@ -51,7 +65,14 @@ def test_config2_full_one_row_per_ask(oracle):
 
 
 def test_config3_full(oracle):
-    _check(synth.perf(masks=True), oracle, batch=2048)
+    st = _check(synth.perf(masks=True), oracle, batch=2048)
+    assert st["device"]["lattice_asks"] == 50_000 and st["device"]["sweep_launches"] == 0
+
+
+def test_reference_benchmark_shape_full(oracle):
+    """the reference's own benchmark shape: every pod identical (pkg/shim/scheduler_perf_test.go:283-288)"""
+    st = _check(synth.reference_shape(), oracle, batch=4096)
+    assert st["device"]["lattice_asks"] == 50_000
 
 
 def test_overcommitted_cluster(oracle):
@@ -98,6 +119,9 @@ def test_config5_gangs_in_drf_tree(oracle):
 def test_config5_full(oracle):
     st = _check(synth.gangs(), oracle, batch=4096)
     assert st["nofit"] > 0
+    # the device commit places the gangs until the cluster is full; the first gang that has to be rolled back hands the
+    # rest of the cycle to the host commit
+    assert st["device"]["lattice_asks"] > 10_000 and st["device"]["lattice_handoffs"] == 1
 
 
 def test_gang_larger_than_batch_is_an_error(oracle):
@@ -132,22 +156,24 @@ def test_max_bindings_and_second_cycle(oracle):
     s = synth.perf(50, 4, 50, masks=True)
     want = oracle.run(s, max_bindings=77)
     full = oracle.run(s)
-    with Engine.for_snapshot(s, batch=32) as e:
-        ask, node, _ = e.cycle(77)
-        assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
-        ask2, node2, _ = e.cycle(s.n_asks)                        # the rest, on the state the first cycle left
-        assert np.array_equal(np.concatenate([ask, ask2]), full["ask"])
-        assert np.array_equal(np.concatenate([node, node2]), full["node"])
+    for commit in ("device", "host"):
+        with Engine.for_snapshot(s, batch=32, commit=commit) as e:
+            ask, node, _ = e.cycle(77)
+            assert np.array_equal(ask, want["ask"]) and np.array_equal(node, want["node"])
+            ask2, node2, _ = e.cycle(s.n_asks)                        # the rest, on the state the first cycle left
+            assert np.array_equal(np.concatenate([ask, ask2]), full["ask"])
+            assert np.array_equal(np.concatenate([node, node2]), full["node"])
 
 
 def test_release_gives_resources_back(oracle):
     s = synth.perf(6, 2, 300)                                     # overcommitted
     want = oracle.run(s)
-    with Engine.for_snapshot(s, batch=64) as e:
-        ask, node, _ = e.cycle(s.n_asks)
-        assert np.array_equal(ask, want["ask"])
-        e.release(ask)
-        assert np.array_equal(e.nodes_available(np.arange(s.n_nodes)), s.node_avail)
+    for commit in ("device", "host"):
+        with Engine.for_snapshot(s, batch=64, commit=commit) as e:
+            ask, node, _ = e.cycle(s.n_asks)
+            assert np.array_equal(ask, want["ask"])
+            e.release(ask)
+            assert np.array_equal(e.nodes_available(np.arange(s.n_nodes)), s.node_avail)
 
 
 def test_device_score_and_evaluate_match_oracle(oracle):

@@ -27,7 +27,9 @@
 #include <x86intrin.h>
 
 #include "yk_kernels.cuh"
+#include "yk_lattice.cuh"
 #include "yk_commit.hpp"
+#include "yk_lattice_host.hpp"
 #include "yk_orderer.hpp"
 
 namespace {
@@ -201,6 +203,18 @@ struct yk_engine {
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
 
     yk::Orderer ord;
+    // device-resident ordered commit (yk_lattice.h): node records, ping-pong node order, per-batch staging
+    bool lt_allowed = true;                  // !YK_FLAG_HOST_COMMIT, single GPU
+    int lt_force = 0;                        // YK_FLAG_DEVICE_COMMIT / YK_COMMIT=device: every eligible cycle commits on the device
+    bool lt_auto = false;                    // YK_COMMIT=auto: eligible cycles with long windows commit on the device
+    bool lt_active = false;                  // this cycle runs (so far) on the device commit
+    int lt_RS = 0; size_t lt_smem = 0;
+    Dev<int64_t> d_rec; Dev<yklt::Ent> d_ord[2]; Dev<int> d_lt_cur, d_lt_hdr; Dev<int64_t> d_lt_ub;
+    Dev<uint32_t> d_rank, d_lt_asks, d_lt_meta, d_lt_shp, d_lt_sig, d_lt_res;
+    Dev<long long> d_lt_prof; bool lt_prof = false; uint64_t lt_total_subruns = 0;   // YK_PROFILE_LATTICE: SM clocks per kernel phase, printed by yk_destroy
+    Pin<uint32_t> h_lt_asks, h_lt_meta, h_lt_shp, h_lt_sig, h_lt_res; Pin<int> h_lt_hdr; Pin<int64_t> h_lt_ub;
+    std::vector<uint32_t> a_shape, a_sigid;
+    cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
     // peer-to-peer exchange (see yk_peer_export): peers' slot buffers and sync blocks, mapped through CUDA IPC
     bool p2p = false;
@@ -225,6 +239,31 @@ struct yk_engine {
 
 namespace {
 
+template <int D>
+cudaError_t lattice_setup_d(size_t* smem) {
+    *smem = sizeof(yklt::Shared<D>);
+    return cudaFuncSetAttribute(yk_lattice_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+}
+cudaError_t lattice_setup(int D, size_t* smem) {
+    switch (D) {
+        case 1: return lattice_setup_d<1>(smem); case 2: return lattice_setup_d<2>(smem); case 3: return lattice_setup_d<3>(smem);
+        case 4: return lattice_setup_d<4>(smem); case 5: return lattice_setup_d<5>(smem); case 6: return lattice_setup_d<6>(smem);
+        case 7: return lattice_setup_d<7>(smem); default: return lattice_setup_d<8>(smem);
+    }
+}
+void launch_lattice(int D, const yklt::Args& a, size_t smem, cudaStream_t s) {
+    switch (D) {
+        case 1: yk_lattice_kernel<1><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 2: yk_lattice_kernel<2><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 3: yk_lattice_kernel<3><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 4: yk_lattice_kernel<4><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 5: yk_lattice_kernel<5><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 6: yk_lattice_kernel<6><<<1, yklt::THREADS, smem, s>>>(a); break;
+        case 7: yk_lattice_kernel<7><<<1, yklt::THREADS, smem, s>>>(a); break;
+        default: yk_lattice_kernel<8><<<1, yklt::THREADS, smem, s>>>(a); break;
+    }
+}
+
 int upload_tables(yk_engine* e) {
     const int D = e->D;
     if (e->rank_stale) {
@@ -239,6 +278,11 @@ int upload_tables(yk_engine* e) {
         if (e->nlive) memcpy(e->by_rank.p, live.data(), sizeof(uint32_t) * e->nlive);
         if (e->nlive) CK(cudaMemcpyAsync(e->d_by_rank.p, e->by_rank.p, sizeof(uint32_t) * e->nlive, cudaMemcpyHostToDevice, e->stream));
         e->st.h2d_bytes += sizeof(uint32_t) * e->nlive;
+        if (e->lt_allowed && e->n_hi) {   // the lattice commit orders ties by the rank itself
+            CK(cudaMemcpyAsync(e->d_rank.p, e->n_rank.data(), sizeof(uint32_t) * e->n_hi, cudaMemcpyHostToDevice, e->stream));
+            CK(cudaStreamSynchronize(e->stream));   // n_rank is pageable memory
+            e->st.h2d_bytes += sizeof(uint32_t) * e->n_hi;
+        }
         e->rank_stale = false;
     }
     if (e->nodes_stale && e->n_hi) {
@@ -304,14 +348,18 @@ void launch_sweep(int D, const YkSweepArgs& a, cudaStream_t s, int slots) {
 }
 
 // Initial node order of a cycle, computed on the device: float64 score per node (yk_key_kernel), stable radix
-// sort by key over NodeID-rank order = ascending (score, NodeID).  Later batches keep it current by merging.
-int initial_order(yk_engine* e) {
-    const int nlive = (int)e->nlive;
+// sort by key over NodeID-rank order = ascending (score, NodeID).  device_order() only enqueues (the lattice commit
+// consumes the result on the stream); initial_order() also brings it to the host commit's working copy.
+void setup_commit_tables(yk_engine* e) {
     yk::CommitTables& ct = e->cm.t;
     ct.D = e->D; ct.policy = e->cfg.policy; ct.w = e->w.w; ct.lda = e->maxA;
     ct.a_req = e->a_req.p; ct.a_tol = e->a_tol.p; ct.a_need = e->a_need.p; ct.a_deny = e->a_deny.p; ct.a_node = e->a_node.p;
     ct.a_gang = e->a_gang.data(); ct.a_app = e->a_app.data();
     e->cm.profile = e->prof;
+}
+
+int device_order(yk_engine* e) {
+    const int nlive = (int)e->nlive;
     if (nlive == 0) return YK_OK;
     cudaStream_t s = e->stream;
     CK(cudaMemsetAsync(e->d_flag.p, 0, sizeof(int), s));
@@ -322,20 +370,99 @@ int initial_order(yk_engine* e) {
     CK(cub::DeviceRadixSort::SortPairs(e->d_cub.p, tb, e->d_key_in.p, e->d_key_out.p, e->d_val_in.p, e->d_val_out.p,
                                        nlive, 0, 64, s));
     CK(cudaEventRecord(e->ev1, s));
+    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    e->st.d2h_bytes += 4;
+    e->st.other_launches += 11;   // key + cub radix sort (histogram, exclusive sum, 8 onesweep passes for 64-bit keys)
+    return YK_OK;
+}
+
+int initial_order(yk_engine* e) {
+    const int nlive = (int)e->nlive;
+    if (nlive == 0) return YK_OK;
+    cudaStream_t s = e->stream;
+    int rc = device_order(e);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(e->h_order[0].p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     // while the device scores and sorts: the commit's working copy of the node table (host only)
     e->cm.build(e->n_hi, e->n_avail.p, e->n_total.p, e->maxN, e->n_taint.p, e->n_label.p, e->n_rank.data());
     CK(cudaStreamSynchronize(s));
-    e->st.d2h_bytes += 12 * (size_t)nlive + 4;
-    e->st.other_launches += 11;   // key + cub radix sort (histogram, exclusive sum, 8 onesweep passes for 64-bit keys)
+    e->st.d2h_bytes += 12 * (size_t)nlive;
     if (e->h_flag[0]) return e->fail(YK_ERR_RANGE, "NaN node score (zero total on a weighted resource)");
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->st.sort_ms += ms;
     e->cur = 0;
     e->cm.set_order(e->h_order[0].p, e->h_skey.p, nlive);   // the cycle's initial order: (key, rank, node) per position
+    return YK_OK;
+}
+
+// ---- device-resident ordered commit (yk_lattice.h) -------------------------------------------------------------------
+// node records + order entries from the sorted keys; capacity bound and header reset
+int lt_prepare(yk_engine* e) {
+    const int nlive = (int)e->nlive;
+    cudaStream_t s = e->stream;
+    if (nlive)
+        yk_lt_init_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(e->D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
+                                                             e->d_flags.p, e->d_rank.p, e->d_key_out.p, e->d_val_out.p, nlive,
+                                                             e->d_rec.p, e->lt_RS, e->d_ord[0].p);
+    CK(cudaGetLastError());
+    for (int k = 0; k < 8; ++k) e->h_lt_ub[(size_t)k] = INT64_MAX;
+    CK(cudaMemcpyAsync(e->d_lt_ub.p, e->h_lt_ub.p, 8 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(e->d_lt_cur.p, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(e->d_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int), s));
+    e->st.other_launches += 1;
+    return YK_OK;
+}
+
+// one batch through yk_lattice_kernel: asks + their three words up (already in the pinned staging buffers), node indices +
+// header back.  Blocks until the batch is decided.
+int lt_batch(yk_engine* e, size_t B, bool insensitive) {
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(e->d_lt_asks.p, e->h_lt_asks.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_meta.p, e->h_lt_meta.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_shp.p, e->h_lt_shp.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_sig.p, e->h_lt_sig.p, 4 * B, cudaMemcpyHostToDevice, s));
+    yklt::Args a{};
+    a.policy = e->cfg.policy;
+    for (int k = 0; k < 8; ++k) a.w[k] = e->w.w[k];
+    a.rec = e->d_rec.p; a.RS = e->lt_RS; a.ord[0] = e->d_ord[0].p; a.ord[1] = e->d_ord[1].p; a.cur = e->d_lt_cur.p;
+    a.nlive = (int)e->nlive;
+    a.a_req = e->d_areq.p; a.lda = e->maxA; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
+    a.asks = e->d_lt_asks.p; a.meta = e->d_lt_meta.p; a.shp = e->d_lt_shp.p; a.sig = e->d_lt_sig.p; a.B = (int)B;
+    a.res = e->d_lt_res.p; a.hdr = e->d_lt_hdr.p; a.ub = e->d_lt_ub.p; a.insensitive = insensitive ? 1 : 0;
+    a.prof = e->lt_prof ? e->d_lt_prof.p : nullptr;
+    CK(cudaEventRecord(e->ev_l0, s));
+    launch_lattice(e->D, a, e->lt_smem, s);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev_l1, s));
+    CK(cudaMemcpyAsync(e->h_lt_res.p, e->d_lt_res.p, 4 * B, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(e->h_lt_hdr.p, e->d_lt_hdr.p, yklt::H_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev_l0, e->ev_l1);
+    e->st.lattice_ms += ms;
+    e->st.lattice_launches += 1;
+    e->st.h2d_bytes += 16 * B;
+    e->st.d2h_bytes += 4 * B + yklt::H_WORDS * sizeof(int);
+    return YK_OK;
+}
+
+// the records' availability back into the column-major device table and the host table (end of the cycle, or hand-over)
+int lt_export(yk_engine* e) {
+    const int nlive = (int)e->nlive;
+    if (nlive == 0) return YK_OK;
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(e->h_flag.p, e->d_lt_cur.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int cur = e->h_flag[0] & 1;
+    yk_lt_export_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(e->D, e->d_rec.p, e->lt_RS, e->d_ord[cur].p, nlive, e->d_avail.p, e->maxN);
+    CK(cudaGetLastError());
+    for (int k = 0; k < e->D; ++k)
+        CK(cudaMemcpyAsync(e->n_avail.p + (size_t)k * e->maxN, e->d_avail.p + (size_t)k * e->maxN, 8 * (size_t)e->n_hi, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    e->st.d2h_bytes += 8 * (size_t)e->n_hi * e->D + 4;
+    e->st.other_launches += 1;
     return YK_OK;
 }
 
@@ -599,12 +726,23 @@ void yk_destroy(yk_engine* e) {
     if (!e) return;
     e->worker.stop();
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->lt_prof && e->d_lt_prof.p) {
+        long long pf[16] = {0};
+        if (cudaMemcpy(pf, e->d_lt_prof.p, sizeof(pf), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char* nm[yklt::PF_N] = {"stage", "scan", "window", "bound", "lattice", "sort", "links+rows", "chain", "apply", "patch", "fullscan"};
+            fprintf(stderr, "[ykgpu] lattice kernel, SM clocks per phase (%llu sub-runs):", (unsigned long long)e->lt_total_subruns);
+            for (int k = 0; k < yklt::PF_N; ++k) fprintf(stderr, " %s=%lld", nm[k], pf[k]);
+            fprintf(stderr, "\n");
+        }
+    }
     for (int g = 0; g < 8; ++g)
         if (e->peer_open[g]) { cudaIpcCloseMemHandle(e->peer_fit[0][g]); cudaIpcCloseMemHandle(e->peer_fit[1][g]); cudaIpcCloseMemHandle(e->peer_sync[g]); }
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ev_l0) cudaEventDestroy(e->ev_l0);
+    if (e->ev_l1) cudaEventDestroy(e->ev_l1);
     for (Slot& sl : e->slot) {
         for (auto ev : sl.ev) if (ev) cudaEventDestroy(ev);
         if (sl.ev_s0) cudaEventDestroy(sl.ev_s0);
@@ -674,6 +812,24 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->prof = getenv("YK_PROFILE_COMMIT") != nullptr;
     if (ok) { int dev = 0; cudaGetDevice(&dev); e->worker.start(dev); }
     T(e->d_dirty_nodes.alloc(N)); T(e->d_dirty_vals.alloc(N * D)); T(e->d_scores.alloc(N));
+    // device-resident ordered commit
+    e->lt_allowed = !(cfg->flags & YK_FLAG_HOST_COMMIT) && cfg->world <= 1;
+    if (cfg->flags & YK_FLAG_DEVICE_COMMIT) e->lt_force = 1;
+    if (const char* cm = getenv("YK_COMMIT")) {
+        if (!strcmp(cm, "host")) e->lt_allowed = false;
+        if (!strcmp(cm, "device")) e->lt_force = 1;
+        if (!strcmp(cm, "auto")) e->lt_auto = true;
+    }
+    e->lt_RS = (2 * D + 3 + 3) / 4 * 4;
+    T(e->d_rec.alloc(N * (size_t)e->lt_RS)); T(e->d_ord[0].alloc(N)); T(e->d_ord[1].alloc(N)); T(e->d_rank.alloc(N));
+    T(e->d_lt_cur.alloc(1)); T(e->d_lt_hdr.alloc(yklt::H_WORDS)); T(e->d_lt_ub.alloc(8));
+    T(e->d_lt_asks.alloc(A)); T(e->d_lt_meta.alloc(A)); T(e->d_lt_shp.alloc(A)); T(e->d_lt_sig.alloc(A)); T(e->d_lt_res.alloc(A));
+    T(e->h_lt_asks.alloc(A)); T(e->h_lt_meta.alloc(A)); T(e->h_lt_shp.alloc(A)); T(e->h_lt_sig.alloc(A)); T(e->h_lt_res.alloc(A)); T(e->h_lt_hdr.alloc(yklt::H_WORDS)); T(e->h_lt_ub.alloc(8));
+    T(cudaEventCreate(&e->ev_l0)); T(cudaEventCreate(&e->ev_l1));
+    e->lt_prof = getenv("YK_PROFILE_LATTICE") != nullptr;
+    T(e->d_lt_prof.alloc(16));
+    if (ok) T(cudaMemset(e->d_lt_prof.p, 0, 16 * sizeof(long long)));
+    if (ok) T(lattice_setup(D, &e->lt_smem));
     T(e->h_snode.alloc(N)); T(e->h_skey.alloc(N));
     T(e->h_dirty_nodes.alloc(N)); T(e->h_dirty_vals.alloc(N * D)); T(e->h_flag.alloc(1)); T(e->h_scores.alloc(N));
     if (ok) {   // does this binary carry an image the device can run?
@@ -686,6 +842,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     }
     if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
     e->n_rank.assign(N, 0); e->n_present.assign(N, 0);
+    e->a_shape.assign(A, 0); e->a_sigid.assign(A, 0);
     e->a_sig.assign(A, 0); e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
     e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
@@ -757,12 +914,26 @@ int yk_queues_set(yk_engine* e, uint32_t q, const uint32_t* parent, const int64_
     if (parent[0] != YK_NONE) return e->fail(YK_ERR_ARG, "yk_queues_set: queue 0 must be the root");
     for (uint32_t i = 1; i < q; ++i) if (parent[i] >= i) return e->fail(YK_ERR_ARG, "yk_queues_set: parent[i] must be < i");
     const int D = e->D;
+    // applications keep pointing at queue indices: a tree that no longer has them (or turned their leaf into a parent) is
+    // refused rather than silently re-homing them
+    for (uint32_t p = 0; p < e->maxP; ++p) {
+        if (!e->p_present[p]) continue;
+        if (e->p_queue[p] >= q) return e->fail(YK_ERR_STATE, "yk_queues_set: an application sits in a queue the new tree does not have (remove or move it first)");
+        for (uint32_t i = 1; i < q; ++i)
+            if (parent[i] == e->p_queue[p]) return e->fail(YK_ERR_STATE, "yk_queues_set: an application sits in a queue the new tree makes a parent");
+    }
     e->nq = q;
     e->q_parent.assign(parent, parent + q);
     e->q_guar.assign((size_t)q * D, -1); e->q_max.assign((size_t)q * D, -1); e->q_alloc.assign((size_t)q * D, 0);
     if (guaranteed) e->q_guar.assign(guaranteed, guaranteed + (size_t)q * D);
     if (max) e->q_max.assign(max, max + (size_t)q * D);
     if (allocated) e->q_alloc.assign(allocated, allocated + (size_t)q * D);
+    else   // what the present applications hold stays accounted: their allocations are summed up the new tree
+        for (uint32_t p = 0; p < e->maxP; ++p) {
+            if (!e->p_present[p]) continue;
+            for (uint32_t qq = e->p_queue[p]; qq != YK_NONE; qq = e->q_parent[qq])
+                for (int k = 0; k < D; ++k) e->q_alloc[(size_t)k * q + qq] += e->p_alloc[(size_t)k * e->maxP + p];
+        }
     e->q_sort.assign(q, 0);
     if (sort) e->q_sort.assign(sort, sort + q);
     e->q_prio_offset.assign(q, 0); e->q_prio_fence.assign(q, 0);   // defaults; yk_queues_priority sets them
@@ -895,70 +1066,139 @@ int yk_release(yk_engine* e, uint32_t n, const uint32_t* idx) {
     return YK_OK;
 }
 
-int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_out, uint32_t* slow, uint32_t slow_cap,
-             uint32_t* n_slow) {
-    if (!e) return YK_ERR_ARG;
-    std::lock_guard<std::mutex> g(e->mu);
-    if (!n_out || (max_bindings && !out)) return e->fail(YK_ERR_ARG, "yk_cycle: null output");
-    *n_out = 0;
-    if (n_slow) *n_slow = 0;
-    if (e->nq == 0) return e->fail(YK_ERR_STATE, "yk_cycle: no queues configured (yk_queues_set)");
-    const double t_start = now_ms();
-    // the orderer's per-cycle setup (host only) runs on the helper thread while this thread uploads stale tables and
-    // gets the initial node order from the device
-    std::vector<uint32_t>& pending = e->pending;
-    double begin_ms = 0;
-    e->worker.submit([&] {
-        const double t_b = now_ms();
-        pending.clear();
-        pending.reserve(e->a_hi);
-        for (uint32_t a = 0; a < e->a_hi; ++a) {
-            uint8_t& st = e->a_state[a];
-            if (st == yk::ST_ABSENT || st == yk::ST_ALLOCATED) continue;
-            st = yk::ST_PENDING;   // failed / skipped asks are tried again every cycle, like the reference
-            if (!e->p_present[e->a_app[a]]) continue;
-            pending.push_back(a);
+}  // extern "C" (reopened after yk_cycle)
+
+// ---- one cycle ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct Cycle {
+    uint32_t max_bindings = 0;
+    yk_binding* out = nullptr;
+    uint32_t n = 0;                 // bindings so far
+    std::vector<uint32_t> result;
+};
+
+// Decided entries [0, consumed) of a batch: orderer bookkeeping + bindings out.  `failed` = the batch ended on an ask /
+// gang that found no node in a placement-sensitive order (the orderer is rewound to just before it).
+void settle(yk_engine* e, Cycle& c, Slot& A, Slot* later, bool later_forked, size_t consumed, bool ins, bool& failed) {
+    failed = false;
+    const std::vector<uint32_t>& result = c.result;
+    if (!ins && consumed > 0 && result[consumed - 1] == YK_NONE) {
+        const double t_r = now_ms();
+        size_t j = consumed - 1;   // first entry of the failed ask / gang
+        while (j > 0 && e->a_gang[A.asks[j]] != YK_NONE && e->a_gang[A.asks[j - 1]] == e->a_gang[A.asks[j]] &&
+               e->a_app[A.asks[j - 1]] == e->a_app[A.asks[j]] && result[j - 1] == YK_NONE) --j;
+        // the speculated fill is undone even when it produced no batch: it may still have marked asks (headroom skips)
+        e->ord.rewind(A.snap, later_forked && later ? &later->snap : nullptr, A.asks, j);
+        e->st.host_ms[2] += now_ms() - t_r;
+        failed = true;
+    }
+    for (size_t i = 0; i < consumed; ++i) {
+        const uint32_t a = A.asks[i];
+        if (result[i] == YK_NONE) {
+            if (ins) e->ord.fail_in_place(a);
+            e->st.nofit++;
+            continue;
         }
-        yk::Tables& t = e->ord.t;
-        t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
-        t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
-        t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
-        t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
-        t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
-        t.q_sort = e->q_sort.data();
-        t.q_prio_offset = e->q_prio_offset.data(); t.q_prio_fence = e->q_prio_fence.data();
-        e->ord.begin_cycle(pending);
-        begin_ms = now_ms() - t_b;
-    });
-    int rc = upload_tables(e);
-    if (!rc) rc = initial_order(e);
-    const double t_a = now_ms();
-    e->worker.wait();
-    e->st.host_ms[0] += t_a - t_start;
-    e->st.host_ms[1] += begin_ms;
+        e->ord.confirm(a);
+        e->a_bound[a] = result[i];
+        c.out[c.n].ask = a; c.out[c.n].node = result[i];
+        ++c.n;
+        e->st.allocations++;
+    }
+}
+
+// fill one batch; YK_ERR_ARG when a gang cannot fit any batch
+int fill_batch(yk_engine* e, size_t& bsz, size_t bmax, size_t cap_user, Slot& sl, yk_stats_t& st) {
+    sl.asks.clear(); sl.B = 0; sl.nchunks = 0;
+    if (cap_user == 0) return YK_OK;
+    const double t_f = now_ms();
+    e->ord.fill(bsz, cap_user, sl.asks, sl.snap);
+    st.host_ms[2] += now_ms() - t_f;
+    if (e->ord.oversize_gang) {
+        if (bsz < bmax) { bsz = bmax; e->ord.fill(bsz, cap_user, sl.asks, sl.snap); }
+        if (e->ord.oversize_gang)
+            return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
+    }
+    return YK_OK;
+}
+
+// The cycle on the device commit.  slot[0] already holds the first batch.  Returns with handoff = true (and slot[0]
+// holding the next, not yet committed batch) when the rest of the cycle belongs to the host commit.
+int run_lattice(yk_engine* e, Cycle& c, bool& handoff) {
+    handoff = false;
+    const bool ins = e->ord.insensitive;
+    Slot& A = e->slot[0];
+    size_t bsz = ins ? (size_t)e->maxA : (size_t)e->batch;
+    const size_t bmax = bsz;
+    int rc = lt_prepare(e);
     if (rc) return rc;
-    e->cm.set_pending(pending);   // smallest pending request per dimension: nodes below it are retired from the walk
+    bool first = true;
+    while (!A.asks.empty()) {
+        const size_t B = A.asks.size();
+        memcpy(e->h_lt_asks.p, A.asks.data(), 4 * B);
+        yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), A.asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+        size_t consumed = 0;
+        int status = yklt::ST_DONE;
+        if (e->nlive == 0) {   // no nodes: nothing fits
+            c.result.assign(B, YK_NONE);
+            consumed = ins ? B : 1;
+            if (!ins && e->a_gang[A.asks[0]] != YK_NONE)
+                while (consumed < B && e->cm.same_gang(A.asks[0], A.asks[consumed])) ++consumed;
+            if (!ins) status = yklt::ST_STOPPED;
+        } else {
+            rc = lt_batch(e, B, ins);
+            if (rc) return rc;
+            if (first && e->h_flag[0]) return e->fail(YK_ERR_RANGE, "NaN node score (zero total on a weighted resource)");
+            status = e->h_lt_hdr[yklt::H_STATUS];
+            consumed = (size_t)e->h_lt_hdr[yklt::H_CONSUMED];
+            if (status == yklt::ST_NAN) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
+            if (consumed > B) return e->fail(YK_ERR_CUDA, "lattice kernel returned a bad header");
+            c.result.assign(e->h_lt_res.p, e->h_lt_res.p + B);
+        }
+        first = false;
+        e->st.lattice_asks += consumed;
+        e->st.batches++;
+        bool failed = false;
+        if (status == yklt::ST_HANDOFF) {
+            e->ord.unfill(A.snap, A.asks, consumed);   // the undecided tail goes back to the orderer
+            bool f2 = false;
+            A.asks.resize(consumed);
+            c.result.resize(consumed);
+            settle(e, c, A, nullptr, false, consumed, true /* no failure cut: every decided entry stands */, f2);
+            // (settle with ins = true calls fail_in_place for NONE entries, which is what a placement-insensitive order
+            //  wants; a placement-sensitive batch never carries a NONE before a hand-over: the kernel stops there instead)
+            e->st.lattice_handoffs++;
+            handoff = true;
+            return YK_OK;
+        }
+        settle(e, c, A, nullptr, false, consumed, ins, failed);
+        if (!failed && consumed < B) return e->fail(YK_ERR_CUDA, "lattice kernel ended a batch early without a failure");
+        bsz = failed ? std::max<size_t>(std::min<size_t>(64, bmax), bsz / 4) : std::min<size_t>(bmax, bsz * 2);
+        rc = fill_batch(e, bsz, bmax, (size_t)c.max_bindings - c.n, A, e->st);
+        if (rc) return rc;
+    }
+    return YK_OK;
+}
+
+// The cycle on the sweep + host commit path.  slot[0] holds the first batch (filled, not yet launched); the host commit's
+// working copy and the epoch view are set up here.
+int run_host(yk_engine* e, Cycle& c) {
+    int rc = initial_order(e);
+    if (rc) return rc;
+    e->cm.set_pending(e->pending);   // smallest pending request per dimension: nodes below it are retired from the walk
     // epoch length: long enough that order merges / view refreshes (and the pipeline bubble they cost) stay rare on big
     // clusters, short enough that the touched set does not slow the walk: 5/8 of the nodes, at least two batches
     e->epoch_limit = e->epoch_env ? e->epoch_env : std::max<uint32_t>(e->epoch_floor, (uint32_t)((uint64_t)e->nlive * 5 / 8));
     rc = begin_epoch(e);
     if (rc) return rc;
-    std::vector<uint32_t> result;
-    uint32_t n = 0;
     size_t bsz = e->batch;
+    const size_t bmax = e->batch;
     const bool ins = e->ord.insensitive;
     // fill + launch one batch into a slot; B == 0 afterwards means the orderer has nothing (more) to offer
     auto next_batch = [&](Slot& sl, size_t cap_user, yk_stats_t& st) -> int {
-        sl.asks.clear(); sl.B = 0; sl.nchunks = 0;
-        if (cap_user == 0) return YK_OK;
-        const double t_f = now_ms();
-        e->ord.fill(bsz, cap_user, sl.asks, sl.snap);
-        st.host_ms[2] += now_ms() - t_f;
-        if (e->ord.oversize_gang) {
-            if (bsz < e->batch) { bsz = e->batch; e->ord.fill(bsz, cap_user, sl.asks, sl.snap); }
-            if (e->ord.oversize_gang)
-                return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
-        }
+        const int rcf = fill_batch(e, bsz, bmax, cap_user, sl, st);
+        if (rcf) return rcf;
         return produce(e, sl, st);
     };
     auto merge_worker_stats = [&]() {
@@ -970,7 +1210,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         w = yk_stats_t{};
     };
     int cur = 0;
-    rc = next_batch(e->slot[0], max_bindings, e->st);
+    rc = produce(e, e->slot[0], e->st);
     if (rc) return rc;
     while (e->slot[cur].B > 0) {
         Slot& A = e->slot[cur];
@@ -978,7 +1218,7 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
         // speculate the next batch on the same epoch view unless this batch may fill the epoch
         Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
         const bool room = e->cm.dirty_list.size() + (size_t)A.B < (size_t)e->epoch_limit;
-        const size_t left = (size_t)max_bindings - n;
+        const size_t left = (size_t)c.max_bindings - c.n;
         bool forked = false;
         int rc_next = YK_OK;
         if (room && !e->no_spec && left > (size_t)A.B) {
@@ -987,42 +1227,21 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
             forked = true;
         }
         size_t consumed = 0;
-        rc = commit(e, A, ins, result, consumed);
+        rc = commit(e, A, ins, c.result, consumed);
         if (forked) { e->worker.wait(); merge_worker_stats(); }
         if (rc) return rc;
-        if (rc_next) return rc_next;
         bool failed = false;
-        if (!ins && consumed > 0 && result[consumed - 1] == YK_NONE) {
-            const double t_r = now_ms();
-            size_t j = consumed - 1;   // first entry of the failed ask / gang
-            while (j > 0 && e->a_gang[A.asks[j]] != YK_NONE && e->a_gang[A.asks[j - 1]] == e->a_gang[A.asks[j]] &&
-                   e->a_app[A.asks[j - 1]] == e->a_app[A.asks[j]] && result[j - 1] == YK_NONE) --j;
-            // the speculated fill is undone even when it produced no batch: it may still have marked asks (headroom skips)
-            e->ord.rewind(A.snap, forked ? &Nx.snap : nullptr, A.asks, j);
-            e->st.host_ms[2] += now_ms() - t_r;
-            failed = true;
-            if (Nx.B > 0) {   // the speculated batch was built on an order that did not happen: drop it
-                rc = drain(e, Nx);
-                if (rc) return rc;
-                Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
-            }
+        settle(e, c, A, &Nx, forked, consumed, ins, failed);
+        if (rc_next) return rc_next;   // this batch's bindings stand; the speculated one never ran
+        if (failed && Nx.B > 0) {   // the speculated batch was built on an order that did not happen: drop it
+            rc = drain(e, Nx);
+            if (rc) return rc;
+            Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0;
         }
-        for (size_t i = 0; i < consumed; ++i) {
-            const uint32_t a = A.asks[i];
-            if (result[i] == YK_NONE) {
-                if (ins) e->ord.fail_in_place(a);
-                e->st.nofit++;
-                continue;
-            }
-            e->ord.confirm(a);
-            e->a_bound[a] = result[i];
-            out[n].ask = a; out[n].node = result[i];
-            ++n;
-            e->st.allocations++;
-        }
+        if (failed) { Nx.asks.clear(); Nx.B = 0; Nx.nchunks = 0; }
         // after a failure in a placement-sensitive order, probe with short batches until placements resume
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, e->batch), bsz / 4) : std::min<size_t>(e->batch, bsz * 2);
-        if (Nx.B == 0 && n < max_bindings) {
+        if (Nx.B == 0 && c.n < c.max_bindings) {
             // nothing in flight: the epoch may end here (merge order, refresh the device view) before the next batch
             if (e->cm.dirty_list.size() * 2 >= (size_t)e->epoch_limit || failed) {
                 rc = end_epoch(e, true);
@@ -1030,27 +1249,167 @@ int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_o
                 rc = begin_epoch(e);
                 if (rc) return rc;
             }
-            rc = next_batch(Nx, (size_t)max_bindings - n, e->st);
+            rc = next_batch(Nx, (size_t)c.max_bindings - c.n, e->st);
             if (rc) return rc;
         }
         cur ^= 1;
     }
-    rc = end_epoch(e, false);   // leave host and device node tables current for the next call
+    return YK_OK;
+}
+
+}  // namespace
+
+extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, uint32_t* n_out, uint32_t* slow, uint32_t slow_cap,
+             uint32_t* n_slow) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (!n_out || (max_bindings && !out)) return e->fail(YK_ERR_ARG, "yk_cycle: null output");
+    *n_out = 0;
+    if (n_slow) *n_slow = 0;
+    if (e->nq == 0) return e->fail(YK_ERR_STATE, "yk_cycle: no queues configured (yk_queues_set)");
+    for (uint32_t p = 0; p < e->maxP; ++p)
+        if (e->p_present[p] && e->p_queue[p] >= e->nq) return e->fail(YK_ERR_STATE, "yk_cycle: an application sits in a queue that no longer exists");
+    const double t_start = now_ms();
+    // the orderer's per-cycle setup (host only) runs on the helper thread while this thread uploads stale tables and
+    // starts the initial node order on the device
+    std::vector<uint32_t>& pending = e->pending;
+    double begin_ms = 0;
+    uint32_t n_shapes = 0;
+    bool gang_too_big = false;
+    setup_commit_tables(e);
+    const bool try_lattice = e->lt_allowed && (e->lt_force || e->lt_auto) && e->cfg.policy == YK_POLICY_FAIR;
+    e->worker.submit([&] {
+        const double t_b = now_ms();
+        pending.clear();
+        pending.reserve(e->a_hi);
+        bool any_gang = false;
+        for (uint32_t a = 0; a < e->a_hi; ++a) {
+            uint8_t& st = e->a_state[a];
+            if (st == yk::ST_ABSENT || st == yk::ST_ALLOCATED) continue;
+            st = yk::ST_PENDING;   // failed / skipped asks are tried again every cycle, like the reference
+            if (!e->p_present[e->a_app[a]]) continue;
+            pending.push_back(a);
+            any_gang = any_gang || e->a_gang[a] != YK_NONE;
+        }
+        if (any_gang) {   // a gang that no batch can hold is an argument error: found before anything is committed
+            std::unordered_map<uint64_t, uint32_t> members;
+            for (uint32_t a : pending)
+                if (e->a_gang[a] != YK_NONE && ++members[((uint64_t)e->a_app[a] << 32) | e->a_gang[a]] > e->batch) gang_too_big = true;
+        }
+        yk::Tables& t = e->ord.t;
+        t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
+        t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
+        t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
+        t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
+        t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
+        t.q_sort = e->q_sort.data();
+        t.q_prio_offset = e->q_prio_offset.data(); t.q_prio_fence = e->q_prio_fence.data();
+        if (!gang_too_big) e->ord.begin_cycle(pending);
+        if (!gang_too_big && try_lattice) {   // dense numbers for request vectors and signatures (what the kernel dedups by)
+            uint32_t n_sigs = 0;
+            yklt::assign_ids(e->cm.t, e->a_sig.data(), pending, e->a_shape, e->a_sigid, &n_shapes, &n_sigs);
+        }
+        begin_ms = now_ms() - t_b;
+    });
+    int rc = upload_tables(e);
+    if (!rc && try_lattice) rc = device_order(e);   // enqueued: the host is free for the eligibility tests below
+    const double t_a = now_ms();
+    e->worker.wait();
+    e->st.host_ms[0] += t_a - t_start;
+    e->st.host_ms[1] += begin_ms;
     if (rc) return rc;
+    if (gang_too_big) return e->fail(YK_ERR_ARG, "yk_cycle: a gang has more members than the sweep batch (raise yk_config.batch)");
+
+    Cycle c;
+    c.max_bindings = max_bindings; c.out = out;
+    // the first batch decides which commit the cycle starts on
+    const bool ins = e->ord.insensitive;
+    bool lattice = false;
+    size_t bsz0 = e->batch;
+    if (try_lattice) {
+        const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending);
+        lattice = el.ok;
+        if (lattice && ins) bsz0 = e->maxA;   // the whole static order in one launch
+    }
+    rc = fill_batch(e, bsz0, std::max<size_t>(bsz0, e->batch), max_bindings, e->slot[0], e->st);
+    if (lattice && !e->lt_force && !e->lt_auto) lattice = false;   // measured (profiles/r2_lattice_*): the host commit is still ahead
+    if (!rc && lattice && !e->lt_force && !e->slot[0].asks.empty()) {
+        // windows long enough to pay for a sub-run (scan + lattice + patch is a few microseconds, an ask on the host
+        // commit about 0.1): otherwise this is a many-shapes workload for the sweep + host commit
+        const size_t B0 = e->slot[0].asks.size();
+        yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+        const size_t w = yklt::estimate_windows(e->h_lt_shp.p, e->h_lt_sig.p, B0);
+        if (e->slot[0].asks.size() < 32 * w) lattice = false;
+    }
+    if (!rc && !lattice && e->slot[0].asks.size() > e->batch) {   // the first fill was sized for the device commit
+        e->ord.unfill(e->slot[0].snap, e->slot[0].asks, 0);
+        size_t b = e->batch;
+        rc = fill_batch(e, b, e->batch, max_bindings, e->slot[0], e->st);
+    }
+    e->lt_active = false;
+    if (!rc) {
+        if (lattice) {
+            e->lt_active = true;
+            e->st.lattice_cycles++;
+            bool handoff = false;
+            rc = run_lattice(e, c, handoff);
+            if (!rc) {
+                const int rce = lt_export(e);   // node tables current again, host and device
+                e->lt_active = false;
+                rc = rce;
+            }
+            if (!rc) {
+                const int* h = e->h_lt_hdr.p;
+                e->lt_total_subruns += (uint64_t)h[yklt::H_SUBRUNS];
+                e->st.lattice_subruns += (uint64_t)h[yklt::H_SUBRUNS]; e->st.lattice_fullscans += (uint64_t)h[yklt::H_FULLSCANS];
+                e->st.lattice_sorts += (uint64_t)h[yklt::H_SORTS]; e->st.lattice_elements += (uint64_t)h[yklt::H_ELEMS];
+                e->st.lattice_quick += (uint64_t)h[yklt::H_QUICK];
+            }
+            if (!rc && handoff && c.n < max_bindings) {
+                size_t b = e->batch;
+                rc = fill_batch(e, b, e->batch, (size_t)max_bindings - c.n, e->slot[0], e->st);
+                if (!rc) rc = run_host(e, c);
+            }
+        } else {
+            rc = run_host(e, c);
+        }
+    }
+    // ---- always: leave host and device node tables current, persist what was bound, no ask left in flight ----
+    int rc_end = YK_OK;
+    if (e->lt_active) { rc_end = lt_export(e); e->lt_active = false; }
+    else rc_end = end_epoch(e, false);
     e->cm.begin_epoch(e->epochW);   // nothing touched any more
     for (int k = 0; k < 4; ++k) { e->st.dbg[k] += e->cm.dbg[k]; e->cm.dbg[k] = 0; }
     for (int k = 0; k < 6; ++k) { e->st.prof[k] += e->cm.prof[k]; e->cm.prof[k] = 0; }
-    CK(cudaStreamSynchronize(e->stream));
-    e->ord.finish();
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess && !rc && !rc_end) rc_end = e->fail(YK_ERR_CUDA, "cudaStreamSynchronize at the end of the cycle");
+    if (rc) {
+        // the cycle broke off: the bindings made so far stand (they are returned), every ask still in flight is pending
+        // again, and the queue / application accounting is rebuilt from exactly the bindings returned
+        e->worker.wait();
+        for (Slot& sl : e->slot) { if (sl.B > 0 && sl.nchunks > 0) cudaEventSynchronize(sl.ev[(size_t)sl.nchunks - 1]); sl.asks.clear(); sl.B = 0; sl.nchunks = 0; }
+        for (uint32_t a : pending) if (e->a_state[a] == yk::ST_TENTATIVE) e->a_state[a] = yk::ST_PENDING;
+        for (uint32_t i = 0; i < c.n; ++i) {
+            const uint32_t a = out[i].ask;
+            for (int k = 0; k < e->D; ++k) {
+                const int64_t r = e->a_req[(size_t)k * e->maxA + a];
+                for (uint32_t q = e->p_queue[e->a_app[a]]; q != YK_NONE; q = e->q_parent[q]) e->q_alloc[(size_t)k * e->nq + q] += r;
+                e->p_alloc[(size_t)k * e->maxP + e->a_app[a]] += r;
+            }
+        }
+    } else {
+        e->ord.finish();
+    }
     for (uint32_t a : e->ord.slow_list) {
         if (slow && n_slow && *n_slow < slow_cap) slow[(*n_slow)++] = a;
     }
     for (uint32_t a : pending) if (e->a_state[a] == yk::ST_SKIPPED) e->st.skipped++;
-    *n_out = n;
+    *n_out = c.n;
     e->st.cycles++;
     e->st.total_ms += now_ms() - t_start;
-    return YK_OK;
+    return rc ? rc : rc_end;
 }
+
+extern "C" {
 
 int yk_ask_states(yk_engine* e, uint32_t n, const uint32_t* idx, uint8_t* out) {
     if (!e) return YK_ERR_ARG;

@@ -38,42 +38,52 @@
 #include <stdint.h>
 #include "yk_score.h"
 
+#ifndef YK_LT_THREADS
+#define YK_LT_THREADS 1024
+#endif
+
 #if defined(__CUDACC__)
 #define LT_DEV 1
 #define LT_HD __host__ __device__ __forceinline__
 #define LT_FN __device__ __forceinline__
-#define LT_FOR(i, n) for (int i = (int)threadIdx.x; i < (int)(n); i += yklt::THREADS)
+#define LT_NI __device__ __noinline__   /* the phases run once per sub-run: code size (instruction fetch), not call overhead, is what costs */
+#define LT_FOR(i, n) _Pragma("unroll 1") for (int i = (int)threadIdx.x; i < (int)(n); i += yklt::THREADS)
+#define LT_FOR32(i, n) _Pragma("unroll 1") for (int i = (int)threadIdx.x; i < (((int)(n) + 31) & ~31); i += yklt::THREADS)   /* whole warps */
 #define LT_SYNC() __syncthreads()
 #define LT_ONE if (threadIdx.x == 0)
+#define LT_PROF(k) do { if (a.prof && threadIdx.x == 0) { const long long _t = clock64(); a.prof[k] += _t - prof_t; prof_t = _t; } } while (0)
 #else
 #define LT_DEV 0
 #define LT_HD inline
 #define LT_FN inline
+#define LT_NI inline
 #define LT_FOR(i, n) for (int i = 0; i < (int)(n); ++i)
+#define LT_FOR32(i, n) for (int i = 0; i < (int)(n); ++i)
 #define LT_SYNC() ((void)0)
 #define LT_ONE if (true)
+#define LT_PROF(k) ((void)0)
 #endif
 
 namespace yklt {
 
-constexpr int THREADS = 1024;
+constexpr int THREADS = YK_LT_THREADS;
 constexpr int LCAP = 2048;              // lattice elements of one sub-run
 constexpr int FW = LCAP / 32;           // words per bitmap over the elements
 constexpr int KCAP = 512;               // asks per sub-run
-constexpr int SIGCAP = 128;             // distinct (consecutive) predicate signatures per sub-run
+constexpr int SIGCAP = 128;             // distinct predicate signatures per sub-run
 constexpr int SMAX = 8;                 // distinct request vectors ("shapes") per sub-run
 constexpr int DCAP = 63;                // deepest a box goes along one shape
 constexpr int VCAP = 256;               // states per node
-constexpr int SHAPE_IDS = 2048;         // shape ids a cycle may use (the host numbers the distinct request vectors)
-constexpr int NCAND = 8;                // candidate key thresholds per sub-run
+constexpr int HT = 1024;                // slots of the per-sub-run id tables (shape ids, signature ids)
+constexpr int NCAND = 6;                // candidate key thresholds per sub-run
+constexpr int ECNT = 512;               // up to this many non-base elements are merged in by counting, more by a bitonic sort
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint16_t NO_CHILD = 0xFFFFu;
 constexpr uint64_t KEY_INF = 0xFFFFFFFFFFFFFFFFull;
 
-// meta[] word of a batch entry (written by the host, which knows requests, signatures and gangs):
-//   bits 0-7 flags, bits 16-31 shape id (dense number of the request vector within the cycle, < SHAPE_IDS)
-constexpr uint32_t M_RUN = 1;           // request vector differs from the previous entry's (or first entry)
-constexpr uint32_t M_SIG = 2;           // predicate signature differs from the previous entry's (always set with M_RUN)
+// Per batch entry the host (which knows requests, signatures and gangs) writes three words:
+//   meta  flags;  shp  a number that is equal exactly for equal request vectors;  sig  a number that is equal exactly for
+//   equal predicate signatures (request, tolerations, required / forbidden labels, node name)
 constexpr uint32_t M_GSTART = 4;        // first member of a gang
 constexpr uint32_t M_GANG = 8;          // member of a gang
 
@@ -93,12 +103,14 @@ struct Args {
     int nlive;
     const int64_t* a_req; size_t lda;      // ask table (column-major, as in yk_kernels.cuh)
     const uint64_t* a_tol; const uint64_t* a_need; const uint64_t* a_deny; const uint32_t* a_node;
-    const uint32_t* asks; const uint32_t* meta; int B;
+    const uint32_t* asks; const uint32_t* meta; const uint32_t* shp; const uint32_t* sig; int B;
     uint32_t* res;                         // [B] node index or NONE
     int* hdr;                              // [H_WORDS]
     int64_t* ub;                           // [8] per-dimension upper bound of what any node can still hold (exact after a full scan)
     int insensitive;                       // 1: a failed ask does not end the batch (placement-insensitive order)
+    long long* prof;                       // optional [16]: SM clocks per phase, accumulated by thread 0 (nullptr: off)
 };
+enum { PF_STAGE = 0, PF_SCAN, PF_WINDOW, PF_BOUND, PF_LATTICE, PF_SORT, PF_LINKS, PF_CHAIN, PF_APPLY, PF_PATCH, PF_FULLSCAN, PF_N };
 
 // can a node in this state (available, total) take `req` once more (same fold as yk_gather_kernel: unusable -> nothing
 // fits; request <= min(max(0,total), max(0,available)) on every dimension)
@@ -115,15 +127,32 @@ LT_HD bool fits(bool usable, const int64_t* avail, const int64_t* total, const i
     return true;
 }
 
+// float64 score -> sort key of a node state; one copy of the divide sequences for the whole kernel
+template <int D>
+LT_NI uint64_t key_of(uint32_t policy, const double* w, const int64_t* total, const int64_t* avail) {
+    return yk_key_bits(yk_node_score(D, policy, w, total, avail, 1));
+}
+
+// would c * r overflow int64 (r >= 0, c >= 0)?  (a 64-bit divide costs a hundred instructions: the product's high word is free)
+LT_HD bool mul_overflows(int64_t r, int64_t c) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi((unsigned long long)r, (unsigned long long)c) != 0ull || (long long)((unsigned long long)r * (unsigned long long)c) < 0;
+#else
+    return c != 0 && r > INT64_MAX / c;
+#endif
+}
+
 LT_HD bool accepts(uint64_t taint, uint64_t label, uint32_t node, uint64_t tol, uint64_t need, uint64_t deny, uint32_t want) {
     if ((taint & ~tol) | (~label & need) | (label & deny)) return false;
     return want == NONE || want == node;
 }
 
+LT_HD int id_slot(uint32_t id) { return (int)((id * 2654435761u) >> 22); }   // 10 bits: HT slots
+
 template <int D>
 struct Shared {
     static constexpr int PMAX = D <= 4 ? 512 : 256;
-    // ---- scalars (written inside LT_ONE or by shared atomics, read after LT_SYNC) ----
+    // ---- scalars (written inside LT_ONE or by the block reductions, read after LT_SYNC) ----
     int n, P, nrows, nshapes, cut, gstart_before_cut;
     int nbase, nvalid, nt, tdone, need_more, status, hit, esc_pos, cnt_elems, total_slots, pick;
     unsigned long long bound_key, bound_sec, pos_key;
@@ -131,9 +160,9 @@ struct Shared {
     int sumv[NCAND];
     double tau[NCAND];
     int64_t sreq[SMAX * 8];       // request vector of each shape of the sub-run
-    // ---- staged positions ----
+    // ---- staged positions (column-major: consecutive threads touch consecutive banks) ----
     uint64_t okey[PMAX], orn[PMAX], taint[PMAX], label[PMAX];
-    int64_t avail[PMAX * D], total[PMAX * D];
+    int64_t avail[D * PMAX], total[D * PMAX];   // [k][p]
     uint8_t usable[PMAX];
     uint8_t depth[PMAX * SMAX];   // box of the node: states c with c_s <= depth[s]
     alignas(4) uint16_t cnt[PMAX * SMAX];   // allocations of each shape the chain gave to the position
@@ -146,38 +175,53 @@ struct Shared {
     uint16_t child[LCAP * SMAX];  // (element, shape) -> element of the node's next state
     uint32_t ROOM[SMAX * FW];     // per shape: the element's node can take one more of it
     uint32_t BASE[FW];            // elements that are a node's initial state
-    alignas(16) uint32_t F[SIGCAP * FW];   // ACCEPT rows; dead after the chain: scratch for the apply / patch phases
+    alignas(16) uint32_t F[SIGCAP * FW];   // ACCEPT rows; before the links phase and after the chain: scratch
     uint32_t scan[LCAP];
     uint64_t r_tol[SIGCAP], r_need[SIGCAP], r_deny[SIGCAP];
     uint32_t r_want[SIGCAP];
     uint8_t k_row[KCAP], k_meta[KCAP], k_ls[KCAP];
+    uint32_t k_shp[KCAP], k_sig[KCAP];
     int32_t sel[KCAP];            // element taken by the ask, -1 none
-    int shape_first[SHAPE_IDS];
-    uint8_t shape_loc[SHAPE_IDS];
-    // touched nodes sorted by their new (key, rn): lives in F after the chain
-    unsigned long long* t_key() { return reinterpret_cast<unsigned long long*>(F + LCAP); }
-    unsigned long long* t_rn() { return reinterpret_cast<unsigned long long*>(F + LCAP) + PMAX; }
-    const unsigned long long* t_key() const { return reinterpret_cast<const unsigned long long*>(F + LCAP); }
-    const unsigned long long* t_rn() const { return reinterpret_cast<const unsigned long long*>(F + LCAP) + PMAX; }
-    uint32_t* tmp() { return F; }   // LCAP words
+    int shp_tab[HT], sig_tab[HT];
+    // scratch inside F: [0, LCAP) words tmp; then the touched nodes sorted by their new (key, rn); then the same unsorted
+    LT_HD uint32_t* tmp() { return F; }
+    LT_HD unsigned long long* t_key() { return reinterpret_cast<unsigned long long*>(F + LCAP); }
+    LT_HD unsigned long long* t_rn() { return reinterpret_cast<unsigned long long*>(F + LCAP) + PMAX; }
+    LT_HD const unsigned long long* t_key() const { return reinterpret_cast<const unsigned long long*>(F + LCAP); }
+    LT_HD const unsigned long long* t_rn() const { return reinterpret_cast<const unsigned long long*>(F + LCAP) + PMAX; }
+    LT_HD unsigned long long* u_key() { return reinterpret_cast<unsigned long long*>(F + LCAP) + 2 * PMAX; }
+    LT_HD unsigned long long* u_rn() { return reinterpret_cast<unsigned long long*>(F + LCAP) + 3 * PMAX; }
+    // sort destination (before the links phase): all of F as LCAP (key, sec) pairs
+    LT_HD unsigned long long* d_key() { return reinterpret_cast<unsigned long long*>(F); }
+    LT_HD unsigned long long* d_sec() { return reinterpret_cast<unsigned long long*>(F) + LCAP; }
 };
-static_assert(SIGCAP * FW >= LCAP + 4 * 512, "scratch after the chain must fit the ACCEPT rows");
+static_assert(SIGCAP * FW >= LCAP + 8 * 512, "scratch after the chain must fit the ACCEPT rows");
+static_assert(SIGCAP * FW * 4 >= LCAP * 16, "the sort destination must fit the ACCEPT rows");
 static_assert(512 * SMAX <= 2 * LCAP, "corner keys use the element arrays as scratch");
 
 // ---- block-wide helpers (each is a sequence of LT_FOR regions: runs unchanged as plain loops on the host) -------
-// exclusive prefix sum of x[0..n) (n <= LCAP) in place, total in *tot (valid on thread 0 / the host); tmp has n words
-LT_FN void block_scan(uint32_t* x, uint32_t* tmp, int n, int* tot) {
+// exclusive prefix sum of x[0..n) (n <= 2 * THREADS) in place, total in *tot (valid on thread 0 / the host); tmp: 40 words
+LT_NI void block_scan(uint32_t* x, uint32_t* tmp, int n, int* tot) {
 #if LT_DEV
-    uint32_t* in = x; uint32_t* out = tmp;   // Hillis-Steele, ping-pong between x and tmp
-    for (int off = 1; off < n; off <<= 1) {
-        LT_FOR(i, n) out[i] = in[i] + (i >= off ? in[i - off] : 0u);
-        LT_SYNC();
-        uint32_t* sw = in; in = out; out = sw;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;
+    const uint32_t va = i0 < n ? x[i0] : 0u, vb = i1 < n ? x[i1] : 0u;
+    uint32_t incl = va + vb;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) tmp[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+        uint32_t wv = lane < THREADS / 32 ? tmp[lane] : 0u, wi = wv;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += u; }
+        tmp[lane] = wi - wv;
+        if (lane == 31) tmp[32] = wi;
     }
-    LT_FOR(i, n) out[i] = i ? in[i - 1] : 0u;   // inclusive -> exclusive, into the other buffer
-    LT_ONE *tot = n ? (int)in[n - 1] : 0;
-    LT_SYNC();
-    if (out != x) { LT_FOR(i, n) x[i] = out[i]; LT_SYNC(); }
+    __syncthreads();
+    const uint32_t base = tmp[wp] + incl - (va + vb);
+    if (i0 < n) x[i0] = base;
+    if (i1 < n) x[i1] = base + va;
+    if (tid == 0) *tot = (int)tmp[32];
+    __syncthreads();
 #else
     uint32_t run = 0;
     for (int i = 0; i < n; ++i) { const uint32_t v = x[i]; x[i] = run; run += v; }
@@ -185,9 +229,10 @@ LT_FN void block_scan(uint32_t* x, uint32_t* tmp, int n, int* tot) {
     (void)tmp;
 #endif
 }
+static_assert(2 * THREADS >= KCAP && 2 * THREADS >= 512, "block_scan covers two items per thread");
 
 // ascending bitonic sort of (key, sec) pairs, n a power of two
-LT_FN void block_sort(unsigned long long* key, unsigned long long* sec, int n) {
+LT_NI void block_sort(unsigned long long* key, unsigned long long* sec, int n) {
     for (int k = 2; k <= n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             LT_FOR(x, n >> 1) {
@@ -202,46 +247,30 @@ LT_FN void block_sort(unsigned long long* key, unsigned long long* sec, int n) {
         }
 }
 
-LT_FN void smin64(unsigned long long* p, unsigned long long v) {
-#if LT_DEV
-    atomicMin(p, v);
-#else
-    if (v < *p) *p = v;
-#endif
+// Sorted merge by counting: src[0, nb) is sorted, src[nb, n) is not (few entries).  Every entry counts the unsorted
+// entries before it (a broadcast loop) and, when it is itself unsorted, binary-searches the sorted part: its final index.
+LT_NI void block_merge_by_count(const unsigned long long* skey, const unsigned long long* ssec, int nb, int n,
+                                unsigned long long* dkey, unsigned long long* dsec) {
+    LT_FOR(i, n) {
+        const unsigned long long k = skey[i], c = ssec[i];
+        int before = 0;
+        for (int x = nb; x < n; ++x) before += ent_less(skey[x], ssec[x], k, c) ? 1 : 0;
+        int lo = i;
+        if (i >= nb) {
+            lo = 0;
+            int hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ent_less(skey[mid], ssec[mid], k, c)) lo = mid + 1; else hi = mid; }
+        }
+        dkey[lo + before] = k; dsec[lo + before] = c;
+    }
+    LT_SYNC();
 }
-LT_FN void smax64(unsigned long long* p, unsigned long long v) {
-#if LT_DEV
-    atomicMax(p, v);
-#else
-    if (v > *p) *p = v;
-#endif
-}
+
 LT_FN void smin32(int* p, int v) {
 #if LT_DEV
     atomicMin(p, v);
 #else
     if (v < *p) *p = v;
-#endif
-}
-LT_FN void smax32(int* p, int v) {
-#if LT_DEV
-    atomicMax(p, v);
-#else
-    if (v > *p) *p = v;
-#endif
-}
-LT_FN int sadd32(int* p, int v) {
-#if LT_DEV
-    return atomicAdd(p, v);
-#else
-    const int o = *p; *p += v; return o;
-#endif
-}
-LT_FN void sor32(uint32_t* p, uint32_t v) {
-#if LT_DEV
-    atomicOr(p, v);
-#else
-    *p |= v;
 #endif
 }
 LT_FN void sinc16(uint16_t* p) {   // 16-bit counter inside a 32-bit word of shared memory
@@ -254,6 +283,75 @@ LT_FN void sinc16(uint16_t* p) {   // 16-bit counter inside a 32-bit word of sha
 #endif
 }
 
+// Block-wide reductions into a shared word.  Every thread of the CTA calls them exactly once (outside LT_FOR) with the
+// value it accumulated over its own loop iterations (the neutral element when it has none): one shuffle tree per warp,
+// then at most one shared atomic per warp -- a 64-bit atomicMin on shared memory is a CAS loop, and a thousand threads
+// on one address serialize for tens of microseconds.  On the host the loop has already accumulated everything.
+LT_FN void red_min64(unsigned long long* p, unsigned long long v) {
+#if LT_DEV
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = u < v ? u : v; }
+    if ((threadIdx.x & 31) == 0 && v != KEY_INF) atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+LT_FN void red_max64(unsigned long long* p, unsigned long long v) {
+#if LT_DEV
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = u > v ? u : v; }
+    if ((threadIdx.x & 31) == 0 && v != 0ull) atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+LT_FN void red_add32(int* p, int v) {
+#if LT_DEV
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+LT_FN void red_max32(int* p, int v) {
+#if LT_DEV
+    v = __reduce_max_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+LT_FN void red_min32(int* p, int v) {
+#if LT_DEV
+    v = __reduce_min_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+// append: reserve one slot of a shared counter for every lane whose `take` is set; all 32 lanes of the warp call it
+// together (loops that use it run over a multiple of 32 items: LT_FOR32)
+LT_FN int warp_append(int* counter, bool take) {
+#if LT_DEV
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
+    int base = 0;
+    if (m && (threadIdx.x & 31) == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+#else
+    if (!take) return 0;
+    return (*counter)++;
+#endif
+}
+// one bitmap word from 32 consecutive items (LT_FOR32 loops: item index = bit index); the host ORs bit by bit
+LT_FN void put_bit(uint32_t* words, int item, bool bit) {
+#if LT_DEV
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, bit);
+    if ((threadIdx.x & 31) == 0) words[item >> 5] = m;
+#else
+    if ((item & 31) == 0) words[item >> 5] = 0u;
+    if (bit) words[item >> 5] |= 1u << (item & 31);
+#endif
+}
+
 template <typename T>
 LT_FN T ldg(const T* p) {
 #if LT_DEV
@@ -263,20 +361,17 @@ LT_FN T ldg(const T* p) {
 #endif
 }
 
-// ---- per node: the depth of its box along every shape for a key threshold tau (score units) ------------------
+// ---- per node: the depth of its box along every shape for a key gap (tau - score, float) ----------------------
 // d_s = how many allocations of shape s alone keep the (linearly estimated) score below tau, capped; then the box is
-// shrunk (deepest side halved) until it has at most VCAP states.  A heuristic: exactness never depends on the depths,
-// only on the bound computed from the true keys just outside the boxes.  Returns the number of states.
-template <int D>
-LT_HD int box_of(double sc, double tau, const double* dlt /*[S]*/, int S, uint8_t* d /*[SMAX]*/) {
+// shrunk (deepest side halved) until it has at most VCAP states.  A heuristic, in single precision: exactness never
+// depends on the depths, only on the bound computed from the true keys just outside the boxes.  Returns the states.
+LT_NI int box_of(float gap, const float* inv /*[S] 1/delta, 0 = the shape does not move the key */, int S, uint8_t* d /*[SMAX]*/) {
     int v = 1;
     for (int s = 0; s < S; ++s) {
         int x = 0;
-        if (sc < tau) {
-            if (dlt[s] > 0.0) {
-                const double q = (tau - sc) / dlt[s];
-                x = q >= (double)DCAP ? DCAP : (int)q;
-            } else x = DCAP;   // the shape does not move the key at all
+        if (gap > 0.0f) {
+            if (inv[s] > 0.0f) { const float q = gap * inv[s]; x = q >= (float)DCAP ? DCAP : (int)q; }
+            else x = DCAP;
         }
         d[s] = (uint8_t)x;
         v *= x + 1;
@@ -292,24 +387,26 @@ LT_HD int box_of(double sc, double tau, const double* dlt /*[S]*/, int S, uint8_
     return v;
 }
 
-// estimated score increase of one allocation of `req` on the node (the weighted mean of req/total, as yk_node_score)
+// 1 / (estimated score increase of one allocation of `req` on the node): the weighted mean of req/total as yk_node_score
 template <int D>
-LT_HD double delta_of(const double* w, const int64_t* total, const int64_t* req) {
-    double u = 0.0, tw = 0.0;
+LT_NI float inv_delta_of(const double* w, const int64_t* total, const int64_t* req) {
+    float u = 0.0f, tw = 0.0f;
     for (int k = 0; k < D; ++k) {
         if (!(w[k] > 0.0) || total[k] <= 0) continue;
-        u += w[k] * ((double)req[k] / (double)total[k]);
-        tw += w[k];
+        u += (float)w[k] * ((float)req[k] / (float)total[k]);
+        tw += (float)w[k];
     }
-    return tw > 0.0 ? u / tw : 0.0;
+    return (tw > 0.0f && u > 0.0f) ? tw / u : 0.0f;
 }
 
 // number of touched entries (sorted t_key/t_rn[0..nt)) that sort before (key, rn)
 template <int D>
-LT_FN int touched_before(const Shared<D>& s, int nt, uint64_t key, uint64_t rn) {
+LT_NI int touched_before(const Shared<D>& s, int nt, uint64_t key, uint64_t rn) {
     const unsigned long long* tk = s.t_key();
     const unsigned long long* tr = s.t_rn();
-    int lo = 0, hi = nt;
+    if (nt == 0 || !ent_less(tk[0], tr[0], key, rn)) return 0;
+    if (ent_less(tk[nt - 1], tr[nt - 1], key, rn)) return nt;
+    int lo = 1, hi = nt - 1;   // tk[0] < x, tk[nt-1] >= x
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (ent_less(tk[mid], tr[mid], key, rn)) lo = mid + 1; else hi = mid;
@@ -321,22 +418,26 @@ LT_FN int touched_before(const Shared<D>& s, int nt, uint64_t key, uint64_t rn) 
 // touched positions: sub-run mode (esc_pos < 0): positions p < P with tb[p+1] > tb[p];
 //                    single mode (esc_pos >= 0): exactly position esc_pos
 template <int D>
-LT_FN void patch_order(const Args& a, Shared<D>& s, const Ent* src, Ent* dst) {
+LT_NI void patch_order(const Args& a, Shared<D>& s, const Ent* src, Ent* dst) {
     const int nt = s.nt, P = s.P, esc = s.esc_pos, nlive = a.nlive;
     const unsigned long long* tk = s.t_key();
     const unsigned long long* tr = s.t_rn();
-    LT_FOR(p, nlive) {
+    LT_FOR32(p, nlive) {
+        const bool in = p < nlive;
         Ent e;
-        e.key = ldg(&src[p].key); e.rn = ldg(&src[p].rn);
+        e.key = in ? ldg(&src[p].key) : KEY_INF; e.rn = in ? ldg(&src[p].rn) : KEY_INF;
+        const int ib = in ? touched_before(s, nt, e.key, e.rn) : nt;
+        // the touched entries that fall between the old tuples of positions p-1 and p are written by position p
+        int ibp;
+#if LT_DEV
+        ibp = __shfl_up_sync(0xFFFFFFFFu, ib, 1);
+        if ((threadIdx.x & 31) == 0) ibp = (in && p > 0) ? touched_before(s, nt, ldg(&src[p - 1].key), ldg(&src[p - 1].rn)) : 0;
+#else
+        ibp = p > 0 ? touched_before(s, nt, src[p - 1].key, src[p - 1].rn) : 0;
+#endif
+        if (!in) continue;
         const bool touched = esc >= 0 ? (p == esc) : (p < P && s.tb[p + 1] != s.tb[p]);
         const int tbp = esc >= 0 ? (p > esc ? 1 : 0) : (p < P ? (int)s.tb[p] : nt);
-        const int ib = touched_before(s, nt, e.key, e.rn);
-        // the touched entries that fall between the old tuples of positions p-1 and p are written by position p
-        int ibp = 0;
-        if (p > 0) {
-            const uint64_t pk = ldg(&src[p - 1].key), pr = ldg(&src[p - 1].rn);
-            ibp = touched_before(s, nt, pk, pr);
-        }
         const int before = p - tbp;   // untouched old entries before position p
         for (int i = ibp; i < ib; ++i) { Ent te; te.key = tk[i]; te.rn = tr[i]; dst[i + before] = te; }
         if (!touched) dst[before + ib] = e;
@@ -352,35 +453,46 @@ LT_FN void patch_order(const Args& a, Shared<D>& s, const Ent* src, Ent* dst) {
 // asks [0, n) of the sub-run.  Sets sel[], tdone (asks decided), need_more (an ask found nothing below the bound: the
 // sub-run ends before it -- before its gang when it is a gang member).
 template <int D>
-LT_FN void chain(Shared<D>& s) {
+LT_NI void chain(Shared<D>& s) {
     const int n = s.n, nw = (s.nvalid + 31) >> 5;
 #if LT_DEV
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
-        uint32_t a0 = lane < nw ? s.BASE[lane] : 0u, a1 = lane + 32 < nw ? s.BASE[lane + 32] : 0u;   // AVAIL words lane, lane+32
+        const bool h0 = lane < nw, h1 = lane + 32 < nw;
+        uint32_t a0 = h0 ? s.BASE[lane] : 0u, a1 = h1 ? s.BASE[lane + 32] : 0u;   // AVAIL words lane, lane+32
         uint32_t g0 = 0, g1 = 0;   // snapshot at the gang start
         int gbeg = -1, done = n, more = 0;
+        // two-deep software pipeline: the indices of ask i+1 and the candidate words of ask i are loaded ahead
+        uint32_t m = s.k_meta[0];
+        int sh = s.k_ls[0], row = s.k_row[0];
+        uint32_t w0 = h0 ? (s.F[row * FW + lane] & s.ROOM[sh * FW + lane]) : 0u;
+        uint32_t w1 = h1 ? (s.F[row * FW + lane + 32] & s.ROOM[sh * FW + lane + 32]) : 0u;
+        uint32_t nm = n > 1 ? s.k_meta[1] : 0u;
+        int nsh = n > 1 ? s.k_ls[1] : 0, nrow = n > 1 ? s.k_row[1] : 0;
         for (int i = 0; i < n; ++i) {
-            const uint32_t m = s.k_meta[i];
+            // loads for the next two asks first: their latency hides behind this ask's ballot / shuffle
+            const uint32_t xw0 = h0 ? (s.F[nrow * FW + lane] & s.ROOM[nsh * FW + lane]) : 0u;
+            const uint32_t xw1 = h1 ? (s.F[nrow * FW + lane + 32] & s.ROOM[nsh * FW + lane + 32]) : 0u;
+            const int i2 = i + 2 < n ? i + 2 : i;
+            const uint32_t m2 = s.k_meta[i2];
+            const int sh2 = s.k_ls[i2], row2 = s.k_row[i2];
             if (m & M_GSTART) { gbeg = i; g0 = a0; g1 = a1; }
             else if (!(m & M_GANG)) gbeg = -1;
-            const int sh = s.k_ls[i];
-            const uint32_t* row = s.F + (int)s.k_row[i] * FW;
-            const uint32_t* room = s.ROOM + sh * FW;
-            const uint32_t f0 = lane < nw ? (row[lane] & room[lane] & a0) : 0u;
-            const uint32_t f1 = lane + 32 < nw ? (row[lane + 32] & room[lane + 32] & a1) : 0u;
+            const uint32_t f0 = w0 & a0, f1 = w1 & a1;
             const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, f0 != 0u);
-            int e = -1, ch = -1;
+            int e = -1;
             if (b0) {
                 const int wl = __ffs((int)b0) - 1;
-                if (lane == wl) { const int bit = __ffs((int)f0) - 1; a0 &= ~(1u << bit); e = wl * 32 + bit; ch = s.child[e * SMAX + sh]; }
-                e = __shfl_sync(0xFFFFFFFFu, e, wl); ch = __shfl_sync(0xFFFFFFFFu, ch, wl);
+                const int bit = __shfl_sync(0xFFFFFFFFu, __ffs((int)f0) - 1, wl);
+                if (lane == wl) a0 &= ~(1u << bit);
+                e = wl * 32 + bit;
             } else {
                 const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, f1 != 0u);
                 if (b1) {
                     const int wl = __ffs((int)b1) - 1;
-                    if (lane == wl) { const int bit = __ffs((int)f1) - 1; a1 &= ~(1u << bit); e = (wl + 32) * 32 + bit; ch = s.child[e * SMAX + sh]; }
-                    e = __shfl_sync(0xFFFFFFFFu, e, wl); ch = __shfl_sync(0xFFFFFFFFu, ch, wl);
+                    const int bit = __shfl_sync(0xFFFFFFFFu, __ffs((int)f1) - 1, wl);
+                    if (lane == wl) a1 &= ~(1u << bit);
+                    e = (wl + 32) * 32 + bit;
                 }
             }
             if (e < 0) {
@@ -389,12 +501,15 @@ LT_FN void chain(Shared<D>& s) {
                 else done = i;
                 break;
             }
+            const int ch = s.child[e * SMAX + sh];   // every lane reads the same half-word: a broadcast
             if (ch != (int)NO_CHILD) {   // the node's next state becomes available
                 const int wd = ch >> 5;
                 if (wd == lane) a0 |= 1u << (ch & 31);
                 else if (wd == lane + 32) a1 |= 1u << (ch & 31);
             }
             if (lane == 0) s.sel[i] = e;
+            m = nm; sh = nsh; row = nrow; w0 = xw0; w1 = xw1;
+            nm = m2; nsh = sh2; nrow = row2;
         }
         if (lane == 0) { s.tdone = done; s.need_more = more; }
     }
@@ -429,6 +544,13 @@ LT_FN void chain(Shared<D>& s) {
 #endif
 }
 
+// gather a staged position's columns into contiguous arrays
+template <int D>
+LT_FN void load_pos(const Shared<D>& s, int p, int64_t* av, int64_t* to) {
+    constexpr int PMAX = Shared<D>::PMAX;
+    for (int k = 0; k < D; ++k) { av[k] = s.avail[k * PMAX + p]; to[k] = s.total[k * PMAX + p]; }
+}
+
 // ---- the batch --------------------------------------------------------------------------------------------------
 template <int D>
 LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
@@ -440,69 +562,97 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
     int subruns = 0, fullscans = 0, sorts = 0, quick = 0, escs = 0;
     long long elems = 0;
     int fresh = 0;             // 1: the previous sub-run decided nothing for entry t: decide it by a full scan
-    int dead_sig = 0;          // entry t-1 was a certain NOFIT and nothing was committed since: same signature -> NOFIT too
+    int dead = 0;              // entry t-1 was a certain NOFIT and nothing was committed since: the same signature -> NOFIT too
+    uint32_t dead_sig = 0;
+    int Pwant = PMAX / 2;      // positions to scan: follows what the windows actually use
     LT_ONE s.status = ST_DONE;
-    LT_FOR(i, SHAPE_IDS) s.shape_first[i] = 0x7FFFFFFF;
+    LT_FOR(i, HT) { s.shp_tab[i] = 0x7FFFFFFF; s.sig_tab[i] = 0x7FFFFFFF; }
     LT_SYNC();
+#if LT_DEV
+    long long prof_t = clock64();
+#endif
 
     while (t < B && status == ST_DONE) {
         // ================= stage the asks of the sub-run =================
         const int navail = B - t < KCAP ? B - t : KCAP;
         LT_ONE { s.cut = navail; s.gstart_before_cut = 0; s.nshapes = 0; }
-        LT_FOR(i, navail) {
-            const uint32_t m = ldg(&a.meta[t + i]);
-            s.k_meta[i] = (uint8_t)m;
-            s.sel[i] = (int32_t)(m >> 16);   // shape id, until the chain needs sel[]
+        LT_FOR32(i, navail) {
+            const bool in = i < navail;
+            const uint32_t shp = in ? ldg(&a.shp[t + i]) : 0u, sg = in ? ldg(&a.sig[t + i]) : 0u;
+            if (in) { s.k_meta[i] = (uint8_t)ldg(&a.meta[t + i]); s.k_shp[i] = shp; s.k_sig[i] = sg; s.sel[i] = -1; }
+            // the first entry with an id leads it: lowest index per table slot (one atomic per distinct id and warp)
+#if LT_DEV
+            const unsigned act = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) {
+                const unsigned ms = __match_any_sync(act, shp), mg = __match_any_sync(act, sg);
+                if ((threadIdx.x & 31) == __ffs((int)ms) - 1) atomicMin(&s.shp_tab[id_slot(shp)], i);
+                if ((threadIdx.x & 31) == __ffs((int)mg) - 1) atomicMin(&s.sig_tab[id_slot(sg)], i);
+            }
+#else
+            if (in) { smin32(&s.shp_tab[id_slot(shp)], i); smin32(&s.sig_tab[id_slot(sg)], i); }
+#endif
         }
         LT_SYNC();
-        LT_FOR(i, navail) { if (s.sel[i] >= SHAPE_IDS) smin32(&s.cut, i); else smin32(&s.shape_first[s.sel[i]], i); }
+        // leaders (an entry whose id differs from its slot's leader leads itself: never a wrong merge, at worst a
+        // duplicate shape / row); local shape numbers and rows in order of first appearance: one scan, two counters
+        LT_FOR(i, navail) {
+            const int ls = s.shp_tab[id_slot(s.k_shp[i])], lg = s.sig_tab[id_slot(s.k_sig[i])];
+            const bool lead_s = ls == i || s.k_shp[ls] != s.k_shp[i], lead_g = lg == i || s.k_sig[lg] != s.k_sig[i];
+            s.scan[i] = (lead_s ? 1u : 0u) | (lead_g ? 0x10000u : 0u);
+        }
         LT_SYNC();
-        // local shape numbers in order of first appearance; rows: a new one wherever the signature changes
-        LT_FOR(i, navail) s.scan[i] = (s.sel[i] < SHAPE_IDS && s.shape_first[s.sel[i]] == i) ? 1u : 0u;
-        LT_SYNC();
-        { int tot; block_scan(s.scan, (uint32_t*)s.e_sec, navail, &tot); (void)tot; }
-        LT_FOR(i, navail) if (s.sel[i] < SHAPE_IDS && s.shape_first[s.sel[i]] == i) {
-            const int loc = (int)s.scan[i];
-            s.shape_loc[s.sel[i]] = (uint8_t)(loc < 255 ? loc : 255);
-            if (loc < SMAX) {
-                const uint32_t ask = ldg(&a.asks[t + i]);
-                for (int k = 0; k < D; ++k) s.sreq[loc * 8 + k] = ldg(&a.a_req[(size_t)k * a.lda + ask]);
+        { int tot; block_scan(s.scan, s.tmp(), navail, &tot); (void)tot; }
+        LT_FOR(i, navail) {
+            const int ls = s.shp_tab[id_slot(s.k_shp[i])], lg = s.sig_tab[id_slot(s.k_sig[i])];
+            const bool lead_s = ls == i || s.k_shp[ls] != s.k_shp[i], lead_g = lg == i || s.k_sig[lg] != s.k_sig[i];
+            if (lead_s) {
+                const int loc = (int)(s.scan[i] & 0xFFFFu);
+                if (loc >= SMAX) smin32(&s.cut, i);
+                else {
+                    s.k_ls[i] = (uint8_t)loc;
+                    const uint32_t ask = ldg(&a.asks[t + i]);
+                    for (int k = 0; k < D; ++k) s.sreq[loc * 8 + k] = ldg(&a.a_req[(size_t)k * a.lda + ask]);
+                }
+            }
+            if (lead_g) {
+                const int row = (int)(s.scan[i] >> 16);
+                if (row >= SIGCAP) smin32(&s.cut, i);
+                else {
+                    s.k_row[i] = (uint8_t)row;
+                    const uint32_t ask = ldg(&a.asks[t + i]);
+                    s.r_tol[row] = ldg(&a.a_tol[ask]); s.r_need[row] = ldg(&a.a_need[ask]); s.r_deny[row] = ldg(&a.a_deny[ask]);
+                    s.r_want[row] = ldg(&a.a_node[ask]);
+                }
             }
         }
         LT_SYNC();
-        LT_FOR(i, navail) if (s.sel[i] < SHAPE_IDS) {
-            const int loc = s.shape_loc[s.sel[i]];
-            if (loc >= SMAX) smin32(&s.cut, i); else s.k_ls[i] = (uint8_t)loc;
-        }
-        LT_FOR(i, navail) s.scan[i] = (i == 0 || (s.k_meta[i] & M_SIG)) ? 1u : 0u;
-        LT_SYNC();
-        { int tot; block_scan(s.scan, (uint32_t*)s.e_sec, navail, &tot); (void)tot; }
+        int n = s.cut;   // everything before the first entry that would need a 9th shape / 129th row
+        int my_shapes = 0, my_rows = 0;
         LT_FOR(i, navail) {
-            const int row = (int)s.scan[i] + ((i == 0 || (s.k_meta[i] & M_SIG)) ? 1 : 0) - 1;
-            if (row >= SIGCAP) smin32(&s.cut, i); else s.k_row[i] = (uint8_t)row;
-            if (s.sel[i] < SHAPE_IDS) s.shape_first[s.sel[i]] = 0x7FFFFFFF;   // leave the table clean for the next sub-run
+            const int ls = s.shp_tab[id_slot(s.k_shp[i])], lg = s.sig_tab[id_slot(s.k_sig[i])];
+            if (i < n) {
+                if (ls != i && s.k_shp[ls] == s.k_shp[i]) s.k_ls[i] = s.k_ls[ls];
+                if (lg != i && s.k_sig[lg] == s.k_sig[i]) s.k_row[i] = s.k_row[lg];
+                my_shapes = (int)s.k_ls[i] + 1 > my_shapes ? (int)s.k_ls[i] + 1 : my_shapes;
+                my_rows = (int)s.k_row[i] + 1 > my_rows ? (int)s.k_row[i] + 1 : my_rows;
+            }
         }
+        red_max32(&s.nshapes, my_shapes);
+        LT_ONE s.nrows = 0;
         LT_SYNC();
-        int n = s.cut;
+        red_max32(&s.nrows, my_rows);
+        LT_FOR(i, navail) { s.shp_tab[id_slot(s.k_shp[i])] = 0x7FFFFFFF; s.sig_tab[id_slot(s.k_sig[i])] = 0x7FFFFFFF; }   // clean for the next sub-run
         // never cut inside a gang
         const uint32_t mnext = n < navail ? (uint32_t)s.k_meta[n] : (t + n < B ? ldg(&a.meta[t + n]) : 0u);
         if (n > 0 && (mnext & M_GANG) && !(mnext & M_GSTART)) {
-            LT_FOR(i, n) if (s.k_meta[i] & M_GSTART) smax32(&s.gstart_before_cut, i);
+            int my_g = 0;
+            LT_FOR(i, n) if (s.k_meta[i] & M_GSTART) my_g = i > my_g ? i : my_g;
+            red_max32(&s.gstart_before_cut, my_g);
             LT_SYNC();
             n = s.gstart_before_cut;   // 0: the gang does not fit a sub-run
         }
         if (n == 0) { status = ST_HANDOFF; break; }
-        LT_FOR(i, n) {
-            smax32(&s.nshapes, (int)s.k_ls[i] + 1);
-            s.sel[i] = -1;
-            if (i == 0 || (s.k_meta[i] & M_SIG)) {
-                const uint32_t ask = ldg(&a.asks[t + i]);
-                const int row = s.k_row[i];
-                s.r_tol[row] = ldg(&a.a_tol[ask]); s.r_need[row] = ldg(&a.a_need[ask]); s.r_deny[row] = ldg(&a.a_deny[ask]);
-                s.r_want[row] = ldg(&a.a_node[ask]);
-            }
-        }
-        LT_ONE { s.n = n; s.nrows = (int)s.k_row[n - 1] + 1; }   // rows are numbered in entry order
+        LT_ONE s.n = n;
         LT_SYNC();
         const int nrows = s.nrows, S = s.nshapes;
         const bool gang0 = (s.k_meta[0] & M_GANG) != 0;
@@ -511,23 +661,25 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
         // ================= hopeless request: some dimension exceeds what any node has left =================
         bool hopeless = false;
         for (int k = 0; k < D; ++k) if (req0[k] > ldg(&a.ub[k])) hopeless = true;
-        if (dead_sig && !(s.k_meta[0] & M_SIG) && !gang0) hopeless = true;   // same signature as the NOFIT just decided, same state
+        if (dead && s.k_sig[0] == dead_sig && !gang0) hopeless = true;   // same signature as the NOFIT just decided, same state
         if (hopeless) {
             // the first entry (its whole gang when it is a gang member) is a certain NOFIT
             int g1 = 1;
             if (gang0) while (g1 < n && (s.k_meta[g1] & M_GANG) && !(s.k_meta[g1] & M_GSTART)) ++g1;
+            const uint32_t sg0 = s.k_sig[0];
             LT_FOR(i, g1) a.res[t + i] = NONE;
             LT_SYNC();
             ++quick;
             t += g1;
-            dead_sig = gang0 ? 0 : 1;
+            dead = gang0 ? 0 : 1; dead_sig = sg0;
             if (!a.insensitive) status = ST_STOPPED;
             continue;
         }
 
+        LT_PROF(PF_STAGE);
         if (!fresh) {
             // ================= scan: stage the first P positions =================
-            const int P = nlive < PMAX ? nlive : PMAX;
+            const int P = nlive < Pwant ? nlive : Pwant;
             const Ent* cur = a.ord[buf];
             LT_ONE {
                 s.P = P; s.nt = 0; s.esc_pos = -1; s.bound_sec = KEY_INF;
@@ -540,14 +692,15 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 const uint64_t key = ldg(&cur[p].key), rn = ldg(&cur[p].rn);
                 const uint32_t node = (uint32_t)rn;
                 const int64_t* r = a.rec + (size_t)node * RS;
-                for (int k = 0; k < D; ++k) { s.avail[p * D + k] = ldg(&r[k]); s.total[p * D + k] = ldg(&r[D + k]); }
+                for (int k = 0; k < D; ++k) { s.avail[k * PMAX + p] = ldg(&r[k]); s.total[k * PMAX + p] = ldg(&r[D + k]); }
                 s.okey[p] = key; s.orn[p] = rn;
                 s.taint[p] = (uint64_t)ldg(&r[2 * D]); s.label[p] = (uint64_t)ldg(&r[2 * D + 1]);
                 const uint32_t fl = (uint32_t)(uint64_t)ldg(&r[2 * D + 2]);
                 s.usable[p] = ((fl & 1u) && !(fl & 2u)) ? 1 : 0;
-                for (int x = 0; x < SMAX; ++x) s.cnt[p * SMAX + x] = 0;
+                for (int x = 0; x < SMAX; x += 2) *reinterpret_cast<uint32_t*>(&s.cnt[p * SMAX + x]) = 0u;
             }
             LT_SYNC();
+            LT_PROF(PF_SCAN);
             // ================= window: key threshold and the boxes =================
             // candidates: the keys at positions P, P/2, P/4 ...; the largest whose boxes hold at most LCAP states wins
             LT_ONE {
@@ -557,17 +710,24 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 }
             }
             LT_SYNC();
-            LT_FOR(p, P) {
-                double dlt[SMAX];
-                uint8_t d[SMAX];
-                for (int x = 0; x < S; ++x) dlt[x] = delta_of<D>(a.w, s.total + p * D, s.sreq + x * 8);
-                const double sc = yk_key_to_score(s.okey[p]);
-                for (int c = 0; c < NCAND; ++c) {
-                    const int v = s.usable[p] ? box_of<D>(sc, s.tau[c], dlt, S, d) : 1;
-                    sadd32(&s.sumv[c], v);
+            {
+                int my_v[NCAND];
+                for (int c = 0; c < NCAND; ++c) my_v[c] = 0;
+                LT_FOR(p, P) {
+                    float inv[SMAX];
+                    uint8_t d[SMAX];
+                    int64_t av[D], to[D];
+                    load_pos<D>(s, p, av, to);
+                    for (int x = 0; x < S; ++x) inv[x] = inv_delta_of<D>(a.w, to, s.sreq + x * 8);
+                    const double sc = yk_key_to_score(s.okey[p]);
+                    for (int c = 0; c < NCAND; ++c) {
+                        const double g = s.tau[c] - sc;
+                        my_v[c] += s.usable[p] ? box_of(g > 1e30 ? 1e30f : (float)g, inv, S, d) : 1;
+                    }
                 }
+                for (int c = 0; c < NCAND; ++c) red_add32(&s.sumv[c], my_v[c]);
+                LT_SYNC();
             }
-            LT_SYNC();
             LT_ONE {
                 int pick = NCAND - 1;
                 for (int c = NCAND - 1; c >= 0; --c) if (s.sumv[c] <= LCAP) pick = c;
@@ -575,11 +735,17 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             }
             LT_SYNC();
             const double tau = s.tau[s.pick];
+            // the next sub-run scans what this window used: twice as far when the widest candidate won, half when a
+            // quarter would have done
+            Pwant = s.pick == 0 ? (2 * P < PMAX ? 2 * P : PMAX) : (s.pick >= 3 ? (P / 2 > 64 ? P / 2 : 64) : P);
             LT_FOR(p, P) {
-                double dlt[SMAX];
+                float inv[SMAX];
                 uint8_t d[SMAX];
-                for (int x = 0; x < S; ++x) { dlt[x] = delta_of<D>(a.w, s.total + p * D, s.sreq + x * 8); d[x] = 0; }
-                const int v = s.usable[p] ? box_of<D>(yk_key_to_score(s.okey[p]), tau, dlt, S, d) : 1;
+                int64_t av[D], to[D];
+                load_pos<D>(s, p, av, to);
+                for (int x = 0; x < S; ++x) { inv[x] = inv_delta_of<D>(a.w, to, s.sreq + x * 8); d[x] = 0; }
+                const double g = tau - yk_key_to_score(s.okey[p]);
+                const int v = s.usable[p] ? box_of(g > 1e30 ? 1e30f : (float)g, inv, S, d) : 1;
                 for (int x = 0; x < SMAX; ++x) s.depth[p * SMAX + x] = x < S && s.usable[p] ? d[x] : 0;
                 s.scan[p] = (uint32_t)v;
             }
@@ -599,39 +765,47 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             }
             LT_ONE s.off[P] = (uint32_t)total_slots;
             LT_SYNC();
+            LT_PROF(PF_WINDOW);
             // ================= bound: the smallest key just outside any box =================
             // element order = (key, NodeID rank, allocations in the state); sec packs rank << 32 | allocations << 22 | slot
+            unsigned long long my_bound = KEY_INF;
             LT_FOR(x, P * S) {
                 const int p = x / S, sh = x % S;
                 const int j = s.depth[p * SMAX + sh] + 1;
-                int64_t av[D];
+                int64_t av[D], to[D];
+                load_pos<D>(s, p, av, to);
                 bool ok = s.usable[p] != 0;
                 for (int k = 0; k < D && ok; ++k) {
                     const int64_t r = s.sreq[sh * 8 + k];
-                    if (r > 0 && r > INT64_MAX / j) ok = false;
-                    av[k] = s.avail[p * D + k] - (int64_t)(j - 1) * r;   // the state before the j-th allocation
+                    if (r > 0 && mul_overflows(r, j)) ok = false;
+                    av[k] -= (int64_t)(j - 1) * r;   // the state before the j-th allocation
                 }
                 uint64_t tk = KEY_INF;
-                if (ok && fits<D>(true, av, s.total + p * D, s.sreq + sh * 8)) {
+                if (ok && fits<D>(true, av, to, s.sreq + sh * 8)) {
                     for (int k = 0; k < D; ++k) av[k] -= s.sreq[sh * 8 + k];
-                    tk = yk_key_bits(yk_node_score(D, a.policy, a.w, s.total + p * D, av, 1));
-                    smin64(&s.bound_key, tk);
+                    tk = key_of<D>(a.policy, a.w, to, av);
+                    my_bound = tk < my_bound ? tk : my_bound;
                 }
                 if (x < LCAP) s.e_key[x] = tk; else s.e_sec[x - LCAP] = tk;   // scratch until the elements are written (P * S <= 2 LCAP)
             }
+            red_min64(&s.bound_key, my_bound);
             LT_SYNC();
             {
                 const uint64_t bk0 = s.bound_key;
+                unsigned long long my_sec = KEY_INF;
                 LT_FOR(x, P * S) if ((x < LCAP ? s.e_key[x] : s.e_sec[x - LCAP]) == bk0 && bk0 != KEY_INF) {
                     const int p = x / S, sh = x % S;
-                    smin64(&s.bound_sec, ((s.orn[p] >> 32) << 32) | ((unsigned long long)(s.depth[p * SMAX + sh] + 1) << 22));
+                    const unsigned long long v = ((s.orn[p] >> 32) << 32) | ((unsigned long long)(s.depth[p * SMAX + sh] + 1) << 22);
+                    my_sec = v < my_sec ? v : my_sec;
                 }
-                LT_ONE if (P < nlive && s.pos_key == bk0) smin64(&s.bound_sec, (ldg(&cur[P].rn) >> 32) << 32);
+                LT_ONE if (P < nlive && s.pos_key == bk0) { const unsigned long long v = (ldg(&cur[P].rn) >> 32) << 32; my_sec = v < my_sec ? v : my_sec; }
+                red_min64(&s.bound_sec, my_sec);
                 LT_SYNC();
             }
             const uint64_t bk = s.bound_key, bs = s.bound_sec;
+            LT_PROF(PF_BOUND);
             // ================= lattice: the states of every box =================
-            // bases (state 0) keep their position order; the other states are appended and sorted in afterwards
+            // bases (state 0) keep their position order; the other states are appended and merged in afterwards
             LT_FOR(p, P) {
                 const uint64_t sec = ((s.orn[p] >> 32) << 32) | (unsigned long long)s.off[p];
                 s.scan[p] = (s.usable[p] && ent_less(s.okey[p], sec, bk, bs)) ? 1u : 0u;
@@ -644,98 +818,101 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 if (s.usable[p] && ent_less(s.okey[p], sec, bk, bs)) { const int x = (int)s.scan[p]; s.e_key[x] = s.okey[p]; s.e_sec[x] = sec; }
             }
             LT_SYNC();
-            LT_FOR(x, total_slots) {
-                const int p = s.slot_p[x];
-                int loc = x - (int)s.off[p];
-                if (loc == 0) continue;   // the base
-                int64_t av[D];
-                for (int k = 0; k < D; ++k) av[k] = s.avail[p * D + k];
-                int csum = 0;
-                bool ok = true;
-                // the state is reachable iff its allocations fit one after the other (any order: the tests are monotone)
-                for (int sh = 0; sh < S; ++sh) {
-                    const int dim = s.depth[p * SMAX + sh] + 1;
-                    const int c = loc % dim;
-                    loc /= dim;
-                    csum += c;
-                    for (int k = 0; k < D && ok; ++k) {
-                        const int64_t r = s.sreq[sh * 8 + k];
-                        if (c > 0 && r > 0) {
-                            if (r > INT64_MAX / c) { ok = false; break; }
-                            const int64_t tt = s.total[p * D + k] < 0 ? 0 : s.total[p * D + k];
-                            if (r > tt) { ok = false; break; }
-                            av[k] -= (int64_t)c * r;
-                            if (av[k] < 0) { ok = false; break; }
+            LT_FOR32(x, total_slots) {
+                bool take = false;
+                uint64_t key = 0, sec = 0;
+                if (x < total_slots && x != (int)s.off[s.slot_p[x]]) {   // (the base of a box was written above)
+                    const int p = s.slot_p[x];
+                    int loc = x - (int)s.off[p];
+                    int64_t av[D], to[D];
+                    load_pos<D>(s, p, av, to);
+                    int csum = 0;
+                    bool ok = true;
+                    // the state is reachable iff its allocations fit one after the other (any order: the tests are monotone)
+                    for (int sh = 0; sh < S; ++sh) {
+                        const int dim = s.depth[p * SMAX + sh] + 1;
+                        const int c = loc % dim;
+                        loc /= dim;
+                        csum += c;
+                        for (int k = 0; k < D && ok; ++k) {
+                            const int64_t r = s.sreq[sh * 8 + k];
+                            if (c > 0 && r > 0) {
+                                if (mul_overflows(r, c) || r > (to[k] < 0 ? 0 : to[k])) { ok = false; break; }
+                                av[k] -= (int64_t)c * r;
+                                if (av[k] < 0) { ok = false; break; }
+                            }
                         }
                     }
+                    if (ok) {
+                        key = key_of<D>(a.policy, a.w, to, av);
+                        sec = ((s.orn[p] >> 32) << 32) | ((unsigned long long)csum << 22) | (unsigned long long)x;
+                        take = ent_less(key, sec, bk, bs);
+                    }
                 }
-                if (!ok) continue;
-                const uint64_t key = yk_key_bits(yk_node_score(D, a.policy, a.w, s.total + p * D, av, 1));
-                const uint64_t sec = ((s.orn[p] >> 32) << 32) | ((unsigned long long)csum << 22) | (unsigned long long)x;
-                if (ent_less(key, sec, bk, bs)) {
-                    const int y = sadd32(&s.cnt_elems, 1);
-                    s.e_key[y] = key; s.e_sec[y] = sec;
-                }
+                const int y = warp_append(&s.cnt_elems, take);
+                if (take) { s.e_key[y] = key; s.e_sec[y] = sec; }
             }
             LT_SYNC();
             const int nvalid = s.cnt_elems;
-            if (nvalid > nbase) {   // deeper states interleave with the bases: sort (bases alone are already in order)
-                int pn = 1;
-                while (pn < nvalid) pn <<= 1;
-                LT_FOR(x, pn - nvalid) { s.e_key[nvalid + x] = KEY_INF; s.e_sec[nvalid + x] = KEY_INF; }
-                LT_SYNC();
-                block_sort(s.e_key, s.e_sec, pn);
+            LT_PROF(PF_LATTICE);
+            if (nvalid > nbase) {   // deeper states interleave with the bases (which are in order already)
+                if (nvalid - nbase <= ECNT) {
+                    block_merge_by_count(s.e_key, s.e_sec, nbase, nvalid, s.d_key(), s.d_sec());
+                    LT_FOR(x, nvalid) { s.e_key[x] = s.d_key()[x]; s.e_sec[x] = s.d_sec()[x]; }
+                    LT_SYNC();
+                } else {
+                    int pn = 1;
+                    while (pn < nvalid) pn <<= 1;
+                    LT_FOR(x, pn - nvalid) { s.e_key[nvalid + x] = KEY_INF; s.e_sec[nvalid + x] = KEY_INF; }
+                    LT_SYNC();
+                    block_sort(s.e_key, s.e_sec, pn);
+                }
                 ++sorts;
             }
             LT_ONE s.nvalid = nvalid;
             elems += nvalid;
-            // ================= links: slot -> element, child of (element, shape), ROOM and BASE bitmaps =================
-            const int nw = (nvalid + 31) >> 5;
+            LT_PROF(PF_SORT);
+            // ================= links: slot -> element, then per element its ROOM / BASE / ACCEPT bits and children =================
             LT_FOR(x, total_slots) s.idx_of[x] = NO_CHILD;
-            LT_FOR(x, (SMAX + 1) * FW) { if (x < SMAX * FW) s.ROOM[x] = 0u; else s.BASE[x - SMAX * FW] = 0u; }
             LT_SYNC();
             LT_FOR(e, nvalid) s.idx_of[(int)(s.e_sec[e] & 0x3FFFFFu)] = (uint16_t)e;
             LT_SYNC();
-            LT_FOR(x, nvalid * S) {
-                const int e = x / S, sh = x % S;
-                const int slot = (int)(s.e_sec[e] & 0x3FFFFFu);
-                const int p = s.slot_p[slot];
+            LT_FOR32(e, nvalid) {
+                const bool in = e < nvalid;
+                const int slot = in ? (int)(s.e_sec[e] & 0x3FFFFFu) : 0;
+                const int p = in ? (int)s.slot_p[slot] : 0;
                 int loc = slot - (int)s.off[p];
-                if (sh == 0 && loc == 0) sor32(&s.BASE[e >> 5], 1u << (e & 31));
-                // decode the state, test one more allocation of shape sh
-                int64_t av[D];
-                for (int k = 0; k < D; ++k) av[k] = s.avail[p * D + k];
-                int stride = 1, my_c = 0, my_stride = 0;
+                put_bit(s.BASE, e, in && loc == 0);
+                int64_t av[D], to[D];
+                load_pos<D>(s, p, av, to);
+                unsigned long long cvec = 0;   // the state, one byte per shape
                 for (int q = 0; q < S; ++q) {
                     const int dim = s.depth[p * SMAX + q] + 1;
                     const int c = loc % dim;
                     loc /= dim;
-                    if (q == sh) { my_c = c; my_stride = stride; }
-                    stride *= dim;
+                    cvec |= (unsigned long long)c << (8 * q);
                     for (int k = 0; k < D; ++k) av[k] -= (int64_t)c * s.sreq[q * 8 + k];
                 }
-                const bool room = fits<D>(true, av, s.total + p * D, s.sreq + sh * 8);
-                if (room) sor32(&s.ROOM[sh * FW + (e >> 5)], 1u << (e & 31));
-                s.child[e * SMAX + sh] = (room && my_c < s.depth[p * SMAX + sh]) ? s.idx_of[slot + my_stride] : NO_CHILD;
-            }
-            // ================= ACCEPT rows =================
-            LT_FOR(x, nrows * nw) {
-                const int row = x / nw, wd = x % nw;
-                const uint64_t tol = s.r_tol[row], need = s.r_need[row], deny = s.r_deny[row];
-                const uint32_t want = s.r_want[row];
-                uint32_t bits = 0;
-                const int e1 = wd * 32 + 32 < nvalid ? wd * 32 + 32 : nvalid;
-                for (int e = wd * 32; e < e1; ++e) {
-                    const int p = s.slot_p[(int)(s.e_sec[e] & 0x3FFFFFu)];
-                    if (accepts(s.taint[p], s.label[p], (uint32_t)s.orn[p], tol, need, deny, want)) bits |= 1u << (e & 31);
+                int stride = 1;
+                for (int sh = 0; sh < S; ++sh) {
+                    const bool room = in && fits<D>(true, av, to, s.sreq + sh * 8);
+                    put_bit(s.ROOM + sh * FW, e, room);
+                    const int c = (int)((cvec >> (8 * sh)) & 0xFFu), dep = s.depth[p * SMAX + sh];
+                    if (in) s.child[e * SMAX + sh] = (room && c < dep) ? s.idx_of[slot + stride] : NO_CHILD;
+                    stride *= dep + 1;
                 }
-                s.F[row * FW + wd] = bits;
+                const uint64_t tnt = s.taint[p], lbl = s.label[p];
+                const uint32_t node = (uint32_t)s.orn[p];
+                for (int r = 0; r < nrows; ++r)
+                    put_bit(s.F + r * FW, e, in && accepts(tnt, lbl, node, s.r_tol[r], s.r_need[r], s.r_deny[r], s.r_want[r]));
             }
             LT_SYNC();
+            LT_PROF(PF_LINKS);
             // ================= chain =================
             chain<D>(s);
             ++subruns;
             const int tdone = s.tdone;
+            LT_PROF(PF_CHAIN);
             if (tdone == 0) {   // nothing decided: the first entry needs the full scan
                 fresh = 1;
                 continue;
@@ -757,39 +934,38 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             { int nt; block_scan(s.scan, s.tmp(), P, &nt); LT_ONE s.nt = nt; LT_SYNC(); }
             const int nt = s.nt;
             {
-                unsigned long long* tk = s.t_key();
-                unsigned long long* tr = s.t_rn();
+                unsigned long long* uk = s.u_key();
+                unsigned long long* ur = s.u_rn();
                 LT_FOR(p, P) {
                     s.tb[p] = s.scan[p];
                     uint32_t any = 0;
                     for (int x = 0; x < S; ++x) any |= s.cnt[p * SMAX + x];
                     if (any) {
-                        int64_t na[D];
+                        int64_t na[D], to[D];
+                        load_pos<D>(s, p, na, to);
                         int64_t* r = a.rec + (size_t)(uint32_t)s.orn[p] * RS;
                         for (int k = 0; k < D; ++k) {
-                            int64_t v = s.avail[p * D + k];
+                            int64_t v = na[k];
                             for (int x = 0; x < S; ++x) v -= (int64_t)s.cnt[p * SMAX + x] * s.sreq[x * 8 + k];
                             na[k] = v; r[k] = v;
                         }
-                        const uint64_t nk = yk_key_bits(yk_node_score(D, a.policy, a.w, s.total + p * D, na, 1));
+                        const uint64_t nk = key_of<D>(a.policy, a.w, to, na);
                         if (nk == YK_KEY_NAN) s.status = ST_NAN;
                         const int x = (int)s.scan[p];
-                        tk[x] = nk; tr[x] = s.orn[p];
+                        uk[x] = nk; ur[x] = s.orn[p];
                     }
                 }
                 LT_ONE { s.tb[P] = (uint32_t)nt; }
                 LT_SYNC();
                 if (s.status == ST_NAN) { status = ST_NAN; break; }
-                int pn = 1;   // touched nodes by their new keys
-                while (pn < nt) pn <<= 1;
-                LT_FOR(x, pn - nt) { tk[nt + x] = KEY_INF; tr[nt + x] = KEY_INF; }
-                LT_SYNC();
-                if (pn > 1) block_sort(tk, tr, pn);
+                block_merge_by_count(uk, ur, 0, nt, s.t_key(), s.t_rn());   // touched nodes by their new keys
             }
+            LT_PROF(PF_APPLY);
             patch_order<D>(a, s, a.ord[buf], a.ord[buf ^ 1]);
+            LT_PROF(PF_PATCH);
             buf ^= 1;
             t += tdone;
-            dead_sig = 0;
+            dead = 0;
             continue;
         }
 
@@ -804,6 +980,9 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             LT_SYNC();
             for (int base = 0; base < nlive && s.hit == nlive; base += THREADS * 4) {
                 const int lim = nlive - base < THREADS * 4 ? nlive - base : THREADS * 4;
+                unsigned long long my_ub[D];
+                for (int k = 0; k < D; ++k) my_ub[k] = 0;
+                int my_hit = nlive;
                 LT_FOR(x, lim) {
                     const int p = base + x;
                     const uint64_t rn = ldg(&cur[p].rn);
@@ -816,24 +995,29 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                     if (usable)
                         for (int k = 0; k < D; ++k) {
                             const int64_t aa = av[k] < 0 ? 0 : av[k], tt = to[k] < 0 ? 0 : to[k];
-                            smax64(&s.ubx[k], (unsigned long long)(aa < tt ? aa : tt));
+                            const unsigned long long cc = (unsigned long long)(aa < tt ? aa : tt);
+                            my_ub[k] = cc > my_ub[k] ? cc : my_ub[k];
                         }
                     if (fits<D>(usable, av, to, req0) &&
                         accepts((uint64_t)ldg(&r[2 * D]), (uint64_t)ldg(&r[2 * D + 1]), node, tol, need, deny, want))
-                        smin32(&s.hit, p);
+                        my_hit = p < my_hit ? p : my_hit;
                 }
+                for (int k = 0; k < D; ++k) red_max64(&s.ubx[k], my_ub[k]);
+                red_min32(&s.hit, my_hit);
                 LT_SYNC();
             }
             const int hit = s.hit;
             if (hit == nlive) {   // certain NOFIT (of the whole gang when the entry leads one); every node was seen: the
                 int g1 = 1;       // capacity bound is exact now
                 if (gang0) while (g1 < n && (s.k_meta[g1] & M_GANG) && !(s.k_meta[g1] & M_GSTART)) ++g1;
+                const uint32_t sg0 = s.k_sig[0];
                 LT_FOR(i, g1) a.res[t + i] = NONE;
                 LT_ONE { for (int k = 0; k < D; ++k) a.ub[k] = (int64_t)s.ubx[k]; }
                 LT_SYNC();
                 t += g1;
-                dead_sig = gang0 ? 0 : 1;
+                dead = gang0 ? 0 : 1; dead_sig = sg0;
                 if (!a.insensitive) status = ST_STOPPED;
+                LT_PROF(PF_FULLSCAN);
                 continue;
             }
             // a gang whose first member fits somewhere but that could not be placed from the front of the order: the
@@ -847,7 +1031,7 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 int64_t* r = a.rec + (size_t)node * RS;
                 int64_t na[D], to[D];
                 for (int k = 0; k < D; ++k) { na[k] = ldg(&r[k]) - req0[k]; to[k] = ldg(&r[D + k]); r[k] = na[k]; }
-                const uint64_t nk = yk_key_bits(yk_node_score(D, a.policy, a.w, to, na, 1));
+                const uint64_t nk = key_of<D>(a.policy, a.w, to, na);
                 if (nk == YK_KEY_NAN) s.status = ST_NAN;
                 s.t_key()[0] = nk; s.t_rn()[0] = rn;
                 s.nt = 1; s.esc_pos = hit; s.P = 0;
@@ -858,7 +1042,8 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             patch_order<D>(a, s, a.ord[buf], a.ord[buf ^ 1]);
             buf ^= 1;
             t += 1;
-            dead_sig = 0;
+            dead = 0;
+            LT_PROF(PF_FULLSCAN);
         }
     }
     LT_ONE {

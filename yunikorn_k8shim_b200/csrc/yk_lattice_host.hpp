@@ -17,47 +17,76 @@ inline bool same_request(const yk::CommitTables& t, uint32_t a, uint32_t b) {
     return true;
 }
 
-// Dense numbers for the distinct request vectors of the cycle's pending asks ("shapes"): a_shape[ask].  Returns how many.
-inline uint32_t assign_shapes(const yk::CommitTables& t, const std::vector<uint32_t>& pending, std::vector<uint32_t>& a_shape) {
+// Dense numbers for the distinct request vectors ("shapes") and the distinct predicate signatures of the cycle's pending
+// asks: a_shape[ask], a_sigid[ask].  Equal numbers <=> equal vectors / signatures (hash table, equality always confirmed
+// on the full data).  a_sig = the 64-bit signature hashes computed when the asks were upserted.
+inline void assign_ids(const yk::CommitTables& t, const uint64_t* a_sig, const std::vector<uint32_t>& pending,
+                       std::vector<uint32_t>& a_shape, std::vector<uint32_t>& a_sigid, uint32_t* n_shapes, uint32_t* n_sigs) {
     struct Slot { uint32_t ask; uint32_t id; };
     size_t cap = 64;
     while (cap < 4 * pending.size()) cap <<= 1;
-    std::vector<Slot> tab(cap, Slot{yk::CNONE, 0});
-    uint32_t n = 0;
+    std::vector<Slot> shapes(cap, Slot{yk::CNONE, 0}), sigs(cap, Slot{yk::CNONE, 0});
+    uint32_t ns = 0, ng = 0;
     for (uint32_t a : pending) {
         uint64_t h = 0x9E3779B97F4A7C15ull;
         for (int k = 0; k < t.D; ++k) { h ^= (uint64_t)t.a_req[(size_t)k * t.lda + a] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xD6E8FEB86659FD93ull; }
         size_t x = (size_t)(h ^ (h >> 29)) & (cap - 1);
         for (;;) {
-            Slot& s = tab[x];
-            if (s.ask == yk::CNONE) { s.ask = a; s.id = n++; a_shape[a] = s.id; break; }
+            Slot& s = shapes[x];
+            if (s.ask == yk::CNONE) { s.ask = a; s.id = ns++; a_shape[a] = s.id; break; }
             if (same_request(t, s.ask, a)) { a_shape[a] = s.id; break; }
             x = (x + 1) & (cap - 1);
         }
+        const uint64_t g = a_sig[a];
+        x = (size_t)(g ^ (g >> 29)) & (cap - 1);
+        for (;;) {
+            Slot& s = sigs[x];
+            if (s.ask == yk::CNONE) { s.ask = a; s.id = ng++; a_sigid[a] = s.id; break; }
+            if (a_sig[s.ask] == g && yk::same_signature(t, s.ask, a)) { a_sigid[a] = s.id; break; }
+            x = (x + 1) & (cap - 1);
+        }
     }
-    return n;
+    *n_shapes = ns; *n_sigs = ng;
 }
 
-// meta word of every batch entry (M_* flags | shape id << 16, yk_lattice.h); returns the number of runs (maximal stretches
-// of equal requests)
-inline size_t build_meta(const yk::CommitTables& t, const uint64_t* a_sig, const uint32_t* a_shape, const std::vector<uint32_t>& batch,
-                         std::vector<uint32_t>& meta) {
+// the three words per batch entry that the kernel reads (yk_lattice.h): gang flags, shape number, signature number
+inline void build_meta(const yk::CommitTables& t, const uint32_t* a_shape, const uint32_t* a_sigid, const std::vector<uint32_t>& batch,
+                       uint32_t* meta, uint32_t* shp, uint32_t* sig) {
     const size_t B = batch.size();
-    meta.resize(B);
-    size_t runs = 0;
     for (size_t i = 0; i < B; ++i) {
         const uint32_t a = batch[i];
         uint32_t m = 0;
-        if (i == 0 || !same_request(t, a, batch[i - 1])) { m |= M_RUN | M_SIG; ++runs; }
-        else if (a_sig[a] != a_sig[batch[i - 1]] || !yk::same_signature(t, a, batch[i - 1])) m |= M_SIG;
         if (t.a_gang[a] != yk::CNONE) {
             m |= M_GANG;
             const uint32_t b = i ? batch[i - 1] : a;
             if (i == 0 || t.a_gang[b] != t.a_gang[a] || t.a_app[b] != t.a_app[a]) m |= M_GSTART;
         }
-        meta[i] = m | (a_shape[a] << 16);
+        meta[i] = m; shp[i] = a_shape[a]; sig[i] = a_sigid[a];
     }
-    return runs;
+}
+
+// How many sub-run windows the kernel's staging rules (at most SMAX shapes, SIGCAP signatures, KCAP asks) cut the batch
+// into at least: the engine only starts a cycle on the device commit when the windows are long enough to pay for a sub-run.
+inline size_t estimate_windows(const uint32_t* shp, const uint32_t* sig, size_t B) {
+    size_t windows = 0, i = 0;
+    std::vector<uint32_t> seen(512, 0xFFFFFFFFu);
+    while (i < B) {
+        uint32_t shapes[SMAX];
+        int ns = 0, rows = 0;
+        std::fill(seen.begin(), seen.end(), 0xFFFFFFFFu);
+        size_t j = i;
+        for (; j < B && j - i < (size_t)KCAP; ++j) {
+            int k = 0;
+            while (k < ns && shapes[k] != shp[j]) ++k;
+            if (k == ns) { if (ns == SMAX) break; shapes[ns++] = shp[j]; }
+            size_t x = (sig[j] * 2654435761u) >> 23;   // 9 bits
+            while (seen[x] != 0xFFFFFFFFu && seen[x] != sig[j]) x = (x + 1) & 511;
+            if (seen[x] == 0xFFFFFFFFu) { if (rows == SIGCAP) break; seen[x] = sig[j]; ++rows; }
+        }
+        ++windows;
+        i = j > i ? j : i + 1;
+    }
+    return windows;
 }
 
 // What the lattice commit relies on (DESIGN.md "lattice commit"):

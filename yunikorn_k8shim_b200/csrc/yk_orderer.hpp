@@ -309,6 +309,22 @@ public:
         for (uint32_t m : mem) mark_dead(m, ST_NOFIT);
     }
 
+    // The batch is given up after its first j entries were decided (all placed, or failed in place): the entries from
+    // j on go back to where fill() took them from.  Used when a cycle moves from the device commit to the host commit.
+    void unfill(Snap& snap, const std::vector<uint32_t>& batch, size_t j) {
+        if (insensitive) { static_next -= batch.size() - j; return; }
+        for (auto it = snap.journal.rbegin(); it != snap.journal.rend(); ++it) t.a_state[it->first] = it->second;
+        snap.journal.clear();
+        q = snap.q; ap = snap.ap; q_set = snap.sets; slow_list.resize(snap.slow_mark);
+        if (!uniform_prio) q_prio_cnt = snap.prio_cnt;
+        snap.valid = false;
+        jr = nullptr;
+        std::fill(q_sorted_ok.begin(), q_sorted_ok.end(), 0);
+        for (auto& v : q_changed) v.clear();
+        std::vector<uint32_t> replay;
+        while (replay.size() < j && step(j, (size_t)-1, replay)) {}
+    }
+
     // insensitive batches: ask `a` (tentatively accounted) found no node
     void fail_in_place(uint32_t a) {
         if (insensitive) { t.a_state[a] = ST_NOFIT; return; }

@@ -34,6 +34,8 @@ class Config(C.Structure):
 
 
 FLAG_NO_ROW_SHARING = 1
+FLAG_HOST_COMMIT = 2
+FLAG_DEVICE_COMMIT = 4
 
 
 class Stats(C.Structure):
@@ -43,7 +45,11 @@ class Stats(C.Structure):
                 ("sweep_ms", C.c_double), ("sort_ms", C.c_double), ("commit_ms", C.c_double), ("total_ms", C.c_double),
                 ("last_sweep_ms", C.c_double), ("last_sweep_pairs", C.c_uint64),
                 ("host_ms", C.c_double * 8), ("dbg", C.c_uint64 * 4), ("prof", C.c_uint64 * 6),
-                ("asks_swept", C.c_uint64), ("rows_swept", C.c_uint64)]
+                ("asks_swept", C.c_uint64), ("rows_swept", C.c_uint64),
+                ("lattice_launches", C.c_uint64), ("lattice_subruns", C.c_uint64), ("lattice_asks", C.c_uint64),
+                ("lattice_elements", C.c_uint64), ("lattice_sorts", C.c_uint64), ("lattice_fullscans", C.c_uint64),
+                ("lattice_quick", C.c_uint64), ("lattice_handoffs", C.c_uint64), ("lattice_ms", C.c_double),
+                ("lattice_cycles", C.c_uint64)]
 
     def as_dict(self):
         d = {f: getattr(self, f) for f, _ in self._fields_}
@@ -113,7 +119,7 @@ class Engine:
     """One yk_engine.  Method names and arguments mirror include/ykgpu.h one to one."""
 
     def __init__(self, D=4, policy=0, weights=None, max_nodes=1024, max_asks=4096, max_apps=64, max_queues=8,
-                 batch=0, device=-1, rank=0, world=1, share_rows=True):
+                 batch=0, device=-1, rank=0, world=1, share_rows=True, commit="auto"):
         self._lib = load_library()
         cfg = Config()
         cfg.abi_version = self._lib.yk_abi_version()
@@ -128,7 +134,8 @@ class Engine:
         for i in range(8):
             cfg.weights[i] = float(w[i])
         cfg.max_nodes, cfg.max_asks, cfg.max_apps, cfg.max_queues = max_nodes, max_asks, max_apps, max_queues
-        cfg.device, cfg.flags, cfg.rank, cfg.world = device, (0 if share_rows else FLAG_NO_ROW_SHARING), rank, world
+        cfg.device, cfg.rank, cfg.world = device, rank, world
+        cfg.flags = (0 if share_rows else FLAG_NO_ROW_SHARING) | {"auto": 0, "host": FLAG_HOST_COMMIT, "device": FLAG_DEVICE_COMMIT}[commit]
         self.D = D
         self._h = C.c_void_p()
         rc = self._lib.yk_create(C.byref(cfg), C.byref(self._h))

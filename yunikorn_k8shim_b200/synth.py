@@ -245,6 +245,24 @@ def perf(n_nodes=10_000, n_apps=400, tasks=125, masks=False, policy=POLICY_FAIR,
                    meta={"config": 3 if masks else 2, "seed": seed})
 
 
+def reference_shape(n_nodes=5_000, n_apps=400, tasks=125, policy=POLICY_FAIR) -> Snapshot:
+    """The reference's own in-process benchmark (BenchmarkSchedulingThroughPut): identical kwok-sized nodes, 400 applications
+    x 125 tasks = 50 000 pods, every pod requesting 10 mCPU / 1 MB
+    (/root/reference/pkg/shim/scheduler_perf_test.go:62-63 nodes and pods, :151-171 apps x tasks, :283-288 the request)."""
+    D = 4
+    tot = np.tile(np.array([32_000, 256 * GI, 110, 0], dtype=np.int64), (n_nodes, 1))
+    ids = [f"kwok-node-{i}" for i in range(n_nodes)]
+    z_n = np.zeros(n_nodes, dtype=np.uint64)
+    A = n_apps * tasks
+    app = np.repeat(np.arange(n_apps, dtype=np.int32), tasks)
+    req = np.zeros((A, D), dtype=np.int64)
+    req[:, 0], req[:, 1], req[:, 2] = 10, 1_000_000, 1
+    z = np.zeros(A, dtype=np.uint64)
+    return _finish(f"reference-shape-{n_nodes}x{A}", D, policy, tot, tot.copy(), z_n, z_n.copy(), ids,
+                   _single_queue(D), np.ones(n_apps, dtype=np.int32), app, req, z, z.copy(), z.copy(),
+                   meta={"config": "reference", "seed": 0})
+
+
 def hier(n_nodes=50_000, n_parents=8, leaves_per_parent=8, apps_per_leaf=5, tasks=625, masks=False,
          policy=POLICY_FAIR, seed=4, quota_frac=1.2, priorities=False, big_nodes=False, leaf_sort=SORT_FIFO) -> Snapshot:
     """BASELINE config 4: 3-level queue tree (root -> parents -> leaves), guaranteed + max per leaf, fifo apps
