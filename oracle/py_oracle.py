@@ -26,9 +26,15 @@ def node_score(policy, w, total, avail):
     usage = 0.0
     tw = 0.0
     for k in range(len(w)):
-        if w[k] == 0.0 or total[k] == 0:
+        if w[k] == 0.0:
             continue
-        share = 1.0 - float(avail[k]) / float(total[k])
+        t, v = float(total[k]), float(avail[k])
+        if t == 0.0:        # Go float division: x/0 = +-Inf, 0/0 = NaN (the NaN share is skipped, the infinite one counts)
+            if v == 0.0:
+                continue
+            share = 1.0 - math.copysign(math.inf, v)
+        else:
+            share = 1.0 - v / t
         if math.isnan(share):
             continue
         usage += share * w[k]
@@ -186,17 +192,18 @@ def run(s, max_bindings=-1):
                         return None
                     if state[a] == ST_ALLOCATED or dead[a]:
                         continue
-                    if int(s.ask_flags[a]) & 1:
-                        state[a], dead[a] = ST_SLOWPATH, True
-                        continue
-                    if any(hr[k] != UNSET and req[a][k] > hr[k] for k in range(D)):
-                        state[a], dead[a] = ST_SKIPPED, True
-                        continue
-                    if not strictly_gt_zero(req[a]):
-                        state[a], dead[a] = ST_INVALID, True
-                        continue
                     g = int(s.ask_gang[a])
-                    if g >= 0:
+                    if g < 0:
+                        if int(s.ask_flags[a]) & 1:
+                            state[a], dead[a] = ST_SLOWPATH, True
+                            continue
+                        if any(hr[k] != UNSET and req[a][k] > hr[k] for k in range(D)):
+                            state[a], dead[a] = ST_SKIPPED, True
+                            continue
+                        if not strictly_gt_zero(req[a]):
+                            state[a], dead[a] = ST_INVALID, True
+                            continue
+                    if g >= 0:      # a gang member: the gang-wide checks below decide for every member (all or nothing)
                         members = [m for m in app_asks[p] if int(s.ask_gang[m]) == g and state[m] != ST_ALLOCATED and not dead[m]]
                         placed, cause = [], 0
                         hrm = headroom(q)           # queue-side checks of all members first, headroom shrinking

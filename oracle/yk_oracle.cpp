@@ -60,7 +60,7 @@ double node_score(int D, int policy, const double* w, const int64_t* total, cons
     double usage = 0.0, tw = 0.0;
     for (int k = 0; k < D; ++k) {
         if (w[k] == 0.0) continue;       // unweighted types do not count
-        if (total[k] == 0) continue;     // type absent from total (0/0 would be NaN -> skipped)
+        // Go float division: x/0 = +-Inf (the infinite share counts), 0/0 = NaN (skipped below)
         double share = 1.0 - (double)avail[k] / (double)total[k];
         if (std::isnan(share)) continue;
         usage += share * w[k];
@@ -327,14 +327,14 @@ struct Engine {
             int a = ap.asks[i];
             if (state[(size_t)a] == YKO_ST_ALLOCATED) continue;
             if (done[(size_t)a] && !retry) continue;
-            if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { state[(size_t)a] = YKO_ST_SLOWPATH; done[(size_t)a] = 1; continue; }
-            if (!fit_in_max_undef(hr, req(a))) { state[(size_t)a] = YKO_ST_SKIPPED; done[(size_t)a] = 1; continue; }
-            if (!strictly_gt_zero(D, req(a))) { state[(size_t)a] = YKO_ST_INVALID; done[(size_t)a] = 1; continue; }
-            if (gang_of(a) >= 0) {
+            if (gang_of(a) >= 0) {   // a gang member: the gang-wide checks decide for every member (all or nothing)
                 if (try_gang(p, a, out, room)) return true;
                 if (stop) return false;   // the gang does not fit in max_bindings: end of the cycle
                 continue;
             }
+            if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { state[(size_t)a] = YKO_ST_SLOWPATH; done[(size_t)a] = 1; continue; }
+            if (!fit_in_max_undef(hr, req(a))) { state[(size_t)a] = YKO_ST_SKIPPED; done[(size_t)a] = 1; continue; }
+            if (!strictly_gt_zero(D, req(a))) { state[(size_t)a] = YKO_ST_INVALID; done[(size_t)a] = 1; continue; }
             int n = try_nodes(a);
             if (n >= 0) { commit(a, n); out.emplace_back(a, n); return true; }
             state[(size_t)a] = YKO_ST_NOFIT;

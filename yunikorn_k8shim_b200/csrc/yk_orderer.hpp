@@ -232,15 +232,20 @@ public:
             if (sa_pos >= v.size()) { ++sa_app; sa_pos = 0; continue; }
             const uint32_t a = v[sa_pos++];
             if (t.a_state[a] != ST_PENDING) continue;
-            const uint8_t c = cause_of(a);
-            if (c) { if (c == ST_SLOWPATH) slow_list.push_back(a); t.a_state[a] = c; continue; }
-            if (t.a_gang[a] == NONE) { static_order.push_back(a); continue; }
+            if (t.a_gang[a] == NONE) {
+                const uint8_t c = cause_of(a);
+                if (c) { if (c == ST_SLOWPATH) slow_list.push_back(a); t.a_state[a] = c; continue; }
+                static_order.push_back(a);
+                continue;
+            }
+            // a gang member: the first cause among the members (in ask order) sinks every member, all or nothing
             sa_mem.clear();
             uint8_t gc = 0;
             for (uint32_t m : v)
                 if (t.a_gang[m] == t.a_gang[a] && t.a_state[m] == ST_PENDING) { sa_mem.push_back(m); if (!gc) gc = cause_of(m); }
             for (uint32_t m : sa_mem) {
-                if (gc) t.a_state[m] = gc; else { t.a_state[m] = ST_TENTATIVE; static_order.push_back(m); }
+                if (gc) { if (gc == ST_SLOWPATH && (t.a_flags[m] & 1u)) slow_list.push_back(m); t.a_state[m] = gc; }
+                else { t.a_state[m] = ST_TENTATIVE; static_order.push_back(m); }
             }
         }
     }
@@ -547,6 +552,7 @@ private:
                 for (uint32_t i = A.head; i < v.size(); ++i) {
                     uint32_t a = v[i];
                     if (t.a_state[a] != ST_PENDING) continue;
+                    if (t.a_gang[a] != NONE) return a;   // a gang member: step() checks the whole gang, all or nothing
                     if (t.a_flags[a] & 1u) { slow_list.push_back(a); mark_dead(a, ST_SLOWPATH); continue; }
                     bool fits = true;
                     for (int k = 0; k < d; ++k) if (hr[k] != UNSET && req(a, k) > hr[k]) { fits = false; break; }

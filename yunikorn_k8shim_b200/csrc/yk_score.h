@@ -25,7 +25,7 @@ YK_HD double yk_node_score(int D, uint32_t policy, const double* w, const int64_
     for (int k = 0; k < D; ++k) {
         if (w[k] == 0.0) continue;
         int64_t t = total[(size_t)k * ld];
-        if (t == 0) continue;  // type absent from the node's total
+        // Go float division [EXT GetResourceUsageShares]: x/0 = +-Inf (the infinite share counts), 0/0 = NaN (skipped)
         double share = 1.0 - (double)avail[(size_t)k * ld] / (double)t;
         if (share != share) continue;
         usage += share * w[k];
