@@ -9,7 +9,62 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+// ---- bench arm "cpu_engine" (bench.py): the same orderer + ordered commit with the sweep done by the host cores ----
+// g_sweep_threads == 0: the plain scalar test loop below (what the CPU test suite runs).  > 0: rows are swept by that many
+// threads, eight sorted positions per AVX-512 compare when the CPU has it (a column-major copy of the epoch view is kept
+// for it) -- the honest "no GPU" version of this engine, timed next to the GPU one.  g_skip_checks drops the O(N)
+// self-checks the test harness runs after every epoch.
+static int g_sweep_threads = 0;
+static int g_skip_checks = 0;
+extern "C" void host_set_bench_mode(int threads, int skip_checks) { g_sweep_threads = threads; g_skip_checks = skip_checks; }
+
+namespace {
+struct SoAView { const int64_t* cap; size_t ld; const uint64_t* taint; const uint64_t* label; const uint32_t* node; int D; int Np; };
+
+void sweep_row_scalar(const SoAView& v, const int64_t* rq, uint64_t tol, uint64_t need, uint64_t deny, uint32_t want, uint32_t* row, int W) {
+    row[W] = yk::CNONE;
+    for (int p = 0; p < v.Np; ++p) {
+        bool ok = true;
+        for (int k = 0; k < v.D; ++k) ok = ok && rq[k] <= v.cap[(size_t)k * v.ld + p];
+        ok = ok && !((v.taint[p] & ~tol) | (~v.label[p] & need) | (v.label[p] & deny));
+        ok = ok && (want == yk::CNONE || want == v.node[p]);
+        if (ok) { row[p >> 5] |= 1u << (p & 31); if (row[W] == yk::CNONE) row[W] = (uint32_t)p; }
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+void sweep_row_avx512(const SoAView& v, const int64_t* rq, uint64_t tol, uint64_t need, uint64_t deny, uint32_t want, uint32_t* row, int W) {
+    row[W] = yk::CNONE;
+    const __m512i ntol = _mm512_set1_epi64((long long)~tol), vneed = _mm512_set1_epi64((long long)need), vdeny = _mm512_set1_epi64((long long)deny);
+    const __m512i vwant = _mm512_set1_epi64((long long)want);
+    __m512i r[8];
+    for (int k = 0; k < v.D; ++k) r[k] = _mm512_set1_epi64(rq[k]);
+    for (int w = 0; w < W; ++w) {
+        uint32_t bits = 0;
+        for (int q = 0; q < 4; ++q) {
+            const int p = w * 32 + q * 8;
+            __mmask8 m = 0xFF;
+            for (int k = 0; k < v.D; ++k) m &= _mm512_cmple_epi64_mask(r[k], _mm512_loadu_si512(v.cap + (size_t)k * v.ld + p));
+            const __m512i t = _mm512_loadu_si512(v.taint + p), l = _mm512_loadu_si512(v.label + p);
+            m &= _mm512_testn_epi64_mask(t, ntol);                                   // (taint & ~tol) == 0
+            m &= _mm512_cmpeq_epi64_mask(_mm512_and_si512(l, vneed), vneed);          // (label & need) == need
+            m &= _mm512_testn_epi64_mask(l, vdeny);                                   // (label & deny) == 0
+            if (want != yk::CNONE) m &= _mm512_cmpeq_epi64_mask(_mm512_cvtepu32_epi64(_mm256_loadu_si256((const __m256i*)(v.node + p))), vwant);
+            bits |= (uint32_t)m << (q * 8);
+        }
+        row[w] = bits;
+        if (bits && row[W] == yk::CNONE) row[W] = (uint32_t)w * 32u + (uint32_t)__builtin_ctz(bits);
+    }
+}
+#endif
+}  // namespace
 
 
 // queue priority properties for the next run (priority.offset / priority.policy = fence); NULL = defaults.  Test
@@ -73,6 +128,7 @@ static int engine_host_run_impl(
     const int W = nlive ? (nlive + 511) / 512 * 16 : 0;   // same rounding as the engine: tiles of 512 positions
     const int WS = W + 1;
     std::vector<int64_t> v_cap;   // [pos][D]
+    std::vector<int64_t> v_capT;  // [D][pos]: the column-major copy the vectorised bench sweep reads
     std::vector<uint64_t> v_taint, v_label;
     std::vector<uint32_t> v_node;
     auto refresh_view = [&]() {
@@ -86,6 +142,11 @@ static int engine_host_run_impl(
                 v_cap[(size_t)p * D + k] = usable ? std::min(a, t) : -1;
             }
             v_taint[p] = n_taint[n]; v_label[p] = n_label[n]; v_node[p] = n;
+        }
+        if (g_sweep_threads > 0) {
+            const size_t Np = (size_t)W * 32;
+            v_capT.resize(Np * D);
+            for (size_t p = 0; p < Np; ++p) for (int k = 0; k < D; ++k) v_capT[(size_t)k * Np + p] = v_cap[p * D + k];
         }
         cm.begin_epoch(W);
     };
@@ -105,6 +166,34 @@ static int engine_host_run_impl(
         const size_t G = split ? world : 1, my = split ? rank : 0;
         const size_t rows_per = (R + G - 1) / G, row0 = std::min(R, my * rows_per), row1 = std::min(R, row0 + rows_per);
         sl.fit.assign(rows_per * G * (size_t)WS, 0);
+        if (g_sweep_threads > 0) {   // bench arm: every row by the host cores, vectorised
+            const SoAView view{v_capT.data(), (size_t)W * 32, v_taint.data(), v_label.data(), v_node.data(), D, W * 32};
+#if defined(__x86_64__)
+            const bool avx = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+#else
+            const bool avx = false;
+#endif
+            auto work = [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) {
+                    const uint32_t a = sl.reps[i];
+                    int64_t rq[8];
+                    for (int k = 0; k < D; ++k) rq[k] = a_req[(size_t)k * nA + a];
+                    uint32_t* row = sl.fit.data() + i * WS;
+#if defined(__x86_64__)
+                    if (avx) { sweep_row_avx512(view, rq, a_tol[a], a_need[a], a_deny[a], a_node[a], row, W); continue; }
+#endif
+                    sweep_row_scalar(view, rq, a_tol[a], a_need[a], a_deny[a], a_node[a], row, W);
+                }
+            };
+            const size_t nr = row1 - row0;
+            const size_t T = std::max<size_t>(1, std::min<size_t>((size_t)g_sweep_threads, nr / 64));
+            if (T <= 1) work(row0, row1);
+            else {
+                std::vector<std::thread> th;
+                for (size_t x = 0; x < T; ++x) th.emplace_back(work, row0 + nr * x / T, row0 + nr * (x + 1) / T);
+                for (auto& t : th) t.join();
+            }
+        } else
         for (size_t i = row0; i < row1; ++i) {
             const uint32_t a = sl.reps[i];
             uint32_t* row = sl.fit.data() + i * WS;
@@ -178,7 +267,8 @@ static int engine_host_run_impl(
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
         if (Nx.asks.empty() && n < max_bindings) {
             if (cm.dirty_list.size() * 2 >= (size_t)epoch_limit || failed) {
-                if (!cm.dirty_list.empty()) {
+                if (!cm.dirty_list.empty() && g_skip_checks) cm.merge_order(order_nodes.data(), nlive);
+                else if (!cm.dirty_list.empty()) {
                     cm.merge_order(order_nodes.data(), nlive);
                     // the merged order must be exactly: every node once, ascending by (CURRENT score key, NodeID rank)
                     std::vector<uint8_t> seen_node(nN, 0);

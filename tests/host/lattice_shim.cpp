@@ -52,8 +52,9 @@ int run_d(uint32_t policy, const double* weights,
     std::vector<uint64_t> a_sig(nA);
     std::vector<uint32_t> a_shape(nA, 0), a_sigid(nA, 0);
     for (uint32_t a = 0; a < nA; ++a) a_sig[a] = yk::ask_signature(ct, a);
-    uint32_t n_shapes = 0, n_sigs = 0;
-    yklt::assign_ids(ct, a_sig.data(), pending, a_shape, a_sigid, &n_shapes, &n_sigs);
+    uint32_t n_shapes = 0;
+    yklt::assign_shapes(ct, pending, a_shape, &n_shapes);
+    yklt::assign_sigs(ct, a_sig.data(), pending, a_sigid);
 
     // ---- device state: node records, the order (what yk_key_kernel + the radix sort + yk_lt_init_kernel build) ----
     const int RS = (2 * D + 3 + 3) / 4 * 4;

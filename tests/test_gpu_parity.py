@@ -121,7 +121,7 @@ def test_config5_full(oracle):
     assert st["nofit"] > 0
     # the device commit places the gangs until the cluster is full; the first gang that has to be rolled back hands the
     # rest of the cycle to the host commit
-    assert st["device"]["lattice_asks"] > 10_000 and st["device"]["lattice_handoffs"] == 1
+    assert st["device"]["lattice_asks"] > 5_000 and st["device"]["lattice_handoffs"] == 1
 
 
 def test_gang_larger_than_batch_is_an_error(oracle):
@@ -285,3 +285,30 @@ def test_queue_priority_properties(oracle):
     s.q_prio_offset = (np.arange(s.n_queues) % 3 * 50 - 50).astype(np.int32)
     s.q_prio_fence = (np.arange(s.n_queues) % 4 == 1).astype(np.uint8)
     _check(s, oracle, batch=16)
+
+
+def test_reupserted_asks_get_fresh_signature_numbers(oracle):
+    """signature numbers are handed out when asks are upserted and persist across cycles: overwriting asks -- also ones
+    that represent a number -- with other predicate inputs must never merge them with the old signature's row"""
+    import copy
+    s = synth.perf(80, 4, 60, masks=True, seed=51)
+    s.ask_tol[:] = s.ask_tol[0]
+    s.ask_need[:] = 0
+    s.ask_deny[:] = 0                                    # few signatures: the epoch-rows path
+    first = oracle.run(s, max_bindings=50)
+    for commit in ("host", "device"):
+        with Engine.for_snapshot(s, batch=32, commit=commit) as e:
+            ask, node, _ = e.cycle(50)
+            assert np.array_equal(ask, first["ask"]) and np.array_equal(node, first["node"])
+            t = copy.deepcopy(s)
+            t.node_avail = e.nodes_available(np.arange(s.n_nodes))
+            t.ask_flags[first["ask"]] = 1                # bound: the oracle leaves them alone
+            pend = np.setdiff1d(np.arange(s.n_asks), first["ask"])
+            chg = pend[::3]                              # a third of the pending asks change their predicate inputs
+            t.ask_tol[chg] = np.uint64(0xFFFF)
+            t.ask_need[chg] = np.uint64(1) << (np.arange(len(chg)) % 8).astype(np.uint64)
+            t.ask_req[chg[::2], 0] += 30
+            e.asks_upsert(chg, t.ask_req[chg], t.ask_app[chg], t.ask_create[chg], t.ask_tol[chg], t.ask_need[chg], t.ask_deny[chg])
+            want = oracle.run(t)
+            ask2, node2, _ = e.cycle(s.n_asks)
+            assert np.array_equal(ask2, want["ask"]) and np.array_equal(node2, want["node"]), commit

@@ -123,3 +123,20 @@ def test_other_dimension_counts(lshim, oracle, D):
         check(lshim, oracle, s, tag=(seed, D), batch=64)
     s = synth.redim(synth.perf(200, 8, 40, masks=True), D, 1)
     assert check(lshim, oracle, s, batch=512) is not None
+
+
+def test_many_shapes_and_signatures(lshim, oracle):
+    """windows that hit the shape and signature caps, boxes with six and more sides (their state count overflows an int
+    unless it saturates), ids that collide in the per-sub-run tables (an entry whose id differs from its slot's leader
+    leads itself)"""
+    for seed in range(6):
+        s = synth.perf(60, 6, 50, masks=True, seed=60 + seed)
+        s.ask_req[:, 0] += (np.arange(s.n_asks) * 7919) % 13 * 10          # 13 x 4 request vectors, interleaved
+        assert check(lshim, oracle, s, tag=("shapes", seed), batch=512) is not None
+        s = synth.perf(60, 6, 50, seed=70 + seed)
+        s.ask_req[:, 1] += np.arange(s.n_asks) * 4096                       # every ask its own request vector
+        assert check(lshim, oracle, s, tag=("unique", seed), batch=512) is not None
+        s = synth.perf(40, 4, 200, seed=80 + seed)
+        s.ask_req[:, 0] = 10 + (np.arange(s.n_asks) % 7)                    # seven tiny shapes: deep boxes on every side
+        s.ask_req[:, 1] = 1_000_000
+        assert check(lshim, oracle, s, tag=("tiny7", seed), batch=4096) is not None

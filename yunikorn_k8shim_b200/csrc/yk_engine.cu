@@ -131,6 +131,41 @@ struct Slot {
     uint32_t last_value = 0;        // P2P: sequence value signalled when this slot's previous content was published
 };
 
+// Signature numbers, kept up to date as asks are upserted: equal number <=> equal predicate signature (request vector,
+// tolerations, required / forbidden labels, node name).  Open addressing on the 64-bit signature hash; a hit is always
+// confirmed on the full signature of the entry's representative ask.  (A representative that was later overwritten with
+// another signature just stops matching: the signature then gets a second number -- an extra swept row, never a wrong
+// merge.)  Rebuilt from the present asks when it has handed out more than four numbers per ask slot.
+struct SigTable {
+    struct Ent { uint64_t h; uint32_t rep, id; };
+    static constexpr uint32_t FREE = 0xFFFFFFFFu, TOMB = 0xFFFFFFFEu;
+    std::vector<Ent> tab;
+    std::vector<uint32_t> rep_slot;   // ask -> 1 + the slot it represents, 0 when it represents none
+    uint32_t n = 0;
+    void reset(size_t asks) {
+        size_t cap = 1024;
+        while (cap < 4 * asks) cap <<= 1;
+        tab.assign(cap, Ent{0, FREE, 0});
+        rep_slot.assign(asks, 0);
+        n = 0;
+    }
+    // the ask's row is about to be overwritten: a number it represents is never handed out again (the asks that hold it
+    // stay equal among themselves; the signature gets a fresh number next time it is seen)
+    void retire(uint32_t ask) {
+        if (rep_slot[ask]) { tab[rep_slot[ask] - 1].rep = TOMB; rep_slot[ask] = 0; }
+    }
+    uint32_t get(const yk::CommitTables& t, uint64_t h, uint32_t ask) {
+        const size_t mask = tab.size() - 1;
+        size_t x = (size_t)(h ^ (h >> 29)) & mask;
+        for (;;) {
+            Ent& e = tab[x];
+            if (e.rep == FREE) { e.h = h; e.rep = ask; e.id = n++; rep_slot[ask] = (uint32_t)x + 1; return e.id; }
+            if (e.rep != TOMB && e.h == h && yk::same_signature(t, e.rep, ask)) return e.id;
+            x = (x + 1) & mask;
+        }
+    }
+};
+
 }  // namespace
 
 struct yk_engine {
@@ -203,6 +238,15 @@ struct yk_engine {
     int slots = 296;                         // resident sweep CTAs on this device (SMs x occupancy)
 
     yk::Orderer ord;
+    // epoch rows: when the cycle's pending asks have few distinct predicate signatures, every signature is swept ONCE per
+    // epoch (one launch, one read-back) and the batches of the epoch only index into those rows -- no per-batch device work
+    static constexpr uint32_t EP_MAX = 1024;
+    bool ep_rows = false; uint32_t ep_n = 0; bool ep_uploaded = false, ep_landed = true;
+    std::vector<uint32_t> ep_reps;
+    Dev<uint32_t> ep_d_batch, ep_d_fit; Pin<uint32_t> ep_h_batch, ep_h_fit;
+    cudaEvent_t ep_ev = nullptr, ep_s0 = nullptr, ep_s1 = nullptr;
+    uint32_t n_shapes = 0, n_sigs = 0;
+    SigTable sigs; std::vector<uint32_t> ep_local, ep_seen; uint32_t ep_stamp = 0;
     // device-resident ordered commit (yk_lattice.h): node records, ping-pong node order, per-batch staging
     bool lt_allowed = true;                  // !YK_FLAG_HOST_COMMIT, single GPU
     int lt_force = 0;                        // YK_FLAG_DEVICE_COMMIT / YK_COMMIT=device: every eligible cycle commits on the device
@@ -487,6 +531,32 @@ int begin_epoch(yk_engine* e) {
                                                      e->d_slabel.p, e->d_snode.p);
     CK(cudaGetLastError());
     e->st.other_launches += 1;
+    if (e->ep_rows) {   // every distinct signature of the cycle against the fresh view: one launch, one read-back per epoch
+        const int W = e->epochW, WS = W + 1, R = (int)e->ep_n;
+        if (!e->ep_uploaded) {
+            memcpy(e->ep_h_batch.p, e->ep_reps.data(), sizeof(uint32_t) * (size_t)R);
+            CK(cudaMemcpyAsync(e->ep_d_batch.p, e->ep_h_batch.p, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s));
+            e->st.h2d_bytes += sizeof(uint32_t) * (size_t)R;
+            e->ep_uploaded = true;
+        }
+        CK(cudaMemset2DAsync(e->ep_d_fit.p + W, sizeof(uint32_t) * (size_t)WS, 0xFF, sizeof(uint32_t), (size_t)R, s));
+        CK(cudaEventRecord(e->ep_s0, s));
+        YkSweepArgs a{};
+        a.s_cap = e->d_scap.p; a.s_taint = e->d_staint.p; a.s_label = e->d_slabel.p; a.s_node = e->d_snode.p; a.Np = Np;
+        a.a_req = e->d_areq.p; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
+        a.lda = e->maxA; a.batch = e->ep_d_batch.p; a.row0 = 0; a.rows = R;
+        a.fit = e->ep_d_fit.p; a.W = W; a.WS = WS; a.n_peer = 0;
+        launch_sweep(e->D, a, s, e->slots);
+        CK(cudaEventRecord(e->ep_s1, s));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e->ep_h_fit.p, e->ep_d_fit.p, sizeof(uint32_t) * (size_t)R * WS, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(e->ep_ev, s));
+        e->ep_landed = false;
+        e->st.sweep_launches += 1;
+        e->st.evaluations += (uint64_t)R * (uint64_t)nlive;
+        e->st.rows_swept += (uint64_t)R;
+        e->st.d2h_bytes += sizeof(uint32_t) * (size_t)R * WS;
+    }
     return YK_OK;
 }
 
@@ -536,6 +606,15 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     sl.B = B; sl.R = 0; sl.W = e->epochW; sl.rows = 0; sl.nchunks = 0;
     if (B == 0 || nlive == 0) return YK_OK;
     const double t0 = now_ms();
+    if (e->ep_rows) {   // the rows of every signature were swept when the epoch began: the batch only points at them
+        sl.row_of.resize((size_t)B);
+        for (int i = 0; i < B; ++i) sl.row_of[(size_t)i] = e->ep_local[e->a_sigid[sl.asks[(size_t)i]]];
+        sl.R = (int)e->ep_n;
+        st.batches++;
+        st.asks_swept += (uint64_t)B;
+        st.host_ms[6] += now_ms() - t0;
+        return YK_OK;
+    }
     const int W = e->epochW, Np = W * 32, WS = W + 1;
     cudaStream_t s = e->stream;
     // one row per distinct predicate signature in the batch (yk_commit.hpp "shared rows")
@@ -645,6 +724,30 @@ int commit(yk_engine* e, Slot& sl, bool insensitive, std::vector<uint32_t>& resu
     const std::vector<uint32_t>& batch = sl.asks;
     result.assign((size_t)B, YK_NONE);
     consumed = 0;
+    if (e->ep_rows && e->nlive != 0) {
+        double t_wait = 0;
+        const double t1 = now_ms();
+        if (!e->ep_landed) {
+            const cudaError_t ce = cudaEventSynchronize(e->ep_ev);
+            if (ce != cudaSuccess) return e->cuda_fail(ce, "cudaEventSynchronize(epoch rows)");
+            e->ep_landed = true;
+            t_wait = now_ms() - t1;
+            float ms_sweep = 0;
+            cudaEventElapsedTime(&ms_sweep, e->ep_s0, e->ep_s1);
+            e->st.sweep_ms += ms_sweep;
+            e->st.last_sweep_ms = ms_sweep;
+            e->st.last_sweep_pairs = (uint64_t)e->ep_n * (uint64_t)e->nlive;
+        }
+        const int R = sl.R;
+        const int rc = e->cm.commit_batch(batch, sl.row_of.data(), e->ep_h_fit.p, insensitive, result, consumed, [R](int) { return R; });
+        if (rc == -5) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
+        if (rc < 0) return e->fail(YK_ERR_CUDA, "commit aborted");
+        const double t2 = now_ms();
+        e->st.host_ms[3] += t_wait;
+        e->st.host_ms[4] += (t2 - t1) - t_wait;
+        e->st.commit_ms += (t2 - t1) - t_wait;
+        return YK_OK;
+    }
     if (e->nlive == 0 || sl.nchunks == 0) {   // no nodes: nothing fits
         consumed = insensitive ? (size_t)B : std::min<size_t>(1, (size_t)B);
         if (!insensitive && B > 0 && e->a_gang[batch[0]] != YK_NONE)
@@ -741,6 +844,9 @@ void yk_destroy(yk_engine* e) {
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev2) cudaEventDestroy(e->ev2);
+    if (e->ep_ev) cudaEventDestroy(e->ep_ev);
+    if (e->ep_s0) cudaEventDestroy(e->ep_s0);
+    if (e->ep_s1) cudaEventDestroy(e->ep_s1);
     if (e->ev_l0) cudaEventDestroy(e->ev_l0);
     if (e->ev_l1) cudaEventDestroy(e->ev_l1);
     for (Slot& sl : e->slot) {
@@ -826,6 +932,9 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->d_lt_asks.alloc(A)); T(e->d_lt_meta.alloc(A)); T(e->d_lt_shp.alloc(A)); T(e->d_lt_sig.alloc(A)); T(e->d_lt_res.alloc(A));
     T(e->h_lt_asks.alloc(A)); T(e->h_lt_meta.alloc(A)); T(e->h_lt_shp.alloc(A)); T(e->h_lt_sig.alloc(A)); T(e->h_lt_res.alloc(A)); T(e->h_lt_hdr.alloc(yklt::H_WORDS)); T(e->h_lt_ub.alloc(8));
     T(cudaEventCreate(&e->ev_l0)); T(cudaEventCreate(&e->ev_l1));
+    T(e->ep_d_batch.alloc(yk_engine::EP_MAX)); T(e->ep_h_batch.alloc(yk_engine::EP_MAX));
+    T(e->ep_d_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1))); T(e->ep_h_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1)));
+    T(cudaEventCreateWithFlags(&e->ep_ev, cudaEventDisableTiming)); T(cudaEventCreate(&e->ep_s0)); T(cudaEventCreate(&e->ep_s1));
     e->lt_prof = getenv("YK_PROFILE_LATTICE") != nullptr;
     T(e->d_lt_prof.alloc(16));
     if (ok) T(cudaMemset(e->d_lt_prof.p, 0, 16 * sizeof(long long)));
@@ -843,6 +952,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
     e->n_rank.assign(N, 0); e->n_present.assign(N, 0);
     e->a_shape.assign(A, 0); e->a_sigid.assign(A, 0);
+    e->sigs.reset(A);
     e->a_sig.assign(A, 0); e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
     e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
@@ -1007,8 +1117,18 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
         copy_or_fill<uint32_t>(&e->a_gang[x0], gang, a, YK_NONE);
         std::fill(e->a_state.begin() + x0, e->a_state.begin() + x0 + a, (uint8_t)yk::ST_PENDING);
         std::fill(e->a_bound.begin() + x0, e->a_bound.begin() + x0 + a, YK_NONE);
+        // (the rows [x0, x0+a) were overwritten above: numbers they represented are retired first)
+        const bool full = x0 == 0 && a >= e->a_hi;
+        if (full) e->sigs.reset(e->maxA);
+        else for (uint32_t i = 0; i < a; ++i) e->sigs.retire(x0 + i);
         for (uint32_t i = 0; i < a; ++i) e->a_sig[x0 + i] = yk::ask_signature(sv, x0 + i);
         e->a_hi = std::max(e->a_hi, x0 + a);
+        if (!full && e->sigs.n > 2 * e->maxA) {   // too many stale numbers: renumber every present ask
+            e->sigs.reset(e->maxA);
+            for (uint32_t y = 0; y < e->a_hi; ++y) if (e->a_state[y] != yk::ST_ABSENT) e->a_sigid[y] = e->sigs.get(sv, e->a_sig[y], y);
+        } else {
+            for (uint32_t i = 0; i < a; ++i) e->a_sigid[x0 + i] = e->sigs.get(sv, e->a_sig[x0 + i], x0 + i);
+        }
         e->asks_stale = true;
         return YK_OK;
     }
@@ -1020,6 +1140,12 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
         e->a_deny[x] = deny ? deny[i] : 0;
         e->a_node[x] = required_node ? required_node[i] : YK_NONE;
         e->a_sig[x] = yk::ask_signature(sv, x);
+        e->sigs.retire(x);
+        if (e->sigs.n > 2 * e->maxA) {   // too many stale numbers: renumber the present asks
+            e->sigs.reset(e->maxA);
+            for (uint32_t y = 0; y < e->a_hi; ++y) if (y != x && e->a_state[y] != yk::ST_ABSENT) e->a_sigid[y] = e->sigs.get(sv, e->a_sig[y], y);
+        }
+        e->a_sigid[x] = e->sigs.get(sv, e->a_sig[x], x);
         e->a_prio[x] = prio ? prio[i] : 0;
         e->a_create[x] = create_seq[i];
         e->a_app[x] = app[i];
@@ -1274,7 +1400,6 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     // starts the initial node order on the device
     std::vector<uint32_t>& pending = e->pending;
     double begin_ms = 0;
-    uint32_t n_shapes = 0;
     bool gang_too_big = false;
     setup_commit_tables(e);
     const bool try_lattice = e->lt_allowed && (e->lt_force || e->lt_auto) && e->cfg.policy == YK_POLICY_FAIR;
@@ -1305,10 +1430,30 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         t.q_sort = e->q_sort.data();
         t.q_prio_offset = e->q_prio_offset.data(); t.q_prio_fence = e->q_prio_fence.data();
         if (!gang_too_big) e->ord.begin_cycle(pending);
-        if (!gang_too_big && try_lattice) {   // dense numbers for request vectors and signatures (what the kernel dedups by)
-            uint32_t n_sigs = 0;
-            yklt::assign_ids(e->cm.t, e->a_sig.data(), pending, e->a_shape, e->a_sigid, &n_shapes, &n_sigs);
+        e->ep_rows = false;
+        if (!gang_too_big && e->share_rows && e->cfg.world <= 1) {
+            // how many distinct signatures do the pending asks have?  Few: every one is swept once per epoch (ep_local =
+            // its row), no per-batch device work at all
+            if (e->ep_seen.size() < e->sigs.n) { e->ep_seen.assign(e->sigs.n + 1024, 0); e->ep_local.assign(e->sigs.n + 1024, 0); e->ep_stamp = 0; }
+            if (++e->ep_stamp == 0) { std::fill(e->ep_seen.begin(), e->ep_seen.end(), 0); e->ep_stamp = 1; }
+            e->ep_reps.clear();
+            uint32_t ns = 0;
+            for (uint32_t a : pending) {
+                const uint32_t id = e->a_sigid[a];
+                if (e->ep_seen[id] != e->ep_stamp) {
+                    e->ep_seen[id] = e->ep_stamp;
+                    if (ns < yk_engine::EP_MAX) { e->ep_local[id] = ns; e->ep_reps.push_back(a); }
+                    if (++ns > yk_engine::EP_MAX) break;
+                }
+            }
+            e->n_sigs = ns;
+            e->ep_rows = ns > 0 && ns <= yk_engine::EP_MAX && (uint64_t)ns * 8 <= pending.size();
+            e->ep_n = ns;
         }
+        if (!gang_too_big && try_lattice) {   // request-vector numbers for the lattice kernel's windows
+            yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
+        }
+        e->ep_uploaded = false; e->ep_landed = true;
         begin_ms = now_ms() - t_b;
     });
     int rc = upload_tables(e);

@@ -382,7 +382,7 @@ LT_NI int box_of(float gap, const float* inv /*[S] 1/delta, 0 = the shape does n
         for (int s = 1; s < S; ++s) if (d[s] > d[m]) m = s;
         d[m] = (uint8_t)(d[m] >> 1);
         v = 1;
-        for (int s = 0; s < S; ++s) v *= d[s] + 1;
+        for (int s = 0; s < S; ++s) { v *= d[s] + 1; if (v > (1 << 24)) v = 1 << 24; }   // (eight sides of 64 overflow an int)
     }
     return v;
 }
@@ -898,6 +898,9 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                     const bool room = in && fits<D>(true, av, to, s.sreq + sh * 8);
                     put_bit(s.ROOM + sh * FW, e, room);
                     const int c = (int)((cvec >> (8 * sh)) & 0xFFu), dep = s.depth[p * SMAX + sh];
+#if !LT_DEV && defined(YK_LT_DEBUG)
+                    if (in && room && c < dep && slot + stride >= (int)s.off[s.P]) { fprintf(stderr, "DBG e=%d slot=%d stride=%d p=%d loc0=%d S=%d sh=%d c=%d dep=%d off=%u off1=%u total=%u nvalid=%d depths=%d,%d,%d,%d cvec=%llx\n", e, slot, stride, p, slot-(int)s.off[p], S, sh, c, dep, s.off[p], s.off[p+1], s.off[s.P], nvalid, s.depth[p*SMAX],s.depth[p*SMAX+1],s.depth[p*SMAX+2],s.depth[p*SMAX+3], cvec); abort(); }
+#endif
                     if (in) s.child[e * SMAX + sh] = (room && c < dep) ? s.idx_of[slot + stride] : NO_CHILD;
                     stride *= dep + 1;
                 }

@@ -17,16 +17,14 @@ inline bool same_request(const yk::CommitTables& t, uint32_t a, uint32_t b) {
     return true;
 }
 
-// Dense numbers for the distinct request vectors ("shapes") and the distinct predicate signatures of the cycle's pending
-// asks: a_shape[ask], a_sigid[ask].  Equal numbers <=> equal vectors / signatures (hash table, equality always confirmed
-// on the full data).  a_sig = the 64-bit signature hashes computed when the asks were upserted.
-inline void assign_ids(const yk::CommitTables& t, const uint64_t* a_sig, const std::vector<uint32_t>& pending,
-                       std::vector<uint32_t>& a_shape, std::vector<uint32_t>& a_sigid, uint32_t* n_shapes, uint32_t* n_sigs) {
+// Dense numbers for the distinct request vectors ("shapes") of the cycle's pending asks: a_shape[ask].  Equal numbers <=>
+// equal vectors (hash table, equality always confirmed on the full vector).
+inline void assign_shapes(const yk::CommitTables& t, const std::vector<uint32_t>& pending, std::vector<uint32_t>& a_shape, uint32_t* n_shapes) {
     struct Slot { uint32_t ask; uint32_t id; };
     size_t cap = 64;
     while (cap < 4 * pending.size()) cap <<= 1;
-    std::vector<Slot> shapes(cap, Slot{yk::CNONE, 0}), sigs(cap, Slot{yk::CNONE, 0});
-    uint32_t ns = 0, ng = 0;
+    std::vector<Slot> shapes(cap, Slot{yk::CNONE, 0});
+    uint32_t ns = 0;
     for (uint32_t a : pending) {
         uint64_t h = 0x9E3779B97F4A7C15ull;
         for (int k = 0; k < t.D; ++k) { h ^= (uint64_t)t.a_req[(size_t)k * t.lda + a] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xD6E8FEB86659FD93ull; }
@@ -37,8 +35,21 @@ inline void assign_ids(const yk::CommitTables& t, const uint64_t* a_sig, const s
             if (same_request(t, s.ask, a)) { a_shape[a] = s.id; break; }
             x = (x + 1) & (cap - 1);
         }
+    }
+    *n_shapes = ns;
+}
+
+// Dense numbers for the distinct predicate signatures of the given asks (the engine keeps these up to date as asks are
+// upserted; the CPU test harness computes them here).  a_sig = the 64-bit signature hashes.
+inline void assign_sigs(const yk::CommitTables& t, const uint64_t* a_sig, const std::vector<uint32_t>& pending, std::vector<uint32_t>& a_sigid) {
+    struct Slot { uint32_t ask; uint32_t id; };
+    size_t cap = 64;
+    while (cap < 4 * pending.size()) cap <<= 1;
+    std::vector<Slot> sigs(cap, Slot{yk::CNONE, 0});
+    uint32_t ng = 0;
+    for (uint32_t a : pending) {
         const uint64_t g = a_sig[a];
-        x = (size_t)(g ^ (g >> 29)) & (cap - 1);
+        size_t x = (size_t)(g ^ (g >> 29)) & (cap - 1);
         for (;;) {
             Slot& s = sigs[x];
             if (s.ask == yk::CNONE) { s.ask = a; s.id = ng++; a_sigid[a] = s.id; break; }
@@ -46,7 +57,6 @@ inline void assign_ids(const yk::CommitTables& t, const uint64_t* a_sig, const s
             x = (x + 1) & (cap - 1);
         }
     }
-    *n_shapes = ns; *n_sigs = ng;
 }
 
 // the three words per batch entry that the kernel reads (yk_lattice.h): gang flags, shape number, signature number
