@@ -259,6 +259,7 @@ struct yk_engine {
     Pin<uint32_t> h_lt_asks, h_lt_meta, h_lt_shp, h_lt_sig, h_lt_res; Pin<int> h_lt_hdr; Pin<int64_t> h_lt_ub;
     std::vector<uint32_t> a_shape, a_sigid;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
+    Dev<uint32_t> pre_q; Dev<int64_t> pre_v; Dev<int32_t> pre_o;   // yk_preemption_search staging, grown on demand
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
     // peer-to-peer exchange (see yk_peer_export): peers' slot buffers and sync blocks, mapped through CUDA IPC
     bool p2p = false;
@@ -641,7 +642,7 @@ int produce(yk_engine* e, Slot& sl, yk_stats_t& st) {
     const bool p2p_on = G > 1 && e->p2p;   // peers can write into this rank's slots
     const bool p2p = split && p2p_on;      // ... and do, for this batch
     uint32_t value = 0;
-    const long long spin_limit = 20000000000ll;   // ~10 s of SM clocks: a dead peer becomes YK_ERR_COMM, not a hang
+    const long long spin_limit = 4000000000ll;   // ~2 s of SM clocks: a dead peer becomes YK_ERR_COMM, not a hang
     if (p2p_on) {
         // The slot's previous content must have been consumed by every rank before anybody overwrites it.  Batches that
         // are not split take part in this hand-shake too (not in the "rows ready" one): ranks are not in lock-step, and
@@ -1632,8 +1633,11 @@ int yk_preemption_search(yk_engine* e, uint32_t nq, const uint32_t* ask, const u
     int rc = upload_tables(e);
     if (rc) return rc;
     const int D = e->D;
-    Dev<uint32_t> d_q; Dev<int64_t> d_v; Dev<int32_t> d_o;
-    CK(d_q.alloc((size_t)nq * 4 + 1)); CK(d_v.alloc((size_t)std::max<uint32_t>(nv, 1) * D)); CK(d_o.alloc(nq));
+    // device buffers are kept between calls and only grow (a cudaMalloc per call costs more than the search)
+    Dev<uint32_t>& d_q = e->pre_q; Dev<int64_t>& d_v = e->pre_v; Dev<int32_t>& d_o = e->pre_o;
+    if (d_q.n < (size_t)nq * 4 + 1) CK(d_q.alloc(((size_t)nq * 4 + 1) * 2));
+    if (d_v.n < (size_t)std::max<uint32_t>(nv, 1) * D) CK(d_v.alloc((size_t)std::max<uint32_t>(nv, 1) * D * 2));
+    if (d_o.n < nq) CK(d_o.alloc((size_t)nq * 2));
     cudaStream_t s = e->stream;
     CK(cudaMemcpyAsync(d_q.p, ask, 4 * (size_t)nq, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_q.p + nq, node, 4 * (size_t)nq, cudaMemcpyHostToDevice, s));
