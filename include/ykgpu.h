@@ -179,6 +179,18 @@ int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t
                    const int64_t* submit_time);
 int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx);
 
+/* User / group resource limits: the core's queue `limits:` entries [EXT yunikorn-core ugm]; the shim sends the user and its
+ * groups with every application (si.AddApplicationRequest.Ugi, pkg/cache/application.go:430).  yk_apps_user names the user
+ * of each application (dense index, YK_NONE = none).  yk_user_limits_set replaces the whole table: entry l says "user
+ * user[l] may hold at most max[.][l] ([D][n], -1 = not limited in that dimension) below queue queue[l]", summed over the
+ * user's applications in that queue's subtree; an ask that exceeds what is left is SKIPPED for the cycle exactly like one
+ * that exceeds the queue headroom.  The adapter resolves which entry applies to a user (its own, its group's, the
+ * wildcard).  held[.][l] = what the user holds there now ([D][n], NULL = 0); the engine keeps it current afterwards
+ * (cycle, yk_release).  maxapplications is not modelled (it gates application acceptance, not this path). */
+int yk_apps_user(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t* user);
+int yk_user_limits_set(yk_engine* e, uint32_t n, const uint32_t* queue, const uint32_t* user, const int64_t* max,
+                       const int64_t* held);
+
 /* asks: req is [D][a].  create_seq is the total-order key within an application (ties pre-broken by the
  * caller: the reference's CreationTime is second-granular, pkg/common/si_helper.go:109).
  * required_node = YK_NONE or the node index pod.Spec.NodeName names.  gang = YK_NONE or a gang id
@@ -209,6 +221,11 @@ int yk_ask_states(yk_engine* e, uint32_t n, const uint32_t* idx, uint8_t* state_
 int yk_nodes_available(yk_engine* e, uint32_t n, const uint32_t* idx, int64_t* avail_out);
 /* one (ask,node) answer on the current state, evaluated on the device: 0 fits / YK_FAIL_* / <0 error */
 int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node);
+/* the same answer for the reservation phase, Predicates(Allocate = false): the reference then runs the same plugins WITHOUT
+ * NodeResourcesFit (pkg/plugin/predicates/predicate_manager.go:130-135, reservation filter set :353-368) and the core does
+ * not ask for available resources: YK_FAIL_AVAILABLE / YK_FAIL_RESOURCES cannot come back.  (Reservations themselves --
+ * an old unplaceable ask pinning a node -- are not made by yk_cycle: SURVEY A.1, DESIGN.md.) */
+int yk_evaluate_reserve(yk_engine* e, uint32_t ask, uint32_t node);
 /* node sort keys as the device computes them (float64 score bits), for known-answer tests */
 int yk_node_scores(yk_engine* e, uint32_t n, const uint32_t* idx, double* score_out);
 

@@ -27,6 +27,8 @@ class _Snap(C.Structure):
         ("ask_prio", C.c_void_p), ("ask_create", C.c_void_p), ("ask_node", C.c_void_p),
         ("ask_flags", C.c_void_p), ("ask_gang", C.c_void_p),
         ("q_prio_offset", C.c_void_p), ("q_prio_fence", C.c_void_p),
+        ("app_user", C.c_void_p), ("n_limits", C.c_int32), ("ul_queue", C.c_void_p), ("ul_user", C.c_void_p),
+        ("ul_max", C.c_void_p), ("ul_alloc", C.c_void_p),
     ]
 
 
@@ -85,6 +87,12 @@ def _pack(s):
         ask_flags=arr(s.ask_flags, np.uint32), ask_gang=arr(s.ask_gang, np.int32),
         q_prio_offset=(arr(s.q_prio_offset, np.int32) if getattr(s, "q_prio_offset", None) is not None else None),
         q_prio_fence=(arr(s.q_prio_fence, np.uint8) if getattr(s, "q_prio_fence", None) is not None else None))
+    if getattr(s, "ul_queue", None) is not None and len(s.ul_queue):
+        st.app_user = arr(s.app_user, np.int32)
+        st.n_limits = len(s.ul_queue)
+        st.ul_queue, st.ul_user = arr(s.ul_queue, np.int32), arr(s.ul_user, np.int32)
+        st.ul_max = arr(s.ul_max, np.int64)
+        st.ul_alloc = arr(s.ul_alloc, np.int64) if getattr(s, "ul_alloc", None) is not None else None
     return st, keep
 
 
@@ -110,6 +118,12 @@ def run(s, max_bindings: int = -1, retry_failed: bool = False):
 def predicate(s, ask: int, node: int) -> int:
     st, keep = _pack(s)
     return lib().yko_predicate(C.byref(st), C.c_int32(ask), C.c_int32(node))
+
+
+def predicate_reserve(s, ask: int, node: int) -> int:
+    st, keep = _pack(s)
+    lib().yko_predicate_reserve.restype = C.c_int
+    return lib().yko_predicate_reserve(C.byref(st), C.c_int32(ask), C.c_int32(node))
 
 
 def preemption_index(s, ask: int, node: int, victim_req, start: int) -> int:

@@ -107,6 +107,31 @@ def run(s, max_bindings=-1):
             for k in range(D):
                 q_pending[q][k] += req[a][k]
 
+    has_limits = getattr(s, "ul_queue", None) is not None and len(s.ul_queue) > 0
+    ualloc = [[int(x) for x in (s.ul_alloc[l] if getattr(s, "ul_alloc", None) is not None else [0] * D)] for l in range(len(s.ul_queue))] if has_limits else []
+    app_limits = {}
+
+    def limits_of(p):
+        """the user-limit entries that apply to the application: its user, a queue on its chain"""
+        if p not in app_limits:
+            out = []
+            if has_limits and int(s.app_user[p]) >= 0:
+                ch = set(chain(int(s.app_queue[p])))
+                out = [l for l in range(len(s.ul_queue)) if int(s.ul_user[l]) == int(s.app_user[p]) and int(s.ul_queue[l]) in ch]
+            app_limits[p] = out
+        return app_limits[p]
+
+    def with_user_headroom(p, hr):
+        hr = list(hr)
+        for l in limits_of(p):
+            for k in range(D):
+                mx = int(s.ul_max[l][k])
+                if mx == UNSET:
+                    continue
+                own = max(0, mx - ualloc[l][k])
+                hr[k] = own if hr[k] == UNSET else min(hr[k], own)
+        return hr
+
     def headroom(q):
         hr = [UNSET] * D
         for qq in reversed(list(chain(q))):
@@ -152,6 +177,9 @@ def run(s, max_bindings=-1):
         p = int(s.ask_app[a])
         for k in range(D):
             app_alloc[p][k] += sign * req[a][k]
+        for l in limits_of(p):
+            for k in range(D):
+                ualloc[l][k] += sign * req[a][k]
         for qq in chain(int(s.app_queue[p])):
             q_npend[qq] -= sign
             for k in range(D):
@@ -184,9 +212,11 @@ def run(s, max_bindings=-1):
                 cand.sort(key=functools.cmp_to_key(cmp))
             else:
                 cand.sort(key=lambda p: (-app_prio(p), int(s.app_submit[p]), p))
+            hr_queue = hr
             for p in cand:
                 if stop[0]:
                     return None
+                hr = with_user_headroom(p, hr_queue)
                 for a in app_asks[p]:
                     if stop[0]:
                         return None
@@ -206,7 +236,7 @@ def run(s, max_bindings=-1):
                     if g >= 0:      # a gang member: the gang-wide checks below decide for every member (all or nothing)
                         members = [m for m in app_asks[p] if int(s.ask_gang[m]) == g and state[m] != ST_ALLOCATED and not dead[m]]
                         placed, cause = [], 0
-                        hrm = headroom(q)           # queue-side checks of all members first, headroom shrinking
+                        hrm = with_user_headroom(p, headroom(q))   # queue-side checks of all members first, headroom shrinking
                         for m in members:
                             if int(s.ask_flags[m]) & 1:
                                 cause = ST_SLOWPATH

@@ -133,7 +133,20 @@ struct Engine {
         int64_t pending_asks = 0;
         size_t head = 0;          // first ask not yet allocated (asks are in priority order)
         std::vector<int64_t> alloc;
+        std::vector<int> limits;  // user-limit entries that apply: the app's user, a queue on the app's chain
     };
+    std::vector<int64_t> ualloc;  // [l][D] what each user-limit entry's user holds below its queue
+
+    // the application's user headroom folded into the queue headroom [EXT ugm Headroom]: hr = min(hr, max - held)
+    void user_headroom(int p, int64_t* hr) {
+        for (int l : apps[(size_t)p].limits)
+            for (int k = 0; k < D; ++k) {
+                const int64_t mx = s->ul_max[(size_t)l * D + k];
+                if (mx == UNSET) continue;
+                const int64_t own = clamp0(mx - ualloc[(size_t)l * D + k]);
+                hr[k] = (hr[k] == UNSET) ? own : std::min(hr[k], own);
+            }
+    }
     std::vector<App> apps;
     std::vector<uint8_t> state;
     std::vector<uint8_t> done;   // allocated, or known-unplaceable (shortcut)
@@ -155,6 +168,19 @@ struct Engine {
         // NodeResourcesFit on the shim's NodeInfo: allocatable - requested is the same column as
         // the core's available in this model (DESIGN.md "one availability column")
         if (!fit_in(D, av(n), req(a))) return YKO_FAIL_RESOURCES;
+        return 0;
+    }
+
+    // Predicates(Allocate = false): the reservation phase runs the same plugins without NodeResourcesFit ("during reservation,
+    // node resources are not enough", predicate_manager.go:353-368) and the core does not ask for available resources either
+    int evaluate_reserve(int a, int n) {
+        if (!(s->node_flags[n] & YKO_NODE_SCHEDULABLE)) return YKO_FAIL_NODE_NOT_SCHEDULABLE;
+        if (!fit_in(D, total(n), req(a))) return YKO_FAIL_TOTAL;
+        if (!strictly_gt_zero(D, req(a))) return YKO_FAIL_REQUEST_NOT_POSITIVE;
+        if (s->ask_node[a] >= 0 && s->ask_node[a] != n) return YKO_FAIL_NODENAME;
+        if (s->node_taint[n] & ~s->ask_tol[a]) return YKO_FAIL_TAINT;
+        if ((s->node_label[n] & s->ask_need[a]) != s->ask_need[a]) return YKO_FAIL_AFFINITY;
+        if (s->node_label[n] & s->ask_deny[a]) return YKO_FAIL_AFFINITY;
         return 0;
     }
 
@@ -214,6 +240,7 @@ struct Engine {
         App& ap = apps[(size_t)p];
         ap.pending_asks--;
         for (int k = 0; k < D; ++k) ap.alloc[(size_t)k] += r[k];
+        for (int l : ap.limits) for (int k = 0; k < D; ++k) ualloc[(size_t)l * D + k] += r[k];
         for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
             Queue& Q = queues[(size_t)q];
             Q.pending_asks--;
@@ -234,6 +261,7 @@ struct Engine {
         App& ap = apps[(size_t)p];
         ap.pending_asks++;
         for (int k = 0; k < D; ++k) ap.alloc[(size_t)k] -= r[k];
+        for (int l : ap.limits) for (int k = 0; k < D; ++k) ualloc[(size_t)l * D + k] -= r[k];
         for (int q = s->app_queue[p]; q >= 0; q = queues[(size_t)q].parent) {
             Queue& Q = queues[(size_t)q];
             Q.pending_asks++;
@@ -266,6 +294,7 @@ struct Engine {
         {
             int64_t hr[YKO_MAX_D];
             headroom(s->app_queue[p], hr);
+            user_headroom(p, hr);
             for (int a : members) {
                 if (s->ask_flags[a] & YKO_ASK_SLOWPATH) { cause = YKO_ST_SLOWPATH; break; }
                 if (!fit_in_max_undef(hr, req(a))) { cause = YKO_ST_SKIPPED; break; }
@@ -320,9 +349,12 @@ struct Engine {
     }
 
     // appends the pass's allocation(s) to out (one ask, or a whole gang); returns true if anything was allocated
-    bool try_app(int p, const int64_t* hr, std::vector<std::pair<int, int>>& out, int room) {
+    bool try_app(int p, const int64_t* hr_queue, std::vector<std::pair<int, int>>& out, int room) {
         bool retry = (mode & YKO_MODE_RETRY_FAILED) != 0;
         App& ap = apps[(size_t)p];
+        int64_t hr[YKO_MAX_D];
+        for (int k = 0; k < D; ++k) hr[k] = hr_queue[k];
+        user_headroom(p, hr);
         for (size_t i = ap.head; i < ap.asks.size(); ++i) {
             int a = ap.asks[i];
             if (state[(size_t)a] == YKO_ST_ALLOCATED) continue;
@@ -451,6 +483,14 @@ int yko_predicate(const yko_snapshot* s, int32_t ask, int32_t node) {
     return e.evaluate(ask, node);
 }
 
+int yko_predicate_reserve(const yko_snapshot* s, int32_t ask, int32_t node) {
+    if (!s || ask < 0 || ask >= s->n_asks || node < 0 || node >= s->n_nodes) return -1;
+    Engine e;
+    e.s = s; e.D = s->D; e.mode = 0;
+    e.avail.assign(s->node_avail, s->node_avail + (size_t)s->n_nodes * s->D);
+    return e.evaluate_reserve(ask, node);
+}
+
 int yko_preemption_index(const yko_snapshot* s, int32_t ask, int32_t node, int32_t n_victims,
                          const int64_t* victim_req, int32_t start) {
     if (!s || ask < 0 || ask >= s->n_asks || node < 0 || node >= s->n_nodes) return -2;
@@ -513,7 +553,15 @@ int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings, int32_t*
         if (!e.queues[(size_t)s->app_queue[p]].children.empty()) return -10;  // apps live in leaves
         e.queues[(size_t)s->app_queue[p]].apps.push_back(p);
         e.apps[(size_t)p].alloc.assign((size_t)D, 0);
+        if (s->app_user && s->n_limits > 0 && s->app_user[p] >= 0)
+            for (int l = 0; l < s->n_limits; ++l) {
+                if (s->ul_user[l] != s->app_user[p]) continue;
+                for (int q = s->app_queue[p]; q >= 0; q = e.queues[(size_t)q].parent)
+                    if (q == s->ul_queue[l]) { e.apps[(size_t)p].limits.push_back(l); break; }
+            }
     }
+    e.ualloc.assign((size_t)std::max(s->n_limits, 0) * D, 0);
+    if (s->ul_alloc) e.ualloc.assign(s->ul_alloc, s->ul_alloc + (size_t)s->n_limits * D);
     e.state.assign((size_t)s->n_asks, YKO_ST_PENDING);
     e.done.assign((size_t)s->n_asks, 0);
     for (int a = 0; a < s->n_asks; ++a) {

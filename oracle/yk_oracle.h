@@ -85,6 +85,16 @@ typedef struct {
     /* queue priority properties (priority.offset, priority.policy = fence) [EXT yunikorn-core configs]; may be NULL = 0 */
     const int32_t* q_prio_offset;   /* [q] */
     const uint8_t* q_prio_fence;    /* [q] 1 = fence: the queue shows its parent only its offset */
+    /* user / group resource limits (the core's queue `limits:` entries, [EXT yunikorn-core ugm]; the shim sends the
+     * user with every application, pkg/cache/application.go:430): entry l = "user ul_user[l] may hold at most ul_max[l]
+     * below queue ul_queue[l]" (summed over the user's applications in that queue's subtree).  The group / wildcard entry
+     * that applies to a user is resolved by the caller.  All may be NULL / 0 = no limits. */
+    const int32_t* app_user;        /* [p] user index or -1 */
+    int32_t n_limits;
+    const int32_t* ul_queue;        /* [l] */
+    const int32_t* ul_user;         /* [l] */
+    const int64_t* ul_max;          /* [l][D], -1 = not set */
+    const int64_t* ul_alloc;        /* [l][D] held at cycle start; may be NULL = 0 */
 } yko_snapshot;
 
 typedef struct {
@@ -119,6 +129,9 @@ int yko_run(const yko_snapshot* s, uint32_t mode, int32_t max_bindings,
 #define YKO_FAIL_AFFINITY             7  /* k8s NodeAffinity (nodeSelector + required terms) */
 #define YKO_FAIL_RESOURCES            8  /* k8s NodeResourcesFit */
 int yko_predicate(const yko_snapshot* s, int32_t ask, int32_t node);
+/* the same for the reservation phase, Predicates(Allocate = false): no NodeResourcesFit, no available check
+ * (/root/reference/pkg/plugin/predicates/predicate_manager.go:130-135,353-368) */
+int yko_predicate_reserve(const yko_snapshot* s, int32_t ask, int32_t node);
 
 /* Preemption victim search for one (ask,node): /root/reference/pkg/plugin/predicates/predicate_manager.go:137-175.
  * victim_req is [n][D] (what removing each victim gives back).  Returns the first index >= start that fits, or -1. */

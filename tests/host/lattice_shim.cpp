@@ -18,6 +18,13 @@
 static const int32_t* g_q_prio_offset = nullptr;
 static const uint8_t* g_q_prio_fence = nullptr;
 extern "C" void host_set_queue_priority(const int32_t* offset, const uint8_t* fence) { g_q_prio_offset = offset; g_q_prio_fence = fence; }
+// user / group limits for the next run (same convenience): application users, then the entries [D][n] column-major
+static const uint32_t* g_p_user = nullptr; static uint32_t g_n_ul = 0;
+static const uint32_t* g_ul_queue = nullptr; static const uint32_t* g_ul_user = nullptr;
+static const int64_t* g_ul_max = nullptr; static int64_t* g_ul_alloc = nullptr;
+extern "C" void host_set_user_limits(const uint32_t* p_user, uint32_t n, const uint32_t* queue, const uint32_t* user, const int64_t* max, int64_t* alloc) {
+    g_p_user = p_user; g_n_ul = n; g_ul_queue = queue; g_ul_user = user; g_ul_max = max; g_ul_alloc = alloc;
+}
 
 namespace {
 
@@ -39,6 +46,7 @@ int run_d(uint32_t policy, const double* weights,
     o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
     o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.p_alloc = p_alloc.data(); o.t.q_sort = q_sort;
     o.t.q_prio_offset = g_q_prio_offset; o.t.q_prio_fence = g_q_prio_fence;
+    o.t.p_user = g_p_user; o.t.n_ul = g_n_ul; o.t.ul_queue = g_ul_queue; o.t.ul_user = g_ul_user; o.t.ul_max = g_ul_max; o.t.ul_alloc = g_ul_alloc;
     std::vector<uint32_t> pending(nA);
     for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
     o.begin_cycle(pending);

@@ -58,6 +58,16 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
     setter = getattr(shim, "host_set_queue_priority", None)
     if setter is not None:
         setter(_p(k["qoff"]) if k["qoff"] is not None else None, _p(k["qfen"]) if k["qfen"] is not None else None)
+    setter = getattr(shim, "host_set_user_limits", None)
+    if setter is not None:
+        if getattr(s, "ul_queue", None) is not None and len(s.ul_queue):
+            k["puser"] = _u32(s.app_user)
+            k["ulq"], k["ulu"] = _u32(s.ul_queue), _u32(s.ul_user)
+            k["ulm"] = np.ascontiguousarray(np.asarray(s.ul_max, dtype=np.int64).T)
+            k["ula"] = np.ascontiguousarray(np.asarray(s.ul_alloc if s.ul_alloc is not None else np.zeros_like(s.ul_max), dtype=np.int64).T).copy()
+            setter(_p(k["puser"]), C.c_uint32(len(s.ul_queue)), _p(k["ulq"]), _p(k["ulu"]), _p(k["ulm"]), _p(k["ula"]))
+        else:
+            setter(None, C.c_uint32(0), None, None, None, None)
     out_ask = np.zeros(max(A, 1), dtype=np.uint32)
     out_node = np.zeros(max(A, 1), dtype=np.uint32)
     n = C.c_uint32(0)

@@ -312,3 +312,39 @@ def test_reupserted_asks_get_fresh_signature_numbers(oracle):
             want = oracle.run(t)
             ask2, node2, _ = e.cycle(s.n_asks)
             assert np.array_equal(ask2, want["ask"]) and np.array_equal(node2, want["node"]), commit
+
+
+def test_user_limits(oracle):
+    """user / group resource limits through the C ABI (yk_apps_user, yk_user_limits_set), both commits; the held amounts
+    follow the cycle and yk_release"""
+    for seed in (1, 5, 8, 13, 21):
+        _check(synth.with_user_limits(synth.fuzz(seed), seed=seed), oracle, batch=64)
+    s = synth.with_user_limits(synth.hier(300, 3, 4, 2, 40, seed=21), n_users=4, seed=1, frac=0.3)
+    st = _check(s, oracle, batch=128)
+    assert st["skipped"] > 0
+    # second cycle after releasing everything: the limits bind again exactly as in the first
+    want = oracle.run(s)
+    with Engine.for_snapshot(s, batch=128) as e:
+        ask, node, _ = e.cycle(s.n_asks)
+        e.release(ask)
+        e.load_snapshot(s)
+        ask2, node2, _ = e.cycle(s.n_asks)
+    assert np.array_equal(ask2, want["ask"]) and np.array_equal(node2, want["node"])
+
+
+def test_reservation_phase_predicates(oracle):
+    """Predicates(Allocate = false): same plugins without NodeResourcesFit / available (predicate_manager.go:353-368);
+    device answer vs the oracle's, and the reference's reserve tables (TestReserveAlloc / TestReserveNodeSelector: the
+    golden file's reserve cases fit in the reservation phase exactly when the test expects no error)"""
+    s = synth.perf(60, 4, 30, masks=True, seed=77)
+    s.node_avail[::3, 0] = 0                                       # full nodes: allocate phase fails, reserve phase may pass
+    s.node_flags[5] = 0
+    s.ask_node[7] = 3
+    with Engine.for_snapshot(s) as e:
+        diff = 0
+        for a in range(0, s.n_asks, 5):
+            for n in range(0, s.n_nodes, 3):
+                got, exp = e.evaluate_reserve(a, n), oracle.predicate_reserve(s, a, n)
+                assert got == exp, (a, n, got, exp)
+                diff += int((got == 0) != (e.evaluate(a, n) == 0))
+        assert diff > 0

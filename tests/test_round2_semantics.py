@@ -99,3 +99,20 @@ def test_quota_sinks_a_gang_whole(shims, oracle):
     s.q_max[leaf, 2] = 3                      # three pods fit the leaf's quota, the gang has four members
     want = everywhere(shims, oracle, s, batch=16)
     assert list(want["state"][:4]) == [3] * 4
+
+
+def test_user_limits_through_orderer_and_commits(shims, oracle):
+    """user / group resource limits (a14): per (queue, user) maxima fold into the headroom of the user's applications, on
+    leaves and on their ancestors, in placement-sensitive orders with rewinds, gangs and fair leaves"""
+    changed = 0
+    for seed in range(40):
+        s = synth.with_user_limits(synth.fuzz(seed), seed=seed)
+        if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > 64:
+            continue
+        want = everywhere(shims, oracle, s, batch=64)
+        changed += int(list(want["ask"]) != list(oracle.run(synth.fuzz(seed))["ask"]))
+    assert changed > 10
+    for s in (synth.with_user_limits(synth.hier(300, 3, 4, 2, 40, seed=21), n_users=4, seed=1, frac=0.3),
+              synth.with_user_limits(synth.perf(200, 6, 50), n_users=2, seed=2, frac=0.4)):
+        want = everywhere(shims, oracle, s, batch=128)
+        assert (want["state"] == 3).sum() > 0          # some asks end SKIPPED on the user's headroom

@@ -207,6 +207,7 @@ struct yk_engine {
     uint32_t nq = 0;
     std::vector<uint32_t> q_parent; std::vector<int64_t> q_guar, q_max, q_alloc; std::vector<uint8_t> q_sort;
     std::vector<int32_t> q_prio_offset; std::vector<uint8_t> q_prio_fence;   // queue properties priority.offset / priority.policy=fence
+    std::vector<uint32_t> p_user, ul_queue, ul_user; std::vector<int64_t> ul_max, ul_alloc; uint32_t n_ul = 0;   // user / group limits
 
     // ---- device ----
     Dev<int64_t> d_total, d_avail; Dev<uint64_t> d_taint, d_label; Dev<uint32_t> d_flags, d_by_rank;
@@ -801,6 +802,19 @@ static bool contiguous_run(const uint32_t* idx, uint32_t n) {
     for (uint32_t i = 1; i < n; ++i) if (idx[i] != idx[0] + i) return false;
     return n > 0;
 }
+// what the user of application p holds under every limit entry that applies to it moves by sign * request(ask)
+static void user_held_add(yk_engine* e, uint32_t p, uint32_t ask, int sign) {
+    if (!e->n_ul || e->p_user[p] == YK_NONE) return;
+    for (uint32_t l = 0; l < e->n_ul; ++l) {
+        if (e->ul_user[l] != e->p_user[p]) continue;
+        for (uint32_t q = e->p_queue[p]; q != YK_NONE; q = e->q_parent[q])
+            if (q == e->ul_queue[l]) {
+                for (int k = 0; k < e->D; ++k) e->ul_alloc[(size_t)k * e->n_ul + l] += sign * e->a_req[(size_t)k * e->maxA + ask];
+                break;
+            }
+    }
+}
+
 template <typename T>
 static void copy_or_fill(T* dst, const T* src, uint32_t n, T dflt) {
     if (src) memcpy(dst, src, sizeof(T) * (size_t)n);
@@ -956,7 +970,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     e->sigs.reset(A);
     e->a_sig.assign(A, 0); e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
-    e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0);
+    e->p_queue.assign(e->maxP, 0); e->p_submit.assign(e->maxP, 0); e->p_present.assign(e->maxP, 0); e->p_user.assign(e->maxP, YK_NONE);
     e->p_alloc.assign((size_t)e->maxP * D, 0);
     // default queue tree: root only would have no leaf for apps; root + one leaf "root.default"
     e->nq = 0;
@@ -1078,6 +1092,28 @@ int yk_apps_upsert(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t
     return YK_OK;
 }
 
+int yk_apps_user(yk_engine* e, uint32_t n, const uint32_t* idx, const uint32_t* user) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!idx || !user)) return e->fail(YK_ERR_ARG, "yk_apps_user: null array");
+    for (uint32_t i = 0; i < n; ++i) if (idx[i] >= e->maxP) return e->fail(YK_ERR_ARG, "yk_apps_user: index beyond max_apps");
+    for (uint32_t i = 0; i < n; ++i) e->p_user[idx[i]] = user[i];
+    return YK_OK;
+}
+
+int yk_user_limits_set(yk_engine* e, uint32_t n, const uint32_t* queue, const uint32_t* user, const int64_t* max, const int64_t* held) {
+    if (!e) return YK_ERR_ARG;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (n && (!queue || !user || !max)) return e->fail(YK_ERR_ARG, "yk_user_limits_set: null array");
+    for (uint32_t i = 0; i < n; ++i) if (queue[i] >= e->nq) return e->fail(YK_ERR_ARG, "yk_user_limits_set: unknown queue (call yk_queues_set first)");
+    const int D = e->D;
+    e->n_ul = n;
+    e->ul_queue.assign(queue, queue + n); e->ul_user.assign(user, user + n);
+    e->ul_max.assign(max, max + (size_t)n * D);
+    if (held) e->ul_alloc.assign(held, held + (size_t)n * D); else e->ul_alloc.assign((size_t)n * D, 0);
+    return YK_OK;
+}
+
 int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx) {
     if (!e) return YK_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
@@ -1186,6 +1222,7 @@ int yk_release(yk_engine* e, uint32_t n, const uint32_t* idx) {
             for (uint32_t q = e->p_queue[e->a_app[a]]; q != YK_NONE; q = e->q_parent[q]) e->q_alloc[(size_t)k * e->nq + q] -= r;
             e->p_alloc[(size_t)k * e->maxP + e->a_app[a]] -= r;
         }
+        user_held_add(e, e->a_app[a], a, -1);
         e->a_state[a] = yk::ST_ABSENT;
         e->a_bound[a] = YK_NONE;
     }
@@ -1430,6 +1467,8 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
         t.q_sort = e->q_sort.data();
         t.q_prio_offset = e->q_prio_offset.data(); t.q_prio_fence = e->q_prio_fence.data();
+        t.p_user = e->p_user.data(); t.n_ul = e->n_ul; t.ul_queue = e->ul_queue.data(); t.ul_user = e->ul_user.data();
+        t.ul_max = e->ul_max.data(); t.ul_alloc = e->ul_alloc.data();
         if (!gang_too_big) e->ord.begin_cycle(pending);
         e->ep_rows = false;
         if (!gang_too_big && e->share_rows && e->cfg.world <= 1) {
@@ -1541,6 +1580,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
                 for (uint32_t q = e->p_queue[e->a_app[a]]; q != YK_NONE; q = e->q_parent[q]) e->q_alloc[(size_t)k * e->nq + q] += r;
                 e->p_alloc[(size_t)k * e->maxP + e->a_app[a]] += r;
             }
+            user_held_add(e, e->a_app[a], a, +1);
         }
     } else {
         e->ord.finish();
@@ -1579,7 +1619,7 @@ int yk_nodes_available(yk_engine* e, uint32_t n, const uint32_t* idx, int64_t* o
     return YK_OK;
 }
 
-int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node) {
+static int evaluate_phase(yk_engine* e, uint32_t ask, uint32_t node, int allocate) {
     if (!e) return YK_ERR_ARG;
     std::lock_guard<std::mutex> g(e->mu);
     if (ask >= e->maxA || node >= e->maxN) return e->fail(YK_ERR_ARG, "yk_evaluate: index out of range");
@@ -1588,13 +1628,16 @@ int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node) {
     if (rc) return rc;
     yk_evaluate_kernel<<<1, 32, 0, e->stream>>>(e->D, e->d_total.p, e->d_avail.p, e->maxN, e->d_taint.p, e->d_label.p,
                                                 e->d_flags.p, e->d_areq.p, e->d_atol.p, e->d_aneed.p, e->d_adeny.p,
-                                                e->d_anode.p, e->maxA, ask, node, e->d_flag.p);
+                                                e->d_anode.p, e->maxA, ask, node, allocate, e->d_flag.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_flag.p, e->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->st.other_launches++;
     return e->h_flag[0];
 }
+
+int yk_evaluate(yk_engine* e, uint32_t ask, uint32_t node) { return evaluate_phase(e, ask, node, 1); }
+int yk_evaluate_reserve(yk_engine* e, uint32_t ask, uint32_t node) { return evaluate_phase(e, ask, node, 0); }
 
 int yk_node_scores(yk_engine* e, uint32_t n, const uint32_t* idx, double* out) {
     if (!e) return YK_ERR_ARG;

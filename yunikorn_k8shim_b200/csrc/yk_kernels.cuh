@@ -264,7 +264,7 @@ __global__ void yk_evaluate_kernel(int D, const int64_t* __restrict__ total, con
                                    const uint32_t* __restrict__ flags, const int64_t* __restrict__ a_req,
                                    const uint64_t* __restrict__ a_tol, const uint64_t* __restrict__ a_need,
                                    const uint64_t* __restrict__ a_deny, const uint32_t* __restrict__ a_node, size_t lda,
-                                   uint32_t ask, uint32_t node, int* __restrict__ out) {
+                                   uint32_t ask, uint32_t node, int allocate, int* __restrict__ out) {
     if (threadIdx.x || blockIdx.x) return;
     int r = 0;
     bool pos = false, neg = false, fit_total = true, fit_avail = true;
@@ -279,7 +279,7 @@ __global__ void yk_evaluate_kernel(int D, const int64_t* __restrict__ total, con
     if (!(flags[node] & 1u)) r = 1;
     else if (!fit_total) r = 2;
     else if (neg || !pos) r = 3;
-    else if (!fit_avail) r = 4;
+    else if (allocate && !fit_avail) r = 4;   // reservation phase (Allocate = false): no NodeResourcesFit, no available check
     else if (a_node[ask] != YK_NONE_U32 && a_node[ask] != node) r = 5;
     else if (taint[node] & ~a_tol[ask]) r = 6;
     else if ((label[node] & a_need[ask]) != a_need[ask] || (label[node] & a_deny[ask])) r = 7;

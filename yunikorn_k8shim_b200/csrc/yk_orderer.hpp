@@ -48,6 +48,14 @@ struct Tables {   // views into the engine's host tables
     const uint8_t* q_sort = nullptr;
     const int32_t* q_prio_offset = nullptr;   // [nq] queue property priority.offset; null = all 0
     const uint8_t* q_prio_fence = nullptr;    // [nq] 1 = priority.policy fence: the parent sees only the offset; null = none
+    // user / group resource limits (the core's queue `limits:` [EXT ugm]; the shim sends the user with every application,
+    // pkg/cache/application.go:430): entry l = user ul_user[l] may hold at most ul_max[.][l] below queue ul_queue[l]
+    const uint32_t* p_user = nullptr;         // [maxP] user index or NONE; null = no users
+    uint32_t n_ul = 0;
+    const uint32_t* ul_queue = nullptr;       // [n_ul]
+    const uint32_t* ul_user = nullptr;        // [n_ul]
+    const int64_t* ul_max = nullptr;          // [D][n_ul], UNSET = not limited
+    int64_t* ul_alloc = nullptr;              // [D][n_ul] persistent: what the user holds there (updated at finish())
 };
 
 class Orderer {
@@ -107,6 +115,8 @@ public:
     // skipped.  Otherwise every leaf keeps {priority of an application's best pending ask -> how many such applications}.
     bool uniform_prio = true;
     std::vector<std::map<int32_t, int>> q_prio_cnt;
+    std::vector<int64_t> ua;                        // [n_ul][8] held under each user-limit entry, this cycle
+    std::vector<std::vector<uint32_t>> ap_ul;       // application -> the entries that apply to it
     std::vector<AState> ap;
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
@@ -123,6 +133,7 @@ public:
         std::vector<AState> ap;
         std::vector<std::set<AppKey>> sets;
         std::vector<std::map<int32_t, int>> prio_cnt;
+        std::vector<int64_t> ua;
         std::vector<std::pair<uint32_t, uint8_t>> journal;   // (ask, previous state) written while the batch was filled
         size_t slow_mark = 0;
         bool valid = false;
@@ -193,6 +204,20 @@ public:
             if (t.p_alloc) for (int k = 0; k < d; ++k) A.alloc[k] = t.p_alloc[(size_t)k * t.maxP + p];
             if (A.live > 0) { q_set[t.p_queue[p]].insert(make_key(p)); A.in_set = true; }
         }
+        // user limits: which entries apply to which application (its user, a queue on its chain)
+        ua.assign((size_t)t.n_ul * 8, 0);
+        if (ap_ul.size() < t.maxP) ap_ul.resize(t.maxP);
+        bool any_limit = false;
+        for (uint32_t p = 0; p < t.maxP; ++p) {
+            ap_ul[p].clear();
+            if (!t.n_ul || !t.p_user || ap_asks[p].empty() || t.p_user[p] == NONE) continue;
+            for (uint32_t l = 0; l < t.n_ul; ++l) {
+                if (t.ul_user[l] != t.p_user[p]) continue;
+                for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq])
+                    if (qq == t.ul_queue[l]) { ap_ul[p].push_back(l); any_limit = true; break; }
+            }
+        }
+        for (uint32_t l = 0; l < t.n_ul; ++l) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] = t.ul_alloc ? t.ul_alloc[(size_t)k * t.n_ul + l] : 0;
         // placement-insensitive?  one leaf with pending asks, fifo, no max on its chain, one priority level
         int leaves = 0; uint32_t leaf = NONE;
         for (uint32_t i = 0; i < t.nq; ++i)
@@ -205,7 +230,7 @@ public:
             bool quota = false;
             for (uint32_t qq = leaf; qq != NONE; qq = t.q_parent[qq])
                 for (int k = 0; k < d; ++k) if (t.q_max[(size_t)k * t.nq + qq] != UNSET) quota = true;
-            insensitive = !quota;
+            insensitive = !quota && !any_limit;   // a user limit makes headroom depend on what was placed, like a quota
         }
         static_order.clear();
         static_next = 0;
@@ -272,7 +297,7 @@ public:
             return batch.size();
         }
         snap.journal.clear(); snap.slow_mark = slow_list.size();
-        snap.q = q; snap.ap = ap; snap.sets = q_set; snap.valid = true;   // only placement-sensitive orders ever rewind
+        snap.q = q; snap.ap = ap; snap.sets = q_set; snap.ua = ua; snap.valid = true;   // only placement-sensitive orders ever rewind
         if (!uniform_prio) snap.prio_cnt = q_prio_cnt;
         jr = &snap.journal;
         while (step(cap_batch, cap_user, batch)) {}
@@ -291,7 +316,7 @@ public:
         }
         for (auto it = snap.journal.rbegin(); it != snap.journal.rend(); ++it) t.a_state[it->first] = it->second;
         snap.journal.clear();
-        q = snap.q; ap = snap.ap; q_set = snap.sets; slow_list.resize(snap.slow_mark);
+        q = snap.q; ap = snap.ap; q_set = snap.sets; ua = snap.ua; slow_list.resize(snap.slow_mark);
         if (!uniform_prio) q_prio_cnt = snap.prio_cnt;
         snap.valid = false;
         jr = nullptr;
@@ -320,7 +345,7 @@ public:
         if (insensitive) { static_next -= batch.size() - j; return; }
         for (auto it = snap.journal.rbegin(); it != snap.journal.rend(); ++it) t.a_state[it->first] = it->second;
         snap.journal.clear();
-        q = snap.q; ap = snap.ap; q_set = snap.sets; slow_list.resize(snap.slow_mark);
+        q = snap.q; ap = snap.ap; q_set = snap.sets; ua = snap.ua; slow_list.resize(snap.slow_mark);
         if (!uniform_prio) q_prio_cnt = snap.prio_cnt;
         snap.valid = false;
         jr = nullptr;
@@ -338,6 +363,7 @@ public:
         t.a_state[a] = ST_NOFIT;
         ap[p].npend++;
         for (int k = 0; k < d; ++k) ap[p].alloc[k] -= req(a, k);
+        for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] -= req(a, k);
         if (a_pos[a] < ap[p].head) ap[p].head = a_pos[a];
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
             q[qq].npend++;
@@ -369,6 +395,7 @@ public:
                 for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq])
                     for (int k = 0; k < t.D; ++k) q[qq].alloc[k] += delta[k];
             }
+        if (t.ul_alloc) for (uint32_t l = 0; l < t.n_ul; ++l) for (int k = 0; k < t.D; ++k) t.ul_alloc[(size_t)k * t.n_ul + l] = ua[(size_t)l * 8 + k];
         for (uint32_t i = 0; i < t.nq; ++i)
             for (int k = 0; k < t.D; ++k) t.q_alloc[(size_t)k * t.nq + i] = q[i].alloc[k];
         if (t.p_alloc)
@@ -397,6 +424,7 @@ private:
         // engine happens to cut its batches (rewind replays with a different capacity).
         int64_t hr[8];
         headroom(t.p_queue[t.a_app[a]], hr);
+        user_headroom(t.a_app[a], hr);
         uint8_t cause = 0;
         for (uint32_t m : mem) {
             if (t.a_flags[m] & 1u) { cause = ST_SLOWPATH; break; }
@@ -447,6 +475,7 @@ private:
         // advance head; re-key the app if its max pending priority or (fair leaf) its allocation changed
         const auto& v = ap_asks[p];
         while (A.head < v.size() && (t.a_state[v[A.head]] == ST_ALLOCATED || t.a_state[v[A.head]] == ST_TENTATIVE)) A.head++;
+        for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] += req(a, k);
         const bool fair = t.q_sort[t.p_queue[p]] == 1;
         const int32_t np = A.head < v.size() ? t.a_prio[v[A.head]] : A.key_prio;
         if (np != A.key_prio || fair) {
@@ -537,16 +566,31 @@ private:
         }
     }
 
+    // the user headroom of the application's user folded into hr [EXT ugm Headroom]: min over the entries that apply
+    void user_headroom(uint32_t p, int64_t* hr) {
+        const int d = t.D;
+        for (uint32_t l : ap_ul[p])
+            for (int k = 0; k < d; ++k) {
+                const int64_t mx = t.ul_max[(size_t)k * t.n_ul + l];
+                if (mx == UNSET) continue;
+                int64_t own = mx - ua[(size_t)l * 8 + k];
+                if (own < 0) own = 0;
+                hr[k] = (hr[k] == UNSET) ? own : std::min(hr[k], own);
+            }
+    }
+
     uint32_t select(uint32_t qi) {
         if (q[qi].live <= 0) return NONE;
         const int d = t.D;
         if (q_children[qi].empty()) {
-            int64_t hr[8];
-            headroom(qi, hr);
+            int64_t hr_queue[8], hr[8];
+            headroom(qi, hr_queue);
             auto& S = q_set[qi];
             for (auto it = S.begin(); it != S.end();) {
                 uint32_t p = it->app;
                 ++it;   // advance first: the body may erase the current element
+                for (int k = 0; k < d; ++k) hr[k] = hr_queue[k];
+                if (!ap_ul[p].empty()) user_headroom(p, hr);
                 AState& A = ap[p];
                 const auto& v = ap_asks[p];
                 for (uint32_t i = A.head; i < v.size(); ++i) {

@@ -19,8 +19,8 @@ YK_ERR_CUDA = -2
 
 EXPORTS = [
     "yk_abi_version", "yk_create", "yk_destroy", "yk_nodes_upsert", "yk_nodes_remove", "yk_queues_set", "yk_queues_priority",
-    "yk_apps_upsert", "yk_apps_remove", "yk_asks_upsert", "yk_asks_remove", "yk_release", "yk_cycle",
-    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_node_scores", "yk_preemption_search", "yk_set_exchange",
+    "yk_apps_upsert", "yk_apps_remove", "yk_apps_user", "yk_user_limits_set", "yk_asks_upsert", "yk_asks_remove", "yk_release", "yk_cycle",
+    "yk_ask_states", "yk_nodes_available", "yk_evaluate", "yk_evaluate_reserve", "yk_node_scores", "yk_preemption_search", "yk_set_exchange",
     "yk_peer_export", "yk_peer_import", "yk_peer_enable", "yk_stats",
     "yk_stats_reset", "yk_strerror", "yk_last_error",
 ]
@@ -201,6 +201,20 @@ class Engine:
         self._ck(self._lib.yk_apps_upsert(self._h, C.c_uint32(n), _p(idx), _p(_arr(queue, np.uint32, n)),
                                           _p(_arr(submit_time, np.int64, n))))
 
+    def apps_user(self, idx, user):
+        idx = _arr(idx, np.uint32)
+        u = np.asarray(user, dtype=np.int64).copy()
+        u[u < 0] = YK_NONE
+        u = _arr(u.astype(np.uint32), np.uint32, idx.size)
+        self._ck(self._lib.yk_apps_user(self._h, C.c_uint32(idx.size), _p(idx), _p(u)))
+
+    def user_limits_set(self, queue, user, max, held=None):
+        q, u = _arr(queue, np.uint32), _arr(user, np.uint32)
+        n = q.size
+        mx = _colmajor(np.asarray(max, dtype=np.int64).reshape(n, self.D), self.D, n) if n else np.zeros(0, dtype=np.int64)
+        hd = None if held is None or not n else _colmajor(np.asarray(held, dtype=np.int64).reshape(n, self.D), self.D, n)
+        self._ck(self._lib.yk_user_limits_set(self._h, C.c_uint32(n), _p(q), _p(u), _p(mx), _p(hd)))
+
     def apps_remove(self, idx):
         idx = _arr(idx, np.uint32)
         self._ck(self._lib.yk_apps_remove(self._h, C.c_uint32(idx.size), _p(idx)))
@@ -259,6 +273,9 @@ class Engine:
     def evaluate(self, ask, node):
         return self._ck(self._lib.yk_evaluate(self._h, C.c_uint32(ask), C.c_uint32(node)))
 
+    def evaluate_reserve(self, ask, node):
+        return self._ck(self._lib.yk_evaluate_reserve(self._h, C.c_uint32(ask), C.c_uint32(node)))
+
     def node_scores(self, idx):
         idx = _arr(idx, np.uint32)
         out = np.zeros(idx.size, dtype=np.float64)
@@ -314,6 +331,9 @@ class Engine:
             self.queues_priority(s.q_prio_offset, s.q_prio_fence)
         self.nodes_upsert(np.arange(N), s.node_total, s.node_avail, s.node_taint, s.node_label, s.node_rank(), s.node_flags)
         self.apps_upsert(np.arange(P), s.app_queue, s.app_submit)
+        if getattr(s, "ul_queue", None) is not None and len(s.ul_queue):
+            self.apps_user(np.arange(P), s.app_user)
+            self.user_limits_set(s.ul_queue, s.ul_user, s.ul_max, s.ul_alloc)
         self.asks_upsert(np.arange(A), s.ask_req, s.ask_app, s.ask_create, s.ask_tol, s.ask_need, s.ask_deny,
                          s.ask_prio, s.ask_node, s.ask_flags, s.ask_gang)
 

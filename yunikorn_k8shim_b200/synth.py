@@ -92,6 +92,13 @@ class Snapshot:
     meta: dict = field(default_factory=dict)
     q_prio_offset: np.ndarray = None   # [Q] i32 queue property priority.offset (None = all 0)
     q_prio_fence: np.ndarray = None    # [Q] u8  queue property priority.policy == fence (None = none)
+    # user / group resource limits (the core's queue `limits:`): entry l = user ul_user[l] may hold at most ul_max[l] below
+    # queue ul_queue[l]; app_user = the application's user (pkg/cache/application.go:430 sends it), -1 = none
+    app_user: np.ndarray = None        # [P] i32
+    ul_queue: np.ndarray = None        # [L] i32
+    ul_user: np.ndarray = None         # [L] i32
+    ul_max: np.ndarray = None          # [L][D] i64 (-1 unset)
+    ul_alloc: np.ndarray = None        # [L][D] i64 held at cycle start (None = 0)
 
     @property
     def n_nodes(self): return len(self.node_id)
@@ -503,6 +510,43 @@ def priority_offsets(quota_pods: int = 1, done=()) -> Snapshot:
     return s
 
 
+def with_user_limits(s: Snapshot, n_users: int = 3, seed: int = 0, frac: float = 0.5) -> Snapshot:
+    """the same snapshot with `n_users` users owning the applications round-robin and a resource limit for some
+    (queue, user) pairs -- on leaves and on their parents -- at about `frac` of what the user's asks there add up to"""
+    import copy
+    s = copy.deepcopy(s)
+    rng = np.random.default_rng(seed)
+    P, D = s.n_apps, s.D
+    s.app_user = (np.arange(P) % n_users).astype(np.int32)
+    if rng.random() < 0.3:
+        s.app_user[rng.integers(0, P)] = -1
+    demand = {}
+    for a in range(s.n_asks):
+        p = int(s.ask_app[a])
+        u = int(s.app_user[p])
+        if u < 0:
+            continue
+        q = int(s.app_queue[p])
+        while q >= 0:
+            demand.setdefault((q, u), np.zeros(D, dtype=np.int64))
+            demand[(q, u)] += s.ask_req[a]
+            q = int(s.q_parent[q])
+    uq, uu, um = [], [], []
+    for (q, u), d in sorted(demand.items()):
+        if rng.random() < 0.5:
+            continue
+        mx = np.full(D, -1, dtype=np.int64)
+        for k in rng.choice(D, size=int(rng.integers(1, 3)), replace=False):
+            if d[k] > 0:
+                mx[k] = max(1, int(d[k] * frac * (0.5 + rng.random())))
+        uq.append(q); uu.append(u); um.append(mx)
+    s.ul_queue, s.ul_user = np.array(uq, dtype=np.int32), np.array(uu, dtype=np.int32)
+    s.ul_max = np.array(um, dtype=np.int64).reshape(len(uq), D)
+    s.ul_alloc = np.zeros((len(uq), D), dtype=np.int64)
+    s.name = f"{s.name}-userlimits"
+    return s
+
+
 def redim(s: Snapshot, D2: int, seed: int = 0) -> Snapshot:
     """The same snapshot with D2 resource dimensions (1..8): the first dimensions are kept, extra ones copy random existing
     columns (quotas: unset), weights are extended with 0 / 0.5 / 1 -- for tests of the code paths that depend on D."""
@@ -521,6 +565,8 @@ def redim(s: Snapshot, D2: int, seed: int = 0) -> Snapshot:
         return np.ascontiguousarray(np.concatenate([x, extra], axis=1))
     s.node_total, s.node_avail, s.ask_req = cols(s.node_total, None), cols(s.node_avail, None), cols(s.ask_req, None)
     s.q_guaranteed, s.q_max, s.q_alloc = cols(s.q_guaranteed, -1), cols(s.q_max, -1), cols(s.q_alloc, 0)
+    if s.ul_max is not None and len(s.ul_max):
+        s.ul_max, s.ul_alloc = cols(s.ul_max, -1), cols(s.ul_alloc, 0)
     w = np.zeros(D2)
     w[:min(D, D2)] = s.weights[:min(D, D2)]
     if D2 > D and rng.random() < 0.5:
