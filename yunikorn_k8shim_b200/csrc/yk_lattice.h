@@ -173,8 +173,8 @@ struct Shared {
     uint16_t slot_p[LCAP];        // slot -> position
     uint16_t idx_of[LCAP];        // slot -> sorted element (NO_CHILD: not below the bound)
     uint16_t child[LCAP * SMAX];  // (element, shape) -> element of the node's next state
-    uint32_t ROOM[SMAX * FW];     // per shape: the element's node can take one more of it
-    uint32_t BASE[FW];            // elements that are a node's initial state
+    alignas(8) uint32_t ROOM[SMAX * FW];   // per shape: the element's node can take one more of it
+    alignas(8) uint32_t BASE[FW];          // elements that are a node's initial state
     alignas(16) uint32_t F[SIGCAP * FW];   // ACCEPT rows; before the links phase and after the chain: scratch
     uint32_t scan[LCAP];
     uint64_t r_tol[SIGCAP], r_need[SIGCAP], r_deny[SIGCAP];
@@ -245,6 +245,54 @@ LT_NI void block_sort(unsigned long long* key, unsigned long long* sec, int n) {
             }
             LT_SYNC();
         }
+}
+
+// ascending sort of n <= THREADS (key, sec) pairs, result in key/sec; (bkey, bsec) is a second buffer of the same size.
+// Device: one element per thread in registers; compare-exchange partners less than 32 apart swap through shuffles (no
+// barrier), the others through the two buffers alternately (one barrier per such stage: 15 for 1024 elements instead of
+// the 55 of the plain network above).  Host: the plain network.
+LT_NI void block_sort_fast(unsigned long long* key, unsigned long long* sec, int n, unsigned long long* bkey, unsigned long long* bsec) {
+#if LT_DEV
+    int pn = 32;
+    while (pn < n) pn <<= 1;
+    const int i = threadIdx.x;
+    const bool act = i < pn;
+    unsigned long long k0 = (i < n) ? key[i] : KEY_INF, s0 = (i < n) ? sec[i] : KEY_INF;
+    unsigned long long* buf_k[2] = {key, bkey};
+    unsigned long long* buf_s[2] = {sec, bsec};
+    int cur = 1;   // the first cross-warp stage writes into the second buffer (the input has been read into registers)
+    __syncthreads();
+    for (int k = 2; k <= pn; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long k1, s1;
+            if (j < 32) {
+                k1 = __shfl_xor_sync(0xFFFFFFFFu, k0, j); s1 = __shfl_xor_sync(0xFFFFFFFFu, s0, j);
+            } else {
+                if (act) { buf_k[cur][i] = k0; buf_s[cur][i] = s0; }
+                __syncthreads();
+                k1 = act ? buf_k[cur][i ^ j] : KEY_INF; s1 = act ? buf_s[cur][i ^ j] : KEY_INF;
+                cur ^= 1;
+            }
+            const bool up = (i & k) == 0, lower = (i & j) == 0;
+            const bool other_less = k1 < k0 || (k1 == k0 && s1 < s0);
+            if ((lower == up) == other_less) { k0 = k1; s0 = s1; }   // keep the smaller when (lower == up), else the larger
+        }
+    __syncthreads();
+    if (i < n) { key[i] = k0; sec[i] = s0; }
+    __syncthreads();
+#else
+    int pn = 1;
+    while (pn < n) pn <<= 1;
+    for (int x = n; x < pn; ++x) { bkey[x - n] = 0; }   // (scratch unused on the host)
+    // plain insertion of sentinels is not possible in place when n == capacity: sort the n entries directly
+    for (int a2 = 1; a2 < n; ++a2) {
+        const unsigned long long kk = key[a2], ss = sec[a2];
+        int b2 = a2;
+        for (; b2 > 0 && (key[b2 - 1] > kk || (key[b2 - 1] == kk && sec[b2 - 1] > ss)); --b2) { key[b2] = key[b2 - 1]; sec[b2] = sec[b2 - 1]; }
+        key[b2] = kk; sec[b2] = ss;
+    }
+    (void)bsec;
+#endif
 }
 
 // Sorted merge by counting: src[0, nb) is sorted, src[nb, n) is not (few entries).  Every entry counts the unsorted
@@ -689,17 +737,25 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 for (int c = 0; c < NCAND; ++c) s.sumv[c] = 0;
             }
             LT_FOR(p, P) {
-                const uint64_t key = ldg(&cur[p].key), rn = ldg(&cur[p].rn);
-                const uint32_t node = (uint32_t)rn;
-                const int64_t* r = a.rec + (size_t)node * RS;
-                for (int k = 0; k < D; ++k) { s.avail[k * PMAX + p] = ldg(&r[k]); s.total[k * PMAX + p] = ldg(&r[D + k]); }
-                s.okey[p] = key; s.orn[p] = rn;
-                s.taint[p] = (uint64_t)ldg(&r[2 * D]); s.label[p] = (uint64_t)ldg(&r[2 * D + 1]);
-                const uint32_t fl = (uint32_t)(uint64_t)ldg(&r[2 * D + 2]);
-                s.usable[p] = ((fl & 1u) && !(fl & 2u)) ? 1 : 0;
+                s.okey[p] = ldg(&cur[p].key); s.orn[p] = ldg(&cur[p].rn);
                 for (int x = 0; x < SMAX; x += 2) *reinterpret_cast<uint32_t*>(&s.cnt[p * SMAX + x]) = 0u;
             }
             LT_SYNC();
+            {   // the records: consecutive threads read consecutive words of one record (a few coalesced requests per
+                // record instead of one request per word)
+                constexpr int RW = (2 * D + 3 + 3) / 4 * 4;   // = a.RS
+                LT_FOR(x, P * RW) {
+                    const int p = x / RW, w = x % RW;
+                    if (w > 2 * D + 2) continue;
+                    const int64_t v = ldg(&a.rec[(size_t)(uint32_t)s.orn[p] * RW + w]);
+                    if (w < D) s.avail[w * PMAX + p] = v;
+                    else if (w < 2 * D) s.total[(w - D) * PMAX + p] = v;
+                    else if (w == 2 * D) s.taint[p] = (uint64_t)v;
+                    else if (w == 2 * D + 1) s.label[p] = (uint64_t)v;
+                    else { const uint32_t fl = (uint32_t)(uint64_t)v; s.usable[p] = ((fl & 1u) && !(fl & 2u)) ? 1 : 0; }
+                }
+                LT_SYNC();
+            }
             LT_PROF(PF_SCAN);
             // ================= window: key threshold and the boxes =================
             // candidates: the keys at positions P, P/2, P/4 ...; the largest whose boxes hold at most LCAP states wins
@@ -715,14 +771,24 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 for (int c = 0; c < NCAND; ++c) my_v[c] = 0;
                 LT_FOR(p, P) {
                     float inv[SMAX];
-                    uint8_t d[SMAX];
                     int64_t av[D], to[D];
                     load_pos<D>(s, p, av, to);
                     for (int x = 0; x < S; ++x) inv[x] = inv_delta_of<D>(a.w, to, s.sreq + x * 8);
                     const double sc = yk_key_to_score(s.okey[p]);
                     for (int c = 0; c < NCAND; ++c) {
+                        // an upper bound of the node's box (the product of the sides, capped at VCAP): never below what
+                        // box_of gives, so the candidate that is picked fits
                         const double g = s.tau[c] - sc;
-                        my_v[c] += s.usable[p] ? box_of(g > 1e30 ? 1e30f : (float)g, inv, S, d) : 1;
+                        int v = 1;
+                        if (s.usable[p] && g > 0.0) {
+                            const float gf = g > 1e30 ? 1e30f : (float)g;
+                            for (int x = 0; x < S && v < VCAP; ++x) {
+                                const float q = inv[x] > 0.0f ? gf * inv[x] : (float)DCAP;
+                                v *= (q >= (float)DCAP ? DCAP : (int)q) + 1;
+                            }
+                            if (v > VCAP) v = VCAP;
+                        }
+                        my_v[c] += v;
                     }
                 }
                 for (int c = 0; c < NCAND; ++c) red_add32(&s.sumv[c], my_v[c]);
@@ -856,7 +922,9 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             const int nvalid = s.cnt_elems;
             LT_PROF(PF_LATTICE);
             if (nvalid > nbase) {   // deeper states interleave with the bases (which are in order already)
-                if (nvalid - nbase <= ECNT) {
+                if (nvalid <= THREADS) {
+                    block_sort_fast(s.e_key, s.e_sec, nvalid, s.d_key(), s.d_sec());
+                } else if (nvalid - nbase <= ECNT) {
                     block_merge_by_count(s.e_key, s.e_sec, nbase, nvalid, s.d_key(), s.d_sec());
                     LT_FOR(x, nvalid) { s.e_key[x] = s.d_key()[x]; s.e_sec[x] = s.d_sec()[x]; }
                     LT_SYNC();
@@ -877,7 +945,7 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
             LT_SYNC();
             LT_FOR(e, nvalid) s.idx_of[(int)(s.e_sec[e] & 0x3FFFFFu)] = (uint16_t)e;
             LT_SYNC();
-            LT_FOR32(e, nvalid) {
+            LT_FOR32(e, (nvalid + 63) & ~63) {   // whole 64-bit words of every bitmap get written
                 const bool in = e < nvalid;
                 const int slot = in ? (int)(s.e_sec[e] & 0x3FFFFFu) : 0;
                 const int p = in ? (int)s.slot_p[slot] : 0;
@@ -961,7 +1029,9 @@ LT_FN void lattice_batch(const Args& a, Shared<D>& s) {
                 LT_ONE { s.tb[P] = (uint32_t)nt; }
                 LT_SYNC();
                 if (s.status == ST_NAN) { status = ST_NAN; break; }
-                block_merge_by_count(uk, ur, 0, nt, s.t_key(), s.t_rn());   // touched nodes by their new keys
+                LT_FOR(x, nt) { s.t_key()[x] = uk[x]; s.t_rn()[x] = ur[x]; }
+                LT_SYNC();
+                block_sort_fast(s.t_key(), s.t_rn(), nt, uk, ur);   // touched nodes by their new keys
             }
             LT_PROF(PF_APPLY);
             patch_order<D>(a, s, a.ord[buf], a.ord[buf ^ 1]);
