@@ -132,6 +132,14 @@ func New(maxNodes, maxAsks, maxApps, maxQueues int, src ObjectSource) (*Engine, 
 	return e, nil
 }
 
+// SetObjectSource hands over the shim's cache once the shim has built it (the cache does not exist yet when New runs:
+// pkg/cmd/shim/main.go creates the SchedulerAPI first, then the shim around it).
+func (e *Engine) SetObjectSource(src ObjectSource) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	e.src = src
+}
+
 func (e *Engine) ck(rc C.int, what string) error {
 	if rc == C.YK_OK {
 		return nil

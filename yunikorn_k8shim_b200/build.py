@@ -16,7 +16,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",                 # float64 node score must not be contracted
-] + (["-DYK_LT_THREADS=" + os.environ["YK_LT_THREADS"]] if os.environ.get("YK_LT_THREADS") else []) + [
+] + (["-DYK_LT_THREADS=" + os.environ["YK_LT_THREADS"]] if os.environ.get("YK_LT_THREADS") else []) + \
+    (["-DYK_NPT=" + os.environ["YK_NPT"]] if os.environ.get("YK_NPT") else []) + [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall,-pthread",
     "-shared",
 ]

@@ -34,7 +34,10 @@
 
 namespace {
 
-constexpr int NPT = 2;            // sorted-node positions per sweep thread
+#ifndef YK_NPT
+#define YK_NPT 2
+#endif
+constexpr int NPT = YK_NPT;       // sorted-node positions per sweep thread
 constexpr int AC = 128;           // asks per sweep CTA chunk
 constexpr int NODE_TILE = YK_SWEEP_THREADS * NPT;
 
@@ -1471,7 +1474,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         t.ul_max = e->ul_max.data(); t.ul_alloc = e->ul_alloc.data();
         if (!gang_too_big) e->ord.begin_cycle(pending);
         e->ep_rows = false;
-        if (!gang_too_big && e->share_rows && e->cfg.world <= 1) {
+        if (!gang_too_big && e->share_rows && e->cfg.world <= 1 && !getenv("YK_NO_EPOCH_ROWS")) {
             // how many distinct signatures do the pending asks have?  Few: every one is swept once per epoch (ep_local =
             // its row), no per-batch device work at all
             if (e->ep_seen.size() < e->sigs.n) { e->ep_seen.assign(e->sigs.n + 1024, 0); e->ep_local.assign(e->sigs.n + 1024, 0); e->ep_stamp = 0; }

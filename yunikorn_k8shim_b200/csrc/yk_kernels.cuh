@@ -139,7 +139,7 @@ __device__ __forceinline__ void yk_pair_step(const int64_t (&cap)[NPT][D], const
 // in registers and walks its share of the batch rows in sub-chunks of AC asks staged in shared memory, so the
 // host can size grid.y to fill the machine exactly once (no tail wave) whatever the batch size.
 template <int D, int NPT, int AC>
-__global__ void __launch_bounds__(YK_SWEEP_THREADS, 4) yk_sweep_kernel(const YkSweepArgs p) {
+__global__ void __launch_bounds__(YK_SWEEP_THREADS, NPT <= 2 ? 4 : 2) yk_sweep_kernel(const YkSweepArgs p) {
     __shared__ int64_t sh_req[AC][D];
     __shared__ uint64_t sh_mask[AC][3];
     __shared__ uint32_t sh_node[AC];

@@ -117,6 +117,7 @@ public:
     std::vector<std::map<int32_t, int>> q_prio_cnt;
     std::vector<int64_t> ua;                        // [n_ul][8] held under each user-limit entry, this cycle
     std::vector<std::vector<uint32_t>> ap_ul;       // application -> the entries that apply to it
+    bool any_ul = false;                            // some application of the cycle has a user limit on its chain
     std::vector<AState> ap;
     std::vector<std::vector<uint32_t>> ap_asks;
     std::vector<uint32_t> a_pos;      // ask -> index in its app list
@@ -208,7 +209,7 @@ public:
         ua.assign((size_t)t.n_ul * 8, 0);
         if (ap_ul.size() < t.maxP) ap_ul.resize(t.maxP);
         bool any_limit = false;
-        for (uint32_t p = 0; p < t.maxP; ++p) {
+        if (t.n_ul || any_ul) for (uint32_t p = 0; p < t.maxP; ++p) {
             ap_ul[p].clear();
             if (!t.n_ul || !t.p_user || ap_asks[p].empty() || t.p_user[p] == NONE) continue;
             for (uint32_t l = 0; l < t.n_ul; ++l) {
@@ -218,6 +219,7 @@ public:
             }
         }
         for (uint32_t l = 0; l < t.n_ul; ++l) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] = t.ul_alloc ? t.ul_alloc[(size_t)k * t.n_ul + l] : 0;
+        any_ul = any_limit;
         // placement-insensitive?  one leaf with pending asks, fifo, no max on its chain, one priority level
         int leaves = 0; uint32_t leaf = NONE;
         for (uint32_t i = 0; i < t.nq; ++i)
@@ -363,7 +365,7 @@ public:
         t.a_state[a] = ST_NOFIT;
         ap[p].npend++;
         for (int k = 0; k < d; ++k) ap[p].alloc[k] -= req(a, k);
-        for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] -= req(a, k);
+        if (any_ul) for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] -= req(a, k);
         if (a_pos[a] < ap[p].head) ap[p].head = a_pos[a];
         for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {
             q[qq].npend++;
@@ -424,7 +426,7 @@ private:
         // engine happens to cut its batches (rewind replays with a different capacity).
         int64_t hr[8];
         headroom(t.p_queue[t.a_app[a]], hr);
-        user_headroom(t.a_app[a], hr);
+        if (any_ul) user_headroom(t.a_app[a], hr);
         uint8_t cause = 0;
         for (uint32_t m : mem) {
             if (t.a_flags[m] & 1u) { cause = ST_SLOWPATH; break; }
@@ -475,7 +477,7 @@ private:
         // advance head; re-key the app if its max pending priority or (fair leaf) its allocation changed
         const auto& v = ap_asks[p];
         while (A.head < v.size() && (t.a_state[v[A.head]] == ST_ALLOCATED || t.a_state[v[A.head]] == ST_TENTATIVE)) A.head++;
-        for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] += req(a, k);
+        if (any_ul) for (uint32_t l : ap_ul[p]) for (int k = 0; k < d; ++k) ua[(size_t)l * 8 + k] += req(a, k);
         const bool fair = t.q_sort[t.p_queue[p]] == 1;
         const int32_t np = A.head < v.size() ? t.a_prio[v[A.head]] : A.key_prio;
         if (np != A.key_prio || fair) {
@@ -583,14 +585,14 @@ private:
         if (q[qi].live <= 0) return NONE;
         const int d = t.D;
         if (q_children[qi].empty()) {
-            int64_t hr_queue[8], hr[8];
+            int64_t hr_queue[8], hr_user[8];
             headroom(qi, hr_queue);
+            int64_t* const hr = any_ul ? hr_user : hr_queue;   // without user limits the queue headroom is the headroom
             auto& S = q_set[qi];
             for (auto it = S.begin(); it != S.end();) {
                 uint32_t p = it->app;
                 ++it;   // advance first: the body may erase the current element
-                for (int k = 0; k < d; ++k) hr[k] = hr_queue[k];
-                if (!ap_ul[p].empty()) user_headroom(p, hr);
+                if (any_ul) { for (int k = 0; k < d; ++k) hr[k] = hr_queue[k]; user_headroom(p, hr); }
                 AState& A = ap[p];
                 const auto& v = ap_asks[p];
                 for (uint32_t i = A.head; i < v.size(); ++i) {
