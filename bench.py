@@ -322,7 +322,7 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # NCCL prints its version banner on stdout otherwise: ONE line is the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ykgpu_nccl_%h_%p.log")   # NCCL's version banner goes to stdout otherwise: ONE line is the contract
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     D = dist if world > 1 else None
     from oracle import oracle_ctypes as oc
