@@ -348,3 +348,25 @@ def test_reservation_phase_predicates(oracle):
                 assert got == exp, (a, n, got, exp)
                 diff += int((got == 0) != (e.evaluate(a, n) == 0))
         assert diff > 0
+
+
+def test_queues_set_reconciles_with_present_applications(oracle):
+    """yk_queues_set while applications exist: a tree that drops or re-parents their queue is refused; with
+    allocated == NULL what the applications hold is summed up the new tree, so quotas keep binding"""
+    from yunikorn_k8shim_b200 import YkError
+    s = synth.hier(60, 2, 2, 2, 20, seed=5)
+    with Engine.for_snapshot(s, batch=32) as e:
+        with pytest.raises(YkError) as ei:
+            e.queues_set(s.q_parent[:3], s.q_guaranteed[:3], s.q_max[:3], s.q_alloc[:3], s.q_sort[:3])   # leaves are gone
+        assert ei.value.code == -4
+        par = s.q_parent.copy()
+        par[-1] = s.n_queues - 2                                   # the last leaf's sibling becomes its parent: it holds apps
+        with pytest.raises(YkError):
+            e.queues_set(par, s.q_guaranteed, s.q_max, s.q_alloc, s.q_sort)
+        ask, node, _ = e.cycle(40)                                  # some allocations
+        want = oracle.run(s)
+        assert np.array_equal(ask, want["ask"][:40])
+        e.queues_set(s.q_parent, s.q_guaranteed, s.q_max, None, s.q_sort)   # same tree, allocated left to the library
+        ask2, node2, _ = e.cycle(s.n_asks)
+        assert np.array_equal(np.concatenate([ask, ask2]), want["ask"])     # quotas bound exactly as in one uncut cycle
+        assert np.array_equal(np.concatenate([node, node2]), want["node"])
