@@ -256,6 +256,7 @@ struct yk_engine {
     int lt_force = 0;                        // YK_FLAG_DEVICE_COMMIT / YK_COMMIT=device: every eligible cycle commits on the device
     bool lt_auto = false;                    // YK_COMMIT=auto: eligible cycles with long windows commit on the device
     bool lt_active = false;                  // this cycle runs (so far) on the device commit
+    bool order_enqueued = false;             // device_order() of this cycle is already on the stream
     int lt_RS = 0; size_t lt_smem = 0;
     Dev<int64_t> d_rec; Dev<yklt::Ent> d_ord[2]; Dev<int> d_lt_cur, d_lt_hdr; Dev<int64_t> d_lt_ub;
     Dev<uint32_t> d_rank, d_lt_asks, d_lt_meta, d_lt_shp, d_lt_sig, d_lt_res;
@@ -429,8 +430,11 @@ int initial_order(yk_engine* e) {
     const int nlive = (int)e->nlive;
     if (nlive == 0) return YK_OK;
     cudaStream_t s = e->stream;
-    int rc = device_order(e);
-    if (rc) return rc;
+    if (!e->order_enqueued) {   // (after a hand-over from the device commit the order is computed again from the exported tables)
+        int rc = device_order(e);
+        if (rc) return rc;
+    }
+    e->order_enqueued = false;
     CK(cudaMemcpyAsync(e->h_order[0].p, e->d_val_out.p, sizeof(uint32_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(e->h_skey.p, e->d_key_out.p, sizeof(uint64_t) * (size_t)nlive, cudaMemcpyDeviceToHost, s));
     // while the device scores and sorts: the commit's working copy of the node table (host only)
@@ -1500,7 +1504,9 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         begin_ms = now_ms() - t_b;
     });
     int rc = upload_tables(e);
-    if (!rc && try_lattice) rc = device_order(e);   // enqueued: the host is free for the eligibility tests below
+    // the device scores and sorts the nodes while the helper thread still sets the orderer up
+    e->order_enqueued = false;
+    if (!rc) { rc = device_order(e); e->order_enqueued = rc == YK_OK && e->nlive > 0; }
     const double t_a = now_ms();
     e->worker.wait();
     e->st.host_ms[0] += t_a - t_start;
@@ -1538,6 +1544,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     if (!rc) {
         if (lattice) {
             e->lt_active = true;
+            e->order_enqueued = false;   // consumed by lt_prepare; a hand-over sorts again from the exported tables
             e->st.lattice_cycles++;
             bool handoff = false;
             rc = run_lattice(e, c, handoff);
