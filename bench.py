@@ -16,8 +16,10 @@ pending).  ONE JSON line:
   cpu_engine   THIS engine without a GPU: the same ordering engine and ordered commit, the sweep done by the host cores
                (AVX-512, all threads; tests/host/engine_shim.cpp) -- isolates what the B200 contributes: gpu_over_cpu_engine
   workloads    the same measurement, shorter, on config 3 (taints + nodeAffinity masks: every ask its own row) and on the
-               reference's own benchmark shape (every pod identical, pkg/shim/scheduler_perf_test.go:283-288)
-  device_commit  the same workloads with the ordered commit itself on the device (yk_lattice_kernel, opt-in)
+               reference's own benchmark shape (every pod identical, pkg/shim/scheduler_perf_test.go:283-288), with the
+               engine's default commit choice (commit_ran_on: the reference shape is one uniform run -> decided on the device
+               by a grid-wide sort, csrc/yk_uniform.cuh; config 3 -> sweep + host commit)
+  host_commit / device_commit  the same workloads with the ordered commit forced onto the host / the device
 With --gpus N > 1 (torchrun): `value` = N YuniKorn partitions (disjoint node sets with their own queues: the core
 schedules partitions independently), one per GPU, no data-path exchange -- weak scaling; `multi` = one partition with the
 sweep of every batch split across the N GPUs and exchanged peer-to-peer (strong scaling of config 3), every rank checked
@@ -151,7 +153,7 @@ def run_reference(args, rank, world):
     n = sum(r[3] for r in res)
     v = n / dt
     sample = f"full workload ({res[0][5]} asks x {res[0][6]} nodes per partition, {G} partition(s) on {G} host core(s)) per step, {args.steps} steps"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
@@ -161,7 +163,7 @@ def run_reference(args, rank, world):
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "bindings_hash": f"{res[0][4]:#x}",
-    }))
+    })
 
 
 class Arm:
@@ -292,6 +294,17 @@ def sweep_roofline(st, steps, n_nodes, hbm, hbm_src):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -301,7 +314,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--masks", action="store_true", help="config 3 (taints + nodeAffinity bitmasks) instead of config 2")
     ap.add_argument("--config", default="0", help="workload of the headline arm: 2 (default), 3, 4, 5 or 'reference'")
-    ap.add_argument("--commit", default="host", choices=["host", "device", "auto"], help="ordered commit of the headline arm")
+    ap.add_argument("--commit", default="auto", choices=["host", "device", "auto"],
+                    help="ordered commit of the headline arm (auto = the engine's default: device for cycles made of long uniform runs, host otherwise)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline arm only (no side workloads, no CPU arms)")
     ap.add_argument("--no-row-sharing", action="store_true",
@@ -314,6 +328,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # ONE JSON line on stdout is the contract, and libraries write banners to descriptor 1 behind Python's back (NCCL's
+    # version line at N > 1): descriptor 1 becomes stderr for the whole run, and emit() writes the line to the real stdout.
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -322,7 +342,6 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ykgpu_nccl_%h_%p.log")   # NCCL's version banner goes to stdout otherwise: ONE line is the contract
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     D = dist if world > 1 else None
     from oracle import oracle_ctypes as oc
@@ -417,7 +436,7 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()      # peers may still be signalling into an engine's sync block
         if rank == 0:
-            print(json.dumps(out))
+            emit(out)
         dist.destroy_process_group()
         return
     arm.close()
@@ -435,7 +454,8 @@ def main():
             a.close()
             w = want if name == wl else oc.run(s)
             stx = r["stats"]
-            o = {"workload": WORKLOADS[name], "commit": commit, "value": r["allocations"] / r["seconds"], "unit": UNIT,
+            o = {"workload": WORKLOADS[name], "commit": commit,
+                 "commit_ran_on": "device" if stx["lattice_cycles"] else "host", "value": r["allocations"] / r["seconds"], "unit": UNIT,
                  "ms_per_step": r["seconds"] / side_steps * 1e3, "e2e_value": re_["allocations"] / re_["seconds"],
                  "e2e_ms_per_step": re_["seconds"] / side_steps * 1e3, "steps": side_steps,
                  "identical_to_oracle": bool(np.array_equal(r["ask"], w["ask"]) and np.array_equal(r["node"], w["node"])),
@@ -447,8 +467,9 @@ def main():
                 o["roofline"] = sweep_roofline(stx, side_steps, s.n_nodes, hbm, hbm_src)
             if stx["lattice_launches"]:
                 o["lattice"] = {k: stx[k] / side_steps for k in ("lattice_subruns", "lattice_asks", "lattice_elements", "lattice_sorts",
-                                                                  "lattice_fullscans", "lattice_handoffs")}
-            if cpu_engine and commit == "host":
+                                                                  "lattice_fullscans", "lattice_handoffs", "uniform_runs", "uniform_asks",
+                                                                  "uniform_elements", "uniform_retries")}
+            if cpu_engine:
                 dt, ask_c, node_c = cpu_engine_time(s, threads)
                 o["cpu_engine"] = {"ms_per_step": dt * 1e3, "value": len(ask_c) / dt, "unit": UNIT, "threads": threads,
                                    "identical_to_oracle": bool(np.array_equal(ask_c, w["ask"]) and np.array_equal(node_c, w["node"])),
@@ -468,7 +489,8 @@ def main():
             out["one_row_per_ask"] = o
             if "roofline" in o:
                 out["roofline_one_row_per_ask"] = o["roofline"]
-        out["workloads"] = {name: run_arm(name, "host") for name in ("config3", "reference_shape") if name != wl}
+        out["workloads"] = {name: run_arm(name, "auto") for name in ("config3", "reference_shape") if name != wl}
+        out["host_commit"] = {name: run_arm(name, "host", cpu_engine=False) for name in ("reference_shape",) if name != wl}
         out["device_commit"] = {name: run_arm(name, "device", cpu_engine=False) for name in ("config2", "config3", "reference_shape")}
     if not args.no_cpu_baseline and not args.quick:
         oc.run(snap)
@@ -483,7 +505,7 @@ def main():
         out["cpu_baseline"] = {"value": reps * len(r["ask"]) / dt, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"{reps} full cycles of the same snapshot ({dt:.1f} s)",
                                "host_cores_available": os.cpu_count()}
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":

@@ -148,6 +148,9 @@ typedef struct {
              lattice_quick, lattice_handoffs;
     double lattice_ms;
     uint64_t lattice_cycles;     /* cycles that started on the device commit */
+    /* uniform runs of the device commit (consecutive asks with one request vector and one predicate signature, decided by a
+       grid-wide sort instead of the sequential chain): runs, asks they decided, elements generated, deeper retries */
+    uint64_t uniform_runs, uniform_asks, uniform_elements, uniform_retries;
 } yk_stats_t;
 
 int yk_create(const yk_config* cfg, yk_engine** out);

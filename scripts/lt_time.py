@@ -29,4 +29,4 @@ for name in which:
         print(f"{name} {commit}: {best*1e3:.2f} ms/cycle  {len(ask)/best/1e6:.2f} M alloc/s identical={ok} "
               f"lattice: launches={st['lattice_launches']} subruns={st['lattice_subruns']} asks={st['lattice_asks']} "
               f"elems={st['lattice_elements']} sorts={st['lattice_sorts']} full={st['lattice_fullscans']} handoffs={st['lattice_handoffs']} "
-              f"ms={st['lattice_ms']:.2f} | sweeps={st['sweep_launches']} commit_ms={st['commit_ms']:.2f} d2h={st['d2h_bytes']}", flush=True)
+              f"ms={st['lattice_ms']:.2f} uniform: runs={st['uniform_runs']} asks={st['uniform_asks']} retries={st['uniform_retries']} host_ms={[round(x, 2) for x in st['host_ms']]} total_ms={st['total_ms']:.2f} | sweeps={st['sweep_launches']} commit_ms={st['commit_ms']:.2f} d2h={st['d2h_bytes']}", flush=True)

@@ -7,6 +7,7 @@
 // Where the engine hands a batch over to its host commit (status HANDOFF: a gang that cannot be placed from the front of
 // the order), this shim finishes the batch with a plain sequential first-fit over the current order instead.
 #include "../../yunikorn_k8shim_b200/csrc/yk_lattice_host.hpp"
+#include "../../yunikorn_k8shim_b200/csrc/yk_uniform.h"
 #include "../../yunikorn_k8shim_b200/csrc/yk_orderer.hpp"
 
 #include <algorithm>
@@ -26,7 +27,81 @@ extern "C" void host_set_user_limits(const uint32_t* p_user, uint32_t n, const u
     g_p_user = p_user; g_n_ul = n; g_ul_queue = queue; g_ul_user = user; g_ul_max = max; g_ul_alloc = alloc;
 }
 
+// shortest uniform run that takes the uniform-run path (0: never), and how deep the first attempt generates (0: the engine's rule)
+static int g_un_min = 0, g_un_depth = 0;
+extern "C" void host_set_uniform(int min_run, int first_depth) { g_un_min = min_run; g_un_depth = first_depth; }
+
 namespace {
+
+// The uniform-run path as the engine drives it (csrc/yk_engine.cu lt_uniform), with the kernels of yk_uniform.cuh replaced by
+// loops over the same per-item bodies and the two cub radix sorts by std::stable_sort.
+template <int D>
+int uniform_host(const yklt::Args& la, const uint32_t* asks, int off, int R, bool has_gang, uint32_t* res, size_t* consumed, uint64_t* stats) {
+    const int nlive = la.nlive;
+    *consumed = 0;
+    if (nlive == 0 || R == 0) return ykun::U_FALLBACK;
+    const uint32_t ask = asks[off];
+    std::vector<uint32_t> byrank((size_t)nlive);
+    {
+        const yklt::Ent* e = la.ord[*la.cur & 1];
+        std::vector<uint64_t> rn((size_t)nlive);
+        for (int p = 0; p < nlive; ++p) rn[(size_t)p] = e[p].rn;
+        std::sort(rn.begin(), rn.end());
+        for (int p = 0; p < nlive; ++p) byrank[(size_t)p] = (uint32_t)rn[(size_t)p];
+    }
+    uint32_t max_node = 0;
+    for (uint32_t n : byrank) max_node = std::max(max_node, n);
+    std::vector<uint32_t> cnt((size_t)max_node + 1, 0);
+    std::vector<unsigned long long> bk((size_t)nlive), rkey((size_t)nlive), rrn((size_t)nlive), okey((size_t)nlive), orn((size_t)nlive);
+    ykun::Globals g;
+    ykun::Args a{};
+    a.policy = la.policy;
+    for (int k = 0; k < 8; ++k) { a.w[k] = la.w[k]; a.req[k] = k < D ? la.a_req[(size_t)k * la.lda + ask] : 0; }
+    a.rec = la.rec; a.RS = la.RS; a.ord[0] = la.ord[0]; a.ord[1] = la.ord[1]; a.cur = la.cur; a.nlive = nlive; a.byrank = byrank.data();
+    a.tol = la.a_tol[ask]; a.need = la.a_need[ask]; a.deny = la.a_deny[ask]; a.want = la.a_node[ask];
+    a.R = R; a.insensitive = la.insensitive; a.has_gang = has_gang ? 1 : 0;
+    a.bk = bk.data(); a.cnt = cnt.data(); a.rkey = rkey.data(); a.rrn = rrn.data(); a.okey = okey.data(); a.orn = orn.data();
+    a.res = res + off; a.g = &g;
+    int L = g_un_depth > 0 ? g_un_depth : ykun::first_depth(R, nlive);
+    for (;;) {
+        if ((size_t)L * (size_t)nlive > ((size_t)4 << 20)) return ykun::U_FALLBACK;
+        a.L = L;
+        const size_t ne = (size_t)nlive * (size_t)L;
+        std::vector<unsigned long long> ekey(ne), skey(ne);
+        std::vector<uint32_t> enode(ne), snode(ne), idx(ne);
+        a.ekey = ekey.data(); a.enode = enode.data(); a.skey = skey.data(); a.snode = snode.data();
+        g.bkey = ykun::KEY_INF; g.brank = ykun::KEY_INF; g.last_key = 0; g.last_rank = 0; g.valid = 0; g.nan = 0; g.status = ykun::U_RETRY; g.consumed = 0;
+        for (int i = 0; i < nlive; ++i) {
+            const ykun::DepthOut o = ykun::depth_item<D>(a, i);
+            g.valid += o.valid;
+            if (o.bk < g.bkey) g.bkey = o.bk;
+            if (o.nan) g.nan = 1;
+        }
+        for (int i = 0; i < nlive; ++i) { const unsigned long long r = ykun::brank_item<D>(a, i, g.bkey); if (r < g.brank) g.brank = r; }
+        for (size_t x = 0; x < ne; ++x) idx[x] = (uint32_t)x;
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return ekey[x] < ekey[y]; });
+        for (size_t x = 0; x < ne; ++x) { skey[x] = ekey[idx[x]]; snode[x] = enode[idx[x]]; }
+        for (int q = 0; q < R; ++q) ykun::select_item<D>(a, q, g.valid);
+        ykun::decide(a);
+        int nan_after = 0;
+        for (int i = 0; i < nlive; ++i) { ykun::apply_item<D>(a, i, g.status); nan_after |= ykun::rekey_item<D>(a, i); }
+        {
+            std::vector<uint32_t> ix((size_t)nlive);
+            for (int i = 0; i < nlive; ++i) ix[(size_t)i] = (uint32_t)i;
+            std::stable_sort(ix.begin(), ix.end(), [&](uint32_t x, uint32_t y) { return rkey[x] < rkey[y]; });
+            yklt::Ent* o = la.ord[*la.cur & 1];
+            for (int p = 0; p < nlive; ++p) { o[p].key = rkey[ix[(size_t)p]]; o[p].rn = rrn[ix[(size_t)p]]; }
+        }
+        for (uint32_t c : cnt) if (c) return -99;   // counters must be clean after every attempt
+        stats[8] += 1;
+        if (g.status == ykun::U_RETRY) { stats[9] += 1; L *= 4; continue; }
+        if (g.status == ykun::U_NAN || g.status == ykun::U_FALLBACK) return ykun::U_FALLBACK;
+        if (nan_after) return -5;
+        *consumed = (size_t)g.consumed;
+        stats[10] += (uint64_t)g.consumed;
+        return g.status;
+    }
+}
 
 template <int D>
 int run_d(uint32_t policy, const double* weights,
@@ -138,6 +213,7 @@ int run_d(uint32_t policy, const double* weights,
     size_t bsz = batch;
     uint32_t n = 0;
     uint64_t handoffs = 0, batches = 0;
+    uint64_t ustats[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8] uniform attempts, [9] deeper retries, [10] asks decided by uniform runs
     while (n < max_bindings) {
         o.fill(bsz, (size_t)max_bindings - n, asks, snap);
         if (o.oversize_gang) {
@@ -157,10 +233,37 @@ int run_d(uint32_t policy, const double* weights,
             if (!ins && a_gang[asks[0]] != yk::CNONE)
                 while (consumed < B && a_gang[asks[consumed]] == a_gang[asks[0]] && a_app[asks[consumed]] == a_app[asks[0]]) ++consumed;
         } else {
-            yklt::lattice_batch<D>(la, *sh);
-            if (hdr[yklt::H_STATUS] == yklt::ST_NAN) return -5;
-            if (!order_ok()) return -9;
-            consumed = (size_t)hdr[yklt::H_CONSUMED];
+            // the engine's lt_batch: uniform runs through the uniform-run path, the stretches between them through the kernel
+            std::vector<ykun::Segment> segs;
+            ykun::plan_segments(meta.data(), shp.data(), sig.data(), (int)B, g_un_min > 0 ? g_un_min : (int)B + 1, segs);
+            int status = yklt::ST_DONE;
+            for (const ykun::Segment& sg : segs) {
+                size_t cons = 0;
+                int st = yklt::ST_DONE;
+                bool windowed = !sg.uniform;
+                if (sg.uniform) {
+                    bool has_gang = false;
+                    for (int i = 0; i < sg.len; ++i) has_gang = has_gang || (meta[(size_t)sg.off + i] & yklt::M_GANG);
+                    const int ust = uniform_host<D>(la, asks.data(), sg.off, sg.len, has_gang, result.data(), &cons, ustats);
+                    if (ust < 0) return ust;
+                    if (ust == ykun::U_FALLBACK) windowed = true;
+                    else st = ust == ykun::U_STOPPED ? yklt::ST_STOPPED : yklt::ST_DONE;
+                }
+                if (windowed) {
+                    la.asks = asks.data() + sg.off; la.meta = meta.data() + sg.off; la.shp = shp.data() + sg.off; la.sig = sig.data() + sg.off;
+                    la.B = sg.len; la.res = result.data() + sg.off;
+                    yklt::lattice_batch<D>(la, *sh);
+                    st = hdr[yklt::H_STATUS];
+                    cons = (size_t)hdr[yklt::H_CONSUMED];
+                }
+                if (st == yklt::ST_NAN) return -5;
+                if (!order_ok()) return -9;
+                consumed = (size_t)sg.off + cons;
+                status = st;
+                if (st != yklt::ST_DONE || cons < (size_t)sg.len) break;
+            }
+            hdr[yklt::H_STATUS] = status;
+            hdr[yklt::H_CONSUMED] = (int)consumed;
             if (hdr[yklt::H_STATUS] == yklt::ST_HANDOFF) {
                 ++handoffs;
                 bool stop = false;
@@ -218,6 +321,7 @@ int run_d(uint32_t policy, const double* weights,
         stats_out[0] = (uint64_t)hdr[yklt::H_SUBRUNS]; stats_out[1] = (uint64_t)hdr[yklt::H_FULLSCANS]; stats_out[2] = (uint64_t)hdr[yklt::H_SORTS];
         stats_out[3] = (uint64_t)hdr[yklt::H_ELEMS]; stats_out[4] = (uint64_t)hdr[yklt::H_QUICK]; stats_out[5] = (uint64_t)hdr[yklt::H_ESC];
         stats_out[6] = handoffs; stats_out[7] = batches;
+        stats_out[8] = ustats[8]; stats_out[9] = ustats[9]; stats_out[10] = ustats[10];
     }
     return 0;
 }

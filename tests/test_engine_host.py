@@ -73,7 +73,7 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
     n = C.c_uint32(0)
     state = np.zeros(max(A, 1), dtype=np.uint8)
     avail = np.zeros((D, max(N, 1)), dtype=np.int64)
-    nrows = np.zeros(8, dtype=np.uint64)   # engine shim: [0] rows swept; lattice shim: its eight counters
+    nrows = np.zeros(16, dtype=np.uint64)   # engine shim: [0] rows swept; lattice shim: its counters
     rc = getattr(shim, fn)(
         C.c_int(D), C.c_uint32(s.policy), _p(k["w"]),
         C.c_uint32(N), _p(k["total"]), _p(k["avail"]), _p(k["taint"]), _p(k["label"]), _p(k["nflags"]), _p(k["rank"]),

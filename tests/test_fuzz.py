@@ -56,6 +56,33 @@ def test_engine_matches_oracle_on_fuzz(oracle, batch, share, commit):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch,uniform_min", [(64, 2), (1024, 3), (7, 2)])
+def test_engine_uniform_runs_match_oracle_on_fuzz(oracle, monkeypatch, batch, uniform_min):
+    """asks that come in runs of identical (request, signature): the device commit decides every run of at least
+    uniform_min entries by the grid-wide sort of csrc/yk_uniform.cuh instead of the windowed kernel"""
+    from yunikorn_k8shim_b200 import Engine
+    monkeypatch.setenv("YK_UNIFORM_MIN", str(uniform_min))
+    decided = 0
+    for seed in range(120):
+        s = synth.runny(synth.fuzz(seed), seed)
+        want = oracle.run(s)
+        with Engine.for_snapshot(s, batch=batch, commit="device") as e:
+            try:
+                ask, node, _ = e.cycle(s.n_asks)
+            except Exception as exc:
+                assert batch == 7 and "gang" in str(exc), (seed, exc)
+                continue
+            states = e.ask_states(np.arange(s.n_asks))
+            avail = e.nodes_available(np.arange(s.n_nodes))
+            decided += e.stats()["uniform_asks"]
+        assert np.array_equal(ask, want["ask"]), (seed, batch)
+        assert np.array_equal(node, want["node"]), (seed, batch)
+        assert np.array_equal(states, want["state"]), (seed, batch)
+        assert np.array_equal(avail, want["avail"]), (seed, batch)
+    assert decided > 200
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("policy", [synth.POLICY_FAIR, synth.POLICY_BINPACKING])
 def test_engine_gang_rollback_stress(oracle, policy):
     """placed-then-undone gangs interleaved with plain asks (synth.poisoned_gangs), one long epoch"""

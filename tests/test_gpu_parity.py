@@ -73,6 +73,26 @@ def test_reference_benchmark_shape_full(oracle):
     """the reference's own benchmark shape: every pod identical (pkg/shim/scheduler_perf_test.go:283-288)"""
     st = _check(synth.reference_shape(), oracle, batch=4096)
     assert st["device"]["lattice_asks"] == 50_000
+    assert st["device"]["uniform_asks"] == 50_000 and st["device"]["lattice_subruns"] == 0   # one uniform run: no chain at all
+
+
+def test_uniform_runs_inside_mixed_batches(oracle, monkeypatch):
+    """config-2/3/4-sized snapshots whose asks come in runs: uniform runs and windowed stretches alternate inside one batch,
+    on the same device-resident node state"""
+    monkeypatch.setenv("YK_UNIFORM_MIN", "6")
+    uniform = 0
+    for snap, batch in ((synth.runny(synth.perf(1500, 20, 100), 1), 4096), (synth.runny(synth.perf(1500, 20, 100, masks=True), 2), 4096),
+                        (synth.runny(synth.hier(400, 3, 3, 2, 40), 3), 512), (synth.runny(synth.gangs(300, 60, 5), 4), 1000)):
+        want = oracle.run(snap)
+        st = _run(snap, want, commit="device", batch=batch)
+        assert st["lattice_subruns"] > 0, snap.name
+        uniform += st["uniform_asks"]
+    assert uniform > 1000
+    # more identical pods than the cluster holds
+    snap = synth.reference_shape(6, 3, 300)
+    snap.node_total[:, 2] = snap.node_avail[:, 2] = 110
+    st = _run(snap, oracle.run(snap), commit="device", batch=4096)
+    assert st["allocations"] == 660 and st["uniform_asks"] > 0
 
 
 def test_overcommitted_cluster(oracle):

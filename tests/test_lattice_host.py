@@ -24,11 +24,13 @@ def lshim(tmp_path_factory):
     return C.CDLL(out)
 
 
-def run(lshim, s, stats=None, **kw):
+def run(lshim, s, stats=None, uniform=(0, 0), **kw):
+    lshim.host_set_uniform(C.c_int(uniform[0]), C.c_int(uniform[1]))   # (shortest uniform run, first depth); 0 = off / engine's rule
     rows = []
     r = run_engine_host(lshim, s, fn="lattice_host_run", rows=rows, **kw)
     if stats is not None:
-        stats.append(dict(zip(("subruns", "fullscans", "sorts", "elems", "quick", "escalations", "handoffs", "batches"), rows[0])))
+        stats.append(dict(zip(("subruns", "fullscans", "sorts", "elems", "quick", "escalations", "handoffs", "batches", "uniform_attempts",
+                               "uniform_retries", "uniform_asks"), rows[0])))
     return r
 
 
@@ -140,3 +142,61 @@ def test_many_shapes_and_signatures(lshim, oracle):
         s.ask_req[:, 0] = 10 + (np.arange(s.n_asks) % 7)                    # seven tiny shapes: deep boxes on every side
         s.ask_req[:, 1] = 1_000_000
         assert check(lshim, oracle, s, tag=("tiny7", seed), batch=4096) is not None
+
+
+# ---- uniform runs (csrc/yk_uniform.h): consecutive asks with one request vector and one predicate signature ----------------
+@pytest.mark.parametrize("batch,uniform", [(64, (2, 0)), (1024, (3, 1)), (1024, (2, 2)), (7, (2, 0))])
+def test_uniform_runs_match_oracle_on_fuzz(lshim, oracle, batch, uniform):
+    checked = asks = 0
+    for seed in range(150):
+        s = synth.runny(synth.fuzz(seed), seed)
+        if (s.ask_gang >= 0).any() and np.bincount(s.ask_gang[s.ask_gang >= 0]).max() > batch:
+            continue
+        st = []
+        if check(lshim, oracle, s, tag=(seed, batch, uniform), batch=batch, stats=st, uniform=uniform) is not None:
+            checked += 1
+            asks += st[0]["uniform_asks"]
+    assert checked > 20 and asks > 200
+
+
+def test_uniform_reference_shape(lshim, oracle):
+    """the reference's benchmark shape, small: identical nodes, identical pods -> every key ties across nodes at every depth"""
+    for nodes, apps, tasks in ((50, 4, 125), (7, 3, 50), (100, 10, 110)):
+        s = synth.reference_shape(nodes, apps, tasks)
+        for uniform in ((16, 0), (16, 1), (16, 3)):
+            st = []
+            want = check(lshim, oracle, s, tag=(nodes, uniform), batch=1 << 20, stats=st, uniform=uniform)
+            assert want is not None
+            assert st[0]["uniform_asks"] == len(want["ask"]) == s.n_asks and st[0]["subruns"] == 0
+            if uniform[1] == 1:
+                assert st[0]["uniform_retries"] > 0
+
+
+def test_uniform_run_overflows_the_cluster(lshim, oracle):
+    """more identical pods than the nodes hold: the run places what fits and the rest fail (placement-insensitive order), or the
+    batch stops at the first failure (quota'd queues: the order depends on what was placed)"""
+    s = synth.reference_shape(6, 3, 300)
+    s.node_total[:, 2] = s.node_avail[:, 2] = 110        # 660 pods fit, 900 asked
+    st = []
+    want = check(lshim, oracle, s, batch=1 << 20, stats=st, uniform=(8, 0))
+    assert want is not None and len(want["ask"]) == 660 and st[0]["uniform_asks"] > 0
+    for seed in range(5):
+        s = synth.hier(12, 2, 2, 2, 40, seed=seed)
+        s.ask_req[:] = s.ask_req[0]
+        for col in (s.ask_tol, s.ask_need, s.ask_deny):
+            col[:] = col[0]
+        st = []
+        want = check(lshim, oracle, s, tag=seed, batch=512, stats=st, uniform=(4, 0))
+        assert want is not None and st[0]["uniform_asks"] > 0
+
+
+def test_uniform_gangs(lshim, oracle):
+    """homogeneous gangs inside a run: fine while everything fits; a run that cannot place all of its members goes to the
+    windowed commit (which rolls gangs back)"""
+    for seed in range(6):
+        for fill in (0.5, 1.05, 2.0):
+            s = synth.gangs(60, 30, 5, seed=seed, fill=fill)
+            s.ask_req[:] = s.ask_req[0]
+            st = []
+            assert check(lshim, oracle, s, tag=(seed, fill), batch=1000, stats=st, uniform=(4, 0)) is not None
+            assert st[0]["uniform_attempts"] > 0

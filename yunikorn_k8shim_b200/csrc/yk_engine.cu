@@ -28,6 +28,7 @@
 
 #include "yk_kernels.cuh"
 #include "yk_lattice.cuh"
+#include "yk_uniform.cuh"
 #include "yk_commit.hpp"
 #include "yk_lattice_host.hpp"
 #include "yk_orderer.hpp"
@@ -264,6 +265,14 @@ struct yk_engine {
     Pin<uint32_t> h_lt_asks, h_lt_meta, h_lt_shp, h_lt_sig, h_lt_res; Pin<int> h_lt_hdr; Pin<int64_t> h_lt_ub;
     std::vector<uint32_t> a_shape, a_sigid;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
+    // uniform runs (yk_uniform.h): allocated on first use; element buffers hold UN_EMAX generated elements
+    bool un_alloc = false, un_ranked = false;   // un_ranked: d_un_byrank holds this cycle's nodes
+    int un_min = 2048;                          // shortest run that takes the uniform path (YK_UNIFORM_MIN)
+    Dev<unsigned long long> d_un_ekey[2], d_un_bk, d_un_rkey[2], d_un_rrn[2];
+    Dev<uint32_t> d_un_enode[2], d_un_cnt, d_un_byrank, d_un_rk[2], d_un_nd;
+    Dev<ykun::Globals> d_un_g; Pin<ykun::Globals> h_un_g;
+    Dev<uint8_t> d_un_cub; size_t un_cub_bytes = 0;
+    std::vector<ykun::Segment> un_segs;
     Dev<uint32_t> pre_q; Dev<int64_t> pre_v; Dev<int32_t> pre_o;   // yk_preemption_search staging, grown on demand
     yk_allgather_fn xfn = nullptr; void* xctx = nullptr;
     // peer-to-peer exchange (see yk_peer_export): peers' slot buffers and sync blocks, mapped through CUDA IPC
@@ -450,6 +459,112 @@ int initial_order(yk_engine* e) {
     return YK_OK;
 }
 
+// ---- uniform runs on the device (yk_uniform.h / yk_uniform.cuh) -------------------------------------------------------
+constexpr size_t UN_EMAX = (size_t)4 << 20;   // generated elements per attempt at most (nodes x depth)
+
+int un_ensure(yk_engine* e) {
+    if (e->un_alloc) return YK_OK;
+    const size_t N = e->maxN;
+    for (int b = 0; b < 2; ++b) {
+        CK(e->d_un_ekey[b].alloc(UN_EMAX)); CK(e->d_un_enode[b].alloc(UN_EMAX));
+        CK(e->d_un_rkey[b].alloc(N)); CK(e->d_un_rrn[b].alloc(N)); CK(e->d_un_rk[b].alloc(N));
+    }
+    CK(e->d_un_bk.alloc(N)); CK(e->d_un_cnt.alloc(N)); CK(e->d_un_byrank.alloc(N)); CK(e->d_un_nd.alloc(N));
+    CK(e->d_un_g.alloc(1)); CK(e->h_un_g.alloc(1));
+    CK(cudaMemsetAsync(e->d_un_cnt.p, 0, sizeof(uint32_t) * std::max<size_t>(N, 1), e->stream));
+    size_t t0 = 0, t1 = 0, t2 = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, t0, e->d_un_ekey[0].p, e->d_un_ekey[1].p, e->d_un_enode[0].p, e->d_un_enode[1].p, (int)UN_EMAX, 0, 64, e->stream));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, t1, e->d_un_rkey[0].p, e->d_un_rkey[1].p, e->d_un_rrn[0].p, e->d_un_rrn[1].p, (int)std::max<size_t>(N, 1), 0, 64, e->stream));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, t2, e->d_un_rk[0].p, e->d_un_rk[1].p, e->d_un_nd.p, e->d_un_byrank.p, (int)std::max<size_t>(N, 1), 0, 32, e->stream));
+    e->un_cub_bytes = std::max(t0, std::max(t1, t2));
+    CK(e->d_un_cub.alloc(e->un_cub_bytes));
+    e->un_alloc = true;
+    return YK_OK;
+}
+
+template <int D>
+cudaError_t un_attempt_d(yk_engine* e, const ykun::Args& a) {
+    cudaStream_t s = e->stream;
+    const int nb = (a.nlive + 255) / 256;
+    ykun::un_reset_kernel<<<1, 1, 0, s>>>(a.g);
+    ykun::un_depth_kernel<D><<<nb, 256, 0, s>>>(a);
+    ykun::un_brank_kernel<D><<<nb, 256, 0, s>>>(a);
+    size_t tb = e->un_cub_bytes;
+    cudaError_t rc = cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, a.ekey, const_cast<unsigned long long*>(a.skey), a.enode,
+                                                     const_cast<uint32_t*>(a.snode), a.nlive * a.L, 0, 64, s);
+    if (rc != cudaSuccess) return rc;
+    ykun::un_select_kernel<D><<<(a.R + 255) / 256, 256, 0, s>>>(a);
+    ykun::un_decide_kernel<<<1, 1, 0, s>>>(a);
+    ykun::un_apply_rekey_kernel<D><<<nb, 256, 0, s>>>(a);
+    tb = e->un_cub_bytes;
+    rc = cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, a.rkey, const_cast<unsigned long long*>(a.okey), a.rrn,
+                                         const_cast<unsigned long long*>(a.orn), a.nlive, 0, 64, s);
+    if (rc != cudaSuccess) return rc;
+    ykun::un_order_kernel<<<nb, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t un_attempt(yk_engine* e, const ykun::Args& a) {
+    switch (e->D) {
+        case 1: return un_attempt_d<1>(e, a); case 2: return un_attempt_d<2>(e, a); case 3: return un_attempt_d<3>(e, a);
+        case 4: return un_attempt_d<4>(e, a); case 5: return un_attempt_d<5>(e, a); case 6: return un_attempt_d<6>(e, a);
+        case 7: return un_attempt_d<7>(e, a); default: return un_attempt_d<8>(e, a);
+    }
+}
+
+// One uniform run: entries [off, off + R) of the staged batch (h_lt_asks; results land in d_lt_res at the same offset).
+// status = ykun::U_DONE / U_STOPPED with *consumed entries decided, or U_FALLBACK: nothing was applied, the windowed kernel
+// takes the run.
+int lt_uniform(yk_engine* e, size_t off, size_t R, bool insensitive, bool has_gang, int* status, size_t* consumed) {
+    *status = ykun::U_FALLBACK; *consumed = 0;
+    const int nlive = (int)e->nlive;
+    if (nlive == 0 || R == 0) return YK_OK;
+    int rc = un_ensure(e);
+    if (rc) return rc;
+    cudaStream_t s = e->stream;
+    if (!e->un_ranked) {   // once per cycle: the live nodes in NodeID-rank order (ranks do not change inside a cycle)
+        ykun::un_ranks_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(e->d_ord[0].p, e->d_ord[1].p, e->d_lt_cur.p, nlive, e->d_un_rk[0].p, e->d_un_nd.p);
+        size_t tb = e->un_cub_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, e->d_un_rk[0].p, e->d_un_rk[1].p, e->d_un_nd.p, e->d_un_byrank.p, nlive, 0, 32, s));
+        e->un_ranked = true;
+        e->st.other_launches += 6;
+    }
+    const uint32_t ask = e->h_lt_asks[off];
+    ykun::Args a{};
+    a.policy = e->cfg.policy;
+    for (int k = 0; k < 8; ++k) { a.w[k] = e->w.w[k]; a.req[k] = k < e->D ? e->a_req[(size_t)k * e->maxA + ask] : 0; }
+    a.rec = e->d_rec.p; a.RS = e->lt_RS; a.ord[0] = e->d_ord[0].p; a.ord[1] = e->d_ord[1].p; a.cur = e->d_lt_cur.p;
+    a.nlive = nlive; a.byrank = e->d_un_byrank.p;
+    a.tol = e->a_tol[ask]; a.need = e->a_need[ask]; a.deny = e->a_deny[ask]; a.want = e->a_node[ask];
+    a.R = (int)R; a.insensitive = insensitive ? 1 : 0; a.has_gang = has_gang ? 1 : 0;
+    a.ekey = e->d_un_ekey[0].p; a.skey = e->d_un_ekey[1].p; a.enode = e->d_un_enode[0].p; a.snode = e->d_un_enode[1].p;
+    a.bk = e->d_un_bk.p; a.cnt = e->d_un_cnt.p;
+    a.rkey = e->d_un_rkey[0].p; a.okey = e->d_un_rkey[1].p; a.rrn = e->d_un_rrn[0].p; a.orn = e->d_un_rrn[1].p;
+    a.res = e->d_lt_res.p + off; a.g = e->d_un_g.p;
+    int L = ykun::first_depth((int)R, nlive);
+    for (;;) {
+        if ((size_t)L * (size_t)nlive > UN_EMAX) return YK_OK;   // too deep for the element buffers: fallback
+        a.L = L;
+        CK(cudaEventRecord(e->ev_l0, s));
+        CK(un_attempt(e, a));
+        CK(cudaEventRecord(e->ev_l1, s));
+        CK(cudaMemcpyAsync(e->h_un_g.p, e->d_un_g.p, sizeof(ykun::Globals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev_l0, e->ev_l1);
+        e->st.lattice_ms += ms;
+        e->st.lattice_launches += 1;
+        e->st.other_launches += 24;   // 7 kernels of this file + two cub radix sorts (histogram, scan, 8 onesweep passes each, fewer when small)
+        e->st.d2h_bytes += sizeof(ykun::Globals);
+        const ykun::Globals& g = e->h_un_g[0];
+        if (g.status == ykun::U_RETRY) { e->st.uniform_retries++; L *= 4; continue; }
+        if (g.status == ykun::U_NAN || g.status == ykun::U_FALLBACK) return YK_OK;
+        if (g.nan) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
+        *status = g.status; *consumed = (size_t)g.consumed;
+        e->st.uniform_runs++; e->st.uniform_asks += (uint64_t)g.consumed; e->st.uniform_elements += (uint64_t)L * (uint64_t)nlive;
+        return YK_OK;
+    }
+}
+
 // ---- device-resident ordered commit (yk_lattice.h) -------------------------------------------------------------------
 // node records + order entries from the sorted keys; capacity bound and header reset
 int lt_prepare(yk_engine* e) {
@@ -465,39 +580,80 @@ int lt_prepare(yk_engine* e) {
     CK(cudaMemsetAsync(e->d_lt_cur.p, 0, sizeof(int), s));
     CK(cudaMemsetAsync(e->d_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int), s));
     e->st.other_launches += 1;
+    e->un_ranked = false;
+    memset(e->h_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int));
     return YK_OK;
 }
 
-// one batch through yk_lattice_kernel: asks + their three words up (already in the pinned staging buffers), node indices +
-// header back.  Blocks until the batch is decided.
-int lt_batch(yk_engine* e, size_t B, bool insensitive) {
+// One batch through the device commit: asks + their three words up (already in the pinned staging buffers), node indices +
+// header back.  Uniform runs of at least un_min entries go through lt_uniform, the stretches between them through
+// yk_lattice_kernel; h_lt_hdr[H_STATUS / H_CONSUMED] describe the whole batch afterwards.  Blocks until it is decided.
+int lt_window(yk_engine* e, size_t off, size_t B, bool insensitive) {
     cudaStream_t s = e->stream;
-    CK(cudaMemcpyAsync(e->d_lt_asks.p, e->h_lt_asks.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_meta.p, e->h_lt_meta.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_shp.p, e->h_lt_shp.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_sig.p, e->h_lt_sig.p, 4 * B, cudaMemcpyHostToDevice, s));
     yklt::Args a{};
     a.policy = e->cfg.policy;
     for (int k = 0; k < 8; ++k) a.w[k] = e->w.w[k];
     a.rec = e->d_rec.p; a.RS = e->lt_RS; a.ord[0] = e->d_ord[0].p; a.ord[1] = e->d_ord[1].p; a.cur = e->d_lt_cur.p;
     a.nlive = (int)e->nlive;
     a.a_req = e->d_areq.p; a.lda = e->maxA; a.a_tol = e->d_atol.p; a.a_need = e->d_aneed.p; a.a_deny = e->d_adeny.p; a.a_node = e->d_anode.p;
-    a.asks = e->d_lt_asks.p; a.meta = e->d_lt_meta.p; a.shp = e->d_lt_shp.p; a.sig = e->d_lt_sig.p; a.B = (int)B;
-    a.res = e->d_lt_res.p; a.hdr = e->d_lt_hdr.p; a.ub = e->d_lt_ub.p; a.insensitive = insensitive ? 1 : 0;
+    a.asks = e->d_lt_asks.p + off; a.meta = e->d_lt_meta.p + off; a.shp = e->d_lt_shp.p + off; a.sig = e->d_lt_sig.p + off; a.B = (int)B;
+    a.res = e->d_lt_res.p + off; a.hdr = e->d_lt_hdr.p; a.ub = e->d_lt_ub.p; a.insensitive = insensitive ? 1 : 0;
     a.prof = e->lt_prof ? e->d_lt_prof.p : nullptr;
     CK(cudaEventRecord(e->ev_l0, s));
     launch_lattice(e->D, a, e->lt_smem, s);
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev_l1, s));
-    CK(cudaMemcpyAsync(e->h_lt_res.p, e->d_lt_res.p, 4 * B, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(e->h_lt_hdr.p, e->d_lt_hdr.p, yklt::H_WORDS * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev_l0, e->ev_l1);
     e->st.lattice_ms += ms;
     e->st.lattice_launches += 1;
+    e->st.d2h_bytes += yklt::H_WORDS * sizeof(int);
+    return YK_OK;
+}
+
+int lt_batch(yk_engine* e, size_t B, bool insensitive) {
+    cudaStream_t s = e->stream;
+    CK(cudaMemcpyAsync(e->d_lt_asks.p, e->h_lt_asks.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_meta.p, e->h_lt_meta.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_shp.p, e->h_lt_shp.p, 4 * B, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(e->d_lt_sig.p, e->h_lt_sig.p, 4 * B, cudaMemcpyHostToDevice, s));
     e->st.h2d_bytes += 16 * B;
-    e->st.d2h_bytes += 4 * B + yklt::H_WORDS * sizeof(int);
+    ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B, e->un_min > 0 ? e->un_min : (int)B + 1, e->un_segs);
+    int status = yklt::ST_DONE;
+    size_t done = 0;
+    for (const ykun::Segment& sg : e->un_segs) {
+        size_t consumed = 0;
+        int st = yklt::ST_DONE;
+        bool windowed = !sg.uniform;
+        if (sg.uniform) {
+            bool has_gang = false;
+            for (int i = 0; i < sg.len && !has_gang; ++i) has_gang = (e->h_lt_meta[(size_t)sg.off + i] & yklt::M_GANG) != 0;
+            int ust = ykun::U_FALLBACK;
+            const int rc = lt_uniform(e, (size_t)sg.off, (size_t)sg.len, insensitive, has_gang, &ust, &consumed);
+            if (rc) return rc;
+            if (ust == ykun::U_FALLBACK) windowed = true;
+            else st = ust == ykun::U_STOPPED ? yklt::ST_STOPPED : yklt::ST_DONE;
+        }
+        if (windowed) {
+            const int rc = lt_window(e, (size_t)sg.off, (size_t)sg.len, insensitive);
+            if (rc) return rc;
+            st = e->h_lt_hdr[yklt::H_STATUS];
+            consumed = (size_t)e->h_lt_hdr[yklt::H_CONSUMED];
+            if (consumed > (size_t)sg.len) return e->fail(YK_ERR_CUDA, "lattice kernel returned a bad header");
+        }
+        done = (size_t)sg.off + consumed;
+        status = st;
+        if (st != yklt::ST_DONE || consumed < (size_t)sg.len) break;
+    }
+    e->h_lt_hdr[yklt::H_STATUS] = status;
+    e->h_lt_hdr[yklt::H_CONSUMED] = (int)done;
+    if (done) {
+        CK(cudaMemcpyAsync(e->h_lt_res.p, e->d_lt_res.p, 4 * done, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        e->st.d2h_bytes += 4 * done;
+    }
     return YK_OK;
 }
 
@@ -942,6 +1098,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->d_dirty_nodes.alloc(N)); T(e->d_dirty_vals.alloc(N * D)); T(e->d_scores.alloc(N));
     // device-resident ordered commit
     e->lt_allowed = !(cfg->flags & YK_FLAG_HOST_COMMIT) && cfg->world <= 1;
+    e->lt_auto = true;
     if (cfg->flags & YK_FLAG_DEVICE_COMMIT) e->lt_force = 1;
     if (const char* cm = getenv("YK_COMMIT")) {
         if (!strcmp(cm, "host")) e->lt_allowed = false;
@@ -958,6 +1115,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->ep_d_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1))); T(e->ep_h_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1)));
     T(cudaEventCreateWithFlags(&e->ep_ev, cudaEventDisableTiming)); T(cudaEventCreate(&e->ep_s0)); T(cudaEventCreate(&e->ep_s1));
     e->lt_prof = getenv("YK_PROFILE_LATTICE") != nullptr;
+    if (const char* um = getenv("YK_UNIFORM_MIN")) e->un_min = atoi(um);   // 0: no uniform-run path
     T(e->d_lt_prof.alloc(16));
     if (ok) T(cudaMemset(e->d_lt_prof.p, 0, 16 * sizeof(long long)));
     if (ok) T(lattice_setup(D, &e->lt_smem));
@@ -1447,7 +1605,9 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     double begin_ms = 0;
     bool gang_too_big = false;
     setup_commit_tables(e);
-    const bool try_lattice = e->lt_allowed && (e->lt_force || e->lt_auto) && e->cfg.policy == YK_POLICY_FAIR;
+    // device commit: forced (every eligible cycle), or automatic (cycles whose asks come in long uniform runs: yk_uniform.h)
+    const bool force_lattice = e->lt_allowed && e->lt_force && e->cfg.policy == YK_POLICY_FAIR;
+    const bool auto_lattice = e->lt_allowed && !e->lt_force && e->lt_auto && e->un_min > 0 && e->cfg.policy == YK_POLICY_FAIR;
     e->worker.submit([&] {
         const double t_b = now_ms();
         pending.clear();
@@ -1497,7 +1657,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             e->ep_rows = ns > 0 && ns <= yk_engine::EP_MAX && (uint64_t)ns * 8 <= pending.size();
             e->ep_n = ns;
         }
-        if (!gang_too_big && try_lattice) {   // request-vector numbers for the lattice kernel's windows
+        if (!gang_too_big && force_lattice) {   // request-vector numbers for the lattice kernel's windows
             yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
         }
         e->ep_uploaded = false; e->ep_landed = true;
@@ -1520,20 +1680,43 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     const bool ins = e->ord.insensitive;
     bool lattice = false;
     size_t bsz0 = e->batch;
-    if (try_lattice) {
+    if (force_lattice) {
         const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending);
         lattice = el.ok;
         if (lattice && ins) bsz0 = e->maxA;   // the whole static order in one launch
     }
     rc = fill_batch(e, bsz0, std::max<size_t>(bsz0, e->batch), max_bindings, e->slot[0], e->st);
-    if (lattice && !e->lt_force && !e->lt_auto) lattice = false;   // measured (profiles/r2_lattice_*): the host commit is still ahead
-    if (!rc && lattice && !e->lt_force && !e->slot[0].asks.empty()) {
-        // windows long enough to pay for a sub-run (scan + lattice + patch is a few microseconds, an ask on the host
-        // commit about 0.1): otherwise this is a many-shapes workload for the sweep + host commit
-        const size_t B0 = e->slot[0].asks.size();
-        yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
-        const size_t w = yklt::estimate_windows(e->h_lt_shp.p, e->h_lt_sig.p, B0);
-        if (e->slot[0].asks.size() < 32 * w) lattice = false;
+    if (!rc && auto_lattice && pending.size() >= (size_t)e->un_min && e->slot[0].asks.size() >= (size_t)e->un_min) {
+        // Automatic: the device commit decides a uniform run (one request vector, one predicate signature) by a grid-wide sort,
+        // everything else through a sequential chain that one host core still does faster (profiles/r2_lattice_*).  So the
+        // cycle starts on the device exactly when the order is made of long uniform runs.  Cheap screen first -- the
+        // longest run of one signature id in the first batch -- and only then the eligibility test and the shape numbers.
+        const std::vector<uint32_t>& as = e->slot[0].asks;
+        size_t longest = 0, run = 1;
+        for (size_t i = 1; i <= as.size(); ++i) {
+            if (i < as.size() && e->a_sigid[as[i]] == e->a_sigid[as[i - 1]]) { ++run; continue; }
+            longest = std::max(longest, run);
+            run = 1;
+        }
+        if (longest >= (size_t)e->un_min) {
+            const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending);
+            if (el.ok) {
+                yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
+                if (ins) {   // the whole static order in one batch
+                    e->ord.unfill(e->slot[0].snap, e->slot[0].asks, 0);
+                    size_t b = e->maxA;
+                    rc = fill_batch(e, b, e->maxA, max_bindings, e->slot[0], e->st);
+                }
+                if (!rc) {
+                    const size_t B0 = e->slot[0].asks.size();
+                    yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+                    ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B0, e->un_min, e->un_segs);
+                    size_t covered = 0;
+                    for (const ykun::Segment& sg : e->un_segs) if (sg.uniform) covered += (size_t)sg.len;
+                    lattice = covered * 10 >= B0 * 9;
+                }
+            }
+        }
     }
     if (!rc && !lattice && e->slot[0].asks.size() > e->batch) {   // the first fill was sized for the device commit
         e->ord.unfill(e->slot[0].snap, e->slot[0].asks, 0);

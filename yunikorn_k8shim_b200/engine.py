@@ -49,7 +49,9 @@ class Stats(C.Structure):
                 ("lattice_launches", C.c_uint64), ("lattice_subruns", C.c_uint64), ("lattice_asks", C.c_uint64),
                 ("lattice_elements", C.c_uint64), ("lattice_sorts", C.c_uint64), ("lattice_fullscans", C.c_uint64),
                 ("lattice_quick", C.c_uint64), ("lattice_handoffs", C.c_uint64), ("lattice_ms", C.c_double),
-                ("lattice_cycles", C.c_uint64)]
+                ("lattice_cycles", C.c_uint64),
+                ("uniform_runs", C.c_uint64), ("uniform_asks", C.c_uint64), ("uniform_elements", C.c_uint64),
+                ("uniform_retries", C.c_uint64)]
 
     def as_dict(self):
         d = {f: getattr(self, f) for f, _ in self._fields_}

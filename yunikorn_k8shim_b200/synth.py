@@ -362,6 +362,23 @@ def poisoned_gangs(seed: int, n_nodes=64, n_gangs=80, members=4, policy=POLICY_F
     return s
 
 
+def runny(s: Snapshot, seed: int) -> Snapshot:
+    """Make the snapshot's asks come in runs (in place): blocks of consecutive asks of one application copy everything the
+    commit looks at (request, masks, node name, priority, flags) from the block's first ask -- the replicas of one
+    deployment / the executors of one job."""
+    r = np.random.default_rng(seed)
+    i = 0
+    while i < s.n_asks:
+        ln = int(r.integers(1, 14))
+        j = i + 1
+        while j < s.n_asks and j - i < ln and s.ask_app[j] == s.ask_app[i]:
+            for col in (s.ask_req, s.ask_tol, s.ask_need, s.ask_deny, s.ask_node, s.ask_prio, s.ask_flags):
+                col[j] = col[i]
+            j += 1
+        i = j
+    return s
+
+
 def fuzz(seed: int, n_nodes=None, n_asks=None) -> Snapshot:
     """Small snapshot mixing every feature of the path at once (used by the randomized parity tests): random queue
     tree with guarantees and quotas, fifo and fair leaves, priorities, gangs, taints / selectors, pod.Spec.NodeName,
