@@ -192,6 +192,7 @@ struct yk_engine {
     uint32_t n_hi = 0;                         // 1 + highest node index in use
     bool nodes_stale = true, rank_stale = true;
     Pin<uint32_t> by_rank; uint32_t nlive = 0;
+    bool ranks_unique = true;                // no two live nodes share a NodeID rank (checked where by_rank is rebuilt)
 
     Pin<int64_t> a_req;                        // [D][maxA]
     Pin<uint64_t> a_tol, a_need, a_deny;
@@ -266,10 +267,11 @@ struct yk_engine {
     std::vector<uint32_t> a_shape, a_sigid;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
     // uniform runs (yk_uniform.h): allocated on first use; element buffers hold UN_EMAX generated elements
-    bool un_alloc = false, un_ranked = false;   // un_ranked: d_un_byrank holds this cycle's nodes
+    bool un_alloc = false;
+    const uint32_t* lt_shape_ids = nullptr;     // per ask: a number equal for equal request vectors (a_shape, or a_sigid: finer, still exact)
     int un_min = 2048;                          // shortest run that takes the uniform path (YK_UNIFORM_MIN)
     Dev<unsigned long long> d_un_ekey[2], d_un_bk, d_un_rkey[2], d_un_rrn[2];
-    Dev<uint32_t> d_un_enode[2], d_un_cnt, d_un_byrank, d_un_rk[2], d_un_nd;
+    Dev<uint32_t> d_un_enode[2], d_un_cnt;
     Dev<ykun::Globals> d_un_g; Pin<ykun::Globals> h_un_g;
     Dev<uint8_t> d_un_cub; size_t un_cub_bytes = 0;
     std::vector<ykun::Segment> un_segs;
@@ -334,6 +336,8 @@ int upload_tables(yk_engine* e) {
             return a < b;
         });
         e->nlive = (uint32_t)live.size();
+        e->ranks_unique = true;
+        for (size_t i = 1; i < live.size(); ++i) if (e->n_rank[live[i]] == e->n_rank[live[i - 1]]) e->ranks_unique = false;
         if (e->nlive) memcpy(e->by_rank.p, live.data(), sizeof(uint32_t) * e->nlive);
         if (e->nlive) CK(cudaMemcpyAsync(e->d_by_rank.p, e->by_rank.p, sizeof(uint32_t) * e->nlive, cudaMemcpyHostToDevice, e->stream));
         e->st.h2d_bytes += sizeof(uint32_t) * e->nlive;
@@ -467,16 +471,15 @@ int un_ensure(yk_engine* e) {
     const size_t N = e->maxN;
     for (int b = 0; b < 2; ++b) {
         CK(e->d_un_ekey[b].alloc(UN_EMAX)); CK(e->d_un_enode[b].alloc(UN_EMAX));
-        CK(e->d_un_rkey[b].alloc(N)); CK(e->d_un_rrn[b].alloc(N)); CK(e->d_un_rk[b].alloc(N));
+        CK(e->d_un_rkey[b].alloc(N)); CK(e->d_un_rrn[b].alloc(N));
     }
-    CK(e->d_un_bk.alloc(N)); CK(e->d_un_cnt.alloc(N)); CK(e->d_un_byrank.alloc(N)); CK(e->d_un_nd.alloc(N));
+    CK(e->d_un_bk.alloc(N)); CK(e->d_un_cnt.alloc(N));
     CK(e->d_un_g.alloc(1)); CK(e->h_un_g.alloc(1));
     CK(cudaMemsetAsync(e->d_un_cnt.p, 0, sizeof(uint32_t) * std::max<size_t>(N, 1), e->stream));
-    size_t t0 = 0, t1 = 0, t2 = 0;
+    size_t t0 = 0, t1 = 0;
     CK(cub::DeviceRadixSort::SortPairs(nullptr, t0, e->d_un_ekey[0].p, e->d_un_ekey[1].p, e->d_un_enode[0].p, e->d_un_enode[1].p, (int)UN_EMAX, 0, 64, e->stream));
     CK(cub::DeviceRadixSort::SortPairs(nullptr, t1, e->d_un_rkey[0].p, e->d_un_rkey[1].p, e->d_un_rrn[0].p, e->d_un_rrn[1].p, (int)std::max<size_t>(N, 1), 0, 64, e->stream));
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, t2, e->d_un_rk[0].p, e->d_un_rk[1].p, e->d_un_nd.p, e->d_un_byrank.p, (int)std::max<size_t>(N, 1), 0, 32, e->stream));
-    e->un_cub_bytes = std::max(t0, std::max(t1, t2));
+    e->un_cub_bytes = std::max(t0, t1);
     CK(e->d_un_cub.alloc(e->un_cub_bytes));
     e->un_alloc = true;
     return YK_OK;
@@ -521,19 +524,12 @@ int lt_uniform(yk_engine* e, size_t off, size_t R, bool insensitive, bool has_ga
     int rc = un_ensure(e);
     if (rc) return rc;
     cudaStream_t s = e->stream;
-    if (!e->un_ranked) {   // once per cycle: the live nodes in NodeID-rank order (ranks do not change inside a cycle)
-        ykun::un_ranks_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(e->d_ord[0].p, e->d_ord[1].p, e->d_lt_cur.p, nlive, e->d_un_rk[0].p, e->d_un_nd.p);
-        size_t tb = e->un_cub_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, e->d_un_rk[0].p, e->d_un_rk[1].p, e->d_un_nd.p, e->d_un_byrank.p, nlive, 0, 32, s));
-        e->un_ranked = true;
-        e->st.other_launches += 6;
-    }
     const uint32_t ask = e->h_lt_asks[off];
     ykun::Args a{};
     a.policy = e->cfg.policy;
     for (int k = 0; k < 8; ++k) { a.w[k] = e->w.w[k]; a.req[k] = k < e->D ? e->a_req[(size_t)k * e->maxA + ask] : 0; }
     a.rec = e->d_rec.p; a.RS = e->lt_RS; a.ord[0] = e->d_ord[0].p; a.ord[1] = e->d_ord[1].p; a.cur = e->d_lt_cur.p;
-    a.nlive = nlive; a.byrank = e->d_un_byrank.p;
+    a.nlive = nlive; a.byrank = e->d_by_rank.p;   // live nodes by ascending (NodeID rank, index): upload_tables
     a.tol = e->a_tol[ask]; a.need = e->a_need[ask]; a.deny = e->a_deny[ask]; a.want = e->a_node[ask];
     a.R = (int)R; a.insensitive = insensitive ? 1 : 0; a.has_gang = has_gang ? 1 : 0;
     a.ekey = e->d_un_ekey[0].p; a.skey = e->d_un_ekey[1].p; a.enode = e->d_un_enode[0].p; a.snode = e->d_un_enode[1].p;
@@ -580,7 +576,6 @@ int lt_prepare(yk_engine* e) {
     CK(cudaMemsetAsync(e->d_lt_cur.p, 0, sizeof(int), s));
     CK(cudaMemsetAsync(e->d_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int), s));
     e->st.other_launches += 1;
-    e->un_ranked = false;
     memset(e->h_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int));
     return YK_OK;
 }
@@ -1466,7 +1461,7 @@ int run_lattice(yk_engine* e, Cycle& c, bool& handoff) {
     while (!A.asks.empty()) {
         const size_t B = A.asks.size();
         memcpy(e->h_lt_asks.p, A.asks.data(), 4 * B);
-        yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), A.asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+        yklt::build_meta(e->cm.t, e->lt_shape_ids, e->a_sigid.data(), A.asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
         size_t consumed = 0;
         int status = yklt::ST_DONE;
         if (e->nlive == 0) {   // no nodes: nothing fits
@@ -1659,6 +1654,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         }
         if (!gang_too_big && force_lattice) {   // request-vector numbers for the lattice kernel's windows
             yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
+            e->lt_shape_ids = e->a_shape.data();
         }
         e->ep_uploaded = false; e->ep_landed = true;
         begin_ms = now_ms() - t_b;
@@ -1681,7 +1677,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     bool lattice = false;
     size_t bsz0 = e->batch;
     if (force_lattice) {
-        const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending);
+        const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique);
         lattice = el.ok;
         if (lattice && ins) bsz0 = e->maxA;   // the whole static order in one launch
     }
@@ -1699,9 +1695,11 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             run = 1;
         }
         if (longest >= (size_t)e->un_min) {
-            const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending);
+            const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique);
             if (el.ok) {
-                yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
+                // signature ids double as shape numbers: equal signatures request equal vectors; two signatures with one request
+                // only make the (rare, here) windowed stretches see one more shape
+                e->lt_shape_ids = e->a_sigid.data();
                 if (ins) {   // the whole static order in one batch
                     e->ord.unfill(e->slot[0].snap, e->slot[0].asks, 0);
                     size_t b = e->maxA;
@@ -1709,7 +1707,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
                 }
                 if (!rc) {
                     const size_t B0 = e->slot[0].asks.size();
-                    yklt::build_meta(e->cm.t, e->a_shape.data(), e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+                    yklt::build_meta(e->cm.t, e->lt_shape_ids, e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
                     ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B0, e->un_min, e->un_segs);
                     size_t covered = 0;
                     for (const ykun::Segment& sg : e->un_segs) if (sg.uniform) covered += (size_t)sg.len;

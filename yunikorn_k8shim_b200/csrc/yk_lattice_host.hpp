@@ -108,20 +108,25 @@ struct Eligibility {
     const char* why = "";
 };
 
+// ranks_unique: when the caller already knows whether the live nodes' ranks are distinct (the engine checks it where it sorts
+// the nodes by rank), else nullptr.
 inline Eligibility eligible(const yk::CommitTables& t, uint32_t n_hi, const uint8_t* n_present, const int64_t* n_total,
-                            size_t ldn, const uint32_t* n_rank, const std::vector<uint32_t>& pending) {
+                            size_t ldn, const uint32_t* n_rank, const std::vector<uint32_t>& pending, const bool* ranks_unique = nullptr) {
     Eligibility e;
     if (t.policy != 0u) { e.why = "binpacking node sort"; return e; }
     for (int k = 0; k < t.D; ++k) if (t.w[k] < 0.0 || t.w[k] != t.w[k]) { e.why = "negative node-sort weight"; return e; }
-    {
+    for (int k = 0; k < t.D; ++k) {
+        if (t.w[k] == 0.0) continue;
+        const int64_t* col = n_total + (size_t)k * ldn;
+        for (uint32_t n = 0; n < n_hi; ++n)
+            if (n_present[n] && col[n] < 0) { e.why = "negative total on a weighted resource"; return e; }
+    }
+    if (ranks_unique) {
+        if (!*ranks_unique) { e.why = "duplicate NodeID ranks"; return e; }
+    } else {
         std::vector<uint32_t> ranks;
         ranks.reserve(n_hi);
-        for (uint32_t n = 0; n < n_hi; ++n) {
-            if (!n_present[n]) continue;
-            ranks.push_back(n_rank[n]);
-            for (int k = 0; k < t.D; ++k)
-                if (t.w[k] != 0.0 && n_total[(size_t)k * ldn + n] < 0) { e.why = "negative total on a weighted resource"; return e; }
-        }
+        for (uint32_t n = 0; n < n_hi; ++n) if (n_present[n]) ranks.push_back(n_rank[n]);
         std::sort(ranks.begin(), ranks.end());
         for (size_t i = 1; i < ranks.size(); ++i) if (ranks[i] == ranks[i - 1]) { e.why = "duplicate NodeID ranks"; return e; }
     }

@@ -17,15 +17,6 @@ __global__ void un_reset_kernel(Globals* g) {
     g->bkey = KEY_INF; g->brank = KEY_INF; g->last_key = 0; g->last_rank = 0; g->valid = 0; g->nan = 0; g->status = U_RETRY; g->consumed = 0;
 }
 
-// live nodes by position -> (rank, node) pairs for the rank sort
-__global__ void un_ranks_kernel(const yklt::Ent* ord0, const yklt::Ent* ord1, const int* cur, int nlive,
-                                uint32_t* __restrict__ rank_out, uint32_t* __restrict__ node_out) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= nlive) return;
-    const uint64_t rn = ((*cur & 1) ? ord1 : ord0)[p].rn;
-    rank_out[p] = (uint32_t)(rn >> 32); node_out[p] = (uint32_t)rn;
-}
-
 template <int D>
 __global__ void __launch_bounds__(256) un_depth_kernel(const Args a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
