@@ -97,11 +97,15 @@ typedef enum {
 /* yk_config.flags */
 #define YK_FLAG_NO_ROW_SHARING 1u   /* sweep one row per ask even when asks of a batch have identical predicate inputs
                                       (requests, tolerations, label masks, node name); default: one row per distinct set */
-#define YK_FLAG_HOST_COMMIT 2u      /* never use the device-resident ordered commit (yk_lattice_kernel): every cycle takes the
-                                      sweep + host commit path (the default today: measured, the host commit is still ahead) */
-#define YK_FLAG_DEVICE_COMMIT 4u    /* commit on the device (yk_lattice_kernel: exact, no bitmap read-back, no host work per
-                                      ask) whenever the cycle is eligible: fair node sort, non-negative weights, every gang's
-                                      members requesting one vector.  Ineligible cycles take the sweep + host commit path. */
+/* Where the ordered commit runs.  Default (neither flag): automatic -- a cycle whose order consists of long UNIFORM RUNS
+   (>= 2048 consecutive asks with one request vector and one predicate signature: the replicas of a deployment, the executors of
+   a job, the reference's own benchmark) and that is eligible (fair node sort, non-negative weights and weighted totals, unique
+   NodeID ranks, every gang's members requesting one vector) is decided on the device by a grid-wide sort (csrc/yk_uniform.cuh);
+   every other cycle takes the sweep + host commit path.  The bindings are the same either way. */
+#define YK_FLAG_HOST_COMMIT 2u      /* never commit on the device */
+#define YK_FLAG_DEVICE_COMMIT 4u    /* commit on the device whenever the cycle is eligible, also where the order is not made of
+                                      uniform runs (yk_lattice_kernel: exact, no bitmap read-back, no host work per ask, but
+                                      measured slower than the host commit there) */
 
 typedef struct yk_engine yk_engine;
 

@@ -71,8 +71,8 @@ int uniform_host(const yklt::Args& la, const uint32_t* asks, int off, int R, boo
         std::vector<uint32_t> enode(ne), snode(ne), idx(ne);
         a.ekey = ekey.data(); a.enode = enode.data(); a.skey = skey.data(); a.snode = snode.data();
         g.bkey = ykun::KEY_INF; g.brank = ykun::KEY_INF; g.last_key = 0; g.last_rank = 0; g.valid = 0; g.nan = 0; g.status = ykun::U_RETRY; g.consumed = 0;
-        for (int i = 0; i < nlive; ++i) {
-            const ykun::DepthOut o = ykun::depth_item<D>(a, i);
+        for (long long x = 0; x < (long long)ne; ++x) {
+            const ykun::DepthOut o = ykun::element_item<D>(a, x);
             g.valid += o.valid;
             if (o.bk < g.bkey) g.bkey = o.bk;
             if (o.nan) g.nan = 1;

@@ -267,7 +267,8 @@ struct yk_engine {
     std::vector<uint32_t> a_shape, a_sigid;
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
     // uniform runs (yk_uniform.h): allocated on first use; element buffers hold UN_EMAX generated elements
-    bool un_alloc = false;
+    bool hp_on = false; double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t hp_n = 0;
+    bool un_alloc = false, un_ord_stale = false;   // un_ord_stale: uniform runs moved nodes since d_ord was last written
     const uint32_t* lt_shape_ids = nullptr;     // per ask: a number equal for equal request vectors (a_shape, or a_sigid: finer, still exact)
     int un_min = 2048;                          // shortest run that takes the uniform path (YK_UNIFORM_MIN)
     Dev<unsigned long long> d_un_ekey[2], d_un_bk, d_un_rkey[2], d_un_rrn[2];
@@ -490,7 +491,7 @@ cudaError_t un_attempt_d(yk_engine* e, const ykun::Args& a) {
     cudaStream_t s = e->stream;
     const int nb = (a.nlive + 255) / 256;
     ykun::un_reset_kernel<<<1, 1, 0, s>>>(a.g);
-    ykun::un_depth_kernel<D><<<nb, 256, 0, s>>>(a);
+    ykun::un_depth_kernel<D><<<(unsigned)(((size_t)a.nlive * (size_t)a.L + 255) / 256), 256, 0, s>>>(a);
     ykun::un_brank_kernel<D><<<nb, 256, 0, s>>>(a);
     size_t tb = e->un_cub_bytes;
     cudaError_t rc = cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, a.ekey, const_cast<unsigned long long*>(a.skey), a.enode,
@@ -498,12 +499,7 @@ cudaError_t un_attempt_d(yk_engine* e, const ykun::Args& a) {
     if (rc != cudaSuccess) return rc;
     ykun::un_select_kernel<D><<<(a.R + 255) / 256, 256, 0, s>>>(a);
     ykun::un_decide_kernel<<<1, 1, 0, s>>>(a);
-    ykun::un_apply_rekey_kernel<D><<<nb, 256, 0, s>>>(a);
-    tb = e->un_cub_bytes;
-    rc = cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, a.rkey, const_cast<unsigned long long*>(a.okey), a.rrn,
-                                         const_cast<unsigned long long*>(a.orn), a.nlive, 0, 64, s);
-    if (rc != cudaSuccess) return rc;
-    ykun::un_order_kernel<<<nb, 256, 0, s>>>(a);
+    ykun::un_apply_rekey_kernel<D><<<nb, 256, 0, s>>>(a);   // leaves the new order entries (rank order) in rkey / rrn
     return cudaGetLastError();
 }
 cudaError_t un_attempt(yk_engine* e, const ykun::Args& a) {
@@ -512,6 +508,24 @@ cudaError_t un_attempt(yk_engine* e, const ykun::Args& a) {
         case 4: return un_attempt_d<4>(e, a); case 5: return un_attempt_d<5>(e, a); case 6: return un_attempt_d<6>(e, a);
         case 7: return un_attempt_d<7>(e, a); default: return un_attempt_d<8>(e, a);
     }
+}
+
+// The node order after uniform runs: only the windowed kernel reads it, so it is rebuilt (stable sort of the re-keyed entries,
+// which un_apply_rekey_kernel left in rank order) when a windowed stretch follows, not after every run.
+int un_reorder(yk_engine* e) {
+    if (!e->un_ord_stale) return YK_OK;
+    cudaStream_t s = e->stream;
+    const int nlive = (int)e->nlive;
+    size_t tb = e->un_cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(e->d_un_cub.p, tb, e->d_un_rkey[0].p, e->d_un_rkey[1].p, e->d_un_rrn[0].p, e->d_un_rrn[1].p, nlive, 0, 64, s));
+    ykun::Args a{};
+    a.ord[0] = e->d_ord[0].p; a.ord[1] = e->d_ord[1].p; a.cur = e->d_lt_cur.p; a.nlive = nlive;
+    a.okey = e->d_un_rkey[1].p; a.orn = e->d_un_rrn[1].p;
+    ykun::un_order_kernel<<<(nlive + 255) / 256, 256, 0, s>>>(a);
+    CK(cudaGetLastError());
+    e->st.other_launches += 11;
+    e->un_ord_stale = false;
+    return YK_OK;
 }
 
 // One uniform run: entries [off, off + R) of the staged batch (h_lt_asks; results land in d_lt_res at the same offset).
@@ -549,13 +563,14 @@ int lt_uniform(yk_engine* e, size_t off, size_t R, bool insensitive, bool has_ga
         cudaEventElapsedTime(&ms, e->ev_l0, e->ev_l1);
         e->st.lattice_ms += ms;
         e->st.lattice_launches += 1;
-        e->st.other_launches += 24;   // 7 kernels of this file + two cub radix sorts (histogram, scan, 8 onesweep passes each, fewer when small)
+        e->st.other_launches += 16;   // 6 kernels of yk_uniform.cuh + one cub radix sort (histogram, exclusive sum, 8 onesweep passes)
         e->st.d2h_bytes += sizeof(ykun::Globals);
         const ykun::Globals& g = e->h_un_g[0];
         if (g.status == ykun::U_RETRY) { e->st.uniform_retries++; L *= 4; continue; }
         if (g.status == ykun::U_NAN || g.status == ykun::U_FALLBACK) return YK_OK;
         if (g.nan) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
         *status = g.status; *consumed = (size_t)g.consumed;
+        e->un_ord_stale = true;
         e->st.uniform_runs++; e->st.uniform_asks += (uint64_t)g.consumed; e->st.uniform_elements += (uint64_t)L * (uint64_t)nlive;
         return YK_OK;
     }
@@ -577,6 +592,7 @@ int lt_prepare(yk_engine* e) {
     CK(cudaMemsetAsync(e->d_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int), s));
     e->st.other_launches += 1;
     memset(e->h_lt_hdr.p, 0, yklt::H_WORDS * sizeof(int));
+    e->un_ord_stale = false;
     return YK_OK;
 }
 
@@ -585,6 +601,7 @@ int lt_prepare(yk_engine* e) {
 // yk_lattice_kernel; h_lt_hdr[H_STATUS / H_CONSUMED] describe the whole batch afterwards.  Blocks until it is decided.
 int lt_window(yk_engine* e, size_t off, size_t B, bool insensitive) {
     cudaStream_t s = e->stream;
+    { const int rco = un_reorder(e); if (rco) return rco; }
     yklt::Args a{};
     a.policy = e->cfg.policy;
     for (int k = 0; k < 8; ++k) a.w[k] = e->w.w[k];
@@ -1002,6 +1019,10 @@ void yk_destroy(yk_engine* e) {
     if (!e) return;
     e->worker.stop();
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->hp_on && e->hp_n)
+        fprintf(stderr, "[ykgpu] host ms per cycle (%llu cycles): prologue %.3f  upload+device_order %.3f  wait orderer setup %.3f  first fill + commit choice %.3f  "
+                        "run %.3f  epoch end / export + sync %.3f  finish %.3f\n", (unsigned long long)e->hp_n, e->hp[0] / e->hp_n, e->hp[1] / e->hp_n,
+                e->hp[2] / e->hp_n, e->hp[3] / e->hp_n, e->hp[4] / e->hp_n, e->hp[5] / e->hp_n, e->hp[6] / e->hp_n);
     if (e->lt_prof && e->d_lt_prof.p) {
         long long pf[16] = {0};
         if (cudaMemcpy(pf, e->d_lt_prof.p, sizeof(pf), cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -1110,6 +1131,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     T(e->ep_d_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1))); T(e->ep_h_fit.alloc((size_t)yk_engine::EP_MAX * (e->Wmax + 1)));
     T(cudaEventCreateWithFlags(&e->ep_ev, cudaEventDisableTiming)); T(cudaEventCreate(&e->ep_s0)); T(cudaEventCreate(&e->ep_s1));
     e->lt_prof = getenv("YK_PROFILE_LATTICE") != nullptr;
+    e->hp_on = getenv("YK_PROFILE_HOST") != nullptr;
     if (const char* um = getenv("YK_UNIFORM_MIN")) e->un_min = atoi(um);   // 0: no uniform-run path
     T(e->d_lt_prof.alloc(16));
     if (ok) T(cudaMemset(e->d_lt_prof.p, 0, 16 * sizeof(long long)));
@@ -1594,6 +1616,8 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     for (uint32_t p = 0; p < e->maxP; ++p)
         if (e->p_present[p] && e->p_queue[p] >= e->nq) return e->fail(YK_ERR_STATE, "yk_cycle: an application sits in a queue that no longer exists");
     const double t_start = now_ms();
+    double hp_t = t_start;   // YK_PROFILE_HOST: where the host time of the cycle goes (printed by yk_destroy)
+    auto hp = [&](int k) { if (e->hp_on) { const double t = now_ms(); e->hp[k] += t - hp_t; hp_t = t; } };
     // the orderer's per-cycle setup (host only) runs on the helper thread while this thread uploads stale tables and
     // starts the initial node order on the device
     std::vector<uint32_t>& pending = e->pending;
@@ -1659,12 +1683,15 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         e->ep_uploaded = false; e->ep_landed = true;
         begin_ms = now_ms() - t_b;
     });
+    hp(0);
     int rc = upload_tables(e);
     // the device scores and sorts the nodes while the helper thread still sets the orderer up
     e->order_enqueued = false;
     if (!rc) { rc = device_order(e); e->order_enqueued = rc == YK_OK && e->nlive > 0; }
     const double t_a = now_ms();
+    hp(1);
     e->worker.wait();
+    hp(2);
     e->st.host_ms[0] += t_a - t_start;
     e->st.host_ms[1] += begin_ms;
     if (rc) return rc;
@@ -1722,6 +1749,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         rc = fill_batch(e, b, e->batch, max_bindings, e->slot[0], e->st);
     }
     e->lt_active = false;
+    hp(3);
     if (!rc) {
         if (lattice) {
             e->lt_active = true;
@@ -1750,6 +1778,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             rc = run_host(e, c);
         }
     }
+    hp(4);
     // ---- always: leave host and device node tables current, persist what was bound, no ask left in flight ----
     int rc_end = YK_OK;
     if (e->lt_active) { rc_end = lt_export(e); e->lt_active = false; }
@@ -1758,6 +1787,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     for (int k = 0; k < 4; ++k) { e->st.dbg[k] += e->cm.dbg[k]; e->cm.dbg[k] = 0; }
     for (int k = 0; k < 6; ++k) { e->st.prof[k] += e->cm.prof[k]; e->cm.prof[k] = 0; }
     if (cudaStreamSynchronize(e->stream) != cudaSuccess && !rc && !rc_end) rc_end = e->fail(YK_ERR_CUDA, "cudaStreamSynchronize at the end of the cycle");
+    hp(5);
     if (rc) {
         // the cycle broke off: the bindings made so far stand (they are returned), every ask still in flight is pending
         // again, and the queue / application accounting is rebuilt from exactly the bindings returned
@@ -1782,6 +1812,8 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     for (uint32_t a : pending) if (e->a_state[a] == yk::ST_SKIPPED) e->st.skipped++;
     *n_out = c.n;
     e->st.cycles++;
+    hp(6);
+    e->hp_n++;
     e->st.total_ms += now_ms() - t_start;
     return rc ? rc : rc_end;
 }

@@ -19,9 +19,9 @@ __global__ void un_reset_kernel(Globals* g) {
 
 template <int D>
 __global__ void __launch_bounds__(256) un_depth_kernel(const Args a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (node, depth) element
     DepthOut o; o.valid = 0; o.bk = KEY_INF; o.nan = 0;
-    if (i < a.nlive) o = depth_item<D>(a, i);
+    if (x < (long long)a.nlive * a.L) o = element_item<D>(a, x);
     const unsigned v = __reduce_add_sync(0xFFFFFFFFu, o.valid);
     const unsigned long long b = warp_min64(o.bk);
     const unsigned nn = __ballot_sync(0xFFFFFFFFu, o.nan != 0);

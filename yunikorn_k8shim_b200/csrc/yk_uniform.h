@@ -80,36 +80,36 @@ LT_HD int64_t cap_of(bool usable, const int64_t* avail, const int64_t* total, co
 
 struct DepthOut { unsigned int valid; unsigned long long bk; int nan; };
 
-// node i (rank order): its elements, and the key of the first one not generated
+// element x = i * L + j: state j of node i (rank order).  The thread of j = 0 also reports the node's depth and, where the
+// node was cut at L, the key of its first element that is not generated.
 template <int D>
-LT_FN DepthOut depth_item(const Args& a, int i) {
+LT_FN DepthOut element_item(const Args& a, long long x) {
+    const int L = a.L;
+    const int i = (int)(x / L), j = (int)(x % L);
     const uint32_t n = a.byrank[i];
     const int64_t* r = a.rec + (size_t)n * a.RS;
     const uint32_t fl = (uint32_t)(uint64_t)r[2 * D + 2];
     const bool usable = (fl & 1u) && !(fl & 2u);
     const bool acc = yklt::accepts((uint64_t)r[2 * D], (uint64_t)r[2 * D + 1], n, a.tol, a.need, a.deny, a.want);
     const int64_t cap = acc ? cap_of<D>(usable, r, r + D, a.req, (int64_t)a.R) : 0;
-    const int L = a.L;
-    const int d = cap < (int64_t)L ? (int)cap : L;
-    DepthOut o; o.valid = (unsigned)d; o.bk = KEY_INF; o.nan = 0;
+    DepthOut o; o.valid = 0; o.bk = KEY_INF; o.nan = 0;
     int64_t av[D];
-    for (int k = 0; k < D; ++k) av[k] = r[k];
-    unsigned long long* ek = a.ekey + (size_t)i * L;
-    uint32_t* en = a.enode + (size_t)i * L;
-    for (int j = 0; j < L; ++j) {
-        unsigned long long key = KEY_INF;
-        if (j < d) {
-            key = yklt::key_of<D>(a.policy, a.w, r + D, av);
-            if (key == KEY_INF) o.nan = 1;
-            for (int k = 0; k < D; ++k) av[k] -= a.req[k];
+    unsigned long long key = KEY_INF;
+    if ((int64_t)j < cap) {
+        for (int k = 0; k < D; ++k) av[k] = r[k] - (int64_t)j * a.req[k];
+        key = yklt::key_of<D>(a.policy, a.w, r + D, av);
+        if (key == KEY_INF) o.nan = 1;
+    }
+    a.ekey[x] = key; a.enode[x] = n;
+    if (j == 0) {
+        o.valid = (unsigned)(cap < (int64_t)L ? cap : (int64_t)L);
+        if (cap > (int64_t)L) {
+            for (int k = 0; k < D; ++k) av[k] = r[k] - (int64_t)L * a.req[k];
+            o.bk = yklt::key_of<D>(a.policy, a.w, r + D, av);   // state L
+            if (o.bk == KEY_INF) o.nan = 1;
         }
-        ek[j] = key; en[j] = n;
+        a.bk[i] = o.bk;
     }
-    if (cap > (int64_t)L) {
-        o.bk = yklt::key_of<D>(a.policy, a.w, r + D, av);   // state L
-        if (o.bk == KEY_INF) o.nan = 1;
-    }
-    a.bk[i] = o.bk;
     return o;
 }
 
