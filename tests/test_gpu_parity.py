@@ -76,6 +76,23 @@ def test_reference_benchmark_shape_full(oracle):
     assert st["device"]["uniform_asks"] == 50_000 and st["device"]["lattice_subruns"] == 0   # one uniform run: no chain at all
 
 
+def test_default_commit_choice(oracle):
+    """the engine's default (auto): cycles made of long uniform runs are decided on the device, everything else by the sweep +
+    host commit -- same bindings either way"""
+    snap = synth.reference_shape(2_000, 40, 125)                     # one run of 5 000 identical asks
+    st = _run(snap, oracle.run(snap), batch=4096)
+    assert st["lattice_cycles"] == 1 and st["uniform_asks"] == 5_000 and st["sweep_launches"] == 0
+    snap = synth.perf(2_000, 40, 125)                                # every ask draws its own request class: no runs
+    st = _run(snap, oracle.run(snap), batch=4096)
+    assert st["lattice_cycles"] == 0 and st["sweep_launches"] > 0
+    snap = synth.reference_shape(2_000, 40, 125, policy=synth.POLICY_BINPACKING)   # not eligible: binpacking node sort
+    st = _run(snap, oracle.run(snap), batch=4096)
+    assert st["lattice_cycles"] == 0 and st["sweep_launches"] > 0
+    snap = synth.reference_shape(300, 8, 125)                        # 1 000 asks: below the shortest run worth a device pass
+    st = _run(snap, oracle.run(snap), batch=4096)
+    assert st["lattice_cycles"] == 0
+
+
 def test_uniform_runs_inside_mixed_batches(oracle, monkeypatch):
     """config-2/3/4-sized snapshots whose asks come in runs: uniform runs and windowed stretches alternate inside one batch,
     on the same device-resident node state"""

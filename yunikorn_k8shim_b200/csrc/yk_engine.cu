@@ -1736,9 +1736,11 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
                     const size_t B0 = e->slot[0].asks.size();
                     yklt::build_meta(e->cm.t, e->lt_shape_ids, e->a_sigid.data(), e->slot[0].asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
                     ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B0, e->un_min, e->un_segs);
-                    size_t covered = 0;
-                    for (const ykun::Segment& sg : e->un_segs) if (sg.uniform) covered += (size_t)sg.len;
-                    lattice = covered * 10 >= B0 * 9;
+                    // measured costs (profiles/r2b_*, r2_lattice_*): a uniform run ~0.25 ms whatever its length (16 launches, one
+                    // round trip), a windowed ask ~0.35 us, an ask on the host commit ~0.08 us
+                    double dev_us = 0;
+                    for (const ykun::Segment& sg : e->un_segs) dev_us += sg.uniform ? 250.0 : 0.35 * sg.len;
+                    lattice = dev_us < 0.7 * 0.08 * (double)B0;
                 }
             }
         }
