@@ -268,6 +268,8 @@ struct yk_engine {
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
     // uniform runs (yk_uniform.h): allocated on first use; element buffers hold UN_EMAX generated elements
     bool hp_on = false; double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t hp_n = 0;
+    bool un_hint = false;                       // this cycle's pending asks look like long uniform runs (auto commit: size the first batch for it)
+    bool lt_plan_ready = false;                 // h_lt_meta/shp/sig and un_segs already describe slot[0]'s batch (built by the commit choice)
     bool un_alloc = false, un_ord_stale = false;   // un_ord_stale: uniform runs moved nodes since d_ord was last written
     const uint32_t* lt_shape_ids = nullptr;     // per ask: a number equal for equal request vectors (a_shape, or a_sigid: finer, still exact)
     int un_min = 2048;                          // shortest run that takes the uniform path (YK_UNIFORM_MIN)
@@ -627,12 +629,18 @@ int lt_window(yk_engine* e, size_t off, size_t B, bool insensitive) {
 
 int lt_batch(yk_engine* e, size_t B, bool insensitive) {
     cudaStream_t s = e->stream;
-    CK(cudaMemcpyAsync(e->d_lt_asks.p, e->h_lt_asks.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_meta.p, e->h_lt_meta.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_shp.p, e->h_lt_shp.p, 4 * B, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(e->d_lt_sig.p, e->h_lt_sig.p, 4 * B, cudaMemcpyHostToDevice, s));
-    e->st.h2d_bytes += 16 * B;
-    ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B, e->un_min > 0 ? e->un_min : (int)B + 1, e->un_segs);
+    // the segments (e->un_segs) were planned by the caller; only the windowed kernel reads the per-entry words
+    bool staged = false;
+    auto stage = [&]() -> int {
+        if (staged) return YK_OK;
+        CK(cudaMemcpyAsync(e->d_lt_asks.p, e->h_lt_asks.p, 4 * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(e->d_lt_meta.p, e->h_lt_meta.p, 4 * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(e->d_lt_shp.p, e->h_lt_shp.p, 4 * B, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(e->d_lt_sig.p, e->h_lt_sig.p, 4 * B, cudaMemcpyHostToDevice, s));
+        e->st.h2d_bytes += 16 * B;
+        staged = true;
+        return YK_OK;
+    };
     int status = yklt::ST_DONE;
     size_t done = 0;
     for (const ykun::Segment& sg : e->un_segs) {
@@ -649,6 +657,8 @@ int lt_batch(yk_engine* e, size_t B, bool insensitive) {
             else st = ust == ykun::U_STOPPED ? yklt::ST_STOPPED : yklt::ST_DONE;
         }
         if (windowed) {
+            const int rcs = stage();
+            if (rcs) return rcs;
             const int rc = lt_window(e, (size_t)sg.off, (size_t)sg.len, insensitive);
             if (rc) return rc;
             st = e->h_lt_hdr[yklt::H_STATUS];
@@ -1483,7 +1493,11 @@ int run_lattice(yk_engine* e, Cycle& c, bool& handoff) {
     while (!A.asks.empty()) {
         const size_t B = A.asks.size();
         memcpy(e->h_lt_asks.p, A.asks.data(), 4 * B);
-        yklt::build_meta(e->cm.t, e->lt_shape_ids, e->a_sigid.data(), A.asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+        if (!e->lt_plan_ready) {
+            yklt::build_meta(e->cm.t, e->lt_shape_ids, e->a_sigid.data(), A.asks, e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p);
+            ykun::plan_segments(e->h_lt_meta.p, e->h_lt_shp.p, e->h_lt_sig.p, (int)B, e->un_min > 0 ? e->un_min : (int)B + 1, e->un_segs);
+        }
+        e->lt_plan_ready = false;
         size_t consumed = 0;
         int status = yklt::ST_DONE;
         if (e->nlive == 0) {   // no nodes: nothing fits
@@ -1676,6 +1690,18 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             e->ep_rows = ns > 0 && ns <= yk_engine::EP_MAX && (uint64_t)ns * 8 <= pending.size();
             e->ep_n = ns;
         }
+        e->un_hint = false;
+        if (!gang_too_big && auto_lattice && pending.size() >= (size_t)e->un_min) {
+            // a hint only (it sizes the first batch, never decides): asks are usually upserted application by application,
+            // so a long run of one signature in index order promises one in the orderer's order
+            size_t run = 1, longest = 0;
+            for (size_t i = 1; i <= pending.size(); ++i) {
+                if (i < pending.size() && e->a_sigid[pending[i]] == e->a_sigid[pending[i - 1]]) { ++run; continue; }
+                longest = std::max(longest, run);
+                run = 1;
+            }
+            e->un_hint = longest >= (size_t)e->un_min;
+        }
         if (!gang_too_big && force_lattice) {   // request-vector numbers for the lattice kernel's windows
             yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
             e->lt_shape_ids = e->a_shape.data();
@@ -1708,6 +1734,8 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         lattice = el.ok;
         if (lattice && ins) bsz0 = e->maxA;   // the whole static order in one launch
     }
+    if (auto_lattice && e->un_hint && ins) bsz0 = e->maxA;
+    e->lt_plan_ready = false;
     rc = fill_batch(e, bsz0, std::max<size_t>(bsz0, e->batch), max_bindings, e->slot[0], e->st);
     if (!rc && auto_lattice && pending.size() >= (size_t)e->un_min && e->slot[0].asks.size() >= (size_t)e->un_min) {
         // Automatic: the device commit decides a uniform run (one request vector, one predicate signature) by a grid-wide sort,
@@ -1727,7 +1755,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
                 // signature ids double as shape numbers: equal signatures request equal vectors; two signatures with one request
                 // only make the (rare, here) windowed stretches see one more shape
                 e->lt_shape_ids = e->a_sigid.data();
-                if (ins) {   // the whole static order in one batch
+                if (ins && e->slot[0].asks.size() < pending.size() && bsz0 < (size_t)e->maxA) {   // the whole static order in one batch
                     e->ord.unfill(e->slot[0].snap, e->slot[0].asks, 0);
                     size_t b = e->maxA;
                     rc = fill_batch(e, b, e->maxA, max_bindings, e->slot[0], e->st);
@@ -1741,6 +1769,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
                     double dev_us = 0;
                     for (const ykun::Segment& sg : e->un_segs) dev_us += sg.uniform ? 250.0 : 0.35 * sg.len;
                     lattice = dev_us < 0.7 * 0.08 * (double)B0;
+                    e->lt_plan_ready = lattice;
                 }
             }
         }
