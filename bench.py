@@ -20,6 +20,7 @@ pending).  ONE JSON line:
                engine's default commit choice (commit_ran_on: the reference shape is one uniform run -> decided on the device
                by a grid-wide sort, csrc/yk_uniform.cuh; config 3 -> sweep + host commit)
   host_commit / device_commit  the same workloads with the ordered commit forced onto the host / the device
+  scale_up     the reference shape x 10 (50k nodes / 500k pods), default commit choice and forced host commit
 With --gpus N > 1 (torchrun): `value` = N YuniKorn partitions (disjoint node sets with their own queues: the core
 schedules partitions independently), one per GPU, no data-path exchange -- weak scaling; `multi` = one partition with the
 sweep of every batch split across the N GPUs and exchanged peer-to-peer (strong scaling of config 3), every rank checked
@@ -52,6 +53,7 @@ WORKLOADS = {
     "config2": "config2: 10k nodes / 50k pending pods, D=4, no affinity, fair node sort, 1 leaf queue, 400 apps x 125",
     "config3": "config3: 10k nodes / 50k pods + taints + nodeAffinity bitmasks (64-bit sets), fair node sort, 400 apps x 125",
     "reference_shape": "reference benchmark shape: 5k identical nodes / 50k identical pods 10 mCPU + 1 MB (scheduler_perf_test.go:62-63,283-288)",
+    "reference_shape_x10": "reference benchmark shape x 10: 50k identical nodes / 500k identical pods (4000 apps x 125)",
     "config4": "config4: 50k nodes / 200k pods, 73 queues (DRF parents, quotas), fifo leaves",
     "config5": "config5: 10k nodes / 2000 gangs x 10, all-or-nothing",
 }
@@ -65,6 +67,8 @@ def make_snapshot(name, seed_shift=0):
         return synth.perf(N_NODES, N_APPS, TASKS, masks=True, seed=2 + seed_shift)
     if name == "reference_shape":
         return synth.reference_shape()
+    if name == "reference_shape_x10":
+        return synth.reference_shape(50_000, 4_000, 125)
     if name == "config4":
         return synth.hier()
     if name == "config5":
@@ -446,13 +450,18 @@ def main():
         threads = max(1, min(os.cpu_count() or 1, 64))
         side_steps = max(3, min(args.steps, 5))
 
+        snaps, wants = {wl: snap}, {wl: want}
+
         def run_arm(name, commit, share=True, cpu_engine=True):
-            s = snap if name == wl else make_snapshot(name)
+            if name not in snaps:
+                snaps[name] = make_snapshot(name)
+                wants[name] = oc.run(snaps[name])
+            s = snaps[name]
             a = Arm(s, torch, None, local_rank, batch=args.batch, share_rows=share, commit=commit)
             r = a.measure(side_steps, 2, e2e=False)
             re_ = a.measure(side_steps, 1, e2e=True)
             a.close()
-            w = want if name == wl else oc.run(s)
+            w = wants[name]
             stx = r["stats"]
             o = {"workload": WORKLOADS[name], "commit": commit,
                  "commit_ran_on": "device" if stx["lattice_cycles"] else "host", "value": r["allocations"] / r["seconds"], "unit": UNIT,
@@ -491,6 +500,8 @@ def main():
                 out["roofline_one_row_per_ask"] = o["roofline"]
         out["workloads"] = {name: run_arm(name, "auto") for name in ("config3", "reference_shape") if name != wl}
         out["host_commit"] = {name: run_arm(name, "host", cpu_engine=False) for name in ("reference_shape",) if name != wl}
+        # the same shape ten times larger: the device's share of the cycle grows with the cluster, the host commit's does not shrink
+        out["scale_up"] = {"auto": run_arm("reference_shape_x10", "auto"), "host": run_arm("reference_shape_x10", "host", cpu_engine=False)}
         out["device_commit"] = {name: run_arm(name, "device", cpu_engine=False) for name in ("config2", "config3", "reference_shape")}
     if not args.no_cpu_baseline and not args.quick:
         oc.run(snap)
