@@ -11,6 +11,7 @@
 #include "../../yunikorn_k8shim_b200/csrc/yk_orderer.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -124,7 +125,10 @@ int run_d(uint32_t policy, const double* weights,
     o.t.p_user = g_p_user; o.t.n_ul = g_n_ul; o.t.ul_queue = g_ul_queue; o.t.ul_user = g_ul_user; o.t.ul_max = g_ul_max; o.t.ul_alloc = g_ul_alloc;
     std::vector<uint32_t> pending(nA);
     for (uint32_t i = 0; i < nA; ++i) pending[i] = i;
+    auto now_ns = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    uint64_t t_begin = now_ns(), t_fill = 0, t_settle = 0, t_finish = 0;
     o.begin_cycle(pending);
+    t_begin = now_ns() - t_begin;
     const bool ins = o.insensitive;
 
     yk::CommitTables ct;
@@ -215,7 +219,7 @@ int run_d(uint32_t policy, const double* weights,
     uint64_t handoffs = 0, batches = 0;
     uint64_t ustats[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8] uniform attempts, [9] deeper retries, [10] asks decided by uniform runs
     while (n < max_bindings) {
-        o.fill(bsz, (size_t)max_bindings - n, asks, snap);
+        { const uint64_t t0 = now_ns(); o.fill(bsz, (size_t)max_bindings - n, asks, snap); t_fill += now_ns() - t0; }
         if (o.oversize_gang) {
             if (bsz < batch) { bsz = batch; o.fill(bsz, (size_t)max_bindings - n, asks, snap); }
             if (o.oversize_gang) return -1;
@@ -303,16 +307,20 @@ int run_d(uint32_t policy, const double* weights,
         } else if (!ins && consumed < B) {
             return -12;   // a placement-sensitive batch may only end early on a failure
         }
+        const uint64_t t_s0 = now_ns();
         for (size_t i = 0; i < consumed; ++i) {
             const uint32_t a = asks[i];
             if (result[i] == yk::CNONE) { if (ins) o.fail_in_place(a); continue; }
             o.confirm(a);
             out_ask[n] = a; out_node[n] = result[i]; ++n;
         }
+        t_settle += now_ns() - t_s0;
         if (ins && consumed < B) return -13;
         bsz = failed ? std::max<size_t>(std::min<size_t>(64, batch), bsz / 4) : std::min<size_t>(batch, bsz * 2);
     }
+    t_finish = now_ns();
     o.finish();
+    t_finish = now_ns() - t_finish;
     *n_out = n;
     for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
     for (uint32_t nn = 0; nn < nN; ++nn)
@@ -322,6 +330,7 @@ int run_d(uint32_t policy, const double* weights,
         stats_out[3] = (uint64_t)hdr[yklt::H_ELEMS]; stats_out[4] = (uint64_t)hdr[yklt::H_QUICK]; stats_out[5] = (uint64_t)hdr[yklt::H_ESC];
         stats_out[6] = handoffs; stats_out[7] = batches;
         stats_out[8] = ustats[8]; stats_out[9] = ustats[9]; stats_out[10] = ustats[10];
+        stats_out[11] = t_begin; stats_out[12] = t_fill; stats_out[13] = t_settle; stats_out[14] = t_finish;   // ns (development aid)
     }
     return 0;
 }

@@ -88,6 +88,9 @@ def test_default_commit_choice(oracle):
     snap = synth.reference_shape(2_000, 40, 125, policy=synth.POLICY_BINPACKING)   # not eligible: binpacking node sort
     st = _run(snap, oracle.run(snap), batch=4096)
     assert st["lattice_cycles"] == 0 and st["sweep_launches"] > 0
+    snap = synth.kwok(2_000, 20, 250, variant="bare")                # kwok-perf-test pods: {pods: 1} only, keys never move
+    st = _run(snap, oracle.run(snap), batch=4096)
+    assert st["lattice_cycles"] == 1 and st["uniform_asks"] == snap.n_asks and st["uniform_retries"] == 0
     snap = synth.reference_shape(300, 8, 125)                        # 1 000 asks: below the shortest run worth a device pass
     st = _run(snap, oracle.run(snap), batch=4096)
     assert st["lattice_cycles"] == 0

@@ -553,6 +553,23 @@ int lt_uniform(yk_engine* e, size_t off, size_t R, bool insensitive, bool has_ga
     a.rkey = e->d_un_rkey[0].p; a.okey = e->d_un_rkey[1].p; a.rrn = e->d_un_rrn[0].p; a.orn = e->d_un_rrn[1].p;
     a.res = e->d_lt_res.p + off; a.g = e->d_un_g.p;
     int L = ykun::first_depth((int)R, nlive);
+    // no node takes the request more often than its TOTAL allows: beyond that depth nothing is ever cut
+    int64_t capmax = 0;
+    for (uint32_t i = 0; i < e->nlive; ++i) {
+        const uint32_t n = e->by_rank[i];
+        int64_t tot[8];
+        for (int k = 0; k < e->D; ++k) tot[k] = e->n_total[(size_t)k * e->maxN + n];
+        capmax = std::max(capmax, ykun::cap_of_d(e->D, true, tot, tot, a.req, (int64_t)R));
+    }
+    int Lmax = 1;
+    while ((int64_t)Lmax < capmax) Lmax <<= 1;
+    {   // a request with no weighted dimension leaves every key where it is: the run fills the first nodes (by key, NodeID) to
+        // the brim, so the depth that matters is a node's whole capacity, not the mean share
+        bool flat = true;
+        for (int k = 0; k < e->D; ++k) if (e->w.w[k] != 0.0 && a.req[k] != 0) flat = false;
+        if (flat) L = Lmax;
+    }
+    L = std::min(L, Lmax);
     for (;;) {
         if ((size_t)L * (size_t)nlive > UN_EMAX) return YK_OK;   // too deep for the element buffers: fallback
         a.L = L;
@@ -568,7 +585,11 @@ int lt_uniform(yk_engine* e, size_t off, size_t R, bool insensitive, bool has_ga
         e->st.other_launches += 16;   // 6 kernels of yk_uniform.cuh + one cub radix sort (histogram, exclusive sum, 8 onesweep passes)
         e->st.d2h_bytes += sizeof(ykun::Globals);
         const ykun::Globals& g = e->h_un_g[0];
-        if (g.status == ykun::U_RETRY) { e->st.uniform_retries++; L *= 4; continue; }
+        if (g.status == ykun::U_RETRY) {   // deeper; past Lmax only if a node's available exceeds its total (the buffers end it)
+            e->st.uniform_retries++;
+            L = L < Lmax ? (int)std::min<int64_t>((int64_t)L * 4, (int64_t)Lmax) : L * 4;
+            continue;
+        }
         if (g.status == ykun::U_NAN || g.status == ykun::U_FALLBACK) return YK_OK;
         if (g.nan) return e->fail(YK_ERR_RANGE, "NaN node score after commit");
         *status = g.status; *consumed = (size_t)g.consumed;

@@ -78,6 +78,22 @@ LT_HD int64_t cap_of(bool usable, const int64_t* avail, const int64_t* total, co
     return c;
 }
 
+// the same with the dimension count at run time (host side)
+inline int64_t cap_of_d(int D, bool usable, const int64_t* avail, const int64_t* total, const int64_t* req, int64_t limit) {
+    if (!usable) return 0;
+    int64_t c = limit;
+    for (int k = 0; k < D; ++k) {
+        const int64_t r = req[k];
+        if (r <= 0) continue;
+        const int64_t t = total[k] < 0 ? 0 : total[k];
+        const int64_t a = avail[k] < 0 ? 0 : avail[k];
+        if (r > t) return 0;
+        const int64_t q = a / r;
+        c = q < c ? q : c;
+    }
+    return c;
+}
+
 struct DepthOut { unsigned int valid; unsigned long long bk; int nan; };
 
 // element x = i * L + j: state j of node i (rank order).  The thread of j = 0 also reports the node's depth and, where the
