@@ -1758,7 +1758,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
     bool lattice = false;
     size_t bsz0 = e->batch;
     if (force_lattice) {
-        const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique);
+        const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique, &e->cycle_has_gang);
         lattice = el.ok;
         if (lattice && ins) bsz0 = e->maxA;   // the whole static order in one launch
     }
@@ -1778,7 +1778,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             run = 1;
         }
         if (longest >= (size_t)e->un_min) {
-            const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique);
+            const yklt::Eligibility el = yklt::eligible(e->cm.t, e->n_hi, e->n_present.data(), e->n_total.p, e->maxN, e->n_rank.data(), pending, &e->ranks_unique, &e->cycle_has_gang);
             if (el.ok) {
                 // signature ids double as shape numbers: equal signatures request equal vectors; two signatures with one request
                 // only make the (rare, here) windowed stretches see one more shape

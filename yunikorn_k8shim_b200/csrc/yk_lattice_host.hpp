@@ -109,9 +109,10 @@ struct Eligibility {
 };
 
 // ranks_unique: when the caller already knows whether the live nodes' ranks are distinct (the engine checks it where it sorts
-// the nodes by rank), else nullptr.
+// the nodes by rank), else nullptr; any_gang: when it already knows whether any pending ask is a gang member.
 inline Eligibility eligible(const yk::CommitTables& t, uint32_t n_hi, const uint8_t* n_present, const int64_t* n_total,
-                            size_t ldn, const uint32_t* n_rank, const std::vector<uint32_t>& pending, const bool* ranks_unique = nullptr) {
+                            size_t ldn, const uint32_t* n_rank, const std::vector<uint32_t>& pending, const bool* ranks_unique = nullptr,
+                            const bool* any_gang = nullptr) {
     Eligibility e;
     if (t.policy != 0u) { e.why = "binpacking node sort"; return e; }
     for (int k = 0; k < t.D; ++k) if (t.w[k] < 0.0 || t.w[k] != t.w[k]) { e.why = "negative node-sort weight"; return e; }
@@ -130,7 +131,7 @@ inline Eligibility eligible(const yk::CommitTables& t, uint32_t n_hi, const uint
         std::sort(ranks.begin(), ranks.end());
         for (size_t i = 1; i < ranks.size(); ++i) if (ranks[i] == ranks[i - 1]) { e.why = "duplicate NodeID ranks"; return e; }
     }
-    {
+    if (!any_gang || *any_gang) {
         std::unordered_map<uint64_t, uint32_t> first;   // (app, gang) -> first member seen
         for (uint32_t a : pending) {
             if (t.a_gang[a] == yk::CNONE) continue;

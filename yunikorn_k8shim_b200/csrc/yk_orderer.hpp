@@ -287,6 +287,20 @@ public:
             extend_static(cap_batch == (size_t)-1 ? cap_batch : cap_batch + 1);   // one more than fits: the loop below ends on capacity
             while (static_next < static_order.size()) {
                 const uint32_t a = static_order[static_next];
+                if (t.a_gang[a] == NONE) {   // a stretch of plain asks: one copy
+                    const size_t room = std::min(cap_user, cap_batch) - std::min(std::min(cap_user, cap_batch), batch.size());
+                    size_t len1 = 0;
+                    const size_t lim = std::min(room, static_order.size() - static_next);
+                    while (len1 < lim && t.a_gang[static_order[static_next + len1]] == NONE) ++len1;
+                    if (len1 == 0) {   // capacity reached: same outcome as the one-entry case below
+                        if (batch.size() + 1 > cap_user) break;
+                        if (batch.empty()) oversize_gang = true;
+                        break;
+                    }
+                    batch.insert(batch.end(), static_order.begin() + static_next, static_order.begin() + static_next + len1);
+                    static_next += len1;
+                    continue;
+                }
                 size_t len = 1;
                 if (t.a_gang[a] != NONE)
                     while (static_next + len < static_order.size() && t.a_gang[static_order[static_next + len]] == t.a_gang[a] &&
