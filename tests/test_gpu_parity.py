@@ -205,6 +205,23 @@ def test_max_bindings_and_second_cycle(oracle):
             assert np.array_equal(np.concatenate([node, node2]), full["node"])
 
 
+def test_two_uniform_cycles_on_the_device(oracle):
+    """the state a device-committed cycle leaves (host and device node tables, ask states, queue accounting) is what the next
+    cycle starts from: two cycles, both decided as uniform runs on the device, equal one oracle pass"""
+    s = synth.reference_shape(500, 96, 125)                              # 12 000 identical asks
+    full = oracle.run(s)
+    with Engine.for_snapshot(s, batch=4096) as e:
+        ask, node, _ = e.cycle(6000)
+        ask2, node2, _ = e.cycle(s.n_asks)
+        st = e.stats()
+        assert np.array_equal(np.concatenate([ask, ask2]), full["ask"])
+        assert np.array_equal(np.concatenate([node, node2]), full["node"])
+        assert np.array_equal(e.nodes_available(np.arange(s.n_nodes)), full["avail"])
+        assert st["lattice_cycles"] == 2 and st["uniform_asks"] == s.n_asks
+        e.release(np.concatenate([ask, ask2]))
+        assert np.array_equal(e.nodes_available(np.arange(s.n_nodes)), s.node_avail)
+
+
 def test_release_gives_resources_back(oracle):
     s = synth.perf(6, 2, 300)                                     # overcommitted
     want = oracle.run(s)
