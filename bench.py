@@ -254,7 +254,9 @@ def cpu_engine_time(snap, threads, reps=2, batch=4096):
     from test_engine_host import run_engine_host
     so = os.path.join(ROOT, "tests", "host", "_build", "engine_shim.so")
     src = os.path.join(ROOT, "tests", "host", "engine_shim.cpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    csrc = os.path.join(ROOT, "yunikorn_k8shim_b200", "csrc")
+    newest = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc) if f.endswith((".h", ".hpp"))])
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-o", so, src])
     lib = C.CDLL(so)
