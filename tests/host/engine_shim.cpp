@@ -104,6 +104,14 @@ static int engine_host_run_impl(
     std::vector<int64_t> p_alloc((size_t)D * nP, 0);
     o.t.D = D; o.t.maxA = nA; o.t.maxP = nP; o.t.nq = nQ;
     o.t.a_req = a_req; o.t.a_prio = a_prio; o.t.a_create = a_create; o.t.a_app = a_app; o.t.a_flags = a_flags; o.t.a_gang = a_gang;
+    // the per-ask cause table the engine keeps at upsert time (yk::Tables::a_cause): same rule, so the tests walk that branch
+    std::vector<uint8_t> a_cause(nA, 0);
+    for (uint32_t a = 0; a < nA; ++a) {
+        bool pos = false, neg = false;
+        for (int k = 0; k < D; ++k) { const int64_t v = a_req[(size_t)k * nA + a]; neg = neg || v < 0; pos = pos || v > 0; }
+        a_cause[a] = (a_flags[a] & 1u) ? yk::ST_SLOWPATH : ((neg || !pos) ? yk::ST_INVALID : 0);
+    }
+    o.t.a_cause = a_cause.data();
     o.t.a_state = state.data(); o.t.p_queue = p_queue; o.t.p_submit = p_submit; o.t.p_present = present.data();
     o.t.q_parent = q_parent; o.t.q_guar = q_guar; o.t.q_max = q_max; o.t.q_alloc = q_alloc; o.t.p_alloc = p_alloc.data(); o.t.q_sort = q_sort;
     o.t.q_prio_offset = g_q_prio_offset; o.t.q_prio_fence = g_q_prio_fence;

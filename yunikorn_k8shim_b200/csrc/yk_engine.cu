@@ -266,6 +266,7 @@ struct yk_engine {
     Dev<long long> d_lt_prof; bool lt_prof = false; uint64_t lt_total_subruns = 0;   // YK_PROFILE_LATTICE: SM clocks per kernel phase, printed by yk_destroy
     Pin<uint32_t> h_lt_asks, h_lt_meta, h_lt_shp, h_lt_sig, h_lt_res; Pin<int> h_lt_hdr; Pin<int64_t> h_lt_ub;
     std::vector<uint32_t> a_shape, a_sigid;
+    std::vector<uint8_t> a_cause;               // per ask: 0, ST_SLOWPATH or ST_INVALID (yk::Tables::a_cause), kept by yk_asks_upsert
     cudaEvent_t ev_l0 = nullptr, ev_l1 = nullptr;
     // uniform runs (yk_uniform.h): allocated on first use; element buffers hold UN_EMAX generated elements
     bool hp_on = false; double hp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t hp_n = 0;
@@ -1180,7 +1181,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     }
     if (!ok) { yk_destroy(e); return YK_ERR_CUDA; }
     e->n_rank.assign(N, 0); e->n_present.assign(N, 0);
-    e->a_shape.assign(A, 0); e->a_sigid.assign(A, 0);
+    e->a_shape.assign(A, 0); e->a_sigid.assign(A, 0); e->a_cause.assign(A, 0);
     e->sigs.reset(A);
     e->a_sig.assign(A, 0); e->a_prio.assign(A, 0); e->a_create.assign(A, 0); e->a_app.assign(A, 0); e->a_flags.assign(A, 0);
     e->a_gang.assign(A, YK_NONE); e->a_bound.assign(A, YK_NONE); e->a_state.assign(A, yk::ST_ABSENT);
@@ -1339,6 +1340,19 @@ int yk_apps_remove(yk_engine* e, uint32_t n, const uint32_t* idx) {
     return YK_OK;
 }
 
+// what keeps an ask out of the passes whatever the cluster looks like (yk::Tables::a_cause): the slow-path flag, or a request
+// that is not strictly greater than zero ([EXT] preAllocateCheck)
+static uint8_t ask_cause(const yk_engine* e, uint32_t x) {
+    if (e->a_flags[x] & 1u) return yk::ST_SLOWPATH;
+    bool pos = false;
+    for (int k = 0; k < e->D; ++k) {
+        const int64_t v = e->a_req[(size_t)k * e->maxA + x];
+        if (v < 0) return yk::ST_INVALID;
+        if (v > 0) pos = true;
+    }
+    return pos ? 0 : yk::ST_INVALID;
+}
+
 int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t* req, const uint64_t* tol,
                    const uint64_t* need, const uint64_t* deny, const int32_t* prio, const int64_t* create_seq,
                    const uint32_t* app, const uint32_t* required_node, const uint32_t* flags, const uint32_t* gang) {
@@ -1373,6 +1387,7 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
         if (full) e->sigs.reset(e->maxA);
         else for (uint32_t i = 0; i < a; ++i) e->sigs.retire(x0 + i);
         for (uint32_t i = 0; i < a; ++i) e->a_sig[x0 + i] = yk::ask_signature(sv, x0 + i);
+        for (uint32_t i = 0; i < a; ++i) e->a_cause[x0 + i] = ask_cause(e, x0 + i);
         e->a_hi = std::max(e->a_hi, x0 + a);
         if (!full && e->sigs.n > 2 * e->maxA) {   // too many stale numbers: renumber every present ask
             e->sigs.reset(e->maxA);
@@ -1401,6 +1416,7 @@ int yk_asks_upsert(yk_engine* e, uint32_t a, const uint32_t* idx, const int64_t*
         e->a_create[x] = create_seq[i];
         e->a_app[x] = app[i];
         e->a_flags[x] = flags ? flags[i] : 0;
+        e->a_cause[x] = ask_cause(e, x);
         e->a_gang[x] = gang ? gang[i] : YK_NONE;
         e->a_state[x] = yk::ST_PENDING;
         e->a_bound[x] = YK_NONE;
@@ -1690,7 +1706,7 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         yk::Tables& t = e->ord.t;
         t.D = e->D; t.maxA = e->maxA; t.maxP = e->maxP; t.nq = e->nq;
         t.a_req = e->a_req.p; t.a_prio = e->a_prio.data(); t.a_create = e->a_create.data(); t.a_app = e->a_app.data();
-        t.a_flags = e->a_flags.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
+        t.a_flags = e->a_flags.data(); t.a_cause = e->a_cause.data(); t.a_gang = e->a_gang.data(); t.a_state = e->a_state.data();
         t.p_queue = e->p_queue.data(); t.p_submit = e->p_submit.data(); t.p_present = e->p_present.data();
         t.q_parent = e->q_parent.data(); t.q_guar = e->q_guar.data(); t.q_max = e->q_max.data(); t.q_alloc = e->q_alloc.data(); t.p_alloc = e->p_alloc.data();
         t.q_sort = e->q_sort.data();

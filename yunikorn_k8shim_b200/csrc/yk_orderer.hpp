@@ -35,6 +35,8 @@ struct Tables {   // views into the engine's host tables
     const int64_t* a_create = nullptr;
     const uint32_t* a_app = nullptr;
     const uint32_t* a_flags = nullptr;
+    const uint8_t* a_cause = nullptr;    // optional: per ask 0, ST_SLOWPATH (flag bit 0) or ST_INVALID (request not strictly > 0), kept by the
+                                         // owner of the tables where asks are upserted; null = derived from a_flags / a_req on the fly
     const uint32_t* a_gang = nullptr;    // NONE or gang id (all-or-nothing group inside one application)
     uint8_t* a_state = nullptr;          // ST_*
     const uint32_t* p_queue = nullptr;
@@ -182,7 +184,6 @@ public:
             };
             if (!std::is_sorted(v.begin(), v.end(), less)) std::sort(v.begin(), v.end(), less);
             AState& A = ap[p];
-            int64_t psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             int64_t nlive = 0;
             for (uint32_t i = 0; i < v.size(); ++i) {
                 uint32_t a = v[i];
@@ -190,15 +191,13 @@ public:
                 if (!have_prio) { prio0 = t.a_prio[a]; have_prio = true; }
                 else if (t.a_prio[a] != prio0) one_prio = false;
                 if (t.a_state[a] == ST_PENDING) ++nlive;
-                for (int k = 0; k < d; ++k) psum[k] += req(a, k);
             }
             A.npend = (int64_t)v.size();
             A.live = nlive;
             for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq]) {   // once per application, not per ask
                 q[qq].npend += (int64_t)v.size();
                 q[qq].live += nlive;
-                for (int k = 0; k < d; ++k) q[qq].pending[k] += psum[k];
-            }
+            }   // (the queues' pending RESOURCES are summed below, and only when the order can depend on them)
             q_apps[t.p_queue[p]].push_back(p);
             A.key_prio = t.a_prio[v[0]];
             ++q_prio_cnt[t.p_queue[p]][A.key_prio];
@@ -234,6 +233,15 @@ public:
                 for (int k = 0; k < d; ++k) if (t.q_max[(size_t)k * t.nq + qq] != UNSET) quota = true;
             insensitive = !quota && !any_limit;   // a user limit makes headroom depend on what was placed, like a quota
         }
+        if (!insensitive)   // pending resources per queue (fair-share ties, headroom bookkeeping): a placement-insensitive order never reads them
+            for (uint32_t p = 0; p < t.maxP; ++p) {
+                const auto& v = ap_asks[p];
+                if (v.empty()) continue;
+                int64_t psum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (uint32_t a : v) for (int k = 0; k < d; ++k) psum[k] += req(a, k);
+                for (uint32_t qq = t.p_queue[p]; qq != NONE; qq = t.q_parent[qq])
+                    for (int k = 0; k < d; ++k) q[qq].pending[k] += psum[k];
+            }
         static_order.clear();
         static_next = 0;
         static_apps.clear();
@@ -249,11 +257,13 @@ public:
     void extend_static(size_t want) {
         const int d = t.D;
         auto cause_of = [&](uint32_t a) -> uint8_t {
+            if (t.a_cause) return t.a_cause[a];
             if (t.a_flags[a] & 1u) return ST_SLOWPATH;
             int64_t rq[8];
             for (int k2 = 0; k2 < d; ++k2) rq[k2] = req(a, k2);
             return strictly_gt_zero(rq, d) ? 0 : ST_INVALID;
         };
+        static_order.reserve(std::min<size_t>(static_order.size() + (want == (size_t)-1 ? (size_t)t.maxA : want), (size_t)t.maxA + 1));
         while (static_order.size() - static_next < want && sa_app < static_apps.size()) {
             const auto& v = ap_asks[static_apps[sa_app]];
             if (sa_pos >= v.size()) { ++sa_app; sa_pos = 0; continue; }
