@@ -25,6 +25,9 @@ static int g_skip_checks = 0;
 extern "C" void host_set_bench_mode(int threads, int skip_checks) { g_sweep_threads = threads; g_skip_checks = skip_checks; }
 
 namespace {
+static int g_profile = 0;
+extern "C" void host_set_profile(int on) { g_profile = on; }
+
 struct SoAView { const int64_t* cap; size_t ld; const uint64_t* taint; const uint64_t* label; const uint32_t* node; int D; int Np; };
 
 void sweep_row_scalar(const SoAView& v, const int64_t* rq, uint64_t tol, uint64_t need, uint64_t deny, uint32_t want, uint32_t* row, int W) {
@@ -123,6 +126,7 @@ static int engine_host_run_impl(
 
     // ---- committer + initial order (what yk_key_kernel + the stable radix sort produce) ----
     yk::Committer cm;
+    cm.profile = g_profile != 0;
     cm.t.D = D; cm.t.policy = policy; cm.t.w = weights; cm.t.lda = nA;
     cm.t.a_req = a_req; cm.t.a_tol = a_tol; cm.t.a_need = a_need; cm.t.a_deny = a_deny; cm.t.a_node = a_node; cm.t.a_gang = a_gang; cm.t.a_app = a_app;
     cm.build(nN, n_avail, n_total, nN, n_taint, n_label, n_rank);
@@ -308,7 +312,11 @@ static int engine_host_run_impl(
     }
     o.finish();
     *n_out = n;
-    if (rows_out) *rows_out = rows_swept;
+    if (rows_out) {   // [0] rows swept, then the commit's counters (yk_commit.hpp dbg[]: words scanned, touched candidates walked,
+        rows_out[0] = rows_swept;   // asks won by a touched node, re-keys) and its TSC profile when host_set_profile(1) was called
+        for (int k = 0; k < 4; ++k) rows_out[1 + k] = cm.dbg[k];
+        for (int k = 0; k < 6; ++k) rows_out[5 + k] = cm.prof[k];
+    }
     for (uint32_t i = 0; i < nA; ++i) state_out[i] = state[i];
     for (uint32_t nn = 0; nn < nN; ++nn)
         for (int k = 0; k < D; ++k) avail_out[(size_t)k * nN + nn] = cm.node(nn).avail()[k];

@@ -84,6 +84,8 @@ def run_engine_host(shim, s, batch=256, epoch_limit=None, speculate=1, max_bindi
         _p(out_ask), _p(out_node), C.byref(n), _p(state), _p(avail), _p(nrows))
     if rows is not None:
         rows.append(int(nrows[0]) if fn == "engine_host_run" else [int(x) for x in nrows])
+        if fn == "engine_host_run":
+            run_engine_host.last_counters = [int(x) for x in nrows]
     return rc, out_ask[:n.value].astype(np.int64), out_node[:n.value].astype(np.int64), state[:A], avail[:, :N].T.copy()
 
 

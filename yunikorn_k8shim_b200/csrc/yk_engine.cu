@@ -1689,6 +1689,9 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
         pending.clear();
         pending.reserve(e->a_hi);
         bool any_gang = false;
+        // (longest run of one signature id among consecutive pending asks, in index order: the hint for the automatic commit choice)
+        size_t sig_run = 0, sig_longest = 0;
+        uint32_t sig_prev = YK_NONE;
         for (uint32_t a = 0; a < e->a_hi; ++a) {
             uint8_t& st = e->a_state[a];
             if (st == yk::ST_ABSENT || st == yk::ST_ALLOCATED) continue;
@@ -1696,7 +1699,12 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             if (!e->p_present[e->a_app[a]]) continue;
             pending.push_back(a);
             any_gang = any_gang || e->a_gang[a] != YK_NONE;
+            if (auto_lattice) {
+                const uint32_t g = e->a_sigid[a];
+                if (g == sig_prev) ++sig_run; else { sig_longest = std::max(sig_longest, sig_run); sig_run = 1; sig_prev = g; }
+            }
         }
+        sig_longest = std::max(sig_longest, sig_run);
         e->cycle_has_gang = any_gang;
         if (any_gang) {   // a gang that no batch can hold is an argument error: found before anything is committed
             std::unordered_map<uint64_t, uint32_t> members;
@@ -1734,18 +1742,9 @@ extern "C" int yk_cycle(yk_engine* e, uint32_t max_bindings, yk_binding* out, ui
             e->ep_rows = ns > 0 && ns <= yk_engine::EP_MAX && (uint64_t)ns * 8 <= pending.size();
             e->ep_n = ns;
         }
-        e->un_hint = false;
-        if (!gang_too_big && auto_lattice && pending.size() >= (size_t)e->un_min) {
-            // a hint only (it sizes the first batch, never decides): asks are usually upserted application by application,
-            // so a long run of one signature in index order promises one in the orderer's order
-            size_t run = 1, longest = 0;
-            for (size_t i = 1; i <= pending.size(); ++i) {
-                if (i < pending.size() && e->a_sigid[pending[i]] == e->a_sigid[pending[i - 1]]) { ++run; continue; }
-                longest = std::max(longest, run);
-                run = 1;
-            }
-            e->un_hint = longest >= (size_t)e->un_min;
-        }
+        // a hint only (it sizes the first batch, never decides): asks are usually upserted application by application, so a long
+        // run of one signature in index order promises one in the orderer's order
+        e->un_hint = !gang_too_big && auto_lattice && pending.size() >= (size_t)e->un_min && sig_longest >= (size_t)e->un_min;
         if (!gang_too_big && force_lattice) {   // request-vector numbers for the lattice kernel's windows
             yklt::assign_shapes(e->cm.t, pending, e->a_shape, &e->n_shapes);
             e->lt_shape_ids = e->a_shape.data();
