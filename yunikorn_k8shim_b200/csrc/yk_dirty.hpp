@@ -29,9 +29,12 @@ struct DirtyRef {
 
 class DirtyIndex {
 public:
-    static constexpr uint32_t CAP = 64;   // a range splits when it is full
+    #ifndef YK_DIRTY_CAP
+#define YK_DIRTY_CAP 64
+#endif
+    static constexpr uint32_t CAP = YK_DIRTY_CAP;   // a range splits when it is full
 
-    void clear() { used_ = 0; lo_.clear(); id_.clear(); count_ = 0; }
+    void clear() { used_ = 0; free_.clear(); lo_.clear(); id_.clear(); count_ = 0; }
     size_t size() const { return count_; }
 
     void insert(const DirtyRef& x) {
@@ -128,12 +131,21 @@ private:
     struct Meta { unsigned __int128 max; uint32_t n, b, sorted, pad; };   // live entries of the range: body[b, n)
     DirtyRef* body(uint32_t s) { return body_.data() + (size_t)s * CAP; }
     uint32_t fresh() {
-        if (used_ == meta_.size()) { meta_.emplace_back(); body_.resize(body_.size() + CAP); }
-        Meta& m = meta_[used_];
+        uint32_t s;
+        if (!free_.empty()) { s = free_.back(); free_.pop_back(); }   // a slot an emptied range gave back: the working set stays the live ranges
+        else {
+            if (used_ == meta_.size()) {   // grow geometrically: a long epoch splits thousands of times
+                const size_t want = std::max<size_t>(64, meta_.size() * 2);
+                meta_.resize(want); body_.resize(want * CAP);
+            }
+            s = used_++;
+        }
+        Meta& m = meta_[s];
         m.n = 0; m.b = 0; m.sorted = 1; m.max = 0;
-        return used_++;
+        return s;
     }
     void drop_range(uint32_t r) {
+        free_.push_back(id_[r]);
         lo_.erase(lo_.begin() + r); id_.erase(id_.begin() + r);
         lo_[0] = 0;   // the first range always starts at -inf
     }
@@ -185,6 +197,7 @@ private:
     std::vector<uint32_t> id_;            // range -> slot
     std::vector<Meta> meta_;              // per slot: counts, order flag, largest entry (small: stays in L1)
     std::vector<DirtyRef> body_;          // per slot: CAP entries; reused across epochs
+    std::vector<uint32_t> free_;          // slots of ranges that ran empty, reused before new ones are taken
     uint32_t used_ = 0;
     size_t count_ = 0;
 };
