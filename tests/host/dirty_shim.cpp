@@ -54,3 +54,38 @@ extern "C" int dirty_model_check(uint64_t seed, int n_keys, int ops, int key_ran
     if (bad || it != model.end()) return -5;
     return 0;
 }
+
+// The commit's own pattern, for long: take an entry near the front out (erase_at) and put it back further behind under a larger
+// key.  Front ranges run empty and are dropped all the time; their slots are recycled by later splits.
+extern "C" int dirty_model_drain(uint64_t seed, int n, int ops, int max_step) {
+    std::mt19937_64 r(seed);
+    yk::DirtyIndex d;
+    d.clear();
+    std::set<unsigned __int128> model;
+    std::vector<uint64_t> key((size_t)n);
+    for (int i = 0; i < n; ++i) { key[(size_t)i] = (uint64_t)i * 7; yk::DirtyRef x(key[(size_t)i], (uint32_t)i, (uint32_t)i); d.insert(x); model.insert(x.w); }
+    for (int t = 0; t < ops; ++t) {
+        yk::DirtyIndex::Cursor c;
+        const yk::DirtyRef* e = d.first(c);
+        auto it = model.begin();
+        const int skip = (int)(r() % 4);
+        for (int s = 0; s < skip && e; ++s) { if (*it != e->w) return -1; e = d.next(c); ++it; }
+        if (!e || it == model.end() || *it != e->w) return -2;
+        const uint32_t node = e->node();
+        d.erase_at(c); model.erase(it);
+        key[node] += 1 + r() % (uint64_t)max_step;
+        yk::DirtyRef x(key[node], node, node);
+        d.insert(x); model.insert(x.w);
+        if (d.size() != model.size()) return -3;
+        if ((t & 1023) == 0) {   // full order check now and then
+            auto jt = model.begin();
+            int bad = 0;
+            d.for_each([&](const yk::DirtyRef& y) { if (jt == model.end() || *jt != y.w) bad = 1; else ++jt; });
+            if (bad || jt != model.end()) return -4;
+        }
+    }
+    auto jt = model.begin();
+    int bad = 0;
+    d.for_each([&](const yk::DirtyRef& y) { if (jt == model.end() || *jt != y.w) bad = 1; else ++jt; });
+    return (bad || jt != model.end()) ? -5 : 0;
+}

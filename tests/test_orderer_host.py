@@ -164,3 +164,8 @@ def test_dirty_index_model_check(tmp_path):
     for seed in range(120):
         for nk, ops, kr in ((1, 200, 5), (10, 500, 3), (1000, 3000, 50), (5000, 12000, 100000), (64, 1000, 2)):
             assert lib.dirty_model_check(C.c_uint64(seed), nk, ops, kr) == 0, (seed, nk, ops, kr)
+    # the commit's own pattern for long: take from the front, put back further behind (front ranges empty out and their slots
+    # are recycled by later splits)
+    for seed in range(12):
+        for n, ops, step in ((50, 5000, 40), (2000, 60000, 3000), (10000, 100000, 50000), (300, 20000, 2)):
+            assert lib.dirty_model_drain(C.c_uint64(seed), n, ops, step) == 0, (seed, n, ops, step)
