@@ -360,3 +360,16 @@ extern "C" int lattice_host_run(int D, uint32_t policy, const double* weights,
     switch (D) { RUN(1) RUN(2) RUN(3) RUN(4) RUN(5) RUN(6) RUN(7) RUN(8) default: return -2; }
 #undef RUN
 }
+
+// ykun::plan_segments / cap_of_d / first_depth for the unit tests
+extern "C" int host_plan_segments(const uint32_t* meta, const uint32_t* shp, const uint32_t* sig, int B, int min_run, int* off, int* len, int* uniform, int cap) {
+    std::vector<ykun::Segment> segs;
+    ykun::plan_segments(meta, shp, sig, B, min_run, segs);
+    int n = 0;
+    for (const ykun::Segment& s : segs) { if (n < cap) { off[n] = s.off; len[n] = s.len; uniform[n] = s.uniform ? 1 : 0; } ++n; }
+    return n;
+}
+extern "C" int64_t host_cap_of(int D, int usable, const int64_t* avail, const int64_t* total, const int64_t* req, int64_t limit) {
+    return ykun::cap_of_d(D, usable != 0, avail, total, req, limit);
+}
+extern "C" int host_first_depth(int R, int nlive) { return ykun::first_depth(R, nlive); }

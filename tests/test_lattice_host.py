@@ -200,3 +200,44 @@ def test_uniform_gangs(lshim, oracle):
             st = []
             assert check(lshim, oracle, s, tag=(seed, fill), batch=1000, stats=st, uniform=(4, 0)) is not None
             assert st[0]["uniform_attempts"] > 0
+
+
+def test_plan_segments_and_capacity_rules(lshim):
+    """the host-side pieces of the uniform-run path: batches are cut into uniform runs and the stretches between them, never
+    inside a gang; a node's capacity for a request is yklt::fits applied repeatedly"""
+    GANG, GSTART = 8, 4
+
+    def plan(meta, shp, sig, min_run):
+        B = len(shp)
+        m, s, g = (np.ascontiguousarray(x, dtype=np.uint32) for x in (meta, shp, sig))
+        off, ln, un = (np.zeros(B + 1, dtype=np.int32) for _ in range(3))
+        n = lshim.host_plan_segments(m.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), B, min_run,
+                                     off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p), un.ctypes.data_as(C.c_void_p), B + 1)
+        segs = [(int(off[i]), int(ln[i]), bool(un[i])) for i in range(n)]
+        assert sum(l for _, l, _ in segs) == B and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(n - 1))   # a partition, in order
+        return segs
+
+    z = [0] * 10
+    assert plan(z, [1] * 10, [7] * 10, 4) == [(0, 10, True)]
+    assert plan(z, [1] * 10, [7] * 10, 11) == [(0, 10, False)]
+    assert plan(z, [1, 1, 1, 2, 2, 2, 2, 2, 3, 3], [0] * 10, 4) == [(0, 3, False), (3, 5, True), (8, 2, False)]
+    assert plan(z, [1] * 10, [0, 0, 0, 0, 0, 9, 9, 9, 9, 9], 5) == [(0, 5, True), (5, 5, True)]       # same request, two signatures
+    assert plan([], [], [], 1) == []
+    # a gang that straddles the start / the end of a run of equal (shape, signature) is kept whole on the windowed side
+    meta = [0, GANG | GSTART, GANG, GANG, 0, 0, 0, 0, GANG | GSTART, GANG]
+    shp = [5, 5, 1, 1, 1, 1, 1, 1, 1, 2]
+    segs = plan(meta, shp, [0] * 10, 3)
+    assert segs == [(0, 4, False), (4, 4, True), (8, 2, False)]
+    for o, l, u in segs:   # no segment starts inside a gang
+        assert not (meta[o] & GANG) or (meta[o] & GSTART)
+    # capacity: request <= min(max(0, total), max(0, available)) on every dimension, as often as it goes
+    cap = lambda av, to, rq, lim=10**9, usable=1: lshim.host_cap_of(len(rq), usable, (C.c_int64 * len(rq))(*av), (C.c_int64 * len(rq))(*to), (C.c_int64 * len(rq))(*rq), C.c_int64(lim))
+    lshim.host_cap_of.restype = C.c_int64
+    assert cap([1000, 64], [1000, 64], [100, 1]) == 10
+    assert cap([1000, 64], [1000, 64], [100, 0]) == 10            # a zero request never limits
+    assert cap([1000, -5], [1000, 64], [100, 1]) == 0             # over-committed dimension: clamped at 0
+    assert cap([1000, 64], [50, 64], [100, 1]) == 0               # larger than the node's total: never fits
+    assert cap([1000, 64], [1000, 64], [100, 1], lim=3) == 3
+    assert cap([1000, 64], [1000, 64], [100, 1], usable=0) == 0
+    assert cap([5, 5], [5, 5], [0, 0]) == 10**9                   # (never reaches the commit: the orderer marks it invalid)
+    assert lshim.host_first_depth(50_000, 5_000) == 32 and lshim.host_first_depth(10, 5_000) == 4
