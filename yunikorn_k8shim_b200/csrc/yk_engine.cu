@@ -256,7 +256,7 @@ struct yk_engine {
     // device-resident ordered commit (yk_lattice.h): node records, ping-pong node order, per-batch staging
     bool lt_allowed = true;                  // !YK_FLAG_HOST_COMMIT, single GPU
     int lt_force = 0;                        // YK_FLAG_DEVICE_COMMIT / YK_COMMIT=device: every eligible cycle commits on the device
-    bool lt_auto = false;                    // YK_COMMIT=auto: eligible cycles with long windows commit on the device
+    bool lt_auto = false;                    // the default: eligible cycles whose order is made of long uniform runs commit on the device
     bool lt_active = false;                  // this cycle runs (so far) on the device commit
     bool cycle_has_gang = false;             // some pending ask of this cycle is a gang member
     bool order_enqueued = false;             // device_order() of this cycle is already on the stream
@@ -1152,7 +1152,7 @@ int yk_create(const yk_config* cfg, yk_engine** out) {
     if (const char* cm = getenv("YK_COMMIT")) {
         if (!strcmp(cm, "host")) e->lt_allowed = false;
         if (!strcmp(cm, "device")) e->lt_force = 1;
-        if (!strcmp(cm, "auto")) e->lt_auto = true;
+        if (!strcmp(cm, "auto")) { e->lt_auto = true; e->lt_force = 0; e->lt_allowed = !(cfg->flags & YK_FLAG_HOST_COMMIT) && cfg->world <= 1; }
     }
     e->lt_RS = (2 * D + 3 + 3) / 4 * 4;
     T(e->d_rec.alloc(N * (size_t)e->lt_RS)); T(e->d_ord[0].alloc(N)); T(e->d_ord[1].alloc(N)); T(e->d_rank.alloc(N));

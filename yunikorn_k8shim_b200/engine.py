@@ -118,7 +118,10 @@ def _colmajor(x, D, n):
 
 
 class Engine:
-    """One yk_engine.  Method names and arguments mirror include/ykgpu.h one to one."""
+    """One yk_engine.  Method names and arguments mirror include/ykgpu.h one to one.
+
+    commit: where the ordered commit runs -- "auto" (the library's default: on the device for cycles made of long uniform runs,
+    sweep + host commit otherwise), "host" (YK_FLAG_HOST_COMMIT), "device" (YK_FLAG_DEVICE_COMMIT: every eligible cycle)."""
 
     def __init__(self, D=4, policy=0, weights=None, max_nodes=1024, max_asks=4096, max_apps=64, max_queues=8,
                  batch=0, device=-1, rank=0, world=1, share_rows=True, commit="auto"):
